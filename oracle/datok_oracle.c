@@ -1,0 +1,692 @@
+/*
+ * datok_oracle.c -- CPU ORACLE (test infrastructure, see datok_oracle.h).
+ *
+ * Restates, in plain C, the Go reference KorAP/Datok 0.3.1:
+ *   ParseMatrix            matrix.go:235-337
+ *   TransduceTokenWriter   matrix.go:348-698
+ *   NewTokenWriter         token_writer.go:36-175
+ *   utf8.DecodeRune        Go stdlib (borrowed semantics of bufio.ReadRune)
+ * Variable names follow the reference so the two can be read side by side.
+ * Parity pin: tests/test_oracle_golden.py (reference golden vectors).
+ */
+#define _GNU_SOURCE
+#include "datok_oracle.h"
+
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#define FIRSTBIT 0x80000000u /* datok.go:43 */
+#define EOT 4                /* matrix.go:13 */
+#define VERSION 1            /* datok.go:39 */
+#define BUFSZ 1024           /* matrix.go:365 */
+#define RUNE_ERROR 0xFFFD
+
+/* ------------------------------------------------------------------ utf8 */
+
+/* Go unicode/utf8: first[] classes and accept ranges. */
+static void utf8_class(uint8_t b, int *size, uint8_t *lo, uint8_t *hi) {
+  *lo = 0x80;
+  *hi = 0xBF;
+  if (b < 0x80) { *size = 1; return; }
+  if (b < 0xC2) { *size = 0; return; }           /* xx: invalid lead */
+  if (b < 0xE0) { *size = 2; return; }
+  if (b == 0xE0) { *size = 3; *lo = 0xA0; return; }
+  if (b == 0xED) { *size = 3; *hi = 0x9F; return; }
+  if (b < 0xF0) { *size = 3; return; }
+  if (b == 0xF0) { *size = 4; *lo = 0x90; return; }
+  if (b < 0xF4) { *size = 4; return; }
+  if (b == 0xF4) { *size = 4; *hi = 0x8F; return; }
+  *size = 0;
+}
+
+int32_t ora_decode_rune(const uint8_t *p, size_t n, int *width) {
+  if (n < 1) { *width = 0; return RUNE_ERROR; }
+  uint8_t p0 = p[0];
+  int sz; uint8_t lo, hi;
+  utf8_class(p0, &sz, &lo, &hi);
+  if (sz == 1) { *width = 1; return p0; }
+  *width = 1;
+  if (sz == 0) return RUNE_ERROR;
+  if (n < (size_t)sz) return RUNE_ERROR;
+  uint8_t b1 = p[1];
+  if (b1 < lo || hi < b1) return RUNE_ERROR;
+  if (sz == 2) { *width = 2; return ((int32_t)(p0 & 0x1F) << 6) | (b1 & 0x3F); }
+  uint8_t b2 = p[2];
+  if (b2 < 0x80 || 0xBF < b2) return RUNE_ERROR;
+  if (sz == 3) {
+    *width = 3;
+    return ((int32_t)(p0 & 0x0F) << 12) | ((int32_t)(b1 & 0x3F) << 6) | (b2 & 0x3F);
+  }
+  uint8_t b3 = p[3];
+  if (b3 < 0x80 || 0xBF < b3) return RUNE_ERROR;
+  *width = 4;
+  return ((int32_t)(p0 & 0x07) << 18) | ((int32_t)(b1 & 0x3F) << 12) |
+         ((int32_t)(b2 & 0x3F) << 6) | (b3 & 0x3F);
+}
+
+/* Go string(rune): invalid runes become U+FFFD */
+static int encode_rune(int32_t r, uint8_t *out) {
+  if (r < 0 || r > 0x10FFFF || (r >= 0xD800 && r <= 0xDFFF)) r = RUNE_ERROR;
+  if (r < 0x80) { out[0] = (uint8_t)r; return 1; }
+  if (r < 0x800) { out[0] = 0xC0 | (r >> 6); out[1] = 0x80 | (r & 0x3F); return 2; }
+  if (r < 0x10000) {
+    out[0] = 0xE0 | (r >> 12); out[1] = 0x80 | ((r >> 6) & 0x3F); out[2] = 0x80 | (r & 0x3F);
+    return 3;
+  }
+  out[0] = 0xF0 | (r >> 18); out[1] = 0x80 | ((r >> 12) & 0x3F);
+  out[2] = 0x80 | ((r >> 6) & 0x3F); out[3] = 0x80 | (r & 0x3F);
+  return 4;
+}
+
+/* ----------------------------------------------------------------- model */
+
+struct ora_model {
+  int epsilon, unknown, identity, stateCount, sigmaCount;
+  int32_t sigmaASCII[256];
+  /* sigma map[rune]int as an open-addressing table */
+  uint32_t hmask;
+  int32_t *hkey; /* -1 = empty */
+  int32_t *hval;
+  uint32_t *array;
+  size_t arraySize;
+};
+
+static inline uint32_t hash_rune(int32_t r) { return (uint32_t)r * 2654435761u; }
+
+static void sigma_put(ora_model *m, int32_t r, int32_t v) {
+  uint32_t i = (hash_rune(r) >> 7) & m->hmask;
+  while (m->hkey[i] != -1 && m->hkey[i] != r) i = (i + 1) & m->hmask;
+  m->hkey[i] = r;
+  m->hval[i] = v;
+}
+
+static inline int sigma_get(const ora_model *m, int32_t r, int *ok) {
+  uint32_t i = (hash_rune(r) >> 7) & m->hmask;
+  while (m->hkey[i] != -1) {
+    if (m->hkey[i] == r) { *ok = 1; return m->hval[i]; }
+    i = (i + 1) & m->hmask;
+  }
+  *ok = 0;
+  return 0; /* Go map miss yields the zero value */
+}
+
+static uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static uint32_t le32(const uint8_t *p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+/* ParseMatrix matrix.go:235-337 over an in-memory (already gunzipped) image */
+static ora_model *parse_matrix(const uint8_t *d, size_t n) {
+  size_t p = 0;
+  if (n < 5 || memcmp(d, "MATOK", 5) != 0) return NULL; /* :258 */
+  p = 5;
+  if (n - p < 14) return NULL; /* :263-272 */
+  if (le16(d + p) != VERSION) return NULL; /* :274-279 */
+  ora_model *m = (ora_model *)calloc(1, sizeof(*m));
+  m->epsilon = le16(d + p + 2);
+  m->unknown = le16(d + p + 4);
+  m->identity = le16(d + p + 6);
+  m->stateCount = (int)le32(d + p + 8);
+  m->sigmaCount = le16(d + p + 12);
+  p += 14;
+  m->arraySize = ((size_t)m->stateCount + 1) * (size_t)m->sigmaCount; /* :286 */
+  for (int i = 0; i < 256; i++) m->sigmaASCII[i] = m->identity; /* :289-293 (identity is never -1 after a u16 read) */
+  uint32_t cap = 64;
+  while (cap < (uint32_t)m->sigmaCount * 4u) cap <<= 1;
+  m->hmask = cap - 1;
+  m->hkey = (int32_t *)malloc(cap * sizeof(int32_t));
+  m->hval = (int32_t *)malloc(cap * sizeof(int32_t));
+  for (uint32_t i = 0; i < cap; i++) m->hkey[i] = -1;
+  for (int x = 0; x < m->sigmaCount; x++) { /* :295-303 */
+    int w;
+    int32_t sym = ora_decode_rune(d + p, n - p, &w);
+    if (w == 0) continue; /* err != nil (EOF) */
+    p += (size_t)w;
+    if (sym != 0) {
+      if (sym < 256) m->sigmaASCII[sym] = x;
+      sigma_put(m, sym, x);
+    }
+  }
+  if (p >= n || d[p] != 'M') { ora_free(m); return NULL; } /* :305-315 */
+  p++;
+  if (n - p < m->arraySize * 4) { ora_free(m); return NULL; } /* :327-330 */
+  m->array = (uint32_t *)malloc(m->arraySize * 4 + 4);
+  for (size_t x = 0; x < m->arraySize; x++) m->array[x] = le32(d + p + x * 4); /* :332-334 */
+  return m;
+}
+
+/* LoadMatrixFile matrix.go:214-231 (gzip -> ParseMatrix) */
+ora_model *ora_load(const char *path) {
+  gzFile f = gzopen(path, "rb");
+  if (!f) return NULL;
+  /* gzopen transparently reads non-gzip files; the reference's gzip.NewReader
+   * rejects them (matrix.go:222-226).  Check the magic ourselves. */
+  FILE *raw = fopen(path, "rb");
+  unsigned char mg[2] = {0, 0};
+  if (raw) { if (fread(mg, 1, 2, raw) != 2) mg[0] = 0; fclose(raw); }
+  if (mg[0] != 0x1f || mg[1] != 0x8b) { gzclose(f); return NULL; }
+  size_t cap = 1 << 20, len = 0;
+  uint8_t *buf = (uint8_t *)malloc(cap);
+  for (;;) {
+    if (len == cap) { cap *= 2; buf = (uint8_t *)realloc(buf, cap); }
+    int got = gzread(f, buf + len, (unsigned)(cap - len > (1u << 30) ? (1u << 30) : cap - len));
+    if (got < 0) { free(buf); gzclose(f); return NULL; }
+    if (got == 0) break;
+    len += (size_t)got;
+  }
+  gzclose(f);
+  ora_model *m = parse_matrix(buf, len);
+  free(buf);
+  return m;
+}
+
+void ora_free(ora_model *m) {
+  if (!m) return;
+  free(m->hkey); free(m->hval); free(m->array); free(m);
+}
+
+int ora_epsilon(const ora_model *m) { return m->epsilon; }
+int ora_unknown(const ora_model *m) { return m->unknown; }
+int ora_identity(const ora_model *m) { return m->identity; }
+int ora_state_count(const ora_model *m) { return m->stateCount; }
+int ora_sigma_count(const ora_model *m) { return m->sigmaCount; }
+const uint32_t *ora_array(const ora_model *m, size_t *n) { if (n) *n = m->arraySize; return m->array; }
+const int32_t *ora_sigma_ascii(const ora_model *m) { return m->sigmaASCII; }
+
+int ora_sigma_lookup(const ora_model *m, int32_t r, int *ok) {
+  if (r < 256) return m->sigmaASCII[r];       /* matrix.go:421-425 */
+  int a = sigma_get(m, r, ok);                /* :427 */
+  if (!*ok) a = m->identity;                  /* :430-434 */
+  return a;
+}
+
+/* -------------------------------------------------------- growable arrays */
+
+#define VEC(T) struct { T *p; size_t n, cap; }
+#define VPUSH(v, x) do { if ((v).n == (v).cap) { (v).cap = (v).cap ? (v).cap * 2 : 1024; \
+      (v).p = realloc((v).p, (v).cap * sizeof(*(v).p)); } (v).p[(v).n++] = (x); } while (0)
+
+typedef VEC(uint8_t) vec_u8;
+typedef VEC(int32_t) vec_i32;
+typedef VEC(uint32_t) vec_u32;
+typedef VEC(uint64_t) vec_u64;
+
+static void sink_write(vec_u8 *s, const uint8_t *d, size_t n) {
+  if (s->n + n > s->cap) {
+    size_t c = s->cap ? s->cap : 4096;
+    while (c < s->n + n) c *= 2;
+    s->p = (uint8_t *)realloc(s->p, c);
+    s->cap = c;
+  }
+  memcpy(s->p + s->n, d, n);
+  s->n += n;
+}
+static inline void sink_byte(vec_u8 *s, uint8_t b) { sink_write(s, &b, 1); }
+
+static void sink_itoa(vec_u8 *s, long v) { /* strconv.Itoa */
+  char tmp[24];
+  int n = snprintf(tmp, sizeof tmp, "%ld", v);
+  sink_write(s, (const uint8_t *)tmp, (size_t)n);
+}
+
+/* ------------------------------------------------------------ TokenWriter */
+
+/* captured variables of NewTokenWriter, token_writer.go:37-42 */
+typedef struct {
+  uint32_t flags;
+  vec_u8 *writer;
+  long posC;
+  vec_i32 pos;
+  int sentB;
+  vec_i32 sent;
+  int init;
+  int status;
+  /* recorder (test infrastructure, not in the reference) */
+  int record;
+  vec_i32 rec_tok_pos;
+  vec_i32 rec_sent_pos;
+  size_t sent_flushed; /* sent entries already emitted by earlier TextEnds */
+} token_writer;
+
+static void tw_init(token_writer *tw, vec_u8 *sink, uint32_t flags, int record) {
+  memset(tw, 0, sizeof(*tw));
+  tw->flags = flags;
+  tw->writer = sink;
+  tw->posC = 0;
+  tw->sentB = 1;
+  tw->init = (flags & ORA_WRITER_USED) ? 0 : 1;
+  tw->record = record;
+}
+
+static void tw_free(token_writer *tw) {
+  free(tw->pos.p); free(tw->sent.p); free(tw->rec_tok_pos.p); free(tw->rec_sent_pos.p);
+}
+
+/* tw.Token, token_writer.go:59-100 */
+static void tw_token(token_writer *tw, int offset, const int32_t *buf, int len) {
+  uint32_t flags = tw->flags;
+  if (flags & (ORA_TOKEN_POS | ORA_SENTENCE_POS)) {
+    if (tw->posC == 0 && (flags & ORA_NEWLINE_AFTER_EOT)) { /* :66 */
+      if (len < 1) { tw->status = ORA_PANIC_EMPTY_BUF; return; }
+      if (buf[0] == '\n' && !tw->init) tw->posC--;
+    }
+    tw->init = 0;
+    tw->posC += offset;
+    VPUSH(tw->pos, (int32_t)tw->posC);
+    if (tw->record) VPUSH(tw->rec_tok_pos, (int32_t)tw->posC);
+    if (tw->sentB) {
+      tw->sentB = 0;
+      VPUSH(tw->sent, (int32_t)tw->posC);
+      if (tw->record) VPUSH(tw->rec_sent_pos, (int32_t)tw->posC);
+    }
+    tw->posC += len - offset;
+    VPUSH(tw->pos, (int32_t)tw->posC);
+    if (tw->record) VPUSH(tw->rec_tok_pos, (int32_t)tw->posC);
+    if (!(flags & ORA_TOKENS)) return;
+  } else if (!(flags & ORA_TOKENS)) {
+    return; /* :99 */
+  }
+  if (offset > len || offset < 0) { tw->status = ORA_PANIC_TOKEN_SLICE; return; }
+  uint8_t enc[4];
+  for (int i = offset; i < len; i++) { /* string(buf[offset:]) */
+    int w = encode_rune(buf[i], enc);
+    sink_write(tw->writer, enc, (size_t)w);
+  }
+  sink_byte(tw->writer, '\n');
+}
+
+/* tw.SentenceEnd, token_writer.go:103-127 */
+static void tw_sentence_end(token_writer *tw) {
+  uint32_t flags = tw->flags;
+  if (flags & ORA_SENTENCE_POS) {
+    if (tw->pos.n == 0) { tw->status = ORA_PANIC_SENT_NO_TOKEN; return; } /* :108 */
+    int32_t v = tw->pos.p[tw->pos.n - 1];
+    VPUSH(tw->sent, v);
+    if (tw->record) VPUSH(tw->rec_sent_pos, v);
+    tw->sentB = 1;
+    if (flags & ORA_SENTENCES) sink_byte(tw->writer, '\n');
+  } else if (flags & ORA_SENTENCES) {
+    sink_byte(tw->writer, '\n');
+  }
+}
+
+/* tw.TextEnd, token_writer.go:130-167 */
+static void tw_text_end(token_writer *tw) {
+  uint32_t flags = tw->flags;
+  if (flags & (ORA_TOKEN_POS | ORA_SENTENCE_POS)) {
+    if (flags & ORA_TOKEN_POS) {
+      if (tw->pos.n == 0) { tw->status = ORA_PANIC_TEXT_NO_TOKEN; return; } /* :135 */
+      sink_itoa(tw->writer, tw->pos.p[0]);
+      for (size_t i = 1; i < tw->pos.n; i++) { sink_byte(tw->writer, ' '); sink_itoa(tw->writer, tw->pos.p[i]); }
+      sink_byte(tw->writer, '\n');
+    }
+    if (flags & ORA_SENTENCE_POS) {
+      if (tw->sent.n == 0) { tw->status = ORA_PANIC_TEXT_NO_SENT; return; } /* :145 */
+      sink_itoa(tw->writer, tw->sent.p[0]);
+      for (size_t i = 1; i < tw->sent.n; i++) { sink_byte(tw->writer, ' '); sink_itoa(tw->writer, tw->sent.p[i]); }
+      sink_byte(tw->writer, '\n');
+      tw->sent_flushed += tw->sent.n;
+      tw->sent.n = 0;
+      tw->sentB = 1;
+    }
+    tw->posC = 0;
+    tw->pos.n = 0;
+  } else {
+    sink_byte(tw->writer, '\n');
+  }
+}
+
+/* ------------------------------------------------------------------ walk */
+
+typedef struct {
+  vec_u32 tok_byte_start, tok_byte_end, tok_buf_start;
+  vec_i32 tok_offset;
+  vec_u64 sent_tok_idx;
+  vec_u64 text_tok_end, text_sent_end, text_sentpos_end;
+  vec_u32 text_byte_end;
+} recorder;
+
+typedef struct {
+  uint64_t n_runes, n_iter, n_back, n_back_runes, n_hard;
+  uint64_t n_tok, n_sent, n_text;
+  uint32_t max_window;
+} walk_stats;
+
+/* TransduceTokenWriter, matrix.go:348-698.  Returns status. */
+static int transduce(const ora_model *mat, const uint8_t *in, size_t n, token_writer *w,
+                     recorder *rec, const ora_carry *cin, ora_carry *cout, walk_stats *st) {
+  int a = 0;
+  uint32_t t0 = 0;
+  uint32_t t = 1; /* :351 */
+  int ok = 0;
+  int rewindBuffer;
+  uint32_t epsilonState = 0; /* :356 */
+  int epsilonOffset = 0;
+  int sentenceEnd = 0; /* :360 */
+  int textEnd = 0;     /* :363 */
+  if (cin) {
+    if (cin->state) t = cin->state;
+    ok = cin->ok; sentenceEnd = cin->sentence_end; textEnd = cin->text_end;
+  }
+  int32_t buffer[BUFSZ];      /* :365 */
+  uint32_t boff[BUFSZ + 1];   /* byte offset of each buffered rune (recorder) */
+  int bufft = 0, buffc = 0, buffi = 0;
+  size_t rp = 0; /* reader cursor (bufio.Reader over `in`) */
+  int32_t chr = 0;
+  int eof = 0, eot = 0, newchar = 1;
+  const int S = mat->stateCount;
+  const uint32_t *array = mat->array;
+  const int epsilon = mat->epsilon, identity = mat->identity, unknown = mat->unknown;
+  uint64_t iter = 0, iter_cap = 64 * ((uint64_t)n + 64);
+  uint64_t ntok = 0, nsent = 0;
+
+#define BYTE_AT(i) ((i) < buffi ? boff[(i)] : (uint32_t)rp)
+#define EMIT_TOKEN() do { \
+    if (rec) { \
+      if (bufft <= buffc) { VPUSH(rec->tok_byte_start, BYTE_AT(bufft)); } else { VPUSH(rec->tok_byte_start, BYTE_AT(buffc)); } \
+      VPUSH(rec->tok_byte_end, BYTE_AT(buffc)); \
+      VPUSH(rec->tok_buf_start, buffi > 0 ? boff[0] : (uint32_t)rp); \
+      VPUSH(rec->tok_offset, bufft); } \
+    ntok++; st->n_tok++; \
+    tw_token(w, bufft, buffer, buffc); \
+    if (w->status) return w->status; } while (0)
+#define EMIT_SENT() do { \
+    if (rec) VPUSH(rec->sent_tok_idx, ntok); \
+    nsent++; st->n_sent++; \
+    tw_sentence_end(w); \
+    if (w->status) return w->status; } while (0)
+#define EMIT_TEXT() do { \
+    tw_text_end(w); st->n_text++; \
+    if (w->status) return w->status; \
+    if (rec) { VPUSH(rec->text_tok_end, ntok); VPUSH(rec->text_sent_end, nsent); \
+      VPUSH(rec->text_sentpos_end, (uint64_t)w->sent_flushed); \
+      VPUSH(rec->text_byte_end, BYTE_AT(buffc)); } } while (0)
+
+  for (;;) { /* outer: re-entered by the `goto PARSECHARM` of :658,:667 */
+    for (;;) { /* PARSECHARM :384 */
+      if (++iter > iter_cap) return ORA_ERR_LOOP;
+      if (newchar) {
+        if (buffc >= buffi) { /* :388 */
+          if (eof) break;
+          if (rp >= n) { eof = 1; break; } /* io.EOF :396-399 */
+          int width;
+          chr = ora_decode_rune(in + rp, n - rp, &width); /* :392 */
+          if (buffi >= BUFSZ) return ORA_PANIC_BUFFER_OVERFLOW; /* :406 */
+          buffer[buffi] = chr;
+          boff[buffi] = (uint32_t)rp;
+          rp += (size_t)width;
+          buffi++;
+          st->n_runes++;
+          if ((uint32_t)buffi > st->max_window) st->max_window = (uint32_t)buffi;
+        }
+        chr = buffer[buffc]; /* :410 */
+        eot = 0;
+        if (chr < 256) { /* :421 */
+          eot = (chr == EOT);
+          a = mat->sigmaASCII[chr];
+        } else {
+          a = sigma_get(mat, chr, &ok); /* :427 */
+          if (!ok) a = identity;        /* :430-434 */
+        }
+        t0 = t; /* :437 */
+        if (array[(size_t)(epsilon - 1) * S + t0] != 0) { /* :442 */
+          epsilonState = t0;
+          epsilonOffset = buffc;
+        }
+      }
+      if (a == 0) { /* :459 */
+        t = 0;
+      } else {
+        t = array[(size_t)(a - 1) * S + t0]; /* :463 */
+      }
+      st->n_iter++;
+      if (t == 0) { /* :472 */
+        if (!ok && a == identity) { /* :478 */
+          a = unknown;
+        } else if (a != epsilon && epsilonState != 0) { /* :487 */
+          t0 = epsilonState;
+          epsilonState = 0;
+          st->n_back++;
+          st->n_back_runes += (uint64_t)(buffc - epsilonOffset);
+          buffc = epsilonOffset;
+          a = epsilon;
+        } else { /* :499 */
+          st->n_hard++;
+          if (buffc - bufft <= 0) { /* :515 */
+            buffc++;
+            if (buffc == 0) { eof = 1; break; }
+          }
+          EMIT_TOKEN(); /* :528 */
+          sentenceEnd = 0;
+          textEnd = 0;
+          memmove(buffer, buffer + buffc, (size_t)(buffi - buffc) * sizeof(int32_t)); /* :537 */
+          memmove(boff, boff + buffc, (size_t)(buffi - buffc) * sizeof(uint32_t));
+          buffi -= buffc;
+          epsilonState = 0;
+          buffc = 0;
+          bufft = 0;
+          a = epsilon; /* :545 */
+          t = 1;
+          newchar = 1;
+          continue;
+        }
+        newchar = 0; /* :554 */
+        eot = 0;
+        continue;
+      }
+      rewindBuffer = 0; /* :560 */
+      if (a == epsilon) { /* :563 */
+        if (buffc - bufft > 0) {
+          EMIT_TOKEN(); /* :569 */
+          rewindBuffer = 1;
+          sentenceEnd = 0;
+          textEnd = 0;
+        } else {
+          sentenceEnd = 1;
+          EMIT_SENT(); /* :575 */
+        }
+      } else {
+        buffc++; /* :580 */
+        if (buffc - bufft == 1 && (t & FIRSTBIT) != 0) bufft++; /* :584-588 */
+      }
+      if (eot) { /* :593 */
+        eot = 0;
+        if (!sentenceEnd) {
+          sentenceEnd = 1;
+          EMIT_SENT(); /* :597 */
+        }
+        textEnd = 1;
+        EMIT_TEXT(); /* :600 */
+        rewindBuffer = 1;
+      }
+      if (rewindBuffer) { /* :608 */
+        memmove(buffer, buffer + buffc, (size_t)(buffi - buffc) * sizeof(int32_t));
+        memmove(boff, boff + buffc, (size_t)(buffi - buffc) * sizeof(uint32_t));
+        buffi -= buffc;
+        epsilonOffset = 0;
+        epsilonState = 0;
+        buffc = 0;
+        bufft = 0;
+      }
+      t &= ~FIRSTBIT; /* :629 */
+      newchar = 1;
+    }
+    if (!eof) return ORA_ERR_LOOP; /* :638-644 "should never happen" */
+    /* final check :650-668 */
+    t0 = t;
+    t = array[(size_t)(epsilon - 1) * S + t0];
+    a = epsilon;
+    newchar = 0;
+    if (t != 0) continue; /* goto PARSECHARM :658 */
+    if (epsilonState != 0) { /* :660 */
+      t0 = epsilonState;
+      epsilonState = 0;
+      st->n_back++;
+      st->n_back_runes += (uint64_t)(buffc - epsilonOffset);
+      buffc = epsilonOffset;
+      continue; /* goto PARSECHARM :667 */
+    }
+    break;
+  }
+  if (buffc - bufft > 0) { /* :671 */
+    EMIT_TOKEN();
+    sentenceEnd = 0;
+    textEnd = 0;
+  }
+  if (!sentenceEnd) EMIT_SENT(); /* :683 */
+  if (!textEnd) EMIT_TEXT();     /* :690 */
+  if (cout) {
+    /* t is 0 here (the failed final epsilon probe, :652); the state a
+     * continuation would start from is t0 */
+    cout->state = t0; cout->ok = ok; cout->sentence_end = 1; cout->text_end = 1;
+  }
+  return ORA_OK;
+#undef BYTE_AT
+#undef EMIT_TOKEN
+#undef EMIT_SENT
+#undef EMIT_TEXT
+}
+
+/* ------------------------------------------------------------- public API */
+
+ora_result *ora_transduce(const ora_model *m, const uint8_t *in, size_t n, uint32_t flags,
+                          const ora_carry *carry_in) {
+  ora_result *r = (ora_result *)calloc(1, sizeof(*r));
+  vec_u8 sink = {0};
+  token_writer tw;
+  tw_init(&tw, &sink, flags, 1);
+  recorder rec;
+  memset(&rec, 0, sizeof rec);
+  walk_stats st;
+  memset(&st, 0, sizeof st);
+  r->status = transduce(m, in, n, &tw, &rec, carry_in, &r->carry_out, &st);
+  r->text = sink.p; r->text_len = sink.n;
+  r->n_tokens = rec.tok_byte_end.n;
+  r->tok_byte_start = rec.tok_byte_start.p; r->tok_byte_end = rec.tok_byte_end.p;
+  r->tok_buf_start = rec.tok_buf_start.p; r->tok_offset = rec.tok_offset.p;
+  r->n_tok_pos = tw.rec_tok_pos.n; r->tok_pos = tw.rec_tok_pos.p; tw.rec_tok_pos.p = NULL;
+  r->n_sent_events = rec.sent_tok_idx.n; r->sent_tok_idx = rec.sent_tok_idx.p;
+  r->n_sent_pos = tw.rec_sent_pos.n; r->sent_pos = tw.rec_sent_pos.p; tw.rec_sent_pos.p = NULL;
+  r->n_texts = rec.text_tok_end.n;
+  r->text_tok_end = rec.text_tok_end.p; r->text_sent_end = rec.text_sent_end.p;
+  r->text_sentpos_end = rec.text_sentpos_end.p; r->text_byte_end = rec.text_byte_end.p;
+  r->n_runes = st.n_runes; r->n_iterations = st.n_iter; r->n_backtracks = st.n_back;
+  r->n_backtrack_runes = st.n_back_runes; r->n_hardfail = st.n_hard; r->max_window = st.max_window;
+  tw_free(&tw);
+  return r;
+}
+
+void ora_result_free(ora_result *r) {
+  if (!r) return;
+  free(r->text); free(r->tok_byte_start); free(r->tok_byte_end); free(r->tok_buf_start);
+  free(r->tok_offset); free(r->tok_pos); free(r->sent_tok_idx); free(r->sent_pos);
+  free(r->text_tok_end); free(r->text_sent_end); free(r->text_sentpos_end); free(r->text_byte_end);
+  free(r);
+}
+
+/* ---- CPU baseline: one worker per EOT-delimited document ---------------- */
+
+typedef struct {
+  const ora_model *m;
+  const uint8_t *in;
+  const size_t *doc_start; /* ndocs+1 entries */
+  size_t ndocs;
+  uint32_t flags;
+  atomic_size_t next;
+  atomic_ullong tokens, sentences, out_bytes;
+} mt_job;
+
+static void *mt_worker(void *arg) {
+  mt_job *job = (mt_job *)arg;
+  vec_u8 sink = {0};
+  unsigned long long tok = 0, sen = 0, ob = 0;
+  for (;;) {
+    size_t d0 = atomic_fetch_add(&job->next, 16);
+    if (d0 >= job->ndocs) break;
+    size_t d1 = d0 + 16 < job->ndocs ? d0 + 16 : job->ndocs;
+    for (size_t d = d0; d < d1; d++) {
+      sink.n = 0;
+      token_writer tw;
+      tw_init(&tw, &sink, job->flags, 0);
+      walk_stats st;
+      memset(&st, 0, sizeof st);
+      transduce(job->m, job->in + job->doc_start[d], job->doc_start[d + 1] - job->doc_start[d], &tw,
+                NULL, NULL, NULL, &st);
+      tok += st.n_tok;
+      sen += st.n_sent;
+      ob += sink.n;
+      tw_free(&tw);
+    }
+  }
+  free(sink.p);
+  atomic_fetch_add(&job->tokens, tok);
+  atomic_fetch_add(&job->sentences, sen);
+  atomic_fetch_add(&job->out_bytes, ob);
+  return NULL;
+}
+
+uint64_t ora_transduce_docs_mt(const ora_model *m, const uint8_t *in, size_t n, uint32_t flags,
+                               int nthreads, uint64_t *out_bytes, uint64_t *out_sentences,
+                               uint64_t *out_docs) {
+  /* document = bytes up to and including an EOT; a trailing EOT-less rest is a document too */
+  size_t cap = 1024, nd = 0;
+  size_t *ds = (size_t *)malloc(cap * sizeof(size_t));
+  ds[0] = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (in[i] == EOT) {
+      if (nd + 2 >= cap) { cap *= 2; ds = (size_t *)realloc(ds, cap * sizeof(size_t)); }
+      ds[++nd] = i + 1;
+    }
+  }
+  if (ds[nd] < n) {
+    if (nd + 2 >= cap) { cap *= 2; ds = (size_t *)realloc(ds, cap * sizeof(size_t)); }
+    ds[++nd] = n;
+  }
+  mt_job job;
+  memset(&job, 0, sizeof job);
+  job.m = m; job.in = in; job.doc_start = ds; job.ndocs = nd; job.flags = flags;
+  atomic_init(&job.next, 0);
+  atomic_init(&job.tokens, 0); atomic_init(&job.sentences, 0); atomic_init(&job.out_bytes, 0);
+  if (nthreads < 1) nthreads = 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+  for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, mt_worker, &job);
+  for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+  free(th);
+  free(ds);
+  if (out_bytes) *out_bytes = atomic_load(&job.out_bytes);
+  if (out_sentences) *out_sentences = atomic_load(&job.sentences);
+  if (out_docs) *out_docs = nd;
+  return atomic_load(&job.tokens);
+}
+
+/* Drives the TokenWriter restatement alone (token_writer_test.go:11-32).
+ * ops: 0,offset,len,rune...  = Token ; 1 = SentenceEnd ; 2 = TextEnd */
+uint8_t *ora_token_writer_replay(uint32_t flags, const int32_t *ops, size_t nops, size_t *out_len,
+                                 int *status) {
+  vec_u8 sink = {0};
+  token_writer tw;
+  tw_init(&tw, &sink, flags, 0);
+  size_t i = 0;
+  while (i < nops && !tw.status) {
+    if (ops[i] == 0) {
+      int offset = ops[i + 1], len = ops[i + 2];
+      tw_token(&tw, offset, ops + i + 3, len);
+      i += 3 + (size_t)len;
+    } else if (ops[i] == 1) {
+      tw_sentence_end(&tw); i++;
+    } else {
+      tw_text_end(&tw); i++;
+    }
+  }
+  *status = tw.status;
+  *out_len = sink.n;
+  tw_free(&tw);
+  if (!sink.p) sink.p = (uint8_t *)malloc(1);
+  return sink.p;
+}
+
+void ora_free_bytes(uint8_t *p) { free(p); }
