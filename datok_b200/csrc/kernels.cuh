@@ -1,0 +1,34 @@
+// kernels.cuh -- launch interface between the C ABI (api.cu) and the sm_100a
+// kernels (kernels.cu).  Device pointers only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "chunk_core.cuh"
+
+namespace datok {
+
+struct CompactBuffers {
+  Agg* block_agg;
+  Agg* block_carry;
+  Agg* total;              // [0] stream total after finalize
+  uint32_t n_blocks;
+};
+
+constexpr int COMPACT_THREADS = 256;
+constexpr int COMPACT_WPT = 2;  // bitmap words per thread
+
+void launch_classify(const DeviceModel& m, const WalkBuffers& b, cudaStream_t s);
+void launch_walk_spec(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, cudaStream_t s);
+// one fix-up round over `n_list` chunks (list == nullptr: all chunks 1..n_chunks-1)
+void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
+void launch_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk, cudaStream_t s);
+void launch_commit(const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
+void launch_collect_errors(const WalkBuffers& b, cudaStream_t s);
+
+void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
+void launch_compact_scan(const CompactCtx& c, const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s);
+void launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
+void launch_compact_finalize(const CompactCtx& c, const CompactBuffers& cb, bool text_end_in, cudaStream_t s);
+
+}  // namespace datok

@@ -1,0 +1,218 @@
+// model.cpp -- .matok loader + GPU re-layout (host side).  See model.hpp.
+#include "model.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "../../include/datok_b200.h"
+
+namespace datok {
+
+// Go unicode/utf8 semantics: any malformed, overlong, surrogate or out-of-range
+// sequence decodes to U+FFFD consuming exactly one byte.
+int32_t decode_rune(const uint8_t* p, size_t n, int* width) {
+  *width = n ? 1 : 0;
+  if (!n) return 0xFFFD;
+  uint32_t b0 = p[0];
+  if (b0 < 0x80) return (int32_t)b0;
+  int need;
+  uint32_t lo = 0x80, hi = 0xBF, cp;
+  if (b0 >= 0xC2 && b0 <= 0xDF) { need = 2; cp = b0 & 0x1F; }
+  else if (b0 >= 0xE0 && b0 <= 0xEF) { need = 3; cp = b0 & 0x0F; if (b0 == 0xE0) lo = 0xA0; if (b0 == 0xED) hi = 0x9F; }
+  else if (b0 >= 0xF0 && b0 <= 0xF4) { need = 4; cp = b0 & 0x07; if (b0 == 0xF0) lo = 0x90; if (b0 == 0xF4) hi = 0x8F; }
+  else return 0xFFFD;
+  if (n < (size_t)need) return 0xFFFD;
+  for (int i = 1; i < need; i++) {
+    uint32_t b = p[i];
+    if (b < lo || b > hi) return 0xFFFD;
+    cp = (cp << 6) | (b & 0x3F);
+    lo = 0x80; hi = 0xBF;
+  }
+  *width = need;
+  return (int32_t)cp;
+}
+
+static uint32_t rd16(const uint8_t* p) { return p[0] | (p[1] << 8); }
+static uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why) {
+  // magic + 14-byte little-endian header (matrix.go:246-285)
+  if (n < 19 || std::memcmp(d, "MATOK", 5) != 0) { why = "Not a matok file"; return DATOK_ERR_FORMAT; }
+  const uint8_t* h = d + 5;
+  if (rd16(h) != 1) { why = "Version not compatible"; return DATOK_ERR_FORMAT; }
+  m.epsilon = (int)rd16(h + 2);
+  m.unknown = (int)rd16(h + 4);
+  m.identity = (int)rd16(h + 6);
+  m.stateCount = (int)rd32(h + 8);
+  m.sigmaCount = (int)rd16(h + 12);
+  size_t p = 19;
+  for (int i = 0; i < 256; i++) m.sigmaASCII[i] = m.identity;  // matrix.go:289-293
+  m.sigma.clear();
+  for (int x = 0; x < m.sigmaCount; x++) {  // matrix.go:295-303
+    int w;
+    int32_t sym = decode_rune(d + p, n - p, &w);
+    if (w == 0) continue;
+    p += (size_t)w;
+    if (sym != 0) {
+      if (sym < 256) m.sigmaASCII[sym] = x;
+      m.sigma.emplace_back(sym, x);
+    }
+  }
+  if (p >= n || d[p] != 'M') { why = "Not a matok file"; return DATOK_ERR_FORMAT; }  // matrix.go:305-315
+  p++;
+  size_t cells = ((size_t)m.stateCount + 1) * (size_t)m.sigmaCount;  // matrix.go:286
+  if (n - p < cells * 4) { why = "Not enough bytes read"; return DATOK_ERR_FORMAT; }  // matrix.go:327
+  m.array.resize(cells);
+  for (size_t x = 0; x < cells; x++) m.array[x] = rd32(d + p + 4 * x);
+  return DATOK_OK;
+}
+
+int load_matok_file(const char* path, HostModel& m, std::string& why) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { why = std::string("cannot open ") + path; return DATOK_ERR_IO; }
+  unsigned char mg[2] = {0, 0};
+  size_t got = std::fread(mg, 1, 2, f);
+  std::fclose(f);
+  if (got != 2 || mg[0] != 0x1f || mg[1] != 0x8b) { why = "gzip: invalid header"; return DATOK_ERR_IO; }  // matrix.go:222-226
+  gzFile gz = gzopen(path, "rb");
+  if (!gz) { why = "gzopen failed"; return DATOK_ERR_IO; }
+  std::vector<uint8_t> img;
+  std::vector<uint8_t> chunk(1 << 20);
+  for (;;) {
+    int r = gzread(gz, chunk.data(), (unsigned)chunk.size());
+    if (r < 0) { gzclose(gz); why = "gzip: read error"; return DATOK_ERR_IO; }
+    if (r == 0) break;
+    img.insert(img.end(), chunk.begin(), chunk.begin() + r);
+  }
+  gzclose(gz);
+  int rc = parse_matok_image(img.data(), img.size(), m, why);
+  if (rc) return rc;
+  return build_layout(m, why);
+}
+
+int build_layout(HostModel& m, std::string& why) {
+  const int S = m.stateCount, K = m.sigmaCount, eps = m.epsilon;
+  if (S < 1 || S + 1 >= 32768) { why = "state count not in 1..32766"; return DATOK_ERR_UNSUPPORTED_MODEL; }
+  if (eps < 1 || eps >= K) { why = "no epsilon symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
+  if (m.identity < 1 || m.identity >= K) { why = "no identity symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
+  auto cell = [&](int a, int t) -> uint32_t {  // matrix.go:463; a==0 never matches (matrix.go:459)
+    if (a < 1 || a >= K) return 0;
+    return m.array[(size_t)(a - 1) * S + t];
+  };
+  // The reference retries a failed identity transition with the `unknown` symbol
+  // (matrix.go:478-485).  With an empty unknown column that retry can never
+  // succeed, so it is unobservable; that is what the kernels assume.
+  if (m.unknown >= 1 && m.unknown < K)
+    for (int t = 1; t <= S; t++)
+      if (cell(m.unknown, t) != 0) { why = "model has transitions on the unknown symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
+
+  // final rune -> symbol map (later sigma entries win, as Go's map assignment does)
+  std::map<int32_t, int32_t> sym_of_rune;
+  for (auto& kv : m.sigma) sym_of_rune[kv.first] = kv.second;
+  for (auto& kv : sym_of_rune)
+    if (kv.second == eps) { why = "a rune maps to the epsilon symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
+
+  // --- state renumbering: non-epsilon states first, epsilon states last ---
+  m.new_of_old.assign(S + 1, 0);
+  m.old_of_new.assign(S + 1, 0);
+  uint32_t next = 1;
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) m.eps_lo = (uint16_t)next;
+    for (int t = 1; t <= S; t++) {
+      bool has = cell(eps, t) != 0;
+      if ((int)has == pass) { m.new_of_old[t] = (uint16_t)next; m.old_of_new[next] = (uint16_t)t; next++; }
+    }
+  }
+  m.start = m.new_of_old[1];
+  for (int t = 1; t <= S; t++) {
+    uint32_t c = cell(eps, t), tgt = c & 0x7FFFFFFFu;
+    if (tgt > (uint32_t)S) { why = "transition target out of range"; return DATOK_ERR_FORMAT; }
+  }
+  // longest chain of consecutive epsilon transitions (Token, SentenceEnd, ...)
+  m.max_eps_chain = 0;
+  for (int t = 1; t <= S; t++) {
+    uint32_t len = 0;
+    int cur = t;
+    while (len <= 4) {
+      uint32_t c = cell(eps, cur) & 0x7FFFFFFFu;
+      if (!c) break;
+      len++;
+      cur = (int)c;
+    }
+    m.max_eps_chain = std::max(m.max_eps_chain, len);
+  }
+
+  // --- classes: merge symbols with identical columns ---
+  std::map<std::vector<uint32_t>, uint32_t> class_of_column;
+  std::vector<std::vector<uint32_t>> columns;  // per class id >= CLS_FIRST
+  auto column_of = [&](int a) {
+    std::vector<uint32_t> col(S + 1, 0);
+    for (int t = 1; t <= S; t++) col[t] = cell(a, t);
+    return col;
+  };
+  std::map<int, uint32_t> class_of_sym;
+  auto cls_of_sym = [&](int a) -> uint32_t {
+    auto it = class_of_sym.find(a);
+    if (it != class_of_sym.end()) return it->second;
+    auto col = column_of(a);
+    auto jt = class_of_column.find(col);
+    uint32_t c;
+    if (jt == class_of_column.end()) {
+      c = CLS_FIRST + (uint32_t)columns.size();
+      class_of_column.emplace(col, c);
+      columns.push_back(std::move(col));
+    } else {
+      c = jt->second;
+    }
+    class_of_sym[a] = c;
+    return c;
+  };
+  uint32_t raw_ascii[256];
+  for (int r = 0; r < 256; r++) raw_ascii[r] = cls_of_sym(m.sigmaASCII[r]);
+  uint32_t ident = cls_of_sym(m.identity);
+  std::vector<std::pair<uint32_t, uint32_t>> hi;  // runes >= 256
+  for (auto& kv : sym_of_rune)
+    if (kv.first >= 256) hi.emplace_back((uint32_t)kv.first, cls_of_sym(kv.second));
+  m.n_classes = CLS_FIRST + (uint32_t)columns.size();
+  if (m.n_classes > 256) { why = "more than 253 symbol classes"; return DATOK_ERR_UNSUPPORTED_MODEL; }
+  m.row_shift = m.n_classes <= 128 ? 7 : 8;
+  for (int r = 0; r < 128; r++) m.ascii_cls[r] = (uint8_t)raw_ascii[r];
+  for (int r = 0; r < 128; r++) m.latin1_cls[r] = (uint8_t)raw_ascii[128 + r];
+  m.ascii_cls[4] = (uint8_t)CLS_EOT;
+  m.identity_cls = (uint8_t)ident;
+  std::sort(hi.begin(), hi.end());
+  m.rune_key.clear(); m.rune_cls.clear();
+  for (auto& kv : hi) { m.rune_key.push_back(kv.first); m.rune_cls.push_back((uint8_t)kv.second); }
+
+  // --- table ---
+  const size_t R = (size_t)1 << m.row_shift;
+  m.table.assign(((size_t)S + 1) * R, 0);
+  auto conv = [&](uint32_t c) -> uint16_t {
+    uint32_t tgt = c & 0x7FFFFFFFu;
+    if (!tgt) return 0;
+    return (uint16_t)(m.new_of_old[tgt] | ((c & 0x80000000u) ? NT_BIT : 0));
+  };
+  const std::vector<uint32_t> eot_col = column_of(m.sigmaASCII[4]);
+  for (int t = 1; t <= S; t++) {
+    uint16_t* row = &m.table[(size_t)m.new_of_old[t] * R];
+    for (int a = 1; a < K; a++) {
+      uint32_t tgt = cell(a, t) & 0x7FFFFFFFu;
+      if (tgt > (uint32_t)S) { why = "transition target out of range"; return DATOK_ERR_FORMAT; }
+    }
+    row[CLS_EPS] = conv(cell(eps, t));
+    row[CLS_CONT] = (uint16_t)(m.new_of_old[t] | NT_BIT);
+    row[CLS_EOT] = conv(eot_col[t]);
+    for (size_t c = 0; c < columns.size(); c++) row[CLS_FIRST + c] = conv(columns[c][t]);
+  }
+  std::memset(m.sync_mask, 0, sizeof m.sync_mask);
+  const uint16_t* srow = &m.table[(size_t)m.start * R];
+  for (uint32_t c = CLS_EOT; c < m.n_classes; c++)
+    if (srow[c] == (uint16_t)(m.start | NT_BIT)) m.sync_mask[c >> 5] |= 1u << (c & 31);
+  return DATOK_OK;
+}
+
+}  // namespace datok

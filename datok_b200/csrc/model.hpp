@@ -1,0 +1,57 @@
+// model.hpp -- host-side .matok loader and GPU re-layout (no CUDA in this file).
+//
+// Replaces, for the MATOK magic, LoadTokenizerFile (fomafile.go:452-484),
+// LoadMatrixFile (matrix.go:214-231) and ParseMatrix (matrix.go:235-337).
+// The reference keeps a symbol-major uint32 matrix `array[(a-1)*S + t]`
+// (matrix.go:85,442,463).  The GPU layout built here is different by design:
+//   * runes are mapped to *classes* (symbols with identical columns merged;
+//     EOT and UTF-8 continuation bytes get private classes),
+//   * the table is state-major u16: table[t << row_shift | cls], bit 15 = the
+//     reference's FIRSTBIT "non-token" flag (datok.go:43), bits 0..14 = target,
+//   * states are renumbered so that "state has an epsilon transition"
+//     (matrix.go:442) is the comparison  t >= eps_lo.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace datok {
+
+constexpr uint32_t CLS_EPS = 0;   // column of the epsilon symbol (@_TOKEN_BOUND_@)
+constexpr uint32_t CLS_CONT = 1;  // UTF-8 continuation byte of a valid sequence: no-op step
+constexpr uint32_t CLS_EOT = 2;   // the byte 0x04 (matrix.go:13,422)
+constexpr uint32_t CLS_FIRST = 3; // first ordinary class
+constexpr uint16_t NT_BIT = 0x8000;
+
+struct HostModel {
+  // --- reference view (ParseMatrix) ---
+  int epsilon = 0, unknown = 0, identity = 0, stateCount = 0, sigmaCount = 0;
+  int32_t sigmaASCII[256];
+  std::vector<std::pair<int32_t, int32_t>> sigma;  // rune -> symbol id, file order, later wins
+  std::vector<uint32_t> array;
+
+  // --- GPU layout ---
+  uint32_t n_classes = 0;
+  uint32_t row_shift = 7;
+  uint8_t ascii_cls[128];   // class of runes 0x00..0x7F
+  uint8_t latin1_cls[128];  // class of runes 0x80..0xFF
+  std::vector<uint32_t> rune_key;  // runes >= 0x100 present in sigma, ascending
+  std::vector<uint8_t> rune_cls;
+  uint8_t identity_cls = 0;        // class of every rune not in sigma
+  std::vector<uint16_t> table;     // (S+1) << row_shift entries
+  std::vector<uint16_t> new_of_old, old_of_new;
+  uint16_t start = 0;   // new id of the reference's initial state 1 (matrix.go:351)
+  uint16_t eps_lo = 0;  // new ids >= eps_lo have an epsilon transition
+  uint32_t sync_mask[8];  // class c is a sync class iff table[start][c] == (start | NT_BIT)
+  uint32_t max_eps_chain = 0;
+};
+
+// error codes are the DATOK_ERR_* values of include/datok_b200.h
+int load_matok_file(const char* path, HostModel& m, std::string& why);
+int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why);
+int build_layout(HostModel& m, std::string& why);
+
+// Go unicode/utf8.DecodeRune (what bufio.Reader.ReadRune yields, matrix.go:392)
+int32_t decode_rune(const uint8_t* p, size_t n, int* width);
+
+}  // namespace datok

@@ -1,0 +1,159 @@
+/*
+ * datok_b200.h -- C ABI of the B200-native Datok matrix-FSA transduction path.
+ *
+ * Drop-in boundary for KorAP/Datok's `Tokenizer` interface (fomafile.go:29-33)
+ * restricted to MatrixTokenizer (.matok models).  The reference has no FFI layer;
+ * a Go shim type implementing `Tokenizer` binds these symbols through cgo
+ * (see INTEGRATION.md and go/datokb200/).  Plain pointers and sizes only.
+ *
+ * Every transduction runs on the GPU (hand-written sm_100a kernels).  There is no
+ * CPU fallback: without a usable CUDA device datok_load() fails with
+ * DATOK_ERR_NO_DEVICE.
+ */
+#ifndef DATOK_B200_H
+#define DATOK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* TokenWriter flag bits -- same values as token_writer.go:17-25 (type Bits). */
+enum {
+  DATOK_TOKENS = 1,
+  DATOK_SENTENCES = 2,
+  DATOK_TOKEN_POS = 4,
+  DATOK_SENTENCE_POS = 8,
+  DATOK_NEWLINE_AFTER_EOT = 16,
+  DATOK_SIMPLE = 3,
+  /* Not a reference flag: the caller's TokenWriter has already received a Token
+   * call (token_writer.go:42,70: `init` is false), i.e. the writer is being
+   * reused across Transduce calls as in token_writer_test.go:52-56. */
+  DATOK_WRITER_USED = 256
+};
+
+/* Error codes.  1..6 mirror inputs on which the Go reference panics (they are
+ * outside the parity domain and are reported, never undefined behaviour). */
+enum {
+  DATOK_OK = 0,
+  DATOK_ERR_BUFFER_OVERFLOW = 1, /* >1024 runes without a token boundary (matrix.go:365,406) */
+  DATOK_ERR_SENT_NO_TOKEN = 2,   /* SentenceEnd before any token of the text, SENTENCE_POS (token_writer.go:108) */
+  DATOK_ERR_TEXT_NO_TOKEN = 3,   /* TextEnd on a token-less text, TOKEN_POS (token_writer.go:135) */
+  DATOK_ERR_TEXT_NO_SENT = 4,    /* TextEnd on a sentence-less text, SENTENCE_POS (token_writer.go:145) */
+  DATOK_ERR_DEGENERATE = 5,      /* empty/negative token slice or repeated SentenceEnd at one position:
+                                    cannot happen with the shipped models */
+  DATOK_ERR_IO = 16,             /* file cannot be read / not gzip */
+  DATOK_ERR_FORMAT = 17,         /* not a MATOK v1 image (matrix.go:258,276,312,327) */
+  DATOK_ERR_UNSUPPORTED_MODEL = 18, /* >= 32768 states, > 253 symbol classes, non-empty unknown column, ... */
+  DATOK_ERR_NO_DEVICE = 19,      /* no CUDA device / wrong architecture */
+  DATOK_ERR_CUDA = 20,           /* a CUDA call failed; see datok_last_error() */
+  DATOK_ERR_TOO_LARGE = 21,      /* input >= 2^32 - 2^20 bytes in one call (split at EOT) */
+  DATOK_ERR_INVALID_ARG = 22
+};
+
+typedef struct datok_model datok_model;
+typedef struct datok_result datok_result;
+
+/* Walk state carried between byte-adjacent calls / shards (zero = stream start).
+ * `state` uses the reference's state numbering (matrix.go:351: initial state 1). */
+typedef struct {
+  uint32_t state;        /* 0 = initial state 1 */
+  uint32_t sentence_end; /* matrix.go:360 */
+  uint32_t text_end;     /* matrix.go:363 */
+  uint32_t reserved;
+} datok_carry;
+
+/* Flat, host-resident view of one transduction.  All arrays live in pinned host
+ * memory owned by the result; they stay valid until datok_result_free().
+ * Arrays whose flag was not requested are NULL (see datok_transduce). */
+typedef struct {
+  uint64_t n_tokens;       /* Token events                      (matrix.go:528,569,675) */
+  uint64_t n_sentences;    /* SentenceEnd events                (matrix.go:575,597,684) */
+  uint64_t n_texts;        /* TextEnd events                    (matrix.go:600,691)     */
+  uint64_t n_sent_pos;     /* entries of the TokenWriter's `sent` list over all texts   */
+  uint64_t n_runes;        /* runes the reference's ReadRune would have produced        */
+  /* per token k: surface = in[tok_bytes[2k] .. tok_bytes[2k+1])          (DATOK_TOKENS) */
+  const uint32_t *tok_bytes;
+  /* per token k: TokenWriter.pos entries (text-relative rune offsets, after the
+   * NEWLINE_AFTER_EOT shift): start = tok_pos[2k], end = tok_pos[2k+1] (DATOK_TOKEN_POS) */
+  const int32_t *tok_pos;
+  /* TokenWriter.sent entries, flat over all texts                  (DATOK_SENTENCE_POS) */
+  const int32_t *sent_pos;
+  /* per SentenceEnd event: number of tokens emitted before it        (DATOK_SENTENCES) */
+  const uint32_t *sent_tok;
+  /* per TextEnd event d (always present): exclusive prefix bounds of text d */
+  const uint32_t *text_tok_end;     /* tokens emitted up to TextEnd d          */
+  const uint32_t *text_sent_end;    /* SentenceEnd events up to TextEnd d      */
+  const uint32_t *text_sentpos_end; /* `sent` entries flushed up to TextEnd d  */
+  const uint32_t *text_byte_end;    /* byte position of the walk at TextEnd d  */
+  datok_carry carry_out;
+  uint32_t has_invalid_utf8; /* some input byte decodes to U+FFFD (surface re-encoding needed) */
+  /* timing of the last call, milliseconds (CUDA events on the call's stream) */
+  float ms_h2d, ms_kernels, ms_d2h;
+} datok_view;
+
+/* LoadTokenizerFile (fomafile.go:452-484) for the MATOK magic / LoadMatrixFile
+ * (matrix.go:214-231): gunzip, ParseMatrix (matrix.go:235-337), build the GPU
+ * layout on `device`.  NULL on error (the reference returns nil), *err says why. */
+datok_model *datok_load(const char *path, int device, int *err);
+/* same, from an in-memory gunzipped MATOK image (ParseMatrix, matrix.go:235) */
+datok_model *datok_load_image(const uint8_t *image, size_t n, int device, int *err);
+void datok_free(datok_model *m);
+
+/* Tokenizer.Type() (matrix.go:102-104) -> "MATOK" */
+const char *datok_type(void);
+
+/* model introspection (reference numbering) */
+int datok_model_info(const datok_model *m, uint32_t *state_count, uint32_t *sigma_count,
+                     uint32_t *n_classes, uint32_t *epsilon, uint32_t *unknown, uint32_t *identity);
+
+/* TransduceTokenWriter (matrix.go:348-698) over `n` bytes of host memory.
+ * `flags` are TokenWriter Bits (plus DATOK_WRITER_USED); they select which arrays
+ * are produced and copied back.  carry_in may be NULL (stream start).
+ * Synchronous; calls on one model are serialised. Returns DATOK_OK or an error;
+ * on reference-panic inputs (codes 1..5) *out is still a valid, partial result
+ * holding everything up to the failing event is NOT guaranteed -- treat as failed. */
+int datok_transduce(datok_model *m, const uint8_t *in, size_t n, uint32_t flags,
+                    const datok_carry *carry_in, datok_result **out);
+
+/* Same, but `d_in` is a DEVICE pointer (input already resident in HBM) and the
+ * offset arrays stay on the device; *view then holds device pointers.  Used by the
+ * benchmark's kernel-only leg and by callers that post-process on the GPU. */
+int datok_transduce_device(datok_model *m, const uint8_t *d_in, size_t n, uint32_t flags,
+                           const datok_carry *carry_in, datok_result **out);
+
+const datok_view *datok_result_view(const datok_result *r);
+void datok_result_free(datok_result *r);
+
+/* Host half of the TokenWriter (token_writer.go:36-175): formats a host-resident
+ * result exactly as NewTokenWriter(w, flags) would have written it.  Returns the
+ * number of bytes needed; writes at most `cap` bytes to `dst`. */
+size_t datok_format(const datok_result *r, const uint8_t *in, size_t n, uint32_t flags,
+                    uint8_t *dst, size_t cap);
+
+/* Replays one result into caller-supplied TokenWriter callbacks in stream order
+ * (custom TokenWriters, token_writer.go:27-33).  token(): `buf` points at the
+ * input bytes of the Token call's rune buffer, `offset_bytes` at the surface. */
+typedef struct {
+  void *user;
+  void (*token)(void *user, const uint8_t *buf, size_t buf_bytes, size_t offset_bytes, int32_t offset_runes);
+  void (*sentence_end)(void *user);
+  void (*text_end)(void *user);
+} datok_callbacks;
+int datok_replay(const datok_result *r, const uint8_t *in, size_t n, const datok_callbacks *cb);
+
+/* per-kernel device times (ms) of the last call on this model, for bench.py.
+ * names: "classify","walk","stitch","rewalk","compact_reduce","compact_scan","compact_emit" */
+int datok_last_kernel_times(const datok_model *m, const char **names, float *ms, int cap);
+/* number of kernel launches issued by the last call */
+int datok_last_launch_count(const datok_model *m);
+
+const char *datok_last_error(void);
+const char *datok_strerror(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

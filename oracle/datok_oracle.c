@@ -228,9 +228,12 @@ static void sink_write(vec_u8 *s, const uint8_t *d, size_t n) {
 static inline void sink_byte(vec_u8 *s, uint8_t b) { sink_write(s, &b, 1); }
 
 static void sink_itoa(vec_u8 *s, long v) { /* strconv.Itoa */
-  char tmp[24];
-  int n = snprintf(tmp, sizeof tmp, "%ld", v);
-  sink_write(s, (const uint8_t *)tmp, (size_t)n);
+  uint8_t tmp[24];
+  int i = 24;
+  unsigned long u = v < 0 ? (unsigned long)(-v) : (unsigned long)v;
+  do { tmp[--i] = (uint8_t)('0' + u % 10); u /= 10; } while (u);
+  if (v < 0) tmp[--i] = '-';
+  sink_write(s, tmp + i, (size_t)(24 - i));
 }
 
 /* ------------------------------------------------------------ TokenWriter */
@@ -354,6 +357,7 @@ typedef struct {
   uint64_t n_runes, n_iter, n_back, n_back_runes, n_hard;
   uint64_t n_tok, n_sent, n_text;
   uint32_t max_window;
+  uint64_t *hist; /* optional: visits per (state) of the transition lookup, design input */
 } walk_stats;
 
 /* TransduceTokenWriter, matrix.go:348-698.  Returns status. */
@@ -444,6 +448,7 @@ static int transduce(const ora_model *mat, const uint8_t *in, size_t n, token_wr
         t = array[(size_t)(a - 1) * S + t0]; /* :463 */
       }
       st->n_iter++;
+      if (st->hist) st->hist[t0]++;
       if (t == 0) { /* :472 */
         if (!ok && a == identity) { /* :478 */
           a = unknown;
@@ -690,3 +695,17 @@ uint8_t *ora_token_writer_replay(uint32_t flags, const int32_t *ops, size_t nops
 }
 
 void ora_free_bytes(uint8_t *p) { free(p); }
+
+/* design input: how often each state is the source of a transition lookup */
+int ora_state_histogram(const ora_model *m, const uint8_t *in, size_t n, uint64_t *hist) {
+  vec_u8 sink = {0};
+  token_writer tw;
+  tw_init(&tw, &sink, 0, 0);
+  walk_stats st;
+  memset(&st, 0, sizeof st);
+  st.hist = hist;
+  int rc = transduce(m, in, n, &tw, NULL, NULL, NULL, &st);
+  tw_free(&tw);
+  free(sink.p);
+  return rc;
+}

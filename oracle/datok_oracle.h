@@ -127,6 +127,9 @@ uint8_t *ora_token_writer_replay(uint32_t flags, const int32_t *ops, size_t nops
                                  int *status);
 void ora_free_bytes(uint8_t *p);
 
+/* design input: visits per source state of the transition lookup (hist has stateCount+1 slots) */
+int ora_state_histogram(const ora_model *m, const uint8_t *in, size_t n, uint64_t *hist);
+
 /* Go's unicode/utf8.DecodeRune: returns rune, *width in bytes (0 only if n==0) */
 int32_t ora_decode_rune(const uint8_t *p, size_t n, int *width);
 

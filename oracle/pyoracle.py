@@ -90,6 +90,8 @@ def lib():
         L.ora_token_writer_replay.argtypes = [C.c_uint32, C.POINTER(C.c_int32), C.c_size_t,
                                               C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         L.ora_free_bytes.argtypes = [C.POINTER(C.c_uint8)]
+        L.ora_state_histogram.restype = C.c_int
+        L.ora_state_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.ora_decode_rune.restype = C.c_int32
         L.ora_decode_rune.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
         _lib = L
@@ -181,6 +183,12 @@ class OracleModel:
             return OracleResult(rp.contents)
         finally:
             lib().ora_result_free(rp)
+
+    def state_histogram(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        hist = np.zeros(self.state_count + 1, dtype=np.uint64)
+        lib().ora_state_histogram(self._h, arr.ctypes.data, arr.size, hist.ctypes.data)
+        return hist
 
     def transduce_docs_mt(self, arr, flags, nthreads):
         """CPU baseline: one worker per EOT-delimited document. Returns dict of counts."""

@@ -1,0 +1,187 @@
+// emul.cpp -- TEST INFRASTRUCTURE: runs the kernel bodies of datok_b200/csrc/*.cuh
+// (classify_pos, chunk_spec/stitch/rewalk/commit, process_word, agg_combine,
+// finalize_stream) sequentially on the CPU, in the same grid/block/thread
+// decomposition the CUDA kernels use.  It lets the CPU test-suite check the
+// speculative-chunk algorithm against the oracle without a GPU.  It is NOT part
+// of the product library (libdatok_b200.so does not contain it) and is never
+// used as a fallback.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../datok_b200/csrc/chunk_core.cuh"
+#include "../../datok_b200/csrc/model.hpp"
+
+using namespace datok;
+
+extern "C" {
+
+struct EmulResult {
+  int status;
+  uint64_t n_tokens, n_sentences, n_texts, n_sent_pos, n_runes;
+  uint32_t* tok_bytes;
+  int32_t* tok_pos;
+  int32_t* sent_pos;
+  uint32_t* sent_tok;
+  uint32_t *text_tok_end, *text_sent_end, *text_sentpos_end, *text_byte_end;
+  uint32_t carry_state, has_invalid;
+  uint32_t rounds, n_rewalks, n_stitch_mismatch;
+};
+
+struct EmulModel {
+  HostModel hm;
+  DeviceModel dm;
+};
+
+EmulModel* emul_load(const char* path, int* err) {
+  EmulModel* m = new EmulModel();
+  std::string why;
+  int rc = load_matok_file(path, m->hm, why);
+  if (rc) { *err = rc; delete m; return nullptr; }
+  HostModel& h = m->hm;
+  m->dm.table = h.table.data();
+  m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.eps_lo = h.eps_lo; m->dm.n_classes = h.n_classes;
+  m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
+  m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
+  m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls;
+  std::memcpy(m->dm.sync_mask, h.sync_mask, sizeof h.sync_mask);
+  *err = 0;
+  return m;
+}
+void emul_free(EmulModel* m) { delete m; }
+uint32_t emul_n_classes(EmulModel* m) { return m->hm.n_classes; }
+uint32_t emul_new_state(EmulModel* m, uint32_t old_state) { return m->hm.new_of_old[old_state]; }
+uint32_t emul_old_state(EmulModel* m, uint32_t new_state) { return m->hm.old_of_new[new_state]; }
+
+// order: 0 = ascending thread order, 1 = descending (results must not depend on it)
+EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_t flags, uint32_t chunk,
+                           uint32_t carry_state, int sentence_end_in, int text_end_in, int order) {
+  const DeviceModel& m = em->dm;
+  EmulResult* R = (EmulResult*)std::calloc(1, sizeof(EmulResult));
+  WalkBuffers b;
+  std::memset(&b, 0, sizeof b);
+  b.in = in; b.N = N; b.chunk = chunk;
+  b.n_chunks = N / chunk + 1;
+  b.n_words = b.n_chunks * (chunk / 32);
+  std::vector<uint8_t> cls(N + 64, 0);
+  std::vector<uint32_t> rstart(b.n_words, 0), bend(b.n_words, 0), bskip(b.n_words, 0), bsent(b.n_words, 0),
+      btend(b.n_words, 0);
+  std::vector<WState> E(b.n_chunks), exitA(b.n_chunks), Enew(b.n_chunks), Ytmp(b.n_chunks);
+  std::vector<uint32_t> sync(b.n_chunks), first_hw(b.n_chunks), cflags(b.n_chunks);
+  unsigned long long err_key = ~0ull;
+  b.cls = cls.data(); b.rstart = rstart.data(); b.b_end = bend.data(); b.b_skip = bskip.data();
+  b.b_sent = bsent.data(); b.b_tend = btend.data();
+  b.E = E.data(); b.exitA = exitA.data(); b.Enew = Enew.data(); b.Ytmp = Ytmp.data();
+  b.sync = sync.data(); b.first_hw = first_hw.data(); b.cflags = cflags.data();
+  b.err_key = &err_key;
+
+  // K1 classify
+  bool any_invalid = false;
+  for (uint32_t p = 0; p < N; p++) {
+    bool st, inv;
+    cls[p] = (uint8_t)classify_pos(in, N, p, m.cls, &st, &inv);
+    if (st) rstart[p >> 5] |= 1u << (p & 31);
+    any_invalid |= inv;
+  }
+  R->has_invalid = any_invalid;
+
+  // K2a speculative walk
+  const uint32_t start_state = carry_state ? em->hm.new_of_old[carry_state] : m.start;
+  for (uint32_t k = 0; k < b.n_chunks; k++) chunk_spec(m, b, order ? b.n_chunks - 1 - k : k, start_state);
+
+  // K2b-d fix-up rounds
+  std::vector<uint32_t> list, next, rew;
+  for (uint32_t i = 1; i < b.n_chunks; i++) list.push_back(i);
+  while (!list.empty()) {
+    R->rounds++;
+    rew.clear(); next.clear();
+    for (size_t k = 0; k < list.size(); k++) {
+      uint32_t i = list[order ? list.size() - 1 - k : k];
+      if (chunk_stitch(m, b, i)) rew.push_back(i);
+    }
+    R->n_stitch_mismatch += (uint32_t)rew.size();
+    for (size_t k = 0; k < rew.size(); k++) { chunk_rewalk(m, b, rew[order ? rew.size() - 1 - k : k]); R->n_rewalks++; }
+    for (size_t k = 0; k < list.size(); k++) {
+      uint32_t i = list[k];
+      if (chunk_commit(b, i) && i + 1 < b.n_chunks) next.push_back(i + 1);
+    }
+    list.swap(next);
+  }
+  // walk errors
+  for (uint32_t i = 0; i < b.n_chunks; i++) {
+    if (E[i].flags & WS_INVALID) {
+      uint32_t code = E[i].flags >> WS_ERR_SHIFT;
+      unsigned long long key = ((unsigned long long)(i * chunk) << 8) | (code ? code : 0xFF);
+      if (key < err_key) err_key = key;
+    }
+  }
+  if (err_key != ~0ull) { R->status = (int)(err_key & 0xFF); return R; }
+  const WState& last = E[b.n_chunks - 1];
+  if (!(last.flags & WS_DONE)) { R->status = 0xFE; return R; }
+  R->carry_state = em->hm.old_of_new[last.t];
+
+  // K3 compaction: per-thread aggs -> block aggs -> scan -> emit
+  CompactCtx c;
+  std::memset(&c, 0, sizeof c);
+  c.in = in; c.N = N; c.n_words = b.n_words; c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip;
+  c.b_sent = b.b_sent; c.b_tend = b.b_tend; c.flags = flags; c.err_key = &err_key;
+  const uint32_t TPB = 256, WPT = 2, WPB = TPB * WPT;
+  const uint32_t nblk = (b.n_words + WPB - 1) / WPB;
+  std::vector<Agg> block_agg(nblk), block_carry(nblk);
+  for (uint32_t blk = 0; blk < nblk; blk++) {
+    Agg acc = agg_zero();
+    for (uint32_t t = 0; t < TPB; t++) {
+      Agg ta = agg_zero();
+      for (uint32_t k = 0; k < WPT; k++) {
+        uint32_t w = blk * WPB + t * WPT + k;
+        if (w < b.n_words) ta = agg_combine(ta, process_word<false>(c, w, ta));
+      }
+      acc = agg_combine(acc, ta);
+    }
+    block_agg[blk] = acc;
+  }
+  Agg run = agg_stream_start(c, sentence_end_in != 0);
+  for (uint32_t blk = 0; blk < nblk; blk++) { block_carry[blk] = run; run = agg_combine(run, block_agg[blk]); }
+  Agg total = run;
+  R->n_runes = total.n_rune;
+  size_t nt = total.n_tok, ns = total.n_sent + 1, nx = total.n_text + 1, np = total.n_sentpos + 1;
+  R->tok_bytes = (uint32_t*)std::calloc(2 * nt + 2, 4);
+  R->tok_pos = (int32_t*)std::calloc(2 * nt + 2, 4);
+  R->sent_pos = (int32_t*)std::calloc(np + 1, 4);
+  R->sent_tok = (uint32_t*)std::calloc(ns + 1, 4);
+  R->text_tok_end = (uint32_t*)std::calloc(nx + 1, 4);
+  R->text_sent_end = (uint32_t*)std::calloc(nx + 1, 4);
+  R->text_sentpos_end = (uint32_t*)std::calloc(nx + 1, 4);
+  R->text_byte_end = (uint32_t*)std::calloc(nx + 1, 4);
+  c.tok_bytes = R->tok_bytes; c.tok_pos = R->tok_pos; c.sent_pos = R->sent_pos; c.sent_tok = R->sent_tok;
+  c.text_tok_end = R->text_tok_end; c.text_sent_end = R->text_sent_end;
+  c.text_sentpos_end = R->text_sentpos_end; c.text_byte_end = R->text_byte_end;
+  for (uint32_t kb = 0; kb < nblk; kb++) {
+    uint32_t blk = order ? nblk - 1 - kb : kb;
+    Agg carry = block_carry[blk];
+    for (uint32_t t = 0; t < TPB; t++) {
+      for (uint32_t k = 0; k < WPT; k++) {
+        uint32_t w = blk * WPB + t * WPT + k;
+        if (w >= b.n_words) continue;
+        Agg wa = process_word<false>(c, w, carry);
+        process_word<true>(c, w, carry);
+        carry = agg_combine(carry, wa);
+      }
+    }
+  }
+  finalize_stream(c, total, text_end_in != 0);
+  R->n_tokens = total.n_tok; R->n_sentences = total.n_sent; R->n_texts = total.n_text; R->n_sent_pos = total.n_sentpos;
+  if (err_key != ~0ull) R->status = (int)(err_key & 0xFF);
+  return R;
+}
+
+void emul_result_free(EmulResult* r) {
+  if (!r) return;
+  std::free(r->tok_bytes); std::free(r->tok_pos); std::free(r->sent_pos); std::free(r->sent_tok);
+  std::free(r->text_tok_end); std::free(r->text_sent_end); std::free(r->text_sentpos_end); std::free(r->text_byte_end);
+  std::free(r);
+}
+
+}  // extern "C"
