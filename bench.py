@@ -1,0 +1,282 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the Datok matrix-FSA transduction path on B200.
+
+Metric (BASELINE.json): GB/s of input tokenized + sentence-split, tokenizer_de.matok,
+synthetic German corpus of ~10 KB EOT-separated documents,
+flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size BYTES] [--impl reference]
+
+One "step" = one pass of the hot path over one corpus batch of --size bytes per GPU
+(weak scaling: every rank owns its own EOT-aligned shard, generated from its own seed).
+  value       whole-job GB/s, input resident in HBM, offset arrays left in HBM
+              (CUDA events on the library's stream, max over ranks)
+  e2e         same through datok_transduce() with HOST buffers: pinned host input ->
+              H2D -> kernels -> D2H of the offset arrays
+  roofline    (N + 8T + 8S + 8D bytes) / device time of the whole path, vs the measured
+              HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle port (one worker per document, all host cores) on a
+              bounded sample of the same corpus
+--impl reference times that CPU path alone (the Go reference cannot be built here).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLAGS = 1 | 2 | 4 | 8  # TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS  (= `datok tokenize -p --sentence-positions`)
+MODEL = os.path.join(ROOT, "testdata", "tokenizer_de.matok")
+METRIC = "GB/s input tokenized+sentence-split (de .matok)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+def make_corpus(nbytes, seed, pinned_alloc=None):
+    from datok_b200 import corpus
+    if pinned_alloc is not None:
+        ptr = pinned_alloc(nbytes)
+        if not ptr:
+            raise RuntimeError("pinned allocation failed")
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+    else:
+        arr = np.empty(nbytes, dtype=np.uint8)
+    docs = corpus.generate_blocks_into(corpus.GERMAN, seed, arr, block=64 << 20)
+    return arr, docs
+
+
+def cpu_reference_rate(arr, seconds=15.0, threads=None):
+    """the oracle port on host cores, one worker per document, on a bounded sample"""
+    from oracle import pyoracle
+    threads = threads or os.cpu_count() or 1
+    ora = pyoracle.OracleModel(MODEL)
+    probe = arr[: min(arr.size, 4 << 20)]
+    cut = int(np.flatnonzero(probe == 4)[-1]) + 1
+    t0 = time.perf_counter()
+    ora.transduce_docs_mt(probe[:cut], FLAGS, threads)
+    rate = cut / (time.perf_counter() - t0)
+    want = int(min(arr.size, max(cut, rate * seconds)))
+    eots = np.flatnonzero(arr[:want] == 4)
+    n = int(eots[-1]) + 1
+    t0 = time.perf_counter()
+    res = ora.transduce_docs_mt(arr[:n], FLAGS, threads)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"first {n} bytes ({res['docs']} documents) of the same corpus, {dt:.1f} s, "
+                      f"C restatement of matrix.go:348-698 + token_writer.go (Go toolchain absent)",
+            "seconds": dt, "bytes": n, "tokens": res["tokens"]}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    size = min(args.size, 256 << 20)
+    arr, docs = make_corpus(size, 20261018)
+    per = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_reference_rate(arr, seconds=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            per.append(base)
+    tot_b = sum(p["bytes"] for p in per)
+    tot_s = sum(p["seconds"] for p in per)
+    v = tot_b / tot_s / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / len(per) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C2: tokenizer_de.matok, synthetic German corpus, ~10 KB EOT-separated documents, "
+                                   "flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS; each step a bounded sample"},
+            "cpu_baseline": {"value": v, "unit": "GB/s", "cores": base["cores"], "kind": "port",
+                             "sample": base["sample"]},
+            "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=1 << 30, help="corpus bytes per GPU")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import datok_b200 as d
+    from datok_b200 import _lib
+    tok = d.LoadTokenizerFile(MODEL, device=local)
+    if tok is None:
+        raise SystemExit("libdatok_b200.so could not load the model on the GPU (no fallback exists)")
+    L = _lib.lib()
+    arr, docs = make_corpus(args.size, 20261018 + 1000003 * rank, pinned_alloc=L.datok_host_alloc)
+    N = arr.size
+    d_in = torch.empty(N, dtype=torch.uint8, device="cuda")
+    d_in.copy_(torch.from_numpy(arr))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg -------------------------------------------------
+    for _ in range(args.warmup):
+        tok.transduce_device(d_in.data_ptr(), N, FLAGS).close()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, ktimes, launches = [], {}, 0
+    T = S = D = 0
+    for _ in range(args.steps):
+        r = tok.transduce_device(d_in.data_ptr(), N, FLAGS)
+        dev_ms.append(r.ms_kernels)
+        T, S, D = r.n_tokens, r.n_sentences, r.n_texts
+        for k, v in tok.kernel_times().items():
+            ktimes[k] = ktimes.get(k, 0.0) + v
+        launches += tok.launch_count()
+        r.close()
+    barrier()
+    wall_dev = time.perf_counter() - t0
+    clocks = sampler.summary()
+
+    # ---- end-to-end leg (host buffers through the C ABI) -----------------------
+    for _ in range(min(2, args.warmup)):
+        tok.transduce_arrays(arr, FLAGS).close()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = d2h = 0
+    for _ in range(e2e_steps):
+        r = tok.transduce_arrays(arr, FLAGS)
+        h2d = N
+        d2h = 4 * (2 * r.n_tokens * 2 + r.n_sent_pos + r.n_sentences + 4 * r.n_texts)
+        r.close()
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- reduce over ranks (max time; counts summed via the per-shard count exchange) -
+    ms_step = sum(dev_ms) / len(dev_ms)
+    stats = torch.tensor([ms_step, wall_dev / args.steps * 1e3, wall_e2e * 1e3], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([N, T, S, D], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        # the path's only exchange: per-shard counts -> global offset bases
+        gathered = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(gathered, counts)
+        allc = torch.stack(gathered)
+        bases = torch.cumsum(allc, 0) - allc
+        counts = allc.sum(0)
+        _ = bases
+    ms_step, ms_wall, ms_e2e = [float(x) for x in stats.tolist()]
+    Ntot, Ttot, Stot, Dtot = [int(x) for x in counts.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = N + 8 * T + 8 * S + 8 * D  # per launch (one GPU's shard)
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu and world >= 1:
+            try:
+                cpu = cpu_reference_rate(arr)
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
+                cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        kt = {k: round(v / args.steps, 4) for k, v in ktimes.items()}
+        line = {
+            "metric": METRIC, "value": Ntot / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"C2: tokenizer_de.matok, {N} B synthetic German corpus per GPU, ~10 KB "
+                                   "EOT-separated documents, flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS",
+                       "bytes_per_gpu": N, "documents_per_gpu": D, "tokens_per_gpu": T, "sentences_per_gpu": S,
+                       "l2": "input (>= 1 GiB) and outputs exceed the 126 MB L2; no flush needed",
+                       "chunk_bytes": int(os.environ.get("DATOK_CHUNK", "256")),
+                       "timing": "CUDA events on the library's stream around the whole device path, max over ranks",
+                       "ms_per_step_wall": ms_wall},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes, "formula": "N + 8*tokens + 8*sentences + 8*documents",
+                         "kernel": "whole device path (all kernels of one step); per-kernel ms in kernel_ms",
+                         "kernel_ms": kt},
+            "cpu_baseline": cpu,
+            "e2e": {"value": Ntot / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                    "path": "datok_transduce(): pinned host input -> H2D -> kernels -> D2H of offset arrays"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    tok.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,19 @@
+"""datok_b200 -- B200-native (sm_100a) implementation of KorAP/Datok's matrix-FSA
+transduction path (MatrixTokenizer.TransduceTokenWriter over .matok models).
+
+Public surface mirrors the reference's Go API for that path:
+
+    tok = LoadTokenizerFile("tokenizer_de.matok")          # fomafile.go:452
+    tok.Transduce(reader, writer)                           # matrix.go:340
+    tok.TransduceTokenWriter(reader, NewTokenWriter(w, TOKENS | SENTENCES | TOKEN_POS))
+    tok.Type() == "MATOK"
+
+plus the offset-array API (`transduce_arrays`) the C ABI is built around.
+"""
+from ._lib import (NEWLINE_AFTER_EOT, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Carry)
+from .tokenizer import (DatokError, LoadMatrixFile, LoadTokenizerFile, MatrixTokenizer, NewTokenWriter,
+                        ReferencePanic, Result, TokenWriter)
+
+__all__ = ["LoadTokenizerFile", "LoadMatrixFile", "MatrixTokenizer", "NewTokenWriter", "TokenWriter", "Result",
+           "TOKENS", "SENTENCES", "TOKEN_POS", "SENTENCE_POS", "NEWLINE_AFTER_EOT", "SIMPLE", "WRITER_USED",
+           "Carry", "DatokError", "ReferencePanic"]

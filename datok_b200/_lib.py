@@ -1,0 +1,95 @@
+"""ctypes binding of libdatok_b200.so (include/datok_b200.h).
+
+The library holds the CUDA kernels and the C ABI.  There is no Python or CPU
+implementation of the transduction: if the shared object is missing or no B200
+is visible, loading / datok_load fails loudly.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdatok_b200.so")
+
+TOKENS, SENTENCES, TOKEN_POS, SENTENCE_POS, NEWLINE_AFTER_EOT = 1, 2, 4, 8, 16
+SIMPLE = TOKENS | SENTENCES
+WRITER_USED = 256
+
+OK = 0
+ERR_BUFFER_OVERFLOW, ERR_SENT_NO_TOKEN, ERR_TEXT_NO_TOKEN, ERR_TEXT_NO_SENT, ERR_DEGENERATE = 1, 2, 3, 4, 5
+ERR_IO, ERR_FORMAT, ERR_UNSUPPORTED_MODEL, ERR_NO_DEVICE, ERR_CUDA, ERR_TOO_LARGE, ERR_INVALID_ARG = 16, 17, 18, 19, 20, 21, 22
+
+
+class Carry(C.Structure):
+    _fields_ = [("state", C.c_uint32), ("sentence_end", C.c_uint32), ("text_end", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class View(C.Structure):
+    _fields_ = [
+        ("n_tokens", C.c_uint64), ("n_sentences", C.c_uint64), ("n_texts", C.c_uint64),
+        ("n_sent_pos", C.c_uint64), ("n_runes", C.c_uint64),
+        ("tok_bytes", C.POINTER(C.c_uint32)), ("tok_pos", C.POINTER(C.c_int32)),
+        ("sent_pos", C.POINTER(C.c_int32)), ("sent_tok", C.POINTER(C.c_uint32)),
+        ("text_tok_end", C.POINTER(C.c_uint32)), ("text_sent_end", C.POINTER(C.c_uint32)),
+        ("text_sentpos_end", C.POINTER(C.c_uint32)), ("text_byte_end", C.POINTER(C.c_uint32)),
+        ("carry_out", Carry),
+        ("has_invalid_utf8", C.c_uint32),
+        ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float),
+    ]
+
+
+TOKEN_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_int32)
+EVENT_CB = C.CFUNCTYPE(None, C.c_void_p)
+
+
+class Callbacks(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("token", TOKEN_CB), ("sentence_end", EVENT_CB), ("text_end", EVENT_CB)]
+
+
+# every symbol include/datok_b200.h declares
+EXPORTS = ["datok_load", "datok_load_image", "datok_free", "datok_type", "datok_model_info", "datok_transduce",
+           "datok_transduce_device", "datok_result_view", "datok_result_free", "datok_format", "datok_replay",
+           "datok_last_kernel_times", "datok_last_launch_count", "datok_host_alloc", "datok_host_free",
+           "datok_last_error", "datok_strerror"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m datok_b200.build` "
+                           "(there is no fallback implementation)")
+    L = C.CDLL(LIB_PATH)
+    L.datok_load.restype = C.c_void_p
+    L.datok_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+    L.datok_load_image.restype = C.c_void_p
+    L.datok_load_image.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
+    L.datok_free.argtypes = [C.c_void_p]
+    L.datok_type.restype = C.c_char_p
+    L.datok_model_info.restype = C.c_int
+    L.datok_model_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 6
+    for f in (L.datok_transduce, L.datok_transduce_device):
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(Carry), C.POINTER(C.c_void_p)]
+    L.datok_result_view.restype = C.POINTER(View)
+    L.datok_result_view.argtypes = [C.c_void_p]
+    L.datok_result_free.argtypes = [C.c_void_p]
+    L.datok_format.restype = C.c_size_t
+    L.datok_format.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t]
+    L.datok_replay.restype = C.c_int
+    L.datok_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Callbacks)]
+    L.datok_last_kernel_times.restype = C.c_int
+    L.datok_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.datok_last_launch_count.restype = C.c_int
+    L.datok_last_launch_count.argtypes = [C.c_void_p]
+    L.datok_host_alloc.restype = C.c_void_p
+    L.datok_host_alloc.argtypes = [C.c_size_t]
+    L.datok_host_free.argtypes = [C.c_void_p]
+    L.datok_last_error.restype = C.c_char_p
+    L.datok_strerror.restype = C.c_char_p
+    L.datok_strerror.argtypes = [C.c_int]
+    _lib = L
+    return L

@@ -1,0 +1,595 @@
+// api.cu -- C ABI of libdatok_b200.so (include/datok_b200.h).
+//
+// Host-side orchestration of the kernels in kernels.cu: workspace management,
+// the fix-up round loop, output allocation, host<->device copies and timing.
+// There is no CPU transduction path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/datok_b200.h"
+#include "kernels.cuh"
+#include "model.hpp"
+
+using namespace datok;
+
+static thread_local std::string g_last_error;
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      g_last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+      return DATOK_ERR_CUDA;                                                                \
+    }                                                                                       \
+  } while (0)
+
+namespace {
+
+struct Block {
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool host = false;
+};
+
+enum { T_CLASSIFY, T_WALK, T_STITCH, T_REWALK, T_COMMIT, T_REDUCE, T_SCAN, T_EMIT, T_COUNT };
+const char* const kTimerNames[T_COUNT] = {"classify", "walk", "stitch", "rewalk", "commit",
+                                          "compact_reduce", "compact_scan", "compact_emit"};
+
+}  // namespace
+
+struct datok_model {
+  HostModel hm;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // model tables on the device
+  uint16_t* d_table = nullptr;
+  uint8_t* d_cls_tables = nullptr;  // ascii[128] latin1[128] rune_cls[n]
+  uint32_t* d_rune_key = nullptr;
+  DeviceModel dm;
+  // workspace (grow only)
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  // cache of result buffers
+  std::vector<Block> cache;
+  std::mutex mu;
+  uint32_t chunk = 256;
+  // instrumentation of the last call
+  float t_ms[T_COUNT] = {0};
+  int launches = 0;
+  uint32_t last_rounds = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> tev;
+};
+
+struct datok_result {
+  datok_model* model = nullptr;
+  datok_view view;
+  std::vector<Block> blocks;
+  bool device = false;
+};
+
+namespace {
+
+Block acquire(datok_model* m, size_t bytes, bool host, int* rc) {
+  bytes = std::max<size_t>(bytes, 256);
+  int best = -1;
+  for (size_t i = 0; i < m->cache.size(); i++) {
+    const Block& b = m->cache[i];
+    if (b.host == host && b.bytes >= bytes && (best < 0 || b.bytes < m->cache[best].bytes)) best = (int)i;
+  }
+  if (best >= 0 && m->cache[best].bytes <= bytes * 2 + (1 << 20)) {
+    Block b = m->cache[best];
+    m->cache.erase(m->cache.begin() + best);
+    return b;
+  }
+  Block b;
+  b.bytes = bytes + bytes / 8;
+  b.host = host;
+  cudaError_t e = host ? cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) : cudaMalloc(&b.p, b.bytes);
+  if (e != cudaSuccess) {
+    g_last_error = std::string(host ? "cudaHostAlloc: " : "cudaMalloc: ") + cudaGetErrorString(e);
+    *rc = DATOK_ERR_CUDA;
+    b.p = nullptr;
+  }
+  return b;
+}
+
+void release(datok_model* m, const Block& b) {
+  if (!b.p) return;
+  size_t cached = 0;
+  for (auto& c : m->cache) cached += c.bytes;
+  if (m->cache.size() < 64 && cached < ((size_t)24 << 30)) { m->cache.push_back(b); return; }
+  if (b.host) cudaFreeHost(b.p); else cudaFree(b.p);
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// lays the workspace out for an input of N bytes; base == nullptr just measures
+size_t carve(uint8_t* base, uint32_t N, uint32_t chunk, bool need_input_copy, WalkBuffers& b, CompactBuffers& cb) {
+  Carver c{base};
+  b.N = N;
+  b.chunk = chunk;
+  b.n_chunks = N / chunk + 1;
+  b.n_words = b.n_chunks * (chunk / 32);
+  uint8_t* d_in = c.take<uint8_t>(need_input_copy ? (size_t)N + 64 : 0);
+  if (need_input_copy) b.in = d_in;
+  b.cls = c.take<uint8_t>((size_t)N + 64);
+  b.rstart = c.take<uint32_t>(b.n_words);
+  // the four event bitmaps are contiguous so that one memset clears them
+  b.b_end = c.take<uint32_t>((size_t)b.n_words * 4);
+  b.b_skip = b.b_end ? b.b_end + b.n_words : nullptr;
+  b.b_sent = b.b_end ? b.b_end + 2 * (size_t)b.n_words : nullptr;
+  b.b_tend = b.b_end ? b.b_end + 3 * (size_t)b.n_words : nullptr;
+  b.E = c.take<WState>(b.n_chunks);
+  b.exitA = c.take<WState>(b.n_chunks);
+  b.Enew = c.take<WState>(b.n_chunks);
+  b.Ytmp = c.take<WState>(b.n_chunks);
+  b.sync = c.take<uint32_t>(b.n_chunks);
+  b.first_hw = c.take<uint32_t>(b.n_chunks);
+  b.cflags = c.take<uint32_t>(b.n_chunks);
+  b.list_cur = c.take<uint32_t>(b.n_chunks);
+  b.list_next = c.take<uint32_t>(b.n_chunks);
+  b.list_rewalk = c.take<uint32_t>(b.n_chunks);
+  b.counters = c.take<uint32_t>(8);
+  b.err_key = c.take<unsigned long long>(1);
+  const uint32_t wpb = COMPACT_THREADS * COMPACT_WPT;
+  cb.n_blocks = (b.n_words + wpb - 1) / wpb;
+  cb.block_agg = c.take<Agg>(cb.n_blocks);
+  cb.block_carry = c.take<Agg>(cb.n_blocks);
+  cb.total = c.take<Agg>(2);
+  return align_up(c.off, 256);
+}
+
+int ensure_workspace(datok_model* m, size_t need) {
+  if (need <= m->ws_bytes) return DATOK_OK;
+  if (m->ws) cudaFree(m->ws);
+  m->ws = nullptr;
+  m->ws_bytes = 0;
+  size_t want = need + need / 16;
+  CUDA_TRY(cudaMalloc(&m->ws, want));
+  m->ws_bytes = want;
+  return DATOK_OK;
+}
+
+struct PhaseTimer {
+  datok_model* m;
+  size_t used = 0;
+  std::vector<std::pair<int, size_t>> spans;  // (timer id, index of start event)
+  cudaEvent_t next() {
+    if (used == m->tev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      m->tev.push_back(e);
+    }
+    return m->tev[used++];
+  }
+  void begin(int id) {
+    cudaEvent_t e = next();
+    cudaEventRecord(e, m->stream);
+    spans.emplace_back(id, used - 1);
+  }
+  void end() {
+    cudaEvent_t e = next();
+    cudaEventRecord(e, m->stream);
+  }
+  void collect() {  // after a stream synchronize
+    for (auto& sp : spans) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, m->tev[sp.second], m->tev[sp.second + 1]) == cudaSuccess) m->t_ms[sp.first] += ms;
+    }
+  }
+};
+
+int upload_model(datok_model* m) {
+  HostModel& h = m->hm;
+  CUDA_TRY(cudaMalloc(&m->d_table, h.table.size() * sizeof(uint16_t)));
+  CUDA_TRY(cudaMemcpy(m->d_table, h.table.data(), h.table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  const size_t nr = h.rune_key.size();
+  std::vector<uint8_t> blob(256 + nr + 16, 0);
+  std::memcpy(blob.data(), h.ascii_cls, 128);
+  std::memcpy(blob.data() + 128, h.latin1_cls, 128);
+  if (nr) std::memcpy(blob.data() + 256, h.rune_cls.data(), nr);
+  CUDA_TRY(cudaMalloc(&m->d_cls_tables, blob.size()));
+  CUDA_TRY(cudaMemcpy(m->d_cls_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&m->d_rune_key, (nr + 4) * sizeof(uint32_t)));
+  if (nr) CUDA_TRY(cudaMemcpy(m->d_rune_key, h.rune_key.data(), nr * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  DeviceModel& d = m->dm;
+  d.table = m->d_table;
+  d.row_shift = h.row_shift; d.start = h.start; d.eps_lo = h.eps_lo; d.n_classes = h.n_classes;
+  d.cls.ascii_cls = m->d_cls_tables;
+  d.cls.latin1_cls = m->d_cls_tables + 128;
+  d.cls.rune_cls = m->d_cls_tables + 256;
+  d.cls.rune_key = m->d_rune_key;
+  d.cls.n_rune = (uint32_t)nr;
+  d.cls.identity_cls = h.identity_cls;
+  std::memcpy(d.sync_mask, h.sync_mask, sizeof d.sync_mask);
+  return DATOK_OK;
+}
+
+// Keep the transition table resident in L2 (it is gathered from once per input byte).
+void pin_table_in_l2(datok_model* m) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) return;
+  const size_t bytes = m->hm.table.size() * sizeof(uint16_t);
+  if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+  size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes * 2);
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+  cudaStreamAttrValue attr;
+  std::memset(&attr, 0, sizeof attr);
+  attr.accessPolicyWindow.base_ptr = m->d_table;
+  attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+  attr.accessPolicyWindow.hitRatio = 1.0f;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(m->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();
+}
+
+datok_model* finish_load(datok_model* m, int device, int* err) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    g_last_error = "no usable CUDA device (this library has no CPU path)";
+    cudaGetLastError();
+    *err = DATOK_ERR_NO_DEVICE;
+    delete m;
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+      prop.major != 10) {
+    g_last_error = "device is not an sm_100 (B200) GPU; the kernels are built for sm_100a only";
+    cudaGetLastError();
+    *err = DATOK_ERR_NO_DEVICE;
+    delete m;
+    return nullptr;
+  }
+  m->device = device;
+  if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_last_error = "cudaStreamCreate failed";
+    *err = DATOK_ERR_CUDA;
+    delete m;
+    return nullptr;
+  }
+  for (auto& e : m->ev) cudaEventCreate(&e);
+  int rc = upload_model(m);
+  if (rc) { *err = rc; datok_free(m); return nullptr; }
+  pin_table_in_l2(m);
+  if (const char* s = std::getenv("DATOK_CHUNK")) {
+    long v = std::atol(s);
+    if (v >= 32 && v <= 65536 && v % 32 == 0) m->chunk = (uint32_t)v;
+  }
+  *err = DATOK_OK;
+  return m;
+}
+
+int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n, uint32_t flags,
+                 const datok_carry* carry_in, bool device_out, datok_result** out) {
+  if (!m || !out || (!in && n)) { g_last_error = "invalid argument"; return DATOK_ERR_INVALID_ARG; }
+  if (n >= 0xFFFFFFFFull - (1u << 20)) { g_last_error = "input too large for one call"; return DATOK_ERR_TOO_LARGE; }
+  std::lock_guard<std::mutex> lock(m->mu);
+  CUDA_TRY(cudaSetDevice(m->device));
+  const uint32_t N = (uint32_t)n;
+  cudaStream_t s = m->stream;
+  std::memset(m->t_ms, 0, sizeof m->t_ms);
+  m->launches = 0;
+  m->last_rounds = 0;
+
+  uint32_t start_state = m->hm.start;
+  bool sentence_end_in = false, text_end_in = false;
+  if (carry_in) {
+    if (carry_in->state) {
+      if (carry_in->state > (uint32_t)m->hm.stateCount) { g_last_error = "carry state out of range"; return DATOK_ERR_INVALID_ARG; }
+      start_state = m->hm.new_of_old[carry_in->state];
+    }
+    sentence_end_in = carry_in->sentence_end != 0;
+    text_end_in = carry_in->text_end != 0;
+  }
+
+  WalkBuffers b;
+  CompactBuffers cb;
+  std::memset(&b, 0, sizeof b);
+  std::memset(&cb, 0, sizeof cb);
+  const size_t need = carve(nullptr, N, m->chunk, !in_is_device, b, cb);
+  int rc = ensure_workspace(m, need);
+  if (rc) return rc;
+  carve(m->ws, N, m->chunk, !in_is_device, b, cb);
+  if (in_is_device) b.in = in;
+
+  PhaseTimer pt{m};
+  CUDA_TRY(cudaEventRecord(m->ev[0], s));
+  if (!in_is_device && N) CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(b.in), in, N, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaEventRecord(m->ev[1], s));
+
+  // ---- K1 classify, K2a speculative walk ----
+  CUDA_TRY(cudaMemsetAsync(b.b_end, 0, (size_t)b.n_words * 4 * sizeof(uint32_t), s));
+  CUDA_TRY(cudaMemsetAsync(b.counters, 0, 8 * sizeof(uint32_t), s));
+  CUDA_TRY(cudaMemsetAsync(b.err_key, 0xFF, sizeof(unsigned long long), s));
+  pt.begin(T_CLASSIFY);
+  launch_classify(m->dm, b, s);
+  pt.end();
+  pt.begin(T_WALK);
+  launch_walk_spec(m->dm, b, start_state, s);
+  pt.end();
+  m->launches += 2;
+
+  // ---- K2b-d fix-up rounds ----
+  uint32_t n_list = b.n_chunks - 1;
+  const uint32_t* list = nullptr;  // round 1: every chunk but the first
+  uint32_t* cur = b.list_cur;
+  uint32_t* nxt = b.list_next;
+  while (n_list) {
+    m->last_rounds++;
+    b.list_next = nxt;
+    pt.begin(T_STITCH);
+    launch_stitch(m->dm, b, list, n_list, s);
+    pt.end();
+    pt.begin(T_REWALK);
+    launch_rewalk(m->dm, b, n_list, s);
+    pt.end();
+    pt.begin(T_COMMIT);
+    launch_commit(b, list, n_list, s);
+    pt.end();
+    m->launches += 3;
+    uint32_t counts[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(counts, b.counters, sizeof counts, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemsetAsync(b.counters, 0, 2 * sizeof(uint32_t), s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    n_list = counts[0];
+    std::swap(cur, nxt);
+    list = cur;
+  }
+  launch_collect_errors(b, s);
+  m->launches++;
+
+  // ---- K3 compaction ----
+  CompactCtx c;
+  std::memset(&c, 0, sizeof c);
+  c.in = b.in; c.N = N; c.n_words = b.n_words;
+  c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
+  c.flags = flags; c.err_key = b.err_key;
+  pt.begin(T_REDUCE);
+  launch_compact_reduce(c, cb, s);
+  pt.end();
+  pt.begin(T_SCAN);
+  launch_compact_scan(c, cb, sentence_end_in, s);
+  pt.end();
+  m->launches += 2;
+  struct { Agg tot; unsigned long long err; uint32_t invalid; } hdr;
+  CUDA_TRY(cudaMemcpyAsync(&hdr.tot, cb.total, sizeof(Agg), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&hdr.err, b.err_key, sizeof hdr.err, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&hdr.invalid, b.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (hdr.err != ~0ull) {  // the walk itself hit a reference panic
+    pt.collect();
+    const int code = (int)(hdr.err & 0xFF);
+    g_last_error = std::string("reference would panic: ") + datok_strerror(code);
+    return code >= 0xF0 ? DATOK_ERR_CUDA : code;
+  }
+
+  // output arrays: sized from the scan totals (+1 for the end-of-stream events)
+  datok_result* r = new datok_result();
+  r->model = m;
+  r->device = device_out;
+  std::memset(&r->view, 0, sizeof r->view);
+  const size_t nt = hdr.tot.n_tok, ns = (size_t)hdr.tot.n_sent + 1, nx = (size_t)hdr.tot.n_text + 1,
+               np = (size_t)hdr.tot.n_sentpos + 1;
+  const bool want_bytes = (flags & DATOK_TOKENS) != 0, want_pos = (flags & DATOK_TOKEN_POS) != 0;
+  const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
+  struct Out { size_t bytes; bool want; void** dev; Block d, h; };
+  void *d_tok_bytes = nullptr, *d_tok_pos = nullptr, *d_sent_pos = nullptr, *d_sent_tok = nullptr, *d_text = nullptr;
+  Out outs[5] = {{2 * nt * 4, want_bytes, &d_tok_bytes, {}, {}}, {2 * nt * 4, want_pos, &d_tok_pos, {}, {}},
+                 {np * 4, want_spos, &d_sent_pos, {}, {}},       {ns * 4, want_stok, &d_sent_tok, {}, {}},
+                 {nx * 4 * 4, true, &d_text, {}, {}}};
+  for (auto& o : outs) {
+    if (!o.want) continue;
+    o.d = acquire(m, o.bytes, false, &rc);
+    if (!device_out) o.h = acquire(m, o.bytes, true, &rc);
+    r->blocks.push_back(o.d);
+    if (!device_out) r->blocks.push_back(o.h);
+    *o.dev = o.d.p;
+  }
+  if (rc) { datok_result_free(r); return rc; }
+  c.tok_bytes = (uint32_t*)d_tok_bytes;
+  c.tok_pos = (int32_t*)d_tok_pos;
+  c.sent_pos = (int32_t*)d_sent_pos;
+  c.sent_tok = (uint32_t*)d_sent_tok;
+  c.text_tok_end = (uint32_t*)d_text;
+  c.text_sent_end = c.text_tok_end + nx;
+  c.text_sentpos_end = c.text_tok_end + 2 * nx;
+  c.text_byte_end = c.text_tok_end + 3 * nx;
+  pt.begin(T_EMIT);
+  launch_compact_emit(c, cb, s);
+  launch_compact_finalize(c, cb, text_end_in, s);
+  pt.end();
+  m->launches += 2;
+  struct { Agg fin; unsigned long long err; WState last; } tail;
+  CUDA_TRY(cudaMemcpyAsync(&tail.fin, cb.total + 1, sizeof(Agg), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&tail.err, b.err_key, sizeof tail.err, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&tail.last, b.E + (b.n_chunks - 1), sizeof(WState), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord(m->ev[2], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  pt.collect();
+  if (tail.err != ~0ull) {
+    const int code = (int)(tail.err & 0xFF);
+    g_last_error = std::string("reference would panic: ") + datok_strerror(code);
+    datok_result_free(r);
+    return code;
+  }
+  datok_view& v = r->view;
+  v.n_tokens = tail.fin.n_tok;
+  v.n_sentences = tail.fin.n_sent;
+  v.n_texts = tail.fin.n_text;
+  v.n_sent_pos = tail.fin.n_sentpos;
+  v.n_runes = tail.fin.n_rune;
+  v.has_invalid_utf8 = hdr.invalid;
+  v.carry_out.state = m->hm.old_of_new[tail.last.t];
+  v.carry_out.sentence_end = 1;
+  v.carry_out.text_end = 1;
+  // ---- D2H ----
+  for (auto& o : outs) {
+    if (!o.want || device_out) continue;
+    size_t bytes = o.bytes;
+    if (o.dev == &d_tok_bytes || o.dev == &d_tok_pos) bytes = 2 * (size_t)v.n_tokens * 4;
+    else if (o.dev == &d_sent_pos) bytes = (size_t)v.n_sent_pos * 4;
+    else if (o.dev == &d_sent_tok) bytes = (size_t)v.n_sentences * 4;
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(o.h.p, o.d.p, bytes, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaEventRecord(m->ev[3], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  auto pick = [&](int i) -> void* { return outs[i].want ? (device_out ? outs[i].d.p : outs[i].h.p) : nullptr; };
+  v.tok_bytes = (const uint32_t*)pick(0);
+  v.tok_pos = (const int32_t*)pick(1);
+  v.sent_pos = (const int32_t*)pick(2);
+  v.sent_tok = (const uint32_t*)pick(3);
+  const uint32_t* tx = (const uint32_t*)pick(4);
+  v.text_tok_end = tx;
+  v.text_sent_end = tx + nx;
+  v.text_sentpos_end = tx + 2 * nx;
+  v.text_byte_end = tx + 3 * nx;
+  cudaEventElapsedTime(&v.ms_h2d, m->ev[0], m->ev[1]);
+  cudaEventElapsedTime(&v.ms_kernels, m->ev[1], m->ev[2]);
+  cudaEventElapsedTime(&v.ms_d2h, m->ev[2], m->ev[3]);
+  if (!device_out) {  // the device copies are no longer needed
+    std::vector<Block> keep;
+    for (auto& blk : r->blocks) { if (blk.host) keep.push_back(blk); else release(m, blk); }
+    r->blocks.swap(keep);
+  }
+  *out = r;
+  return DATOK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+datok_model* datok_load(const char* path, int device, int* err) {
+  int dummy;
+  if (!err) err = &dummy;
+  datok_model* m = new datok_model();
+  std::string why;
+  int rc = load_matok_file(path, m->hm, why);
+  if (rc) { g_last_error = why; *err = rc; delete m; return nullptr; }
+  return finish_load(m, device, err);
+}
+
+datok_model* datok_load_image(const uint8_t* image, size_t n, int device, int* err) {
+  int dummy;
+  if (!err) err = &dummy;
+  datok_model* m = new datok_model();
+  std::string why;
+  int rc = parse_matok_image(image, n, m->hm, why);
+  if (!rc) rc = build_layout(m->hm, why);
+  if (rc) { g_last_error = why; *err = rc; delete m; return nullptr; }
+  return finish_load(m, device, err);
+}
+
+void datok_free(datok_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (auto& b : m->cache) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
+  if (m->ws) cudaFree(m->ws);
+  if (m->d_table) cudaFree(m->d_table);
+  if (m->d_cls_tables) cudaFree(m->d_cls_tables);
+  if (m->d_rune_key) cudaFree(m->d_rune_key);
+  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : m->tev) cudaEventDestroy(e);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+const char* datok_type(void) { return "MATOK"; }
+
+int datok_model_info(const datok_model* m, uint32_t* state_count, uint32_t* sigma_count, uint32_t* n_classes,
+                     uint32_t* epsilon, uint32_t* unknown, uint32_t* identity) {
+  if (!m) return DATOK_ERR_INVALID_ARG;
+  if (state_count) *state_count = (uint32_t)m->hm.stateCount;
+  if (sigma_count) *sigma_count = (uint32_t)m->hm.sigmaCount;
+  if (n_classes) *n_classes = m->hm.n_classes;
+  if (epsilon) *epsilon = (uint32_t)m->hm.epsilon;
+  if (unknown) *unknown = (uint32_t)m->hm.unknown;
+  if (identity) *identity = (uint32_t)m->hm.identity;
+  return DATOK_OK;
+}
+
+int datok_transduce(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, const datok_carry* carry_in,
+                    datok_result** out) {
+  return run_pipeline(m, in, false, n, flags, carry_in, false, out);
+}
+
+int datok_transduce_device(datok_model* m, const uint8_t* d_in, size_t n, uint32_t flags,
+                           const datok_carry* carry_in, datok_result** out) {
+  return run_pipeline(m, d_in, true, n, flags, carry_in, true, out);
+}
+
+const datok_view* datok_result_view(const datok_result* r) { return r ? &r->view : nullptr; }
+
+void datok_result_free(datok_result* r) {
+  if (!r) return;
+  if (r->model) {
+    std::lock_guard<std::mutex> lock(r->model->mu);
+    for (auto& b : r->blocks) release(r->model, b);
+  }
+  delete r;
+}
+
+int datok_last_kernel_times(const datok_model* m, const char** names, float* ms, int cap) {
+  if (!m) return 0;
+  int n = 0;
+  for (int i = 0; i < T_COUNT && n < cap; i++, n++) {
+    if (names) names[n] = kTimerNames[i];
+    if (ms) ms[n] = m->t_ms[i];
+  }
+  return n;
+}
+
+int datok_last_launch_count(const datok_model* m) { return m ? m->launches : 0; }
+
+void* datok_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void datok_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+const char* datok_last_error(void) { return g_last_error.c_str(); }
+
+const char* datok_strerror(int code) {
+  switch (code) {
+    case DATOK_OK: return "ok";
+    case DATOK_ERR_BUFFER_OVERFLOW: return "more than 1024 runes without a token boundary (matrix.go:365,406)";
+    case DATOK_ERR_SENT_NO_TOKEN: return "SentenceEnd before any token of the text under SENTENCE_POS (token_writer.go:108)";
+    case DATOK_ERR_TEXT_NO_TOKEN: return "TextEnd on a token-less text under TOKEN_POS (token_writer.go:135)";
+    case DATOK_ERR_TEXT_NO_SENT: return "TextEnd on a sentence-less text under SENTENCE_POS (token_writer.go:145)";
+    case DATOK_ERR_DEGENERATE: return "degenerate event sequence (empty token slice or repeated SentenceEnd)";
+    case DATOK_ERR_IO: return "cannot read model file";
+    case DATOK_ERR_FORMAT: return "not a MATOK v1 model";
+    case DATOK_ERR_UNSUPPORTED_MODEL: return "model not supported by the GPU layout";
+    case DATOK_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case DATOK_ERR_CUDA: return "CUDA error";
+    case DATOK_ERR_TOO_LARGE: return "input too large for one call";
+    case DATOK_ERR_INVALID_ARG: return "invalid argument";
+    default: return "unknown error";
+  }
+}
+
+}  // extern "C"

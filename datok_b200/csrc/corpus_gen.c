@@ -21,6 +21,7 @@ typedef struct {
   uint8_t *out;
   size_t n, cap;
   int kind;
+  size_t open_quote; /* byte position by which an attribute value left open must meet a '<' (0 = none) */
 } gen_t;
 
 static inline uint64_t rnd(gen_t *g) { /* xorshift64* */
@@ -146,12 +147,20 @@ static void word_slot(gen_t *g, int first) {
   uint32_t p_abbr = heavy ? 1500 : 200, p_num = 100, p_url = 50, p_xml = heavy ? 500 : 50, p_typo = 30;
   uint32_t p_clitic = en ? 300 : 0, p_emot = heavy ? 100 : 0, p_hyph = heavy ? 100 : 0;
   uint32_t acc = 0;
+  if (g->open_quote && g->n >= g->open_quote) {
+    g->open_quote = 0;
+    /* an unterminated attribute value makes the automaton read ahead until it meets
+     * '<' (or the quote); bound that lookahead well below the 1024-rune buffer */
+    puts_(g, chance(g, 5000) ? "<b>" : "\"> <i>");
+    return;
+  }
   if (r < (acc += p_abbr)) { puts_(g, en ? PICK(g, EN_ABBR) : PICK(g, DE_ABBR)); return; }
   if (r < (acc += p_num)) { number_like(g); return; }
   if (r < (acc += p_url)) { url_like(g, en); return; }
   if (r < (acc += p_xml)) {
     if (heavy && chance(g, 2000)) { /* unclosed tag / attribute with spaces */
-      puts_(g, chance(g, 5000) ? "<x y=\"alte zeit" : "<br class=\"a b c\" ");
+      if (g->open_quote == 0 && chance(g, 5000)) { puts_(g, "<x y=\"alte zeit"); g->open_quote = g->n + 20 + rndn(g, 400); }
+      else puts_(g, "<br class=\"a b c\" ");
     } else {
       puts_(g, PICK(g, XML_TAGS));
     }
@@ -161,8 +170,9 @@ static void word_slot(gen_t *g, int first) {
   if (r < (acc += p_clitic)) { puts_(g, PICK(g, EN_COMMON)); puts_(g, PICK(g, EN_CLITIC)); return; }
   if (r < (acc += p_emot)) { puts_(g, PICK(g, EMOTICONS)); return; }
   if (r < (acc += p_hyph)) { /* long hyphen compound, up to ~500 runes */
-    int parts = 2 + (int)rndn(g, heavy ? 60 : 4);
-    for (int i = 0; i < parts; i++) { if (i) putc_(g, '-'); synth_word(g, en, 1); }
+    int parts = 2 + (int)rndn(g, (heavy && !g->open_quote) ? 60 : 4);
+    size_t st = g->n;
+    for (int i = 0; i < parts && g->n - st < 440; i++) { if (i) putc_(g, '-'); synth_word(g, en, 1); }
     return;
   }
   if (en && chance(g, 100)) { puts_(g, "I."); return; }
@@ -232,7 +242,7 @@ size_t datok_corpus_generate(int kind, uint64_t seed, uint8_t *out, size_t nbyte
   gen_t g;
   g.s = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
   if (g.s == 0) g.s = 88172645463325252ull;
-  g.out = out; g.n = 0; g.cap = nbytes; g.kind = kind;
+  g.out = out; g.n = 0; g.cap = nbytes; g.kind = kind; g.open_quote = 0;
   for (int i = 0; i < 8; i++) rnd(&g);
   if (nbytes == 0) return 0;
   if (kind == 1) { simple_doc(&g); return 1; }

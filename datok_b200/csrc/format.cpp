@@ -1,0 +1,143 @@
+// format.cpp -- host half of the TokenWriter (token_writer.go:36-175): turns the
+// offset arrays of a result into the exact text NewTokenWriter(w, flags) writes,
+// or replays the events into caller-supplied callbacks (custom TokenWriters,
+// token_writer.go:27-33).  Pure formatting: all boundaries and offsets were
+// computed on the GPU.
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/datok_b200.h"
+#include "model.hpp"
+
+namespace {
+
+struct Sink {
+  uint8_t* dst;
+  size_t cap, n = 0;
+  inline void put(const uint8_t* p, size_t len) {
+    if (n + len <= cap) std::memcpy(dst + n, p, len);
+    else if (n < cap) std::memcpy(dst + n, p, cap - n);
+    n += len;
+  }
+  inline void byte(uint8_t b) {
+    if (n < cap) dst[n] = b;
+    n++;
+  }
+  inline void itoa(int32_t v) {  // strconv.Itoa
+    uint8_t tmp[12];
+    int i = 12;
+    uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    do { tmp[--i] = (uint8_t)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) tmp[--i] = '-';
+    put(tmp + i, (size_t)(12 - i));
+  }
+};
+
+// string(buf[offset:]) -- Go re-encodes runes, so malformed bytes come out as U+FFFD
+void put_surface(Sink& s, const uint8_t* in, size_t lo, size_t hi, bool reencode) {
+  if (!reencode) { s.put(in + lo, hi - lo); return; }
+  static const uint8_t kRep[3] = {0xEF, 0xBF, 0xBD};
+  size_t p = lo;
+  while (p < hi) {
+    int w;
+    int32_t r = datok::decode_rune(in + p, hi - p, &w);
+    if (r == 0xFFFD && w == 1) s.put(kRep, 3); else s.put(in + p, (size_t)w);
+    p += (size_t)w;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t flags, uint8_t* dst, size_t cap) {
+  const datok_view* v = datok_result_view(r);
+  if (!v) return (size_t)-1;
+  const bool tokens = flags & DATOK_TOKENS, sentences = flags & DATOK_SENTENCES;
+  const bool tpos = flags & DATOK_TOKEN_POS, spos = flags & DATOK_SENTENCE_POS;
+  if ((tokens && !v->tok_bytes) || (sentences && !v->sent_tok && v->n_sentences) || (tpos && !v->tok_pos) ||
+      (spos && !v->sent_pos))
+    return (size_t)-1;  // the array was not requested at transduce time
+  (void)n;
+  Sink s{dst, dst ? cap : 0};
+  const bool re = v->has_invalid_utf8 != 0;
+  uint64_t tok = 0, sen = 0, sp = 0;
+  auto emit_tokens = [&](uint64_t upto) {
+    if (tokens)
+      for (; tok < upto; tok++) {
+        put_surface(s, in, v->tok_bytes[2 * tok], v->tok_bytes[2 * tok + 1], re);
+        s.byte('\n');
+      }
+    tok = upto;
+  };
+  auto emit_sentences = [&](uint64_t upto) {
+    if (sentences) {
+      for (; sen < upto; sen++) {
+        emit_tokens(v->sent_tok[sen]);
+        s.byte('\n');  // token_writer.go:112-114,119-122
+      }
+    }
+    sen = upto;
+  };
+  for (uint64_t d = 0; d < v->n_texts; d++) {
+    const uint64_t t0 = tok, t1 = v->text_tok_end[d];
+    emit_sentences(v->text_sent_end[d]);
+    emit_tokens(t1);
+    if (tpos || spos) {  // token_writer.go:131-159
+      if (tpos) {
+        for (uint64_t k = 2 * t0; k < 2 * t1; k++) {
+          if (k != 2 * t0) s.byte(' ');
+          s.itoa(v->tok_pos[k]);
+        }
+        s.byte('\n');
+      }
+      if (spos) {
+        const uint64_t p1 = v->text_sentpos_end[d];
+        for (uint64_t k = sp; k < p1; k++) {
+          if (k != sp) s.byte(' ');
+          s.itoa(v->sent_pos[k]);
+        }
+        s.byte('\n');
+        sp = p1;
+      }
+    } else {
+      s.byte('\n');  // token_writer.go:163-166
+    }
+  }
+  emit_sentences(v->n_sentences);  // SentenceEnd events after the last TextEnd
+  return s.n;
+}
+
+int datok_replay(const datok_result* r, const uint8_t* in, size_t n, const datok_callbacks* cb) {
+  const datok_view* v = datok_result_view(r);
+  if (!v || !cb) return DATOK_ERR_INVALID_ARG;
+  if ((v->n_tokens && !v->tok_bytes) || (v->n_sentences && !v->sent_tok)) return DATOK_ERR_INVALID_ARG;
+  (void)n;
+  uint64_t tok = 0, sen = 0;
+  size_t bufstart = 0;  // the reference's buffer[0]: the last rewind point (matrix.go:608-622)
+  auto emit_tokens = [&](uint64_t upto) {
+    for (; tok < upto; tok++) {
+      const size_t lo = v->tok_bytes[2 * tok], hi = v->tok_bytes[2 * tok + 1];
+      int32_t runes = 0;
+      for (size_t p = bufstart; p < lo;) { int w; datok::decode_rune(in + p, lo - p, &w); p += (size_t)w; runes++; }
+      if (cb->token) cb->token(cb->user, in + bufstart, hi - bufstart, lo - bufstart, runes);
+      bufstart = hi;
+    }
+  };
+  auto emit_sentences = [&](uint64_t upto) {
+    for (; sen < upto; sen++) {
+      emit_tokens(v->sent_tok[sen]);
+      if (cb->sentence_end) cb->sentence_end(cb->user);
+    }
+  };
+  for (uint64_t d = 0; d < v->n_texts; d++) {
+    emit_sentences(v->text_sent_end[d]);
+    emit_tokens(v->text_tok_end[d]);
+    if (cb->text_end) cb->text_end(cb->user);
+    bufstart = v->text_byte_end[d];
+  }
+  emit_sentences(v->n_sentences);
+  return DATOK_OK;
+}
+
+}  // extern "C"

@@ -150,6 +150,11 @@ int datok_last_kernel_times(const datok_model *m, const char **names, float *ms,
 /* number of kernel launches issued by the last call */
 int datok_last_launch_count(const datok_model *m);
 
+/* Page-locked host memory for inputs: host->device copies from it run at full
+ * PCIe speed and asynchronously.  Any other host pointer works too, slower. */
+void *datok_host_alloc(size_t bytes);
+void datok_host_free(void *p);
+
 const char *datok_last_error(void);
 const char *datok_strerror(int code);
 

@@ -1,0 +1,110 @@
+"""CPU tests of the kernel bodies (datok_b200/csrc/*.cuh) run through tests/emul, a
+sequential emulation of the kernels' grid decomposition, against the oracle.
+They exercise the speculative-chunk algorithm (sync points, probe hand-off, stitch,
+re-walk rounds) and the bit compaction without a GPU.  The CUDA kernels themselves
+are checked by the -m gpu tests."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import parity_util as P
+from golden_util import case_id, load_cases
+
+MODELS = ("tokenizer_de.matok", "tokenizer_en.matok", "simpletok.matok", "clitic_test.matok")
+
+
+@pytest.fixture(scope="module")
+def emul_models(testdata):
+    return {n: P.EmulModel(os.path.join(testdata, n)) for n in MODELS}
+
+
+@pytest.fixture(scope="module")
+def corpus_lib():
+    from datok_b200 import corpus
+    return corpus
+
+
+@pytest.mark.parametrize("case", load_cases(), ids=case_id)
+def test_reference_vectors(case, oracle_models, emul_models):
+    data = bytes.fromhex(case["input_hex"])
+    for flags in {case["flags"], 15, 31}:
+        o = oracle_models[case["model"]].transduce(data, flags)
+        for chunk, order in ((32, 0), (96, 1)):
+            s = emul_models[case["model"]].transduce(data, flags, chunk, order)
+            P.assert_matches_oracle(s, o, flags, f'{case["src"]} chunk={chunk}')
+
+
+ODD = [b"", b" ", b"\x04a", b"a\x04\x04b", b"\x04", b"\x04\x04", b" " * 1025, b"a" * 1100, b"a" * 1024 + b" b",
+       b" " * 1023 + b"a", b" " * 1024 + b"a", b"x\x04 y", b"\n\x04\n\x04\n", b"abc", b"abc\x04",
+       b"\xff\xfe abc \xc3", b"\xc3\xa4\xc3", b"\xe2\x82", b"a\xe2\x82\xacb \xed\xa0\x80 \xf4\x90\x80\x80 \xc0\xaf",
+       "ä ö ü ß „Zitat“ – …".encode(), b"\x80\x80\x80", b"a\x80b", b"\xf0\x9f\x98\x80 \xf0\x9f\x98",
+       "日本語のテキスト。次の文。".encode(), b"\x00\x01\x02 \x7f", b"a.\x04b.\x04c", b"Hallo.\x04\nWelt.\x04\n\nEnde",
+       b"...", b". . .", b"!!! ??? ...", b"<x y=\"a b", b"\"\"\"", b"\n\n\n", b"a\n\nb", ("é" * 1030).encode(),
+       ("é" * 600).encode(), ("日" * 600).encode(), ("日" * 1100).encode()]
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_edge_and_panic_inputs(model, oracle_models, emul_models):
+    """empty / EOT-only / token-less texts, invalid UTF-8, and the inputs on which the
+    reference panics: the error code must match the panic."""
+    seen = set()
+    for data in ODD:
+        for flags in (0, 3, 15, 31, 4, 8, 8 | 16, 2 | 4):
+            o = oracle_models[model].transduce(data, flags)
+            seen.add(o.status)
+            for chunk in (32, 64, 1024):
+                s = emul_models[model].transduce(data, flags, chunk, 0)
+                P.assert_matches_oracle(s, o, flags, f"{model} {data[:24]!r} flags={flags} chunk={chunk}")
+    assert {0, 1, 2, 3}.issubset(seen)
+
+
+@pytest.mark.parametrize("kind,model", [(2, "tokenizer_de.matok"), (3, "tokenizer_en.matok"),
+                                        (1, "simpletok.matok"), (4, "tokenizer_de.matok")])
+def test_synthetic_corpora(kind, model, oracle_models, emul_models, corpus_lib):
+    """the bench corpora, scaled down, for several chunk sizes"""
+    a = corpus_lib.generate(kind, 1 << 19, seed=11 + kind)
+    for flags in (15, 31):
+        o = oracle_models[model].transduce_np(a, flags)
+        assert o.status == 0
+        for chunk, order in ((64, 1), (256, 0), (2048, 0)):
+            s = emul_models[model].transduce(a, flags, chunk, order)
+            P.assert_matches_oracle(s, o, flags, f"kind={kind} chunk={chunk}")
+
+
+def _fuzz_text(rng, n):
+    alphabet = [b" ", b" ", b" ", b"\n", b"\t", b".", b",", b"!", b"?", b"\x04", b"<", b">", b"\"", b"'", b"&", b";",
+                b"-", b"/", b":", b"@", b"a", b"e", b"n", b"r", b"S", b"T", b"1", b"9", "ä".encode(), "ß".encode(),
+                "„".encode(), "“".encode(), "…".encode(), "日".encode(), "\U0001F600".encode(), b"\xc3", b"\xa4",
+                b"\xe2", b"\x80", b"\xff", b"z.B.", b"Dr.", b"usw.", b"http://", b"www.", b".de", b"&amp;", b"<b>",
+                b"</b>", b"...", b"'s", b"n't", b"I."]
+    out = bytearray()
+    while len(out) < n:
+        out += rng.choice(alphabet)
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_fuzz(model, oracle_models, emul_models):
+    """differential fuzzing over a markup/abbreviation/invalid-UTF-8 heavy alphabet"""
+    rng = random.Random(20261018)
+    for it in range(120):
+        data = _fuzz_text(rng, rng.choice((7, 33, 64, 200, 1500)))
+        flags = rng.choice((3, 15, 31, 4, 12, 28))
+        o = oracle_models[model].transduce(data, flags)
+        chunk = rng.choice((32, 64, 128, 512))
+        s = emul_models[model].transduce(data, flags, chunk, rng.randint(0, 1))
+        P.assert_matches_oracle(s, o, flags, f"{model} it={it} {data[:40]!r} chunk={chunk}")
+
+
+def test_carry_between_calls(oracle_models, emul_models):
+    """a stream cut after an EOT continues from the carried state (shard hand-over)"""
+    om, em = oracle_models["tokenizer_de.matok"], emul_models["tokenizer_de.matok"]
+    a, b = "Erster Text. Zwei Sätze.\n\x04".encode(), "\nZweiter Text <a href=\"x y\">hier</a>.\x04".encode()
+    oa = om.transduce(a, 15)
+    ob = om.transduce(b, 15 | 256, carry_in=dict(state=oa.carry_out["state"], ok=0, sentence_end=1, text_end=1))
+    sb = em.transduce(b, 15 | 256, 32, 0, carry_state=oa.carry_out["state"], sentence_end=1, text_end=1)
+    P.assert_matches_oracle(sb, ob, 15, "second shard")
+    whole = om.transduce(a + b, 15)
+    assert whole.text == oa.text + ob.text

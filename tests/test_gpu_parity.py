@@ -1,0 +1,215 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (datok_b200 ->
+libdatok_b200.so), against the CPU oracle on identical inputs.  Bit-exact:
+token byte spans, TokenWriter.pos / .sent rune offsets, sentence and text
+structure, formatted output for every flag combination, and the error code on
+inputs where the reference panics."""
+import io
+import os
+import random
+
+import numpy as np
+import pytest
+
+import parity_util as P
+from golden_util import case_id, check_output, load_cases
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ("tokenizer_de.matok", "tokenizer_en.matok", "simpletok.matok", "clitic_test.matok")
+
+
+@pytest.fixture(scope="module")
+def gpu_models(testdata):
+    import datok_b200 as d
+    ms = {n: d.LoadTokenizerFile(os.path.join(testdata, n)) for n in MODELS}
+    assert all(m is not None for m in ms.values()), "CUDA extension failed to load a model (no fallback exists)"
+    yield ms
+    for m in ms.values():
+        m.close()
+
+
+class _Status:
+    def __init__(self, code):
+        self.status = code
+
+
+def gpu_arrays(tok, data, flags, **kw):
+    import datok_b200 as d
+    try:
+        return tok.transduce_arrays(data, flags, **kw)
+    except d.ReferencePanic as e:
+        return _Status(e.code)
+
+
+def test_native_library_is_loaded(gpu_models):
+    from datok_b200 import _lib
+    assert os.path.basename(_lib.LIB_PATH) == "libdatok_b200.so" and os.path.exists(_lib.LIB_PATH)
+    assert gpu_models["tokenizer_de.matok"].Type() == "MATOK"
+    assert gpu_models["tokenizer_de.matok"].state_count == 18400
+    loaded = open("/proc/self/maps").read()
+    assert "libdatok_b200.so" in loaded
+
+
+@pytest.mark.parametrize("case", load_cases(), ids=case_id)
+def test_reference_vectors(case, gpu_models, oracle_models):
+    """the reference's own golden vectors, through Transduce/TransduceTokenWriter"""
+    import datok_b200 as d
+    tok = gpu_models[case["model"]]
+    data = bytes.fromhex(case["input_hex"])
+    w = io.BytesIO()
+    tw = d.NewTokenWriter(w, case["flags"] & 0xFF)
+    if case["flags"] & d.WRITER_USED:
+        tw._stock["init"] = False
+    assert tok.TransduceTokenWriter(io.BytesIO(data), tw)
+    check_output(case, w.getvalue())
+    o = oracle_models[case["model"]].transduce(data, case["flags"])
+    assert w.getvalue() == o.text
+    for flags in (15, 31):
+        o = oracle_models[case["model"]].transduce(data, flags)
+        P.assert_matches_oracle(gpu_arrays(tok, data, flags), o, flags, case["src"])
+
+
+from test_emul_parity import ODD, _fuzz_text  # noqa: E402  (same inputs as the CPU emulation tests)
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_edge_and_panic_inputs(model, gpu_models, oracle_models):
+    for data in ODD:
+        for flags in (0, 3, 15, 31, 4, 8, 8 | 16, 2 | 4):
+            o = oracle_models[model].transduce(data, flags)
+            P.assert_matches_oracle(gpu_arrays(gpu_models[model], data, flags), o, flags,
+                                    f"{model} {data[:24]!r} flags={flags}")
+
+
+@pytest.mark.parametrize("kind,model", [(2, "tokenizer_de.matok"), (3, "tokenizer_en.matok"),
+                                        (1, "simpletok.matok"), (4, "tokenizer_de.matok")])
+def test_synthetic_corpora(kind, model, gpu_models, oracle_models):
+    from datok_b200 import corpus
+    a = corpus.generate(kind, 4 << 20, seed=corpus.SEED + kind)
+    for flags in (15, 31):
+        o = oracle_models[model].transduce_np(a, flags)
+        assert o.status == 0
+        s = gpu_arrays(gpu_models[model], a, flags)
+        P.assert_matches_oracle(s, o, flags, f"kind={kind} flags={flags}")
+        assert gpu_models[model].format(s, a, flags & 31) == o.text
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_fuzz(model, gpu_models, oracle_models):
+    rng = random.Random(7)
+    for it in range(150):
+        data = _fuzz_text(rng, rng.choice((7, 33, 64, 200, 1500, 9000)))
+        flags = rng.choice((3, 15, 31, 4, 12, 28))
+        o = oracle_models[model].transduce(data, flags)
+        P.assert_matches_oracle(gpu_arrays(gpu_models[model], data, flags), o, flags, f"{model} it={it} {data[:40]!r}")
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3, 4, 5, 6, 7, 8, 12, 15, 16 | 15, 16 | 12, 16 | 8, 0])
+def test_format_every_flag_combination(flags, gpu_models, oracle_models):
+    """host half of the TokenWriter (datok_format) == NewTokenWriter(w, flags) output"""
+    import datok_b200 as d
+    data = ("\nErste Zeile. Und <b>noch</b> eine!\n\x04\nZweiter Text – mit „Zitat“ usw. Ende?\x04"
+            "Dritter.\n\x04\n").encode() + b"Kaputt \xff\xc3 hier.\x04"
+    tok = gpu_models["tokenizer_de.matok"]
+    o = oracle_models["tokenizer_de.matok"].transduce(data, flags)
+    w = io.BytesIO()
+    try:
+        tok.TransduceTokenWriter(data, d.NewTokenWriter(w, flags))
+        assert o.status == 0 and w.getvalue() == o.text
+    except d.ReferencePanic as e:
+        assert e.code == P.ORACLE_TO_ERR[o.status] != 0
+
+
+def test_custom_token_writer_replay(gpu_models, oracle_models):
+    """user-supplied TokenWriter callables (token_writer.go:27-33) see the reference's event stream"""
+    import datok_b200 as d
+    data = "  Der alte Mann.\nEr ging. \x04\nNeu hier?\x04".encode()
+    ev = []
+    tw = d.TokenWriter(Token=lambda off, buf: ev.append(("T", off, "".join(buf))),
+                       SentenceEnd=lambda n: ev.append(("S",)), TextEnd=lambda n: ev.append(("X",)))
+    assert gpu_models["tokenizer_de.matok"].TransduceTokenWriter(data, tw)
+    o = oracle_models["tokenizer_de.matok"].transduce(data, 3)
+    toks = [e for e in ev if e[0] == "T"]
+    assert len(toks) == o.n_tokens
+    for k, (_, off, buf) in enumerate(toks):
+        assert off == o.tok_offset[k]
+        assert buf.encode() == data[o.tok_buf_start[k]:o.tok_byte_end[k]]
+    # same interleaving as the stock SIMPLE writer: Token -> "x\n", SentenceEnd/TextEnd -> "\n"
+    text = "".join(b[off:] + "\n" if k == "T" else "\n" for (k, *rest) in ev for off, b in [rest or (0, "")])
+    assert text.encode() == o.text
+
+
+def test_carry_between_calls(gpu_models, oracle_models):
+    import datok_b200 as d
+    om, tok = oracle_models["tokenizer_de.matok"], gpu_models["tokenizer_de.matok"]
+    a, b = "Erster Text. Zwei Sätze.\n\x04".encode(), "\nZweiter Text <a href=\"x y\">hier</a>.\x04".encode()
+    ra = tok.transduce_arrays(a, 15)
+    oa = om.transduce(a, 15)
+    assert ra.carry_state == oa.carry_out["state"]
+    ob = om.transduce(b, 15 | 256, carry_in=dict(state=oa.carry_out["state"], ok=0, sentence_end=1, text_end=1))
+    rb = tok.transduce_arrays(b, 15 | 256, carry=d.Carry(ra.carry_state, 1, 1, 0))
+    P.assert_matches_oracle(rb, ob, 15, "second shard")
+
+
+def test_chunk_size_independence(testdata, oracle_models, monkeypatch):
+    """the result must not depend on the speculation granularity"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    a = corpus.generate(4, 1 << 20, seed=5)
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
+    for chunk in ("32", "96", "1024", "8192"):
+        monkeypatch.setenv("DATOK_CHUNK", chunk)
+        tok = d.LoadTokenizerFile(os.path.join(testdata, "tokenizer_de.matok"))
+        P.assert_matches_oracle(tok.transduce_arrays(a, 15), o, 15, f"chunk={chunk}")
+        tok.close()
+
+
+def test_large_input_properties(gpu_models, oracle_models):
+    """64 MiB German corpus: size-independent properties plus oracle parity on a prefix."""
+    from datok_b200 import corpus
+    n = 64 << 20
+    a = np.empty(n, dtype=np.uint8)
+    docs = corpus.generate_blocks_into(corpus.GERMAN, corpus.SEED, a, block=16 << 20)
+    tok = gpu_models["tokenizer_de.matok"]
+    r = tok.transduce_arrays(a, 15)
+    tb = r.tok_bytes.astype(np.int64)
+    starts, ends = tb[0::2], tb[1::2]
+    assert r.n_texts == docs == int((a == 4).sum())
+    assert (ends > starts).all() and (starts[1:] >= ends[:-1]).all() and ends[-1] <= n
+    assert (np.diff(r.text_tok_end.astype(np.int64)) > 0).all() and r.text_tok_end[-1] == r.n_tokens
+    assert r.text_sent_end[-1] == r.n_sentences and r.n_sent_pos == 2 * r.n_sentences
+    tp = r.tok_pos.astype(np.int64)
+    assert (tp[1::2] > tp[0::2]).all()
+    # rune offsets restart at 0..few in every text and never exceed the text's rune count
+    first = np.concatenate(([0], r.text_tok_end[:-1].astype(np.int64)))
+    assert (tp[2 * first] >= 0).all() and (tp[2 * first] < 64).all()
+    # every token surface is free of whitespace bytes the root state skips
+    sample = np.random.default_rng(1).integers(0, r.n_tokens, 20000)
+    for k in sample:
+        s = a[starts[k]:ends[k]]
+        assert s.size and s[0] not in (32, 10, 9, 4)
+    # oracle parity on the first block (documents are independent given the carried state)
+    cut = int(r.text_byte_end[np.searchsorted(r.text_byte_end, 8 << 20)])
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a[:cut], 15)
+    k = o.n_tokens
+    np.testing.assert_array_equal(r.tok_bytes[:2 * k:2], o.tok_byte_start)
+    np.testing.assert_array_equal(r.tok_pos[:2 * k], o.tok_pos)
+    np.testing.assert_array_equal(r.sent_pos[:o.sent_pos.size], o.sent_pos)
+
+
+def test_device_resident_path(gpu_models, oracle_models):
+    """datok_transduce_device: input and offset arrays stay in HBM"""
+    import torch
+    from datok_b200 import corpus
+    a = corpus.generate(2, 2 << 20, seed=3)
+    tok = gpu_models["tokenizer_de.matok"]
+    d_in = torch.from_numpy(a).cuda()
+    r = tok.transduce_device(d_in.data_ptr(), a.size, 15)
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
+    assert (r.n_tokens, r.n_sentences, r.n_texts) == (o.n_tokens, o.n_sent_events, o.n_texts)
+    import ctypes as C
+    host = np.empty(2 * r.n_tokens, dtype=np.int32)
+    torch.cuda.synchronize()
+    rc = torch.cuda.cudart().cudaMemcpy(host.ctypes.data, r.device_ptr("tok_pos"), host.nbytes, 2)
+    assert int(rc) == 0
+    np.testing.assert_array_equal(host, o.tok_pos)
