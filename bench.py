@@ -106,13 +106,15 @@ def cpu_reference_rate(arr, seconds=15.0, threads=None):
     want = int(min(arr.size, max(cut, rate * seconds)))
     eots = np.flatnonzero(arr[:want] == 4)
     n = int(eots[-1]) + 1
+    passes = max(1, int(round(rate * seconds / n)))
     t0 = time.perf_counter()
-    res = ora.transduce_docs_mt(arr[:n], FLAGS, threads)
+    for _ in range(passes):
+        res = ora.transduce_docs_mt(arr[:n], FLAGS, threads)
     dt = time.perf_counter() - t0
-    return {"value": n / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-            "sample": f"first {n} bytes ({res['docs']} documents) of the same corpus, {dt:.1f} s, "
-                      f"C restatement of matrix.go:348-698 + token_writer.go (Go toolchain absent)",
-            "seconds": dt, "bytes": n, "tokens": res["tokens"]}
+    return {"value": passes * n / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"{passes} pass(es) over the first {n} bytes ({res['docs']} documents) of the same corpus, "
+                      f"{dt:.1f} s, C restatement of matrix.go:348-698 + token_writer.go (Go toolchain absent)",
+            "seconds": dt, "bytes": passes * n, "tokens": res["tokens"]}
 
 
 def run_reference(args, rank, world):

@@ -66,6 +66,9 @@ struct datok_model {
   uint32_t last_rounds = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> tev;
+  // results hold pooled buffers of their model: the model outlives them
+  int live_results = 0;
+  bool freed_by_user = false;
 };
 
 struct datok_result {
@@ -107,6 +110,28 @@ void release(datok_model* m, const Block& b) {
   for (auto& c : m->cache) cached += c.bytes;
   if (m->cache.size() < 64 && cached < ((size_t)24 << 30)) { m->cache.push_back(b); return; }
   if (b.host) cudaFreeHost(b.p); else cudaFree(b.p);
+}
+
+// caller holds m->mu
+void free_result_locked(datok_result* r) {
+  datok_model* m = r->model;
+  for (auto& b : r->blocks) release(m, b);
+  m->live_results--;
+  delete r;
+}
+
+void destroy_model(datok_model* m) {
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (auto& b : m->cache) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
+  if (m->ws) cudaFree(m->ws);
+  if (m->d_table) cudaFree(m->d_table);
+  if (m->d_cls_tables) cudaFree(m->d_cls_tables);
+  if (m->d_rune_key) cudaFree(m->d_rune_key);
+  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : m->tev) cudaEventDestroy(e);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -388,6 +413,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   // output arrays: sized from the scan totals (+1 for the end-of-stream events)
   datok_result* r = new datok_result();
   r->model = m;
+  m->live_results++;
   r->device = device_out;
   std::memset(&r->view, 0, sizeof r->view);
   const size_t nt = hdr.tot.n_tok, ns = (size_t)hdr.tot.n_sent + 1, nx = (size_t)hdr.tot.n_text + 1,
@@ -407,7 +433,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
     if (!device_out) r->blocks.push_back(o.h);
     *o.dev = o.d.p;
   }
-  if (rc) { datok_result_free(r); return rc; }
+  if (rc) { free_result_locked(r); return rc; }
   c.tok_bytes = (uint32_t*)d_tok_bytes;
   c.tok_pos = (int32_t*)d_tok_pos;
   c.sent_pos = (int32_t*)d_sent_pos;
@@ -431,7 +457,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   if (tail.err != ~0ull) {
     const int code = (int)(tail.err & 0xFF);
     g_last_error = std::string("reference would panic: ") + datok_strerror(code);
-    datok_result_free(r);
+    free_result_locked(r);
     return code;
   }
   datok_view& v = r->view;
@@ -504,17 +530,13 @@ datok_model* datok_load_image(const uint8_t* image, size_t n, int device, int* e
 
 void datok_free(datok_model* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
-  if (m->stream) cudaStreamSynchronize(m->stream);
-  for (auto& b : m->cache) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
-  if (m->ws) cudaFree(m->ws);
-  if (m->d_table) cudaFree(m->d_table);
-  if (m->d_cls_tables) cudaFree(m->d_cls_tables);
-  if (m->d_rune_key) cudaFree(m->d_rune_key);
-  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
-  for (auto& e : m->tev) cudaEventDestroy(e);
-  if (m->stream) cudaStreamDestroy(m->stream);
-  delete m;
+  bool destroy;
+  {
+    std::lock_guard<std::mutex> lock(m->mu);
+    m->freed_by_user = true;
+    destroy = m->live_results == 0;
+  }
+  if (destroy) destroy_model(m);  // otherwise the last datok_result_free() does it
 }
 
 const char* datok_type(void) { return "MATOK"; }
@@ -545,11 +567,14 @@ const datok_view* datok_result_view(const datok_result* r) { return r ? &r->view
 
 void datok_result_free(datok_result* r) {
   if (!r) return;
-  if (r->model) {
-    std::lock_guard<std::mutex> lock(r->model->mu);
-    for (auto& b : r->blocks) release(r->model, b);
+  datok_model* m = r->model;
+  bool destroy;
+  {
+    std::lock_guard<std::mutex> lock(m->mu);
+    free_result_locked(r);
+    destroy = m->freed_by_user && m->live_results == 0;
   }
-  delete r;
+  if (destroy) destroy_model(m);
 }
 
 int datok_last_kernel_times(const datok_model* m, const char** names, float* ms, int cap) {
