@@ -124,11 +124,12 @@ DATOK_HD bool chunk_stitch(const DeviceModel& m, const WalkBuffers& b, uint32_t 
   SpecInfo si;
   const uint32_t err = walk_run<false>(c, Y, s, &si);
   if (err) { b.Enew[i] = Y; return false; }
-  if ((Y.flags & WS_PEND) && Y.pos == s) { set_bit(b.b_end, s); Y.flags &= ~WS_PEND; }
   const WState A = b.exitA[i];
-  const bool match = Y.pos == s && Y.t == m.start && Y.tstart == s && Y.flags == 0 &&
+  // (a pending hard-fail END bit at s does not disturb the guess: it is set below)
+  const bool match = Y.pos == s && Y.t == m.start && Y.tstart == s && (Y.flags & ~WS_PEND) == 0 &&
                      !(b.cflags[i] & CF_OVERWRITTEN);
-  if (!match) { b.Ytmp[i] = Y; return true; }
+  if (!match) { b.Ytmp[i] = Y; return true; }  // the re-walk clears from Y.pos on, then sets a pending END
+  if (Y.flags & WS_PEND) set_bit(b.b_end, s);
   // the guess was right: the speculative trace stands.  Only the buffer-window
   // accounting of its first window has to be redone with the true window base.
   WState R = A;

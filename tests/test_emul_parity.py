@@ -73,6 +73,16 @@ def test_synthetic_corpora(kind, model, oracle_models, emul_models, corpus_lib):
             P.assert_matches_oracle(s, o, flags, f"kind={kind} chunk={chunk}")
 
 
+def test_tiny_chunks_on_markup_heavy_text(oracle_models, emul_models, corpus_lib):
+    """32-byte chunks on the long-token corpus: tokens span up to 14 chunks, hard-fail tokens end
+    exactly on sync points (regression: a pending END bit must survive the re-walk)"""
+    a = corpus_lib.generate(4, 1 << 20, seed=5)
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
+    s = emul_models["tokenizer_de.matok"].transduce(a, 15, 32, 0)
+    P.assert_matches_oracle(s, o, 15, "kind=4 chunk=32")
+    assert s.stats["rounds"] > 5
+
+
 def _fuzz_text(rng, n):
     alphabet = [b" ", b" ", b" ", b"\n", b"\t", b".", b",", b"!", b"?", b"\x04", b"<", b">", b"\"", b"'", b"&", b";",
                 b"-", b"/", b":", b"@", b"a", b"e", b"n", b"r", b"S", b"T", b"1", b"9", "ä".encode(), "ß".encode(),
