@@ -38,8 +38,8 @@ struct Block {
   bool host = false;
 };
 
-enum { T_CLASSIFY, T_WALK, T_STITCH, T_REWALK, T_COMMIT, T_REDUCE, T_SCAN, T_EMIT, T_COUNT };
-const char* const kTimerNames[T_COUNT] = {"classify", "walk", "stitch", "rewalk", "commit",
+enum { T_CLEAR, T_WALK, T_STITCH, T_REWALK, T_COMMIT, T_REDUCE, T_SCAN, T_EMIT, T_COUNT };
+const char* const kTimerNames[T_COUNT] = {"clear", "walk_fused", "stitch", "rewalk", "commit",
                                           "compact_reduce", "compact_scan", "compact_emit"};
 
 }  // namespace
@@ -48,11 +48,17 @@ struct datok_model {
   HostModel hm;
   int device = 0;
   cudaStream_t stream = nullptr;
-  // model tables on the device
-  uint16_t* d_table = nullptr;
+  // model tables on the device: [fused table u32 | exact table u16] in one allocation
+  uint8_t* d_tables = nullptr;
+  size_t d_tables_bytes = 0;
   uint8_t* d_cls_tables = nullptr;  // ascii[128] latin1[128] rune_cls[n]
   uint32_t* d_rune_key = nullptr;
   DeviceModel dm;
+  int n_sms = 148;
+  size_t smem_optin = 0;
+  uint32_t n_hot = 1;
+  bool calibrated = false;
+  bool auto_calibrate = true;
   // workspace (grow only)
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
@@ -125,7 +131,7 @@ void destroy_model(datok_model* m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   for (auto& b : m->cache) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
   if (m->ws) cudaFree(m->ws);
-  if (m->d_table) cudaFree(m->d_table);
+  if (m->d_tables) cudaFree(m->d_tables);
   if (m->d_cls_tables) cudaFree(m->d_cls_tables);
   if (m->d_rune_key) cudaFree(m->d_rune_key);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -157,7 +163,6 @@ size_t carve(uint8_t* base, uint32_t N, uint32_t chunk, bool need_input_copy, Wa
   b.n_words = b.n_chunks * (chunk / 32);
   uint8_t* d_in = c.take<uint8_t>(need_input_copy ? (size_t)N + 64 : 0);
   if (need_input_copy) b.in = d_in;
-  b.cls = c.take<uint8_t>((size_t)N + 64);
   b.rstart = c.take<uint32_t>(b.n_words);
   // the four event bitmaps are contiguous so that one memset clears them
   b.b_end = c.take<uint32_t>((size_t)b.n_words * 4);
@@ -226,8 +231,15 @@ struct PhaseTimer {
 
 int upload_model(datok_model* m) {
   HostModel& h = m->hm;
-  CUDA_TRY(cudaMalloc(&m->d_table, h.table.size() * sizeof(uint16_t)));
-  CUDA_TRY(cudaMemcpy(m->d_table, h.table.data(), h.table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  if (m->d_tables) { cudaFree(m->d_tables); m->d_tables = nullptr; }
+  if (m->d_cls_tables) { cudaFree(m->d_cls_tables); m->d_cls_tables = nullptr; }
+  if (m->d_rune_key) { cudaFree(m->d_rune_key); m->d_rune_key = nullptr; }
+  const size_t t2_bytes = align_up(h.table2.size() * sizeof(uint32_t), 256);
+  const size_t t1_bytes = h.table.size() * sizeof(uint16_t);
+  m->d_tables_bytes = t2_bytes + t1_bytes;
+  CUDA_TRY(cudaMalloc(&m->d_tables, m->d_tables_bytes));
+  CUDA_TRY(cudaMemcpy(m->d_tables, h.table2.data(), h.table2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(m->d_tables + t2_bytes, h.table.data(), t1_bytes, cudaMemcpyHostToDevice));
   const size_t nr = h.rune_key.size();
   std::vector<uint8_t> blob(256 + nr + 16, 0);
   std::memcpy(blob.data(), h.ascii_cls, 128);
@@ -238,35 +250,70 @@ int upload_model(datok_model* m) {
   CUDA_TRY(cudaMalloc(&m->d_rune_key, (nr + 4) * sizeof(uint32_t)));
   if (nr) CUDA_TRY(cudaMemcpy(m->d_rune_key, h.rune_key.data(), nr * sizeof(uint32_t), cudaMemcpyHostToDevice));
   DeviceModel& d = m->dm;
-  d.table = m->d_table;
-  d.row_shift = h.row_shift; d.start = h.start; d.eps_lo = h.eps_lo; d.n_classes = h.n_classes;
+  d.table2 = reinterpret_cast<const uint32_t*>(m->d_tables);
+  d.table = reinterpret_cast<const uint16_t*>(m->d_tables + t2_bytes);
+  d.row_shift = h.row_shift; d.start = h.start; d.n_classes = h.n_classes; d.stride2 = h.stride2;
   d.cls.ascii_cls = m->d_cls_tables;
   d.cls.latin1_cls = m->d_cls_tables + 128;
   d.cls.rune_cls = m->d_cls_tables + 256;
   d.cls.rune_key = m->d_rune_key;
   d.cls.n_rune = (uint32_t)nr;
   d.cls.identity_cls = h.identity_cls;
-  std::memcpy(d.sync_mask, h.sync_mask, sizeof d.sync_mask);
+  std::memcpy(d.sync_ascii, h.sync_ascii, sizeof d.sync_ascii);
+  m->n_hot = fused_max_hot_rows(d, m->smem_optin, (uint32_t)h.stateCount);
+  if (const char* s = std::getenv("DATOK_HOT_ROWS")) {
+    long v = std::atol(s);
+    if (v >= 1 && (uint32_t)v < m->n_hot) m->n_hot = (uint32_t)v;
+  }
   return DATOK_OK;
 }
 
-// Keep the transition table resident in L2 (it is gathered from once per input byte).
+// Keep the transition tables resident in L2 (they are gathered from once per input byte).
 void pin_table_in_l2(datok_model* m) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) return;
-  const size_t bytes = m->hm.table.size() * sizeof(uint16_t);
+  const size_t bytes = m->d_tables_bytes;
   if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
   size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes * 2);
   cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
   cudaStreamAttrValue attr;
   std::memset(&attr, 0, sizeof attr);
-  attr.accessPolicyWindow.base_ptr = m->d_table;
+  attr.accessPolicyWindow.base_ptr = m->d_tables;
   attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
   attr.accessPolicyWindow.hitRatio = 1.0f;
   attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   cudaStreamSetAttribute(m->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
   cudaGetLastError();
+}
+
+// Re-orders the states by measured visit frequency on a sample of the caller's own
+// text (GPU histogram), so that the rows kept in shared memory are the hot ones.
+int calibrate_locked(datok_model* m, const WalkBuffers& full) {
+  WalkBuffers b = full;
+  const uint32_t sample = std::min<uint32_t>(full.N, 8u << 20);
+  b.N = sample;
+  b.n_chunks = sample / b.chunk + 1;
+  const size_t S = (size_t)m->hm.stateCount;
+  uint32_t* d_hist = nullptr;
+  CUDA_TRY(cudaMalloc(&d_hist, (S + 2) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemsetAsync(d_hist, 0, (S + 2) * sizeof(uint32_t), m->stream));
+  CUDA_TRY(cudaMemsetAsync(b.b_end, 0, (size_t)full.n_words * 4 * sizeof(uint32_t), m->stream));
+  launch_hist(m->dm, b, d_hist, m->stream);
+  std::vector<uint32_t> hist(S + 2);
+  CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, (S + 2) * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  cudaFree(d_hist);
+  std::vector<uint64_t> hist_old(S + 1, 0);
+  for (size_t t = 1; t <= S; t++) hist_old[m->hm.old_of_new[t]] = hist[t];
+  std::string why;
+  int rc = build_layout(m->hm, why, hist_old.data());
+  if (rc) { g_last_error = why; return rc; }
+  rc = upload_model(m);
+  if (rc) return rc;
+  pin_table_in_l2(m);
+  m->calibrated = true;
+  return DATOK_OK;
 }
 
 datok_model* finish_load(datok_model* m, int device, int* err) {
@@ -295,6 +342,9 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
     return nullptr;
   }
   for (auto& e : m->ev) cudaEventCreate(&e);
+  m->n_sms = prop.multiProcessorCount;
+  m->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  if (const char* s = std::getenv("DATOK_NO_CALIBRATE")) m->auto_calibrate = !(s[0] == '1');
   int rc = upload_model(m);
   if (rc) { *err = rc; datok_free(m); return nullptr; }
   pin_table_in_l2(m);
@@ -339,22 +389,34 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   carve(m->ws, N, m->chunk, !in_is_device, b, cb);
   if (in_is_device) b.in = in;
 
+  if (m->auto_calibrate && !m->calibrated && N >= (256u << 10)) {
+    // one-time specialisation of the table layout to the caller's text
+    if (!in_is_device) CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(b.in), in, std::min<uint32_t>(N, 8u << 20),
+                                                cudaMemcpyHostToDevice, s));
+    rc = calibrate_locked(m, b);
+    if (rc) return rc;
+    if (carry_in && carry_in->state) start_state = m->hm.new_of_old[carry_in->state];
+    else start_state = m->hm.start;
+  }
+
   PhaseTimer pt{m};
   CUDA_TRY(cudaEventRecord(m->ev[0], s));
   if (!in_is_device && N) CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(b.in), in, N, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaEventRecord(m->ev[1], s));
 
-  // ---- K1 classify, K2a speculative walk ----
+  // ---- K1+K2a: fused classify + speculative walk ----
+  pt.begin(T_CLEAR);
   CUDA_TRY(cudaMemsetAsync(b.b_end, 0, (size_t)b.n_words * 4 * sizeof(uint32_t), s));
   CUDA_TRY(cudaMemsetAsync(b.counters, 0, 8 * sizeof(uint32_t), s));
   CUDA_TRY(cudaMemsetAsync(b.err_key, 0xFF, sizeof(unsigned long long), s));
-  pt.begin(T_CLASSIFY);
-  launch_classify(m->dm, b, s);
   pt.end();
   pt.begin(T_WALK);
-  launch_walk_spec(m->dm, b, start_state, s);
+  {
+    const int e = launch_walk_fused(m->dm, b, start_state, m->n_hot, m->n_sms, s);
+    if (e != 0) { g_last_error = std::string("walk_fused launch: ") + cudaGetErrorString((cudaError_t)e); return DATOK_ERR_CUDA; }
+  }
   pt.end();
-  m->launches += 2;
+  m->launches += 1;
 
   // ---- K2b-d fix-up rounds ----
   uint32_t n_list = b.n_chunks - 1;

@@ -17,6 +17,7 @@
 // so no atomics are needed.
 #pragma once
 #include "compact_core.cuh"
+#include "fast_core.cuh"
 #include "walk_core.cuh"
 
 namespace datok {
@@ -25,15 +26,15 @@ constexpr uint32_t CF_HAD_REWIND = 1;   // the speculative walk closed at least 
 constexpr uint32_t CF_OVERWRITTEN = 2;  // the speculative trace has been replaced by a re-walk
 
 struct DeviceModel {
-  const uint16_t* table;
-  uint32_t row_shift, start, eps_lo, n_classes;
+  const uint16_t* table;   // exact table (walk_run)
+  const uint32_t* table2;  // fused table (fast_step), stride2 entries per row
+  uint32_t row_shift, start, n_classes, stride2;
   ClsTables cls;           // pointers into device memory
-  uint32_t sync_mask[8];
+  uint32_t sync_ascii[4];  // ASCII bytes the root state skips: a chunk may start right after one
 };
 
 struct WalkBuffers {
   const uint8_t* in;
-  uint8_t* cls;            // N + pad
   uint32_t N;
   uint32_t chunk;          // bytes per chunk (multiple of 32)
   uint32_t n_chunks;       // N / chunk + 1
@@ -48,9 +49,10 @@ struct WalkBuffers {
 
 DATOK_HD WalkCtx make_walk_ctx(const DeviceModel& m, const WalkBuffers& b) {
   WalkCtx c;
-  c.table = m.table; c.row_shift = m.row_shift; c.start = m.start; c.eps_lo = m.eps_lo;
-  c.cls = b.cls; c.N = b.N; c.rstart = b.rstart;
+  c.table = m.table; c.row_shift = m.row_shift; c.start = m.start;
+  c.in = b.in; c.N = b.N; c.cls = m.cls;
   c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
+  c.hist = nullptr;
   return c;
 }
 
@@ -82,30 +84,141 @@ DATOK_HD void chunk_spec(const DeviceModel& m, const WalkBuffers& b, uint32_t i,
     st.pos = st.tstart = st.base = st.hw = 0;
     st.t = (uint16_t)start_state;
     b.sync[0] = 0;
-    walk_run<false>(c, st, hi, &si);
+    walk_run<false, true, false>(c, st, hi, &si);
     b.exitA[0] = st;
     b.E[0] = st;
     b.first_hw[0] = 0;
     b.cflags[0] = CF_HAD_REWIND;
     return;
   }
-  uint32_t s = K_NOPOS;
-  const uint32_t lim = hi < b.N ? hi : b.N;
-  for (uint32_t p = lo; p < lim; p++) {
-    if (sync_class(m.sync_mask, b.cls[p - 1])) { s = p; break; }
-  }
+  const uint32_t s = find_sync(b.in, b.N, m.sync_ascii, lo, hi);
   b.sync[i] = s;
   if (s == K_NOPOS) {  // no sync point: the predecessor's state has to be walked through
     st = wstate_invalid(0);
   } else {
     st.pos = st.tstart = st.base = st.hw = s;
     st.t = (uint16_t)m.start;
-    walk_run<true>(c, st, hi, &si);
+    walk_run<true, true, false>(c, st, hi, &si);
   }
   b.exitA[i] = st;
   b.E[i] = st;
   b.first_hw[i] = si.first_hw;
   b.cflags[i] = si.had_rewind ? CF_HAD_REWIND : 0;
+}
+
+DATOK_HD void note_invalid_utf8(const WalkBuffers& b) {
+#if defined(__CUDA_ARCH__)
+  atomicOr(&b.counters[2], 1u);
+#else
+  b.counters[2] |= 1u;
+#endif
+}
+
+DATOK_HD void store_seg_bits(const WalkBuffers& b, uint32_t w, const SegBits& B) {
+  b.b_end[w] = B.end; b.b_skip[w] = B.skip; b.b_sent[w] = B.sent; b.b_tend[w] = B.tend;
+}
+DATOK_HD void load_seg_bits(const WalkBuffers& b, uint32_t w, SegBits& B) {
+  B.end = b.b_end[w]; B.skip = b.b_skip[w]; B.sent = b.b_sent[w]; B.tend = b.b_tend[w];
+}
+
+// K1+K2a fused: classification and speculative walk of chunk i, segment by segment
+// (fast_core.cuh).  Produces exactly what chunk_spec() produces, plus the rune-start
+// words of the chunk.  seg_cls: 32 bytes of lane-private scratch (shared memory in
+// the kernel).  The boundary bitmaps of the chunk must be zero on entry.
+DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const FastTables& FT, uint32_t i,
+                              uint32_t start_state, uint8_t* seg_cls) {
+  const WalkCtx c = make_walk_ctx(m, b);
+  const uint32_t lo = i * b.chunk, hi = lo + b.chunk, N = b.N;
+  WState st;
+  st.pos = st.tstart = st.base = st.hw = 0;
+  st.eps_pos = 0; st.eps_state = 0; st.flags = 0; st.t = (uint16_t)start_state;
+  SpecInfo si;
+  si.first_hw = 0; si.had_rewind = 0;
+  FastLane L;
+  L.pos = L.tstart = L.base = L.t = L.eps_pos = L.eps_b = L.hw_med = L.hw_med_base = 0;
+  bool started = (i == 0), fast = false, halted = false;
+  bool first_window = (i != 0);  // the first window of a guessed start is walked exactly (SpecInfo)
+  uint32_t sync = (i == 0) ? 0u : K_NOPOS;
+  uint32_t err = 0;
+
+  for (uint32_t seg_start = lo; seg_start < hi; seg_start += SEG) {
+    const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
+    uint32_t rs;
+    bool inv = false;
+    classify_segment(b.in, N, seg_start, m.cls, seg_cls, &rs, &inv);
+    b.rstart[w] = rs;
+    if (inv) note_invalid_utf8(b);
+    if (halted) continue;
+    if (!started) {
+      sync = find_sync(b.in, N, m.sync_ascii, seg_start, seg_end < hi ? seg_end : hi);
+      if (sync == K_NOPOS) continue;
+      started = true;
+      st.pos = st.tstart = st.base = st.hw = sync;
+      st.t = (uint16_t)m.start;
+    }
+    if (fast && seg_end - L.base >= FAST_WINDOW_GUARD) {  // too close to the 1024-rune buffer limit
+      to_exact(L, FT, st);
+      fast = false;
+    }
+    SegBits B;
+    B.end = B.skip = B.sent = B.tend = 0;
+    bool in_regs = true;  // the segment's boundary words live in B (else in memory)
+    for (;;) {
+      if (!fast) {
+        // exact -> fast whenever the state allows it
+        if (!first_window && st.pos >= seg_start && st.pos < seg_end && st.pos < N && can_go_fast(st) &&
+            seg_end - st.base < FAST_WINDOW_GUARD) {
+          if (!in_regs) { load_seg_bits(b, w, B); in_regs = true; }
+          if (st.flags & WS_PEND) { B.end |= 1u << (st.pos - seg_start); st.flags &= ~WS_PEND; }
+          to_fast(st, L);
+          fast = true;
+          continue;
+        }
+        if (st.pos >= seg_end) break;
+        if (in_regs) { store_seg_bits(b, w, B); in_regs = false; }
+        if (first_window) {
+          err = walk_run<true, false, true>(c, st, seg_end, &si);
+          if (si.had_rewind) first_window = false;
+        } else {
+          SpecInfo dummy;
+          err = walk_run<false, false, false>(c, st, seg_end, &dummy);
+        }
+        if (err || (st.flags & WS_DONE)) { halted = true; break; }
+        continue;
+      }
+      // fast path
+      int rc = FAST_OK;
+      while (L.pos < seg_end && L.pos < N) {
+        rc = fast_step(L, FT, seg_cls, seg_start, B);
+        if (rc != FAST_OK) break;
+      }
+      if (rc == FAST_OK && L.pos >= seg_end) break;  // segment done, stay fast
+      to_exact(L, FT, st);                            // slow case or end of input
+      fast = false;
+      if (st.pos >= seg_end) break;
+      store_seg_bits(b, w, B);
+      in_regs = false;
+      SpecInfo dummy;
+      err = walk_run<false, false, false>(c, st, seg_end, &dummy);
+      if (err || (st.flags & WS_DONE)) { halted = true; break; }
+    }
+    if (in_regs) store_seg_bits(b, w, B);
+  }
+
+  b.sync[i] = sync;
+  if (!started) st = wstate_invalid(0);
+  else if (!err && !(st.flags & WS_DONE)) {
+    if (fast) to_exact(L, FT, st);
+    // hand-off at the chunk end (probe, walk_run)
+    if (first_window) err = walk_run<true, true, false>(c, st, hi, &si);
+    else { SpecInfo dummy; err = walk_run<false, true, false>(c, st, hi, &dummy); }
+  } else if (!err && (st.flags & WS_DONE) && first_window) {
+    si.first_hw = st.hw; si.had_rewind = 0;
+  }
+  b.exitA[i] = st;
+  b.E[i] = st;
+  b.first_hw[i] = si.first_hw;
+  b.cflags[i] = (i == 0 || si.had_rewind) ? CF_HAD_REWIND : 0;
 }
 
 // K2b: returns true if chunk i must be re-walked (state in Ytmp[i]); otherwise Enew[i] is set.
@@ -122,7 +235,7 @@ DATOK_HD bool chunk_stitch(const DeviceModel& m, const WalkBuffers& b, uint32_t 
   clear_chunk_bits(b, lo, s);
   WState Y = X;
   SpecInfo si;
-  const uint32_t err = walk_run<false>(c, Y, s, &si);
+  const uint32_t err = walk_run<false, true, false>(c, Y, s, &si);
   if (err) { b.Enew[i] = Y; return false; }
   const WState A = b.exitA[i];
   // (a pending hard-fail END bit at s does not disturb the guess: it is set below)
@@ -136,11 +249,11 @@ DATOK_HD bool chunk_stitch(const DeviceModel& m, const WalkBuffers& b, uint32_t 
   if (!(A.flags & WS_INVALID)) {
     const uint32_t fh = b.first_hw[i] > Y.hw ? b.first_hw[i] : Y.hw;
     if (b.cflags[i] & CF_HAD_REWIND) {
-      if (window_overflow(b.rstart, Y.base, fh)) R = wstate_invalid(E_OVERFLOW);
+      if (window_overflow(c, Y.base, fh)) R = wstate_invalid(E_OVERFLOW);
     } else {
       R.base = Y.base;
       R.hw = fh;
-      if ((A.flags & WS_DONE) && window_overflow(b.rstart, R.base, R.hw)) R = wstate_invalid(E_OVERFLOW);
+      if ((A.flags & WS_DONE) && window_overflow(c, R.base, R.hw)) R = wstate_invalid(E_OVERFLOW);
     }
   }
   b.Enew[i] = R;
@@ -155,7 +268,7 @@ DATOK_HD void chunk_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t 
   const uint32_t from = (b.sync[i] == K_NOPOS) ? lo : Y.pos;
   clear_chunk_bits(b, from, hi);
   SpecInfo si;
-  walk_run<false>(c, Y, hi, &si);
+  walk_run<false, true, false>(c, Y, hi, &si);
   b.Enew[i] = Y;
   b.cflags[i] |= CF_OVERWRITTEN;
 }

@@ -1,7 +1,7 @@
 // kernels.cu -- sm_100a kernels of the Datok matrix-FSA transduction path.
 //
-//   K1  classify_kernel      bytes -> class stream + rune-start bitmap   (matrix.go:388-435)
-//   K2a walk_spec_kernel     speculative per-chunk walk                   (matrix.go:437-695)
+//   K1+K2a walk_fused_kernel UTF-8 decode + sigma map + speculative per-chunk walk, fused
+//                            (matrix.go:388-435 and 437-695); persistent, hot table rows in smem
 //   K2b stitch_kernel        head of each chunk from the predecessor's exit state
 //   K2c rewalk_kernel        chunks whose guessed start state was wrong
 //   K2d commit_kernel        publish changed exit states, queue successors
@@ -15,49 +15,87 @@
 
 namespace datok {
 
-// ------------------------------------------------------------------ K1
-
-// One thread per input byte; a warp's 32 rune-start flags become one bitmap word.
-__global__ void __launch_bounds__(256) classify_kernel(DeviceModel m, WalkBuffers b) {
-  __shared__ uint8_t s_ascii[128];
-  __shared__ uint8_t s_latin1[128];
-  if (threadIdx.x < 128) {
-    s_ascii[threadIdx.x] = m.cls.ascii_cls[threadIdx.x];
-    s_latin1[threadIdx.x] = m.cls.latin1_cls[threadIdx.x];
-  }
-  __syncthreads();
-  ClsTables T = m.cls;
-  T.ascii_cls = s_ascii;
-  T.latin1_cls = s_latin1;
-  const uint32_t total = b.n_words * 32u;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    bool start = false, invalid = false;
-    if (p < b.N) b.cls[p] = (uint8_t)classify_pos(b.in, b.N, p, T, &start, &invalid);
-    const uint32_t word = __ballot_sync(0xFFFFFFFFu, start);
-    const uint32_t inv = __ballot_sync(0xFFFFFFFFu, invalid);
-    if ((threadIdx.x & 31) == 0) {
-      b.rstart[p >> 5] = word;
-      if (inv) atomicOr(&b.counters[2], 1u);
-    }
-  }
-}
-
-void launch_classify(const DeviceModel& m, const WalkBuffers& b, cudaStream_t s) {
-  const uint32_t total = b.n_words * 32u;
-  uint32_t blocks = (total + 255) / 256;
-  const uint32_t cap = 148u * 8u * 16u;
-  if (blocks > cap) blocks = cap;
-  classify_kernel<<<blocks, 256, 0, s>>>(m, b);
-}
-
-// ------------------------------------------------------------------ K2
+// ------------------------------------------------------------------ K1 + K2a (fused)
 
 constexpr int WALK_THREADS = 128;
+constexpr int FUSED_THREADS = 512;
+constexpr int LANE_CLS_STRIDE = 36;  // bytes of class scratch per lane (9 words: bank spread)
 
-__global__ void __launch_bounds__(WALK_THREADS) walk_spec_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < b.n_chunks) chunk_spec(m, b, i, start_state);
+// Persistent kernel, one CTA per SM.  The hottest rows of the fused transition
+// table and the two byte->class LUTs live in shared memory; every lane owns one
+// chunk at a time and walks it segment by segment (chunk_spec_fast).
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n_hot) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* s_hot = smem;
+  uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_hot + (size_t)n_hot * m.stride2);
+  uint8_t* s_lut = s_cls + FUSED_THREADS * LANE_CLS_STRIDE;
+  const uint32_t hot_words = n_hot * m.stride2;
+  for (uint32_t k = threadIdx.x; k < hot_words; k += FUSED_THREADS) s_hot[k] = m.table2[k];
+  if (threadIdx.x < 128) {
+    s_lut[threadIdx.x] = m.cls.ascii_cls[threadIdx.x];
+    s_lut[128 + threadIdx.x] = m.cls.latin1_cls[threadIdx.x];
+  }
+  __syncthreads();
+  DeviceModel lm = m;
+  lm.cls.ascii_cls = s_lut;
+  lm.cls.latin1_cls = s_lut + 128;
+  FastTables FT;
+  FT.hot = s_hot; FT.cold = m.table2; FT.n_hot = n_hot; FT.stride = m.stride2;
+  uint8_t* my_cls = s_cls + threadIdx.x * LANE_CLS_STRIDE;
+  for (uint32_t i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * FUSED_THREADS)
+    chunk_spec_fast(lm, b, FT, i, start_state, my_cls);
 }
+
+size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot) {
+  return (size_t)n_hot * m.stride2 * 4 + (size_t)FUSED_THREADS * LANE_CLS_STRIDE + 256;
+}
+
+uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states) {
+  const size_t fixed = (size_t)FUSED_THREADS * LANE_CLS_STRIDE + 256 + 1024;
+  if (smem_limit <= fixed) return 1;
+  size_t rows = (smem_limit - fixed) / ((size_t)m.stride2 * 4);
+  if (rows > (size_t)n_states + 1) rows = (size_t)n_states + 1;
+  return rows ? (uint32_t)rows : 1u;
+}
+
+int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot,
+                      int n_sms, cudaStream_t s) {
+  const size_t smem = fused_smem_bytes(m, n_hot);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  uint32_t blocks = (b.n_chunks + FUSED_THREADS - 1) / FUSED_THREADS;
+  if (blocks > (uint32_t)n_sms) blocks = (uint32_t)n_sms;
+  walk_fused_kernel<<<blocks, FUSED_THREADS, smem, s>>>(m, b, start_state, n_hot);
+  return (int)cudaGetLastError();
+}
+
+// Calibration: visits per state on a sample, walked speculatively chunk by chunk
+// with the exact walker.  Wrong guesses only add noise to the ranking.
+__global__ void __launch_bounds__(WALK_THREADS) hist_kernel(DeviceModel m, WalkBuffers b, uint32_t* hist) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n_chunks) return;
+  WalkCtx c = make_walk_ctx(m, b);
+  c.hist = hist;
+  const uint32_t lo = i * b.chunk, hi = lo + b.chunk;
+  const uint32_t s = i == 0 ? 0u : find_sync(b.in, b.N, m.sync_ascii, lo, hi);
+  if (s == K_NOPOS) return;
+  WState st;
+  st.pos = st.tstart = st.base = st.hw = s;
+  st.eps_pos = 0; st.eps_state = 0; st.flags = 0; st.t = (uint16_t)m.start;
+  SpecInfo si;
+  walk_run<true, true, false>(c, st, hi, &si);
+}
+
+void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cudaStream_t s) {
+  hist_kernel<<<(b.n_chunks + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, hist);
+}
+
+// ------------------------------------------------------------------ K2b-d
 
 __global__ void __launch_bounds__(WALK_THREADS) stitch_kernel(DeviceModel m, WalkBuffers b, const uint32_t* list,
                                                               uint32_t n_list) {
@@ -98,9 +136,6 @@ __global__ void __launch_bounds__(256) collect_errors_kernel(WalkBuffers b) {
     atomicMin(b.err_key, ((unsigned long long)(i * b.chunk) << 8) | 0xFEu);
 }
 
-void launch_walk_spec(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, cudaStream_t s) {
-  walk_spec_kernel<<<(b.n_chunks + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, start_state);
-}
 void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s) {
   if (!n_list) return;
   stitch_kernel<<<(n_list + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, list, n_list);

@@ -18,8 +18,13 @@ struct CompactBuffers {
 constexpr int COMPACT_THREADS = 256;
 constexpr int COMPACT_WPT = 2;  // bitmap words per thread
 
-void launch_classify(const DeviceModel& m, const WalkBuffers& b, cudaStream_t s);
-void launch_walk_spec(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, cudaStream_t s);
+// fused classify + speculative walk; returns a cudaError_t value
+int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot, int n_sms,
+                      cudaStream_t s);
+size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot);
+uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states);
+// calibration histogram (visits per state, GPU numbering)
+void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cudaStream_t s);
 // one fix-up round over `n_list` chunks (list == nullptr: all chunks 1..n_chunks-1)
 void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
 void launch_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk, cudaStream_t s);

@@ -94,7 +94,7 @@ int load_matok_file(const char* path, HostModel& m, std::string& why) {
   return build_layout(m, why);
 }
 
-int build_layout(HostModel& m, std::string& why) {
+int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
   const int S = m.stateCount, K = m.sigmaCount, eps = m.epsilon;
   if (S < 1 || S + 1 >= 32768) { why = "state count not in 1..32766"; return DATOK_ERR_UNSUPPORTED_MODEL; }
   if (eps < 1 || eps >= K) { why = "no epsilon symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
@@ -116,17 +116,34 @@ int build_layout(HostModel& m, std::string& why) {
   for (auto& kv : sym_of_rune)
     if (kv.second == eps) { why = "a rune maps to the epsilon symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
 
-  // --- state renumbering: non-epsilon states first, epsilon states last ---
-  m.new_of_old.assign(S + 1, 0);
-  m.old_of_new.assign(S + 1, 0);
-  uint32_t next = 1;
-  for (int pass = 0; pass < 2; pass++) {
-    if (pass == 1) m.eps_lo = (uint16_t)next;
-    for (int t = 1; t <= S; t++) {
-      bool has = cell(eps, t) != 0;
-      if ((int)has == pass) { m.new_of_old[t] = (uint16_t)next; m.old_of_new[next] = (uint16_t)t; next++; }
+  // --- state renumbering: hottest states first ---
+  // rank = measured visit count if given, else breadth-first distance from the root
+  std::vector<uint32_t> bfs_rank(S + 1, 0xFFFFFFFFu);
+  {
+    std::vector<int> queue;
+    queue.push_back(1);
+    bfs_rank[1] = 0;
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+      const int t = queue[qi];
+      for (int a = 1; a < K; a++) {
+        const uint32_t tgt = cell(a, t) & 0x7FFFFFFFu;
+        if (tgt >= 1 && tgt <= (uint32_t)S && bfs_rank[tgt] == 0xFFFFFFFFu) {
+          bfs_rank[tgt] = (uint32_t)queue.size();
+          queue.push_back((int)tgt);
+        }
+      }
     }
   }
+  std::vector<int> order(S);
+  for (int t = 1; t <= S; t++) order[t - 1] = t;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    const uint64_t hx = hist ? hist[x] : 0, hy = hist ? hist[y] : 0;
+    if (hx != hy) return hx > hy;
+    return bfs_rank[x] < bfs_rank[y];
+  });
+  m.new_of_old.assign(S + 1, 0);
+  m.old_of_new.assign(S + 1, 0);
+  for (int i = 0; i < S; i++) { m.new_of_old[order[i]] = (uint16_t)(i + 1); m.old_of_new[i + 1] = (uint16_t)order[i]; }
   m.start = m.new_of_old[1];
   for (int t = 1; t <= S; t++) {
     uint32_t c = cell(eps, t), tgt = c & 0x7FFFFFFFu;
@@ -209,9 +226,50 @@ int build_layout(HostModel& m, std::string& why) {
     for (size_t c = 0; c < columns.size(); c++) row[CLS_FIRST + c] = conv(columns[c][t]);
   }
   std::memset(m.sync_mask, 0, sizeof m.sync_mask);
+  std::memset(m.sync_ascii, 0, sizeof m.sync_ascii);
   const uint16_t* srow = &m.table[(size_t)m.start * R];
   for (uint32_t c = CLS_EOT; c < m.n_classes; c++)
     if (srow[c] == (uint16_t)(m.start | NT_BIT)) m.sync_mask[c >> 5] |= 1u << (c & 31);
+  for (uint32_t bch = 0; bch < 128; bch++) {
+    const uint32_t c = m.ascii_cls[bch];
+    if ((m.sync_mask[c >> 5] >> (c & 31)) & 1u) m.sync_ascii[bch >> 5] |= 1u << (bch & 31);
+  }
+
+  // --- fused table T2 ---
+  // At the loop top in state t reading class c the reference (matrix.go:437-497):
+  //   records the epsilon point (t, here) if t has an epsilon transition, looks up
+  //   (t, c); on failure with that point recorded it backtracks by 0 runes, takes the
+  //   epsilon transition (Token or SentenceEnd), and re-reads c from the new state.
+  // T2[t][c] is the transition that finally consumes c, with the number of epsilon
+  // steps before it.  0: failure in a state without epsilon transition (backtrack to an
+  // older point or hard fail).  T2_SLOW: anything else the fast path leaves to walk_run().
+  m.stride2 = m.n_classes | 1u;
+  m.table2.assign(((size_t)S + 1) * m.stride2, 0);
+  for (int t = 1; t <= S; t++) {
+    uint32_t* row2 = &m.table2[(size_t)t * m.stride2];
+    const uint16_t* row = &m.table[(size_t)t * R];
+    row2[CLS_EPS] = row[CLS_EPS];
+    for (uint32_t c = CLS_CONT; c < m.n_classes; c++) {
+      uint32_t cur = (uint32_t)t, k = 0, e = 0;
+      for (;;) {
+        const uint16_t* r = &m.table[(size_t)cur * R];
+        if (r[c] != 0) {
+          e = r[c] | (k << T2_K_SHIFT) | (r[CLS_EPS] != 0 ? T2_EPSBIT : 0);
+          break;
+        }
+        if (r[CLS_EPS] == 0) {
+          // failure in a state without epsilon transition.  k == 0: the walk backtracks to an
+          // OLDER point or fails hard (entry 0).  k > 0: hard fail right after the epsilon steps.
+          if (k) e = T2_SLOW;
+          break;
+        }
+        if (k == 2) { e = T2_SLOW; break; }  // more than two epsilon steps at one position
+        cur = r[CLS_EPS] & 0x7FFFu;
+        k++;
+      }
+      row2[c] = e;
+    }
+  }
   return DATOK_OK;
 }
 

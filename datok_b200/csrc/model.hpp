@@ -8,8 +8,11 @@
 //     EOT and UTF-8 continuation bytes get private classes),
 //   * the table is state-major u16: table[t << row_shift | cls], bit 15 = the
 //     reference's FIRSTBIT "non-token" flag (datok.go:43), bits 0..14 = target,
-//   * states are renumbered so that "state has an epsilon transition"
-//     (matrix.go:442) is the comparison  t >= eps_lo.
+//   * states are renumbered by expected visit frequency, so that the hottest
+//     rows are the ones with the smallest ids (they are kept in shared memory),
+//   * a second, "fused" table T2 (u32) folds the reference's fail -> backtrack to
+//     the epsilon recorded at the same position -> take epsilon -> re-read
+//     sequence (matrix.go:472-497,563-576) into one lookup per input byte.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -22,6 +25,12 @@ constexpr uint32_t CLS_CONT = 1;  // UTF-8 continuation byte of a valid sequence
 constexpr uint32_t CLS_EOT = 2;   // the byte 0x04 (matrix.go:13,422)
 constexpr uint32_t CLS_FIRST = 3; // first ordinary class
 constexpr uint16_t NT_BIT = 0x8000;
+// fused table entry: [14:0] target, [15] non-token, [17:16] number of epsilon
+// transitions taken before the byte is consumed, [18] the state the byte is finally
+// consumed from has an epsilon transition itself.  0 = not decidable locally.
+constexpr uint32_t T2_K_SHIFT = 16;
+constexpr uint32_t T2_EPSBIT = 1u << 18;
+constexpr uint32_t T2_SLOW = 1u << 31;  // leave this (state, class) to the exact walker
 
 struct HostModel {
   // --- reference view (ParseMatrix) ---
@@ -41,15 +50,19 @@ struct HostModel {
   std::vector<uint16_t> table;     // (S+1) << row_shift entries
   std::vector<uint16_t> new_of_old, old_of_new;
   uint16_t start = 0;   // new id of the reference's initial state 1 (matrix.go:351)
-  uint16_t eps_lo = 0;  // new ids >= eps_lo have an epsilon transition
   uint32_t sync_mask[8];  // class c is a sync class iff table[start][c] == (start | NT_BIT)
+  uint32_t sync_ascii[4]; // ASCII byte b is a sync byte iff its class is a sync class
   uint32_t max_eps_chain = 0;
+  std::vector<uint32_t> table2;    // fused table, (S+1) * stride2 entries
+  uint32_t stride2 = 0;            // odd (shared-memory bank spread), >= n_classes
 };
 
 // error codes are the DATOK_ERR_* values of include/datok_b200.h
 int load_matok_file(const char* path, HostModel& m, std::string& why);
 int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why);
-int build_layout(HostModel& m, std::string& why);
+// hist (optional): visits per reference state id (stateCount+1 entries) measured on
+// representative text; without it states are ordered breadth-first from the root.
+int build_layout(HostModel& m, std::string& why, const uint64_t* hist = nullptr);
 
 // Go unicode/utf8.DecodeRune (what bufio.Reader.ReadRune yields, matrix.go:392)
 int32_t decode_rune(const uint8_t* p, size_t n, int* width);

@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define DATOK_HD __host__ __device__ __forceinline__
+#define DATOK_HD_SLOW __host__ __device__ __noinline__  // rare paths: keep them out of the hot loop's registers
 #else
 #define DATOK_HD inline
+#define DATOK_HD_SLOW inline
 #endif
 
 namespace datok {
@@ -186,23 +188,37 @@ DATOK_HD bool wstate_equal(const WState& a, const WState& b) {
 }
 
 struct WalkCtx {
-  const uint16_t* table;  // table[t << row_shift | cls]
+  const uint16_t* table;  // exact table: table[t << row_shift | cls], bit 15 = non-token, 0 = no transition
   uint32_t row_shift;
   uint32_t start;         // GPU id of the reference's state 1
-  uint32_t eps_lo;        // states >= eps_lo have an epsilon transition (matrix.go:442)
-  const uint8_t* cls;     // class stream, one byte per input byte
+  const uint8_t* in;      // raw input bytes; classes are derived on demand (classify_pos)
   uint32_t N;             // input bytes
-  const uint32_t* rstart; // rune-start bitmap
+  ClsTables cls;
   uint32_t* b_end;
   uint32_t* b_skip;
   uint32_t* b_sent;
   uint32_t* b_tend;
+  uint32_t* hist;         // optional: visits per state (calibration of the hot-row order)
 };
 
+DATOK_HD uint32_t cls_at(const WalkCtx& c, uint32_t pos) {
+  const uint32_t b = c.in[pos];
+  if (b < 0x80) return c.cls.ascii_cls[b];
+  bool st, inv;
+  return classify_pos(c.in, c.N, pos, c.cls, &st, &inv);
+}
+
 // True iff more than 1024 runes would have been buffered: runes in [base, hw].
-DATOK_HD bool window_overflow(const uint32_t* rstart, uint32_t base, uint32_t hw) {
+// Only ever evaluated when the byte distance alone allows it, i.e. practically never.
+DATOK_HD bool window_overflow(const WalkCtx& c, uint32_t base, uint32_t hw) {
   if (hw < base || hw - base < K_WINDOW) return false;  // bytes >= runes
-  return count_range(rstart, base, hw + 1) > K_WINDOW;
+  uint32_t runes = 0;
+  for (uint32_t p = base; p <= hw && p < c.N; p++) {
+    bool st, inv;
+    classify_pos(c.in, c.N, p, c.cls, &st, &inv);
+    runes += st ? 1u : 0u;
+  }
+  return runes > K_WINDOW;
 }
 
 // Info about the first buffer window of a speculative walk, whose true `base` is
@@ -212,26 +228,32 @@ struct SpecInfo {
   uint32_t had_rewind;
 };
 
-// Runs the reference loop from `st` until its FINAL arrival at the loop top with
-// pos >= stop, or until EOF processing is complete (WS_DONE).
+// Runs the reference loop from `st`.
 //
-// Hand-off rule.  When the walk first arrives at `stop` it may still hold a pending
-// epsilon point before `stop` (matrix.go:448-449) to which a later failure would
-// backtrack (matrix.go:487-497).  The walk therefore continues in PROBE mode --
-// reading on, writing nothing at positions >= stop -- until either that point is
-// dead (it was consumed, or the next state has its own epsilon transition, which
-// replaces it), or a failure backtracks below `stop`, in which case normal walking
-// resumes and `stop` will be reached again.  The state handed to the successor is
-// the snapshot taken at the last arrival, with the dead epsilon point cleared, so
+// PROBE == true: until the FINAL arrival at the loop top with pos >= stop, or until
+// EOF processing is complete (WS_DONE).  Hand-off rule: when the walk first arrives
+// at `stop` it may still hold a pending epsilon point before `stop`
+// (matrix.go:448-449) to which a later failure would backtrack (matrix.go:487-497).
+// The walk therefore continues in PROBE mode -- reading on, writing nothing at
+// positions >= stop -- until either that point is dead (it was consumed, or the
+// next state has its own epsilon transition, which replaces it), or a failure
+// backtracks below `stop`, in which case normal walking resumes and `stop` will be
+// reached again.  The state handed to the successor is the snapshot taken at the
+// last arrival, with the dead epsilon point cleared, so
 //   * every event at a position < stop is written by this walker only, and
 //   * a successor never has to backtrack below its own start.
 // The lookahead is bounded by the reference's own 1024-rune buffer.
 //
-// Returns an error code (0 = none); on error the state is unusable.
+// PROBE == false: plain segment of the same lane; returns at the first arrival at
+// pos >= stop with the epsilon point kept.
+//
 // SPEC: the walk started from a guessed clean state, so the first window's
-// overflow check is deferred to the stitch (SpecInfo).
-template <bool SPEC>
-DATOK_HD uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo* spec) {
+// overflow check is deferred to the stitch (SpecInfo).  STOP_REWIND: return at the
+// loop top that follows the first rewind (used to hand a fresh lane to the fast path).
+//
+// Returns an error code (0 = none); on error the state is unusable.
+template <bool SPEC, bool PROBE, bool STOP_REWIND>
+DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo* spec) {
   uint32_t pos = st.pos, tstart = st.tstart, eps_pos = st.eps_pos, base = st.base, hw = st.hw;
   uint32_t t = st.t, eps_state = st.eps_state, flags = st.flags;
   const uint32_t N = c.N;
@@ -248,20 +270,23 @@ DATOK_HD uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo
 #define DATOK_REWIND(newbase)                                                              \
   do {                                                                                     \
     if (first_window) { spec->first_hw = hw; spec->had_rewind = 1; first_window = false; } \
-    else if (window_overflow(c.rstart, base, hw)) { err = E_OVERFLOW; goto out; }          \
+    else if (window_overflow(c, base, hw)) { err = E_OVERFLOW; goto out; }                 \
     base = (newbase); hw = base; eps_state = 0;                                            \
   } while (0)
 
   for (;;) {
     if (pos >= stop) {
+      if (!PROBE) break;
       if (!probing) {
         probing = true;
         s_pos = pos; s_tstart = tstart; s_base = base; s_t = t; s_flags = flags;
         s_hw = (pos > base && hw < pos - 1) ? pos - 1 : hw;  // everything below pos has been read
         s_first_window = first_window;
       }
-      if (eps_state == 0 || eps_pos >= stop || (pos < N && t >= c.eps_lo)) break;  // final arrival
+      if (eps_state == 0 || eps_pos >= stop) break;  // final arrival
+      if (pos < N && c.table[(t << c.row_shift) | K_CLS_EPS] != 0) break;  // this state replaces the point
     }
+    if (STOP_REWIND && SPEC && !first_window) break;
     if (pos >= N) {
       // ---- EOF tail (matrix.go:650-678) ----
       if (N > 0 && hw < N - 1) hw = N - 1;
@@ -272,7 +297,7 @@ DATOK_HD uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo
             if (pos < stop) set_bit(c.b_end, pos); else flags |= WS_PEND;
             DATOK_REWIND(pos);
             tstart = pos;
-          } else if (!first_window && window_overflow(c.rstart, base, hw)) { err = E_OVERFLOW; goto out; }
+          } else if (!first_window && window_overflow(c, base, hw)) { err = E_OVERFLOW; goto out; }
           flags |= WS_DONE;
           break;
         }
@@ -294,29 +319,39 @@ DATOK_HD uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo
       t = e & 0x7FFFu;
       continue;
     }
-    const uint32_t cl = c.cls[pos];
-    if (t >= c.eps_lo) { eps_state = t; eps_pos = pos; }  // :442-454
-    const uint32_t nt = c.table[(t << c.row_shift) | cl];  // :463
-    if (nt != 0) {
-      // ---- transition consumes the byte (matrix.go:579-605) ----
-      const uint32_t before = pos;
-      pos = before + 1;
-      if (tstart == before && (nt & K_NT)) {  // leading non-token rune (:584-588)
-        if (before < stop) set_bit(c.b_skip, before);
-        tstart = pos;
+    {
+      const uint32_t cl = cls_at(c, pos);
+      const uint16_t* row = c.table + ((size_t)t << c.row_shift);
+      if (c.hist) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&c.hist[t], 1u);
+#else
+        c.hist[t]++;
+#endif
       }
-      if (cl == K_CLS_EOT) {  // :593-605
-        if (probing) { eps_state = 0; continue; }  // the rewind kills the pending epsilon point
-        set_bit(c.b_tend, before);
-        if (hw < before) hw = before;
-        if (tstart > pos) {  // stale bufft is reset by the rewind (:622)
-          clear_range(c.b_skip, pos, tstart < stop ? tstart : stop);
+      if (row[K_CLS_EPS] != 0) { eps_state = t; eps_pos = pos; }  // :442-454
+      const uint32_t nt = row[cl];                                // :463
+      if (nt != 0) {
+        // ---- transition consumes the byte (matrix.go:579-605) ----
+        const uint32_t before = pos;
+        pos = before + 1;
+        if (tstart == before && (nt & K_NT)) {  // leading non-token rune (:584-588)
+          if (before < stop) set_bit(c.b_skip, before);
+          tstart = pos;
         }
-        DATOK_REWIND(pos);
-        tstart = pos;
+        if (cl == K_CLS_EOT) {  // :593-605
+          if (probing) { eps_state = 0; continue; }  // the rewind kills the pending epsilon point
+          set_bit(c.b_tend, before);
+          if (hw < before) hw = before;
+          if (tstart > pos) {  // stale bufft is reset by the rewind (:622)
+            clear_range(c.b_skip, pos, tstart < stop ? tstart : stop);
+          }
+          DATOK_REWIND(pos);
+          tstart = pos;
+        }
+        t = nt & 0x7FFFu;
+        continue;
       }
-      t = nt & 0x7FFFu;
-      continue;
     }
     // ---- no transition (matrix.go:472-557); the unknown retry (:478-485) cannot succeed ----
     if (hw < pos) hw = pos;
@@ -342,7 +377,7 @@ DATOK_HD uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo
     // (cannot happen while probing: probing implies a pending epsilon point)
     if (pos <= tstart) {  // buffc-bufft <= 0 -> buffc++ (one RUNE)
       pos++;
-      while (pos < N && c.cls[pos] == K_CLS_CONT) pos++;
+      while (pos < N && cls_at(c, pos) == K_CLS_CONT) pos++;
       if (hw < pos - 1) hw = pos - 1;
     }
     if (tstart >= pos) { err = E_DEGENERATE; goto out; }  // empty or negative slice (token_writer.go:85)

@@ -5,6 +5,7 @@
 // speculative-chunk algorithm against the oracle without a GPU.  It is NOT part
 // of the product library (libdatok_b200.so does not contain it) and is never
 // used as a fallback.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -42,11 +43,12 @@ EmulModel* emul_load(const char* path, int* err) {
   if (rc) { *err = rc; delete m; return nullptr; }
   HostModel& h = m->hm;
   m->dm.table = h.table.data();
-  m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.eps_lo = h.eps_lo; m->dm.n_classes = h.n_classes;
+  m->dm.table2 = h.table2.data();
+  m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.n_classes = h.n_classes; m->dm.stride2 = h.stride2;
   m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
   m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
   m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls;
-  std::memcpy(m->dm.sync_mask, h.sync_mask, sizeof h.sync_mask);
+  std::memcpy(m->dm.sync_ascii, h.sync_ascii, sizeof h.sync_ascii);
   *err = 0;
   return m;
 }
@@ -56,8 +58,9 @@ uint32_t emul_new_state(EmulModel* m, uint32_t old_state) { return m->hm.new_of_
 uint32_t emul_old_state(EmulModel* m, uint32_t new_state) { return m->hm.old_of_new[new_state]; }
 
 // order: 0 = ascending thread order, 1 = descending (results must not depend on it)
+// mode: 0 = exact walker only (chunk_spec), n > 0 = fused fast path with n hot rows (chunk_spec_fast)
 EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_t flags, uint32_t chunk,
-                           uint32_t carry_state, int sentence_end_in, int text_end_in, int order) {
+                           uint32_t carry_state, int sentence_end_in, int text_end_in, int order, int mode) {
   const DeviceModel& m = em->dm;
   EmulResult* R = (EmulResult*)std::calloc(1, sizeof(EmulResult));
   WalkBuffers b;
@@ -65,31 +68,41 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   b.in = in; b.N = N; b.chunk = chunk;
   b.n_chunks = N / chunk + 1;
   b.n_words = b.n_chunks * (chunk / 32);
-  std::vector<uint8_t> cls(N + 64, 0);
+  uint32_t counters[8] = {0};
+  b.counters = counters;
   std::vector<uint32_t> rstart(b.n_words, 0), bend(b.n_words, 0), bskip(b.n_words, 0), bsent(b.n_words, 0),
       btend(b.n_words, 0);
   std::vector<WState> E(b.n_chunks), exitA(b.n_chunks), Enew(b.n_chunks), Ytmp(b.n_chunks);
   std::vector<uint32_t> sync(b.n_chunks), first_hw(b.n_chunks), cflags(b.n_chunks);
   unsigned long long err_key = ~0ull;
-  b.cls = cls.data(); b.rstart = rstart.data(); b.b_end = bend.data(); b.b_skip = bskip.data();
+  b.rstart = rstart.data(); b.b_end = bend.data(); b.b_skip = bskip.data();
   b.b_sent = bsent.data(); b.b_tend = btend.data();
   b.E = E.data(); b.exitA = exitA.data(); b.Enew = Enew.data(); b.Ytmp = Ytmp.data();
   b.sync = sync.data(); b.first_hw = first_hw.data(); b.cflags = cflags.data();
   b.err_key = &err_key;
 
-  // K1 classify
-  bool any_invalid = false;
-  for (uint32_t p = 0; p < N; p++) {
-    bool st, inv;
-    cls[p] = (uint8_t)classify_pos(in, N, p, m.cls, &st, &inv);
-    if (st) rstart[p >> 5] |= 1u << (p & 31);
-    any_invalid |= inv;
-  }
-  R->has_invalid = any_invalid;
-
-  // K2a speculative walk
   const uint32_t start_state = carry_state ? em->hm.new_of_old[carry_state] : m.start;
-  for (uint32_t k = 0; k < b.n_chunks; k++) chunk_spec(m, b, order ? b.n_chunks - 1 - k : k, start_state);
+  if (mode == 0) {
+    // K1 (rune starts) + K2a exact speculative walk
+    for (uint32_t p = 0; p < N; p++) {
+      bool st, inv;
+      classify_pos(in, N, p, m.cls, &st, &inv);
+      if (st) rstart[p >> 5] |= 1u << (p & 31);
+      if (inv) counters[2] |= 1;
+    }
+    for (uint32_t k = 0; k < b.n_chunks; k++) chunk_spec(m, b, order ? b.n_chunks - 1 - k : k, start_state);
+  } else {
+    // K1+K2a fused fast path
+    FastTables FT;
+    std::vector<uint32_t> hot(em->hm.table2.begin(),
+                              em->hm.table2.begin() + std::min<size_t>(em->hm.table2.size(), (size_t)mode * m.stride2));
+    FT.hot = hot.data(); FT.cold = m.table2; FT.n_hot = (uint32_t)std::min<size_t>(mode, em->hm.stateCount + 1);
+    FT.stride = m.stride2;
+    uint8_t seg_cls[32];
+    for (uint32_t k = 0; k < b.n_chunks; k++)
+      chunk_spec_fast(m, b, FT, order ? b.n_chunks - 1 - k : k, start_state, seg_cls);
+  }
+  R->has_invalid = counters[2];
 
   // K2b-d fix-up rounds
   std::vector<uint32_t> list, next, rew;

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "emul", "libdatok_emul.so")
 SRCS = [os.path.join(HERE, "emul", "emul.cpp"), os.path.join(ROOT, "datok_b200", "csrc", "model.cpp")]
 DEPS = SRCS + [os.path.join(ROOT, "datok_b200", "csrc", f) for f in
-               ("walk_core.cuh", "chunk_core.cuh", "compact_core.cuh", "model.hpp")]
+               ("walk_core.cuh", "chunk_core.cuh", "compact_core.cuh", "fast_core.cuh", "model.hpp")]
 
 
 def build():
@@ -47,7 +47,7 @@ def lib():
         L.emul_n_classes.argtypes = [C.c_void_p]
         L.emul_transduce.restype = C.POINTER(_Res)
         L.emul_transduce.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
-                                     C.c_uint32, C.c_int, C.c_int, C.c_int]
+                                     C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emul_result_free.argtypes = [C.POINTER(_Res)]
         _lib = L
     return _lib
@@ -70,11 +70,12 @@ class EmulModel:
             raise ValueError(f"emul: cannot load {path}: {err.value}")
         self.n_classes = lib().emul_n_classes(self._h)
 
-    def transduce(self, data, flags, chunk=64, order=0, carry_state=0, sentence_end=0, text_end=0):
+    def transduce(self, data, flags, chunk=64, order=0, carry_state=0, sentence_end=0, text_end=0, mode=0):
+        """mode 0: exact walker only; mode n > 0: fused fast path with n hot table rows"""
         a = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data
         a = np.ascontiguousarray(a)
         ptr = a.ctypes.data if a.size else None
-        rp = lib().emul_transduce(self._h, ptr, a.size, flags, chunk, carry_state, sentence_end, text_end, order)
+        rp = lib().emul_transduce(self._h, ptr, a.size, flags, chunk, carry_state, sentence_end, text_end, order, mode)
         r = rp.contents
         s = Structured()
         s.status = r.status

@@ -31,9 +31,10 @@ def test_reference_vectors(case, oracle_models, emul_models):
     data = bytes.fromhex(case["input_hex"])
     for flags in {case["flags"], 15, 31}:
         o = oracle_models[case["model"]].transduce(data, flags)
-        for chunk, order in ((32, 0), (96, 1)):
-            s = emul_models[case["model"]].transduce(data, flags, chunk, order)
-            P.assert_matches_oracle(s, o, flags, f'{case["src"]} chunk={chunk}')
+        # mode 0: exact walker only; mode n: fused fast path with n shared-memory table rows
+        for chunk, order, mode in ((32, 0, 0), (96, 1, 0), (32, 0, 4), (64, 1, 100000)):
+            s = emul_models[case["model"]].transduce(data, flags, chunk, order, mode=mode)
+            P.assert_matches_oracle(s, o, flags, f'{case["src"]} chunk={chunk} mode={mode}')
 
 
 ODD = [b"", b" ", b"\x04a", b"a\x04\x04b", b"\x04", b"\x04\x04", b" " * 1025, b"a" * 1100, b"a" * 1024 + b" b",
@@ -54,9 +55,9 @@ def test_edge_and_panic_inputs(model, oracle_models, emul_models):
         for flags in (0, 3, 15, 31, 4, 8, 8 | 16, 2 | 4):
             o = oracle_models[model].transduce(data, flags)
             seen.add(o.status)
-            for chunk in (32, 64, 1024):
-                s = emul_models[model].transduce(data, flags, chunk, 0)
-                P.assert_matches_oracle(s, o, flags, f"{model} {data[:24]!r} flags={flags} chunk={chunk}")
+            for chunk, mode in ((32, 0), (64, 300), (1024, 2)):
+                s = emul_models[model].transduce(data, flags, chunk, 0, mode=mode)
+                P.assert_matches_oracle(s, o, flags, f"{model} {data[:24]!r} flags={flags} chunk={chunk} mode={mode}")
     assert {0, 1, 2, 3}.issubset(seen)
 
 
@@ -68,9 +69,9 @@ def test_synthetic_corpora(kind, model, oracle_models, emul_models, corpus_lib):
     for flags in (15, 31):
         o = oracle_models[model].transduce_np(a, flags)
         assert o.status == 0
-        for chunk, order in ((64, 1), (256, 0), (2048, 0)):
-            s = emul_models[model].transduce(a, flags, chunk, order)
-            P.assert_matches_oracle(s, o, flags, f"kind={kind} chunk={chunk}")
+        for chunk, order, mode in ((64, 1, 0), (256, 0, 256), (2048, 0, 16), (32, 1, 100000)):
+            s = emul_models[model].transduce(a, flags, chunk, order, mode=mode)
+            P.assert_matches_oracle(s, o, flags, f"kind={kind} chunk={chunk} mode={mode}")
 
 
 def test_tiny_chunks_on_markup_heavy_text(oracle_models, emul_models, corpus_lib):
@@ -78,9 +79,10 @@ def test_tiny_chunks_on_markup_heavy_text(oracle_models, emul_models, corpus_lib
     exactly on sync points (regression: a pending END bit must survive the re-walk)"""
     a = corpus_lib.generate(4, 1 << 20, seed=5)
     o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
-    s = emul_models["tokenizer_de.matok"].transduce(a, 15, 32, 0)
-    P.assert_matches_oracle(s, o, 15, "kind=4 chunk=32")
-    assert s.stats["rounds"] > 5
+    for mode in (0, 256):
+        s = emul_models["tokenizer_de.matok"].transduce(a, 15, 32, 0, mode=mode)
+        P.assert_matches_oracle(s, o, 15, f"kind=4 chunk=32 mode={mode}")
+        assert s.stats["rounds"] > 5
 
 
 def _fuzz_text(rng, n):
@@ -99,13 +101,14 @@ def _fuzz_text(rng, n):
 def test_fuzz(model, oracle_models, emul_models):
     """differential fuzzing over a markup/abbreviation/invalid-UTF-8 heavy alphabet"""
     rng = random.Random(20261018)
-    for it in range(120):
-        data = _fuzz_text(rng, rng.choice((7, 33, 64, 200, 1500)))
+    for it in range(400):
+        data = _fuzz_text(rng, rng.choice((7, 33, 64, 200, 1500, 5000)))
         flags = rng.choice((3, 15, 31, 4, 12, 28))
         o = oracle_models[model].transduce(data, flags)
         chunk = rng.choice((32, 64, 128, 512))
-        s = emul_models[model].transduce(data, flags, chunk, rng.randint(0, 1))
-        P.assert_matches_oracle(s, o, flags, f"{model} it={it} {data[:40]!r} chunk={chunk}")
+        mode = rng.choice((0, 1, 16, 256, 100000))
+        s = emul_models[model].transduce(data, flags, chunk, rng.randint(0, 1), mode=mode)
+        P.assert_matches_oracle(s, o, flags, f"{model} it={it} {data[:40]!r} chunk={chunk} mode={mode}")
 
 
 def test_carry_between_calls(oracle_models, emul_models):
