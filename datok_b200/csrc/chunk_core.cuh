@@ -132,14 +132,15 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   WState st;
   st.pos = st.tstart = st.base = st.hw = 0;
   st.eps_pos = 0; st.eps_state = 0; st.flags = 0; st.t = (uint16_t)start_state;
-  SpecInfo si;
-  si.first_hw = 0; si.had_rewind = 0;
   FastLane L;
-  L.pos = L.tstart = L.base = L.t = L.eps_pos = L.eps_b = L.hw_med = L.hw_med_base = 0;
-  bool started = (i == 0), fast = false, halted = false;
-  bool first_window = (i != 0);  // the first window of a guessed start is walked exactly (SpecInfo)
+  L.pos = L.tstart = L.base = L.eps_pos = L.eps_b = L.hw_med = L.hw_med_base = L.first_hw = 0;
+  L.t = start_state;
+  L.first_window = (i != 0);  // a guessed start: the first window's overflow check is deferred (SpecInfo)
+  bool started = (i == 0), fast = true, halted = false;
   uint32_t sync = (i == 0) ? 0u : K_NOPOS;
   uint32_t err = 0;
+  SegBits B;
+  B.end = B.skip = B.sent = B.tend = 0;
 
   for (uint32_t seg_start = lo; seg_start < hi; seg_start += SEG) {
     const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
@@ -153,66 +154,68 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       sync = find_sync(b.in, N, m.sync_ascii, seg_start, seg_end < hi ? seg_end : hi);
       if (sync == K_NOPOS) continue;
       started = true;
-      st.pos = st.tstart = st.base = st.hw = sync;
-      st.t = (uint16_t)m.start;
+      L.pos = L.tstart = L.base = L.hw_med = L.hw_med_base = sync;
+      L.t = m.start;
     }
-    if (fast && seg_end - L.base >= FAST_WINDOW_GUARD) {  // too close to the 1024-rune buffer limit
-      to_exact(L, FT, st);
-      fast = false;
-    }
-    SegBits B;
     B.end = B.skip = B.sent = B.tend = 0;
     bool in_regs = true;  // the segment's boundary words live in B (else in memory)
+    if (fast && seg_end - L.base >= FAST_WINDOW_GUARD) {  // too close to the 1024-rune buffer limit
+      to_exact(L, B, seg_start, FT, st);
+      fast = false;
+    }
     for (;;) {
-      if (!fast) {
-        // exact -> fast whenever the state allows it
-        if (!first_window && st.pos >= seg_start && st.pos < seg_end && st.pos < N && can_go_fast(st) &&
-            seg_end - st.base < FAST_WINDOW_GUARD) {
-          if (!in_regs) { load_seg_bits(b, w, B); in_regs = true; }
-          if (st.flags & WS_PEND) { B.end |= 1u << (st.pos - seg_start); st.flags &= ~WS_PEND; }
-          to_fast(st, L);
-          fast = true;
-          continue;
+      if (fast) {
+        int rc = FAST_OK;
+        while (L.pos < seg_end && L.pos < N) {
+          rc = fast_step(L, FT, seg_cls, seg_start, B);
+          if (rc != FAST_OK) break;
         }
+        if (rc == FAST_OK && L.pos >= seg_end) break;  // segment done, stay fast
+        lane_note_first_rewind(L, B, seg_start);
+        to_exact(L, B, seg_start, FT, st);              // rare case, or end of input
+        fast = false;
         if (st.pos >= seg_end) break;
-        if (in_regs) { store_seg_bits(b, w, B); in_regs = false; }
-        if (first_window) {
-          err = walk_run<true, false, true>(c, st, seg_end, &si);
-          if (si.had_rewind) first_window = false;
-        } else {
-          SpecInfo dummy;
-          err = walk_run<false, false, false>(c, st, seg_end, &dummy);
-        }
-        if (err || (st.flags & WS_DONE)) { halted = true; break; }
+      }
+      // exact walker for the rest of the segment (or until the state allows the fast path again)
+      if (st.pos >= seg_start && st.pos < seg_end && st.pos < N && can_go_fast(st) &&
+          seg_end - st.base < FAST_WINDOW_GUARD && !in_regs) {
+        // (only after the exact walker has made progress: in_regs is false then)
+        load_seg_bits(b, w, B);
+        in_regs = true;
+        if (st.flags & WS_PEND) { B.end |= 1u << (st.pos - seg_start); st.flags &= ~WS_PEND; }
+        to_fast(st, L);
+        fast = true;
         continue;
       }
-      // fast path
-      int rc = FAST_OK;
-      while (L.pos < seg_end && L.pos < N) {
-        rc = fast_step(L, FT, seg_cls, seg_start, B);
-        if (rc != FAST_OK) break;
-      }
-      if (rc == FAST_OK && L.pos >= seg_end) break;  // segment done, stay fast
-      to_exact(L, FT, st);                            // slow case or end of input
-      fast = false;
       if (st.pos >= seg_end) break;
-      store_seg_bits(b, w, B);
-      in_regs = false;
-      SpecInfo dummy;
-      err = walk_run<false, false, false>(c, st, seg_end, &dummy);
+      if (in_regs) { store_seg_bits(b, w, B); in_regs = false; }
+      SpecInfo si;
+      si.first_hw = 0; si.had_rewind = 0;
+      if (L.first_window) {
+        err = walk_run<true, false, true>(c, st, seg_end, &si);
+        if (si.had_rewind) { L.first_hw = si.first_hw; L.first_window = 0; }
+      } else {
+        err = walk_run<false, false, false>(c, st, seg_end, &si);
+      }
       if (err || (st.flags & WS_DONE)) { halted = true; break; }
+    }
+    if (fast) {
+      lane_note_first_rewind(L, B, seg_start);
+      L.base = lane_base(L, B, seg_start);
     }
     if (in_regs) store_seg_bits(b, w, B);
   }
 
   b.sync[i] = sync;
+  SpecInfo si;
+  si.first_hw = L.first_hw; si.had_rewind = L.first_window ? 0u : 1u;
   if (!started) st = wstate_invalid(0);
-  else if (!err && !(st.flags & WS_DONE)) {
-    if (fast) to_exact(L, FT, st);
+  else if (!err && !(halted && (st.flags & WS_DONE))) {
+    if (fast) { B.end = B.skip = B.sent = B.tend = 0; to_exact(L, B, hi, FT, st); }
     // hand-off at the chunk end (probe, walk_run)
-    if (first_window) err = walk_run<true, true, false>(c, st, hi, &si);
+    if (L.first_window) err = walk_run<true, true, false>(c, st, hi, &si);
     else { SpecInfo dummy; err = walk_run<false, true, false>(c, st, hi, &dummy); }
-  } else if (!err && (st.flags & WS_DONE) && first_window) {
+  } else if (!err && L.first_window) {
     si.first_hw = st.hw; si.had_rewind = 0;
   }
   b.exitA[i] = st;

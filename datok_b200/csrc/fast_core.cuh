@@ -16,6 +16,7 @@
 // of the segment.  Both walkers are step-equivalent, so a lane can switch between
 // them at any loop top.
 #pragma once
+#include <stdint.h>
 #include "walk_core.cuh"
 
 namespace datok {
@@ -42,11 +43,21 @@ DATOK_HD uint32_t t2_lookup(const FastTables& T, uint32_t t, uint32_t cl) {
 // steps taken there before the byte was consumed, [18] a token was pending, [19] valid
 constexpr uint32_t EB_PENDING = 1u << 18, EB_VALID = 1u << 19;
 
+#if defined(__CUDACC__)
+#define DATOK_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define DATOK_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#endif
+
 struct FastLane {
-  uint32_t pos, tstart, base;
+  uint32_t pos, tstart;
+  uint32_t base;                 // last rewind point known at the START of the current segment;
+                                 // rewinds inside the segment are read off the END/TEND bits (lane_base)
   uint32_t t;
   uint32_t eps_pos, eps_b;
   uint32_t hw_med, hw_med_base;  // furthest failing position seen by an in-place backtrack since `hw_med_base`
+  uint32_t first_hw;             // SpecInfo of a guessed start: hw at the first rewind
+  uint32_t first_window;         // 1 until the first rewind of a guessed start
 };
 
 struct SegBits {
@@ -54,6 +65,19 @@ struct SegBits {
 };
 
 enum { FAST_OK = 0, FAST_SLOW = 1 };
+
+// last rewind point, taking the boundary bits of the current segment into account
+DATOK_HD uint32_t lane_base(const FastLane& L, const SegBits& B, uint32_t seg_start) {
+  uint32_t base = L.base;
+  if (B.end) { const uint32_t p = seg_start + 31u - clz32(B.end); if (p > base) base = p; }
+  if (B.tend) { const uint32_t p = seg_start + 32u - clz32(B.tend); if (p > base) base = p; }
+  return base;
+}
+// a guessed start's first window closes with the first END/TEND bit of the lane
+DATOK_HD void lane_note_first_rewind(FastLane& L, const SegBits& B, uint32_t seg_start) {
+  const uint32_t m = B.end | B.tend;
+  if (L.first_window && m) { L.first_hw = seg_start + ctz32(m); L.first_window = 0; }
+}
 
 // exact state -> fast lane.  Requires can_go_fast(st).
 DATOK_HD bool can_go_fast(const WState& st) {
@@ -65,9 +89,10 @@ DATOK_HD void to_fast(const WState& st, FastLane& L) {
   L.eps_b = st.eps_state ? (EB_VALID | st.eps_state | (st.eps_pos > st.tstart ? EB_PENDING : 0)) : 0;
   L.hw_med = st.hw; L.hw_med_base = st.base;
 }
-// fast lane -> exact state (resolves the lazily stored epsilon point)
-DATOK_HD void to_exact(const FastLane& L, const FastTables& T, WState& st) {
-  st.pos = L.pos; st.tstart = L.tstart; st.base = L.base; st.t = (uint16_t)L.t;
+// fast lane -> exact state (resolves the lazily stored epsilon point and window base)
+DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, const FastTables& T, WState& st) {
+  const uint32_t base = lane_base(L, B, seg_start);
+  st.pos = L.pos; st.tstart = L.tstart; st.base = base; st.t = (uint16_t)L.t;
   st.flags = 0;
   uint32_t es = 0;
   if (L.eps_b & EB_VALID) {
@@ -76,10 +101,40 @@ DATOK_HD void to_exact(const FastLane& L, const FastTables& T, WState& st) {
   }
   st.eps_state = (uint16_t)es;
   st.eps_pos = es ? L.eps_pos : 0;
-  uint32_t hw = L.base;
-  if (L.hw_med_base == L.base && L.hw_med > hw) hw = L.hw_med;
-  if (L.pos > L.base && hw < L.pos - 1) hw = L.pos - 1;
+  uint32_t hw = base;
+  if (L.hw_med_base == base && L.hw_med > hw) hw = L.hw_med;
+  if (L.pos > base && hw < L.pos - 1) hw = L.pos - 1;
   st.hw = hw;
+}
+
+// In-place backtrack to the epsilon point recorded in this segment (matrix.go:487-497),
+// or FAST_SLOW (nothing changed) when the exact walker has to take over.
+DATOK_HD_SLOW int fast_backtrack(FastLane& L, const FastTables& T, uint32_t seg_start, SegBits& B) {
+  if (!(L.eps_b & EB_VALID) || L.eps_pos < seg_start) return FAST_SLOW;  // hard fail / far backtrack
+  const uint32_t bbit = 1u << (L.eps_pos - seg_start);
+  const bool pending = (L.eps_b & EB_PENDING) != 0;
+  if (!pending && (B.sent & bbit)) return FAST_SLOW;  // second SentenceEnd at one position
+  uint32_t cur = L.eps_b & 0x7FFFu;
+  for (uint32_t k = (L.eps_b >> T2K_SHIFT) & 3u; k; k--) cur = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
+  const uint32_t tgt = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
+  const uint32_t base = lane_base(L, B, seg_start);
+  if (L.hw_med_base != base) { L.hw_med = 0; L.hw_med_base = base; }
+  if (L.hw_med < L.pos) L.hw_med = L.pos;
+  if (pending) {  // Token + rewind (:565-572)
+    if (L.first_window) {
+      const uint32_t m = (B.end | B.tend) & (bbit - 1u);
+      L.first_hw = m ? seg_start + ctz32(m) : L.hw_med;
+      L.first_window = 0;
+    }
+    B.end |= bbit;
+    L.tstart = L.eps_pos;
+  } else {
+    B.sent |= bbit;  // SentenceEnd (:573-576)
+  }
+  L.pos = L.eps_pos;
+  L.eps_b = 0;
+  L.t = tgt;
+  return FAST_OK;
 }
 
 // One loop-top iteration of the reference at L.pos, which must lie in the segment
@@ -90,69 +145,104 @@ DATOK_HD int fast_step(FastLane& L, const FastTables& T, const uint8_t* seg_cls,
   const uint32_t cl = seg_cls[off];
   const uint32_t e = t2_lookup(T, L.t, cl);
   const uint32_t bit = 1u << off;
-  if (e == 0) {
-    // failure in a state without epsilon transition: backtrack to the recorded point
-    // (matrix.go:487-497) if it lies in this segment
-    if (!(L.eps_b & EB_VALID) || L.eps_pos < seg_start) return FAST_SLOW;
-    const uint32_t bbit = 1u << (L.eps_pos - seg_start);
-    const bool pending = (L.eps_b & EB_PENDING) != 0;
-    if (!pending && (B.sent & bbit)) return FAST_SLOW;  // second SentenceEnd at one position
-    uint32_t cur = L.eps_b & 0x7FFFu;
-    for (uint32_t k = (L.eps_b >> T2K_SHIFT) & 3u; k; k--) cur = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
-    const uint32_t tgt = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
-    if (L.hw_med_base != L.base) { L.hw_med = 0; L.hw_med_base = L.base; }
-    if (L.hw_med < L.pos) L.hw_med = L.pos;
-    L.pos = L.eps_pos;
-    if (pending) { B.end |= bbit; L.base = L.pos; L.tstart = L.pos; }  // Token + rewind (:565-572)
-    else B.sent |= bbit;                                                // SentenceEnd (:573-576)
-    L.eps_b = 0;
-    L.t = tgt;
-    return FAST_OK;
+  if (DATOK_UNLIKELY((int32_t)e <= 0)) {  // 0: failure without epsilon transition; bit 31: leave to walk_run
+    if (e != 0) return FAST_SLOW;
+    return fast_backtrack(L, T, seg_start, B);
   }
-  if (e & T2_SLOWMARK) return FAST_SLOW;
   const uint32_t k = (e >> T2K_SHIFT) & 3u;
-  if (k) {
-    const bool pending = L.pos > L.tstart;
-    if ((B.sent & bit) && !(pending && k == 1)) return FAST_SLOW;  // would repeat a SentenceEnd here
-    if (k == 2 && !pending) return FAST_SLOW;
-    if (pending) { B.end |= bit; L.base = L.pos; } else B.sent |= bit;
-    if (k == 2) B.sent |= bit;
-    L.tstart = L.pos;
-    L.eps_b = 0;
-  }
+  const bool is_eps = k != 0;
+  const bool pending = L.pos > L.tstart;
+  const bool two = k == 2;
+  // k epsilon steps before the byte is consumed: Token if something is pending, else SentenceEnd
+  if (DATOK_UNLIKELY(is_eps && (((B.sent & bit) && !(pending && !two)) || (two && !pending)))) return FAST_SLOW;
+  B.end |= (is_eps && pending) ? bit : 0u;
+  B.sent |= ((is_eps && !pending) || two) ? bit : 0u;
+  if (is_eps) { L.tstart = L.pos; L.eps_b = 0; }
   if (e & T2_EPS) {
     L.eps_pos = L.pos;
-    L.eps_b = EB_VALID | L.t | (k << T2K_SHIFT) | ((k == 0 && L.pos > L.tstart) ? EB_PENDING : 0);
+    L.eps_b = EB_VALID | L.t | (e & (3u << T2K_SHIFT)) | ((!is_eps && pending) ? EB_PENDING : 0u);
   }
   const uint32_t next = L.pos + 1;
-  if (L.tstart == L.pos && (e & K_NT)) { B.skip |= bit; L.tstart = next; }  // :584-588
-  if (cl == K_CLS_EOT) {  // :593-605 (the forced SentenceEnd is derived by the compaction)
+  const bool skip = (L.tstart == L.pos) && (e & K_NT);  // :584-588
+  B.skip |= skip ? bit : 0u;
+  L.tstart = skip ? next : L.tstart;
+  if (DATOK_UNLIKELY(cl == K_CLS_EOT)) {  // :593-605 (the forced SentenceEnd is derived by the compaction)
     B.tend |= bit;
-    L.base = next; L.tstart = next; L.eps_b = 0;
+    L.tstart = next; L.eps_b = 0;
   }
   L.t = e & 0x7FFFu;
   L.pos = next;
   return FAST_OK;
 }
 
-// Classes and rune starts of the 32 bytes at seg_start (bytes >= N: class 0, no start).
+// loads the 32 raw bytes at `p` (zero padded beyond N) as 8 little-endian words
+DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_start, uint32_t* words) {
+  const uint8_t* p = in + seg_start;
+  if (seg_start + SEG <= N && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+#if defined(__CUDA_ARCH__)
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint4 c = *reinterpret_cast<const uint4*>(p + 16);
+    words[0] = a.x; words[1] = a.y; words[2] = a.z; words[3] = a.w;
+    words[4] = c.x; words[5] = c.y; words[6] = c.z; words[7] = c.w;
+#else
+    for (int k = 0; k < 8; k++) {
+      words[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+                 ((uint32_t)p[4 * k + 3] << 24);
+    }
+#endif
+    return;
+  }
+  for (int k = 0; k < 8; k++) {
+    uint32_t v = 0;
+    for (int j = 0; j < 4; j++) {
+      const uint32_t q = seg_start + 4 * k + j;
+      if (q < N) v |= (uint32_t)in[q] << (8 * j);
+    }
+    words[k] = v;
+  }
+}
+
+// Classes and rune starts of the 32 bytes at seg_start (bytes >= N: no rune start,
+// class unspecified).  seg_cls must be 4-byte aligned.  ASCII bytes go through the
+// LUT four at a time; the few other bytes are decoded afterwards, one rune each.
 DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start, const ClsTables& T,
                                uint8_t* seg_cls, uint32_t* rstart_word, bool* any_invalid) {
-  uint32_t rs = 0;
-  for (uint32_t j = 0; j < SEG; j++) {
+  uint32_t words[8];
+  load_segment_words(in, N, seg_start, words);
+  uint32_t* out = reinterpret_cast<uint32_t*>(seg_cls);
+  uint32_t nonascii = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 8; k++) {
+    const uint32_t v = words[k];
+    const uint32_t c0 = T.ascii_cls[v & 0x7Fu], c1 = T.ascii_cls[(v >> 8) & 0x7Fu];
+    const uint32_t c2 = T.ascii_cls[(v >> 16) & 0x7Fu], c3 = T.ascii_cls[(v >> 24) & 0x7Fu];
+    out[k] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+    const uint32_t h = v & 0x80808080u;
+    nonascii |= (((h >> 7) | (h >> 14) | (h >> 21) | (h >> 28)) & 0xFu) << (4 * k);
+  }
+  const uint32_t valid = (seg_start + SEG <= N) ? 0xFFFFFFFFu : mask_below(N > seg_start ? N - seg_start : 0);
+  uint32_t rs = ~nonascii & valid;
+  uint32_t m = nonascii & valid;
+  while (m) {
+    const uint32_t j = ctz32(m);
+    m &= m - 1;
     const uint32_t p = seg_start + j;
-    uint32_t cl = 0;
-    if (p < N) {
-      const uint32_t b = in[p];
-      if (b < 0x80) { cl = T.ascii_cls[b]; rs |= 1u << j; }
-      else {
-        bool st, inv;
-        cl = classify_pos(in, N, p, T, &st, &inv);
-        if (st) rs |= 1u << j;
-        if (inv) *any_invalid = true;
+    bool st, inv;
+    const uint32_t cl = classify_pos(in, N, p, T, &st, &inv);
+    seg_cls[j] = (uint8_t)cl;
+    if (st) rs |= 1u << j;
+    if (inv) *any_invalid = true;
+    if (st && !inv) {
+      // a well-formed multi-byte rune: its continuation bytes need no decoding of their own
+      const uint32_t b0 = in[p];
+      const uint32_t wdt = b0 >= 0xF0 ? 4u : b0 >= 0xE0 ? 3u : 2u;
+      for (uint32_t q = 1; q < wdt && j + q < SEG; q++) {
+        seg_cls[j + q] = (uint8_t)K_CLS_CONT;
+        m &= ~(1u << (j + q));
       }
     }
-    seg_cls[j] = (uint8_t)cl;
   }
   *rstart_word = rs;
 }

@@ -23,7 +23,7 @@
 
 #if defined(__CUDACC__)
 #define DATOK_HD __host__ __device__ __forceinline__
-#define DATOK_HD_SLOW __host__ __device__ __noinline__  // rare paths: keep them out of the hot loop's registers
+#define DATOK_HD_SLOW inline __host__ __device__ __noinline__  // rare paths: keep them out of the hot loop's registers
 #else
 #define DATOK_HD inline
 #define DATOK_HD_SLOW inline

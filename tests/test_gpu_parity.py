@@ -210,6 +210,7 @@ def test_device_resident_path(gpu_models, oracle_models):
     import ctypes as C
     host = np.empty(2 * r.n_tokens, dtype=np.int32)
     torch.cuda.synchronize()
-    rc = torch.cuda.cudart().cudaMemcpy(host.ctypes.data, r.device_ptr("tok_pos"), host.nbytes, 2)
-    assert int(rc) == 0
+    cudart = C.CDLL("libcudart.so.12")
+    cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    assert cudart.cudaMemcpy(host.ctypes.data, r.device_ptr("tok_pos"), host.nbytes, 2) == 0  # cudaMemcpyDeviceToHost
     np.testing.assert_array_equal(host, o.tok_pos)
