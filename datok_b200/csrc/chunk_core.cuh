@@ -160,9 +160,13 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     B.end = B.skip = B.sent = B.tend = 0;
     bool in_regs = true;  // the segment's boundary words live in B (else in memory)
     if (fast && seg_end - L.base >= FAST_WINDOW_GUARD) {  // too close to the 1024-rune buffer limit
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+      g_guard++;
+#endif
       to_exact(L, B, seg_start, FT, st);
       fast = false;
     }
+    bool must_walk_exact = false;  // the fast path just gave up at st.pos: the exact walker has to move first
     for (;;) {
       if (fast) {
         int rc = FAST_OK;
@@ -174,14 +178,13 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
         lane_note_first_rewind(L, B, seg_start);
         to_exact(L, B, seg_start, FT, st);              // rare case, or end of input
         fast = false;
+        must_walk_exact = true;
         if (st.pos >= seg_end) break;
       }
       // exact walker for the rest of the segment (or until the state allows the fast path again)
-      if (st.pos >= seg_start && st.pos < seg_end && st.pos < N && can_go_fast(st) &&
-          seg_end - st.base < FAST_WINDOW_GUARD && !in_regs) {
-        // (only after the exact walker has made progress: in_regs is false then)
-        load_seg_bits(b, w, B);
-        in_regs = true;
+      if (!must_walk_exact && st.pos >= seg_start && st.pos < seg_end && st.pos < N && can_go_fast(st) &&
+          seg_end - st.base < FAST_WINDOW_GUARD) {
+        if (!in_regs) { load_seg_bits(b, w, B); in_regs = true; }
         if (st.flags & WS_PEND) { B.end |= 1u << (st.pos - seg_start); st.flags &= ~WS_PEND; }
         to_fast(st, L);
         fast = true;
@@ -192,12 +195,13 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       SpecInfo si;
       si.first_hw = 0; si.had_rewind = 0;
       if (L.first_window) {
-        err = walk_run<true, false, true>(c, st, seg_end, &si);
+        err = walk_run<true, false, true>(c, st, seg_end, &si, seg_start);
         if (si.had_rewind) { L.first_hw = si.first_hw; L.first_window = 0; }
       } else {
-        err = walk_run<false, false, false>(c, st, seg_end, &si);
+        err = walk_run<false, false, false>(c, st, seg_end, &si, seg_start);
       }
       if (err || (st.flags & WS_DONE)) { halted = true; break; }
+      must_walk_exact = false;
     }
     if (fast) {
       lane_note_first_rewind(L, B, seg_start);

@@ -110,6 +110,9 @@ DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, 
 // In-place backtrack to the epsilon point recorded in this segment (matrix.go:487-497),
 // or FAST_SLOW (nothing changed) when the exact walker has to take over.
 DATOK_HD_SLOW int fast_backtrack(FastLane& L, const FastTables& T, uint32_t seg_start, SegBits& B) {
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+  if (!(L.eps_b & EB_VALID)) g_hard++; else if (L.eps_pos < seg_start) g_far++;
+#endif
   if (!(L.eps_b & EB_VALID) || L.eps_pos < seg_start) return FAST_SLOW;  // hard fail / far backtrack
   const uint32_t bbit = 1u << (L.eps_pos - seg_start);
   const bool pending = (L.eps_b & EB_PENDING) != 0;
@@ -141,11 +144,20 @@ DATOK_HD_SLOW int fast_backtrack(FastLane& L, const FastTables& T, uint32_t seg_
 // [seg_start, seg_start+32) whose classes are seg_cls[0..31].  On FAST_SLOW nothing
 // has been changed and the exact walker must take over at L.pos.
 DATOK_HD int fast_step(FastLane& L, const FastTables& T, const uint8_t* seg_cls, uint32_t seg_start, SegBits& B) {
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+  g_fast++;
+#endif
   const uint32_t off = L.pos - seg_start;
   const uint32_t cl = seg_cls[off];
   const uint32_t e = t2_lookup(T, L.t, cl);
   const uint32_t bit = 1u << off;
   if (DATOK_UNLIKELY((int32_t)e <= 0)) {  // 0: failure without epsilon transition; bit 31: leave to walk_run
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+    g_bt++;
+#endif
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+    if (e != 0) g_mark++;
+#endif
     if (e != 0) return FAST_SLOW;
     return fast_backtrack(L, T, seg_start, B);
   }

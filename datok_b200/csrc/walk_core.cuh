@@ -252,13 +252,21 @@ struct SpecInfo {
 // loop top that follows the first rewind (used to hand a fresh lane to the fast path).
 //
 // Returns an error code (0 = none); on error the state is unusable.
+// resume_at (PROBE == false only): additionally return at the first loop top with
+// pos >= resume_at once at least one iteration has been executed -- the fast path
+// uses this to take the lane back as soon as the rare case is dealt with.
 template <bool SPEC, bool PROBE, bool STOP_REWIND>
-DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo* spec) {
+DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo* spec,
+                                uint32_t resume_at = 0xFFFFFFFFu) {
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+  g_exact_calls++;
+#endif
   uint32_t pos = st.pos, tstart = st.tstart, eps_pos = st.eps_pos, base = st.base, hw = st.hw;
   uint32_t t = st.t, eps_state = st.eps_state, flags = st.flags;
   const uint32_t N = c.N;
   bool first_window = SPEC;
   bool probing = false;
+  bool stepped = false;
   uint32_t err = 0;
   // snapshot taken at the (latest) arrival at `stop`
   uint32_t s_pos = 0, s_tstart = 0, s_base = 0, s_hw = 0, s_t = 0, s_flags = 0;
@@ -286,6 +294,8 @@ DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, Spe
       if (eps_state == 0 || eps_pos >= stop) break;  // final arrival
       if (pos < N && c.table[(t << c.row_shift) | K_CLS_EPS] != 0) break;  // this state replaces the point
     }
+    if (!PROBE && stepped && pos >= resume_at) break;
+    stepped = true;
     if (STOP_REWIND && SPEC && !first_window) break;
     if (pos >= N) {
       // ---- EOF tail (matrix.go:650-678) ----
@@ -320,6 +330,9 @@ DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, Spe
       continue;
     }
     {
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+      g_exact_steps++;
+#endif
       const uint32_t cl = cls_at(c, pos);
       const uint16_t* row = c.table + ((size_t)t << c.row_shift);
       if (c.hist) {
