@@ -109,7 +109,7 @@ DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, 
 
 // In-place backtrack to the epsilon point recorded in this segment (matrix.go:487-497),
 // or FAST_SLOW (nothing changed) when the exact walker has to take over.
-DATOK_HD_SLOW int fast_backtrack(FastLane& L, const FastTables& T, uint32_t seg_start, SegBits& B) {
+DATOK_HD int fast_backtrack(FastLane& L, const FastTables& T, uint32_t seg_start, SegBits& B) {
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
   if (!(L.eps_b & EB_VALID)) g_hard++; else if (L.eps_pos < seg_start) g_far++;
 #endif
