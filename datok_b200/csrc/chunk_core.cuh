@@ -125,40 +125,55 @@ DATOK_HD void load_seg_bits(const WalkBuffers& b, uint32_t w, SegBits& B) {
 // (fast_core.cuh).  Produces exactly what chunk_spec() produces, plus the rune-start
 // words of the chunk.  seg_cls: 32 bytes of lane-private scratch (shared memory in
 // the kernel).  The boundary bitmaps of the chunk must be zero on entry.
+//
+// from == nullptr: speculative walk (K2a).  from != nullptr: re-walk (K2c) of the chunk from the
+// known state *from (its position lies in the chunk); the result goes to Enew[i] instead and the
+// rune-start words are left alone.
 DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const FastTables& FT, uint32_t i,
-                              uint32_t start_state, uint8_t* seg_cls) {
+                              uint32_t start_state, uint8_t* seg_cls, const WState* from = nullptr) {
   const WalkCtx c = make_walk_ctx(m, b);
   const uint32_t lo = i * b.chunk, hi = lo + b.chunk, N = b.N;
+  const bool rewalk = from != nullptr;
   WState st;
   st.pos = st.tstart = st.base = st.hw = 0;
   st.eps_pos = 0; st.eps_state = 0; st.flags = 0; st.t = (uint16_t)start_state;
   FastLane L;
-  L.pos = L.tstart = L.base = L.eps_pos = L.eps_b = L.hw_med = L.hw_med_base = L.first_hw = 0;
+  L.pos = L.tstart = L.base = L.eps_pos = L.eps_b = L.hw_med = L.first_hw = 0;
   L.t = start_state;
-  L.first_window = (i != 0);  // a guessed start: the first window's overflow check is deferred (SpecInfo)
-  bool started = (i == 0), fast = true, halted = false;
+  L.first_window = (i != 0 && !rewalk);  // a guessed start: the first window's overflow check is deferred (SpecInfo)
+  bool started = (i == 0) || rewalk, fast = true, halted = false;
   uint32_t sync = (i == 0) ? 0u : K_NOPOS;
   uint32_t err = 0;
   SegBits B;
   B.end = B.skip = B.sent = B.tend = 0;
+  uint32_t first_seg = lo;
+  if (rewalk) {
+    st = *from;
+    fast = false;  // the fast path takes over as soon as the state allows it (see below)
+    first_seg = st.pos & ~(SEG - 1);
+    if (first_seg < lo) first_seg = lo;
+  }
 
-  for (uint32_t seg_start = lo; seg_start < hi; seg_start += SEG) {
+  for (uint32_t seg_start = first_seg; seg_start < hi; seg_start += SEG) {
     const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
     uint32_t rs;
     bool inv = false;
     classify_segment(b.in, N, seg_start, m.cls, seg_cls, &rs, &inv);
-    b.rstart[w] = rs;
-    if (inv) note_invalid_utf8(b);
+    if (!rewalk) {
+      b.rstart[w] = rs;
+      if (inv) note_invalid_utf8(b);
+    }
     if (halted) continue;
     if (!started) {
       sync = find_sync(b.in, N, m.sync_ascii, seg_start, seg_end < hi ? seg_end : hi);
       if (sync == K_NOPOS) continue;
       started = true;
-      L.pos = L.tstart = L.base = L.hw_med = L.hw_med_base = sync;
+      L.pos = L.tstart = L.base = L.hw_med = sync;
       L.t = m.start;
     }
     B.end = B.skip = B.sent = B.tend = 0;
     bool in_regs = true;  // the segment's boundary words live in B (else in memory)
+    if (rewalk && seg_start == first_seg) in_regs = false;  // the words of the first segment were prepared in memory
     if (fast && seg_end - L.base >= FAST_WINDOW_GUARD) {  // too close to the 1024-rune buffer limit
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
       g_guard++;
@@ -210,7 +225,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     if (in_regs) store_seg_bits(b, w, B);
   }
 
-  b.sync[i] = sync;
+  if (!rewalk) b.sync[i] = sync;
   SpecInfo si;
   si.first_hw = L.first_hw; si.had_rewind = L.first_window ? 0u : 1u;
   if (!started) st = wstate_invalid(0);
@@ -222,10 +237,31 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   } else if (!err && L.first_window) {
     si.first_hw = st.hw; si.had_rewind = 0;
   }
+  if (rewalk) {
+    b.Enew[i] = st;
+    return;
+  }
   b.exitA[i] = st;
   b.E[i] = st;
   b.first_hw[i] = si.first_hw;
   b.cflags[i] = (i == 0 || si.had_rewind) ? CF_HAD_REWIND : 0;
+}
+
+DATOK_HD void chunk_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t i);
+
+// K2c through the fast path: clears the chunk's bits from the re-walk position on, then walks.
+DATOK_HD void chunk_rewalk_fast(const DeviceModel& m, const WalkBuffers& b, const FastTables& FT, uint32_t i,
+                                uint8_t* seg_cls) {
+  const uint32_t lo = i * b.chunk, hi = lo + b.chunk;
+  const WState Y = b.Ytmp[i];
+  const uint32_t from = (b.sync[i] == K_NOPOS) ? lo : Y.pos;
+  clear_chunk_bits(b, from, hi);
+  if (Y.pos >= hi || (Y.flags & (WS_INVALID | WS_DONE))) {  // nothing left to walk in this chunk
+    chunk_rewalk(m, b, i);
+    return;
+  }
+  chunk_spec_fast(m, b, FT, i, 0, seg_cls, &Y);
+  b.cflags[i] |= CF_OVERWRITTEN;
 }
 
 // K2b: returns true if chunk i must be re-walked (state in Ytmp[i]); otherwise Enew[i] is set.

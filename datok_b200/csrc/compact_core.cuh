@@ -159,14 +159,18 @@ DATOK_HD void report_error(const CompactCtx& c, uint32_t pos, uint32_t code) {
 // Walks the events of bitmap word `w` in stream order.
 //   EMIT == false: returns the word's Agg (relative ranks), `carry` unused.
 //   EMIT == true : `carry` is the absolute summary of everything before the word
-//                  (including the stream-start pseudo event); writes the outputs.
+//                  (including the stream-start pseudo event); writes the outputs and
+//                  returns the absolute summary including the word.
 template <bool EMIT>
 DATOK_HD Agg process_word(const CompactCtx& c, uint32_t w, const Agg& carry) {
   const uint32_t rs = c.rstart[w], we = c.b_end[w], ws = c.b_sent[w], wt = c.b_tend[w];
   Agg a = agg_zero();
   a.n_rune = popc32(rs);
   uint32_t m = we | ws | wt;
-  if (m == 0) return a;
+  if (m == 0) {
+    if (EMIT) { a = carry; a.n_rune = carry.n_rune + popc32(rs); }
+    return a;
+  }
   // running absolute state (EMIT) / relative state (!EMIT)
   uint32_t lk = EMIT ? carry.last_kind : EV_NONE;
   uint32_t tok = EMIT ? carry.n_tok : 0, sent = EMIT ? carry.n_sent : 0, text = EMIT ? carry.n_text : 0;
@@ -246,6 +250,7 @@ DATOK_HD Agg process_word(const CompactCtx& c, uint32_t w, const Agg& carry) {
       doc_tok = tok;
     }
   }
+  if (EMIT) { a.n_rune = rank0 + popc32(rs); a.first_kind = carry.first_kind; }
   a.n_tok = tok; a.n_sent = sent; a.n_text = text; a.n_sentpos = sentpos;
   a.last_kind = lk;
   a.last_end_pos = last_end_pos; a.last_end_rank = last_end_rank;

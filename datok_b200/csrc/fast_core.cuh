@@ -55,7 +55,8 @@ struct FastLane {
                                  // rewinds inside the segment are read off the END/TEND bits (lane_base)
   uint32_t t;
   uint32_t eps_pos, eps_b;
-  uint32_t hw_med, hw_med_base;  // furthest failing position seen by an in-place backtrack since `hw_med_base`
+  uint32_t hw_med;               // furthest failing position seen by an in-place backtrack (never reset:
+                                 // an over-estimate from an older window cannot fake an overflow, see to_exact)
   uint32_t first_hw;             // SpecInfo of a guessed start: hw at the first rewind
   uint32_t first_window;         // 1 until the first rewind of a guessed start
 };
@@ -87,7 +88,7 @@ DATOK_HD void to_fast(const WState& st, FastLane& L) {
   L.pos = st.pos; L.tstart = st.tstart; L.base = st.base; L.t = st.t;
   L.eps_pos = st.eps_pos;
   L.eps_b = st.eps_state ? (EB_VALID | st.eps_state | (st.eps_pos > st.tstart ? EB_PENDING : 0)) : 0;
-  L.hw_med = st.hw; L.hw_med_base = st.base;
+  L.hw_med = st.hw;
 }
 // fast lane -> exact state (resolves the lazily stored epsilon point and window base)
 DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, const FastTables& T, WState& st) {
@@ -101,8 +102,11 @@ DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, 
   }
   st.eps_state = (uint16_t)es;
   st.eps_pos = es ? L.eps_pos : 0;
+  // hw: furthest byte read in the current buffer window.  hw_med may stem from an older window;
+  // it was a real read then, [base, hw_med] is contained in that older window, so counting its
+  // runes can never exceed what the reference itself had buffered.
   uint32_t hw = base;
-  if (L.hw_med_base == base && L.hw_med > hw) hw = L.hw_med;
+  if (L.hw_med > hw) hw = L.hw_med;
   if (L.pos > base && hw < L.pos - 1) hw = L.pos - 1;
   st.hw = hw;
 }
@@ -120,8 +124,6 @@ DATOK_HD int fast_backtrack(FastLane& L, const FastTables& T, uint32_t seg_start
   uint32_t cur = L.eps_b & 0x7FFFu;
   for (uint32_t k = (L.eps_b >> T2K_SHIFT) & 3u; k; k--) cur = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
   const uint32_t tgt = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
-  const uint32_t base = lane_base(L, B, seg_start);
-  if (L.hw_med_base != base) { L.hw_med = 0; L.hw_med_base = base; }
   if (L.hw_med < L.pos) L.hw_med = L.pos;
   if (pending) {  // Token + rewind (:565-572)
     if (L.first_window) {
@@ -166,7 +168,12 @@ DATOK_HD int fast_step(FastLane& L, const FastTables& T, const uint8_t* seg_cls,
   const bool pending = L.pos > L.tstart;
   const bool two = k == 2;
   // k epsilon steps before the byte is consumed: Token if something is pending, else SentenceEnd
-  if (DATOK_UNLIKELY(is_eps && (((B.sent & bit) && !(pending && !two)) || (two && !pending)))) return FAST_SLOW;
+  {
+    // a second SentenceEnd at one position is left to walk_run (it reports the degenerate case)
+    const uint32_t sent_here = (B.sent & bit) != 0;
+    const uint32_t bad = (uint32_t)is_eps & ((sent_here & (uint32_t)!(pending && !two)) | (uint32_t)(two && !pending));
+    if (DATOK_UNLIKELY(bad)) return FAST_SLOW;
+  }
   B.end |= (is_eps && pending) ? bit : 0u;
   B.sent |= ((is_eps && !pending) || two) ? bit : 0u;
   if (is_eps) { L.tstart = L.pos; L.eps_b = 0; }

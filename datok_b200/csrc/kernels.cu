@@ -108,10 +108,15 @@ __global__ void __launch_bounds__(WALK_THREADS) stitch_kernel(DeviceModel m, Wal
   }
 }
 
+// Re-walks go through the fast path too (fused table straight from L2: there are few of them).
 __global__ void __launch_bounds__(WALK_THREADS) rewalk_kernel(DeviceModel m, WalkBuffers b, uint32_t n_rewalk) {
+  __shared__ __align__(16) uint8_t s_cls[WALK_THREADS * LANE_CLS_STRIDE];
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   // n_rewalk is only the launch bound; the list length was counted on the device by stitch_kernel
-  if (k < n_rewalk && k < b.counters[1]) chunk_rewalk(m, b, b.list_rewalk[k]);
+  if (k >= n_rewalk || k >= b.counters[1]) return;
+  FastTables FT;
+  FT.hot = m.table2; FT.cold = m.table2; FT.n_hot = 0; FT.stride = m.stride2;
+  chunk_rewalk_fast(m, b, FT, b.list_rewalk[k], s_cls + threadIdx.x * LANE_CLS_STRIDE);
 }
 
 __global__ void __launch_bounds__(256) commit_kernel(WalkBuffers b, const uint32_t* list, uint32_t n_list) {
@@ -170,8 +175,9 @@ __device__ __forceinline__ Agg agg_shfl_up(const Agg& v, int delta) {
 
 // Ordered (non-commutative) block scan.  Returns the exclusive prefix of `mine`
 // within the block combined after `seed`; *block_total = all threads' values combined.
+template <int THREADS>
 __device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& seed, Agg* block_total) {
-  __shared__ Agg s_warp[COMPACT_THREADS / 32];
+  __shared__ Agg s_warp[THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Agg incl = mine;
 #pragma unroll
@@ -185,7 +191,7 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& 
   for (int wi = 0; wi < warp; wi++) prefix = agg_combine(prefix, s_warp[wi]);
   if (block_total) {
     Agg tot = s_warp[0];
-    for (int wi = 1; wi < COMPACT_THREADS / 32; wi++) tot = agg_combine(tot, s_warp[wi]);
+    for (int wi = 1; wi < THREADS / 32; wi++) tot = agg_combine(tot, s_warp[wi]);
     *block_total = tot;
   }
   Agg prev = agg_shfl_up(incl, 1);
@@ -203,45 +209,42 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_reduce_kernel(Compact
     if (w < c.n_words) ta = agg_combine(ta, process_word<false>(c, w, ta));
   }
   Agg tot;
-  block_exclusive_scan(ta, agg_zero(), &tot);
+  block_exclusive_scan<COMPACT_THREADS>(ta, agg_zero(), &tot);
   if (threadIdx.x == 0) cb.block_agg[blockIdx.x] = tot;
 }
 
 // Single block: thread t owns a contiguous run of block summaries.
-__global__ void __launch_bounds__(COMPACT_THREADS) compact_scan_kernel(CompactCtx c, CompactBuffers cb,
-                                                                        bool sentence_end_in) {
-  const uint32_t per = (cb.n_blocks + COMPACT_THREADS - 1) / COMPACT_THREADS;
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) compact_scan_kernel(CompactCtx c, CompactBuffers cb,
+                                                                     bool sentence_end_in) {
+  const uint32_t per = (cb.n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t lo = threadIdx.x * per;
   const uint32_t hi = lo + per < cb.n_blocks ? lo + per : cb.n_blocks;
   Agg mine = agg_zero();
   for (uint32_t i = lo; i < hi; i++) mine = agg_combine(mine, cb.block_agg[i]);
   Agg tot;
-  Agg run = block_exclusive_scan(mine, agg_stream_start(c, sentence_end_in), &tot);
+  const Agg start = agg_stream_start(c, sentence_end_in);
+  Agg run = block_exclusive_scan<SCAN_THREADS>(mine, start, &tot);
   for (uint32_t i = lo; i < hi; i++) {
     cb.block_carry[i] = run;
     run = agg_combine(run, cb.block_agg[i]);
   }
-  if (threadIdx.x == 0) cb.total[0] = agg_combine(agg_stream_start(c, sentence_end_in), tot);
+  if (threadIdx.x == 0) cb.total[0] = agg_combine(start, tot);
 }
 
 __global__ void __launch_bounds__(COMPACT_THREADS) compact_emit_kernel(CompactCtx c, CompactBuffers cb) {
   const uint32_t w0 = (blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
-  Agg wa[COMPACT_WPT];
   Agg ta = agg_zero();
 #pragma unroll
   for (int k = 0; k < COMPACT_WPT; k++) {
     const uint32_t w = w0 + k;
-    wa[k] = (w < c.n_words) ? process_word<false>(c, w, ta) : agg_zero();
-    ta = agg_combine(ta, wa[k]);
+    if (w < c.n_words) ta = agg_combine(ta, process_word<false>(c, w, ta));
   }
-  Agg carry = block_exclusive_scan(ta, cb.block_carry[blockIdx.x], nullptr);
-#pragma unroll
+  Agg carry = block_exclusive_scan<COMPACT_THREADS>(ta, cb.block_carry[blockIdx.x], nullptr);
+#pragma unroll 1
   for (int k = 0; k < COMPACT_WPT; k++) {
     const uint32_t w = w0 + k;
-    if (w < c.n_words) {
-      process_word<true>(c, w, carry);
-      carry = agg_combine(carry, wa[k]);
-    }
+    if (w < c.n_words) carry = process_word<true>(c, w, carry);
   }
 }
 
@@ -255,7 +258,7 @@ void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaSt
   compact_reduce_kernel<<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
 }
 void launch_compact_scan(const CompactCtx& c, const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s) {
-  compact_scan_kernel<<<1, COMPACT_THREADS, 0, s>>>(c, cb, sentence_end_in);
+  compact_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(c, cb, sentence_end_in);
 }
 void launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
   compact_emit_kernel<<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);

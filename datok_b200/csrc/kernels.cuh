@@ -16,7 +16,7 @@ struct CompactBuffers {
 };
 
 constexpr int COMPACT_THREADS = 256;
-constexpr int COMPACT_WPT = 2;  // bitmap words per thread
+constexpr int COMPACT_WPT = 4;  // bitmap words per thread
 
 // fused classify + speculative walk; returns a cudaError_t value
 int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot, int n_sms,

@@ -104,6 +104,9 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   }
   R->has_invalid = counters[2];
 
+  FastTables FTr;
+  FTr.hot = m.table2; FTr.cold = m.table2; FTr.n_hot = 0; FTr.stride = m.stride2;
+  uint8_t seg_cls_r[36];
   // K2b-d fix-up rounds
   std::vector<uint32_t> list, next, rew;
   for (uint32_t i = 1; i < b.n_chunks; i++) list.push_back(i);
@@ -115,7 +118,11 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       if (chunk_stitch(m, b, i)) rew.push_back(i);
     }
     R->n_stitch_mismatch += (uint32_t)rew.size();
-    for (size_t k = 0; k < rew.size(); k++) { chunk_rewalk(m, b, rew[order ? rew.size() - 1 - k : k]); R->n_rewalks++; }
+    for (size_t k = 0; k < rew.size(); k++) {
+      const uint32_t ci = rew[order ? rew.size() - 1 - k : k];
+      if (mode == 0) chunk_rewalk(m, b, ci); else chunk_rewalk_fast(m, b, FTr, ci, seg_cls_r);
+      R->n_rewalks++;
+    }
     for (size_t k = 0; k < list.size(); k++) {
       uint32_t i = list[k];
       if (chunk_commit(b, i) && i + 1 < b.n_chunks) next.push_back(i + 1);
@@ -140,7 +147,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   std::memset(&c, 0, sizeof c);
   c.in = in; c.N = N; c.n_words = b.n_words; c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip;
   c.b_sent = b.b_sent; c.b_tend = b.b_tend; c.flags = flags; c.err_key = &err_key;
-  const uint32_t TPB = 256, WPT = 2, WPB = TPB * WPT;
+  const uint32_t TPB = 256, WPT = 4, WPB = TPB * WPT;
   const uint32_t nblk = (b.n_words + WPB - 1) / WPB;
   std::vector<Agg> block_agg(nblk), block_carry(nblk);
   for (uint32_t blk = 0; blk < nblk; blk++) {
@@ -178,9 +185,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       for (uint32_t k = 0; k < WPT; k++) {
         uint32_t w = blk * WPB + t * WPT + k;
         if (w >= b.n_words) continue;
-        Agg wa = process_word<false>(c, w, carry);
-        process_word<true>(c, w, carry);
-        carry = agg_combine(carry, wa);
+        carry = process_word<true>(c, w, carry);
       }
     }
   }
