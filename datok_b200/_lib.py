@@ -13,10 +13,12 @@ LIB_PATH = os.path.join(HERE, "libdatok_b200.so")
 TOKENS, SENTENCES, TOKEN_POS, SENTENCE_POS, NEWLINE_AFTER_EOT = 1, 2, 4, 8, 16
 SIMPLE = TOKENS | SENTENCES
 WRITER_USED = 256
+NOT_FINAL = 512
 
 OK = 0
 ERR_BUFFER_OVERFLOW, ERR_SENT_NO_TOKEN, ERR_TEXT_NO_TOKEN, ERR_TEXT_NO_SENT, ERR_DEGENERATE = 1, 2, 3, 4, 5
 ERR_IO, ERR_FORMAT, ERR_UNSUPPORTED_MODEL, ERR_NO_DEVICE, ERR_CUDA, ERR_TOO_LARGE, ERR_INVALID_ARG = 16, 17, 18, 19, 20, 21, 22
+ERR_NOT_AT_BOUNDARY = 23
 
 
 class Carry(C.Structure):

@@ -388,6 +388,8 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   if (rc) return rc;
   carve(m->ws, N, m->chunk, !in_is_device, b, cb);
   if (in_is_device) b.in = in;
+  const bool final_input = !(flags & DATOK_NOT_FINAL);
+  b.final_input = final_input ? 1u : 0u;
 
   if (m->auto_calibrate && !m->calibrated && N >= (256u << 10)) {
     // one-time specialisation of the table layout to the caller's text
@@ -506,7 +508,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   c.text_byte_end = c.text_tok_end + 3 * nx;
   pt.begin(T_EMIT);
   launch_compact_emit(c, cb, s);
-  launch_compact_finalize(c, cb, text_end_in, s);
+  launch_compact_finalize(c, cb, text_end_in, final_input, s);
   pt.end();
   m->launches += 2;
   struct { Agg fin; unsigned long long err; WState last; } tail;
@@ -532,6 +534,17 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   v.carry_out.state = m->hm.old_of_new[tail.last.t];
   v.carry_out.sentence_end = 1;
   v.carry_out.text_end = 1;
+  if (!final_input) {
+    // the walk stopped at the loop top at N: it must be at a rewind point with nothing pending
+    if (tail.last.tstart != N || tail.last.base != N || tail.last.eps_state != 0 || (tail.last.flags & WS_PEND)) {
+      g_last_error = "DATOK_NOT_FINAL input does not end at a text boundary";
+      free_result_locked(r);
+      return DATOK_ERR_NOT_AT_BOUNDARY;
+    }
+    const uint32_t lk = tail.fin.last_kind;
+    v.carry_out.sentence_end = (lk == EV_SENT || lk == EV_TEND) ? 1u : 0u;
+    v.carry_out.text_end = (tail.fin.n_text > 0 && tail.fin.n_tok == tail.fin.doc_tok) ? 1u : (text_end_in ? 1u : 0u);
+  }
   // ---- D2H ----
   for (auto& o : outs) {
     if (!o.want || device_out) continue;
@@ -675,6 +688,7 @@ const char* datok_strerror(int code) {
     case DATOK_ERR_CUDA: return "CUDA error";
     case DATOK_ERR_TOO_LARGE: return "input too large for one call";
     case DATOK_ERR_INVALID_ARG: return "invalid argument";
+    case DATOK_ERR_NOT_AT_BOUNDARY: return "non-final input does not end at a text boundary";
     default: return "unknown error";
   }
 }

@@ -45,6 +45,7 @@ struct WalkBuffers {
   uint32_t *list_cur, *list_next, *list_rewalk;
   uint32_t* counters;      // [0] next list size, [1] rewalk list size, [2] invalid-utf8 flag
   unsigned long long* err_key;
+  uint32_t final_input;    // see WalkCtx
 };
 
 DATOK_HD WalkCtx make_walk_ctx(const DeviceModel& m, const WalkBuffers& b) {
@@ -53,6 +54,7 @@ DATOK_HD WalkCtx make_walk_ctx(const DeviceModel& m, const WalkBuffers& b) {
   c.in = b.in; c.N = b.N; c.cls = m.cls;
   c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
   c.hist = nullptr;
+  c.final_input = b.final_input;
   return c;
 }
 

@@ -13,25 +13,27 @@
 // The per-thread bodies live in walk_core.cuh / chunk_core.cuh / compact_core.cuh.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace datok {
 
 // ------------------------------------------------------------------ K1 + K2a (fused)
 
 constexpr int WALK_THREADS = 128;
-constexpr int FUSED_THREADS = 512;
 constexpr int LANE_CLS_STRIDE = 36;  // bytes of class scratch per lane (9 words: bank spread)
 
 // Persistent kernel, one CTA per SM.  The hottest rows of the fused transition
 // table and the two byte->class LUTs live in shared memory; every lane owns one
 // chunk at a time and walks it segment by segment (chunk_spec_fast).
-__global__ void __launch_bounds__(FUSED_THREADS, 1)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n_hot) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* s_hot = smem;
   uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_hot + (size_t)n_hot * m.stride2);
-  uint8_t* s_lut = s_cls + FUSED_THREADS * LANE_CLS_STRIDE;
+  uint8_t* s_lut = s_cls + THREADS * LANE_CLS_STRIDE;
   const uint32_t hot_words = n_hot * m.stride2;
-  for (uint32_t k = threadIdx.x; k < hot_words; k += FUSED_THREADS) s_hot[k] = m.table2[k];
+  for (uint32_t k = threadIdx.x; k < hot_words; k += THREADS) s_hot[k] = m.table2[k];
   if (threadIdx.x < 128) {
     s_lut[threadIdx.x] = m.cls.ascii_cls[threadIdx.x];
     s_lut[128 + threadIdx.x] = m.cls.latin1_cls[threadIdx.x];
@@ -43,35 +45,58 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   FastTables FT;
   FT.hot = s_hot; FT.cold = m.table2; FT.n_hot = n_hot; FT.stride = m.stride2;
   uint8_t* my_cls = s_cls + threadIdx.x * LANE_CLS_STRIDE;
-  for (uint32_t i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * FUSED_THREADS)
+  for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * THREADS)
     chunk_spec_fast(lm, b, FT, i, start_state, my_cls);
 }
 
+static int g_fused_threads = 0;
+int fused_threads() {
+  if (!g_fused_threads) {
+    g_fused_threads = 1024;
+    if (const char* s = std::getenv("DATOK_FUSED_THREADS")) {
+      const long v = std::atol(s);
+      if (v == 256 || v == 512 || v == 768 || v == 1024) g_fused_threads = (int)v;
+    }
+  }
+  return g_fused_threads;
+}
+
 size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot) {
-  return (size_t)n_hot * m.stride2 * 4 + (size_t)FUSED_THREADS * LANE_CLS_STRIDE + 256;
+  return (size_t)n_hot * m.stride2 * 4 + (size_t)fused_threads() * LANE_CLS_STRIDE + 256;
 }
 
 uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states) {
-  const size_t fixed = (size_t)FUSED_THREADS * LANE_CLS_STRIDE + 256 + 1024;
+  const size_t fixed = (size_t)fused_threads() * LANE_CLS_STRIDE + 256 + 1024;
   if (smem_limit <= fixed) return 1;
   size_t rows = (smem_limit - fixed) / ((size_t)m.stride2 * 4);
   if (rows > (size_t)n_states + 1) rows = (size_t)n_states + 1;
   return rows ? (uint32_t)rows : 1u;
 }
 
-int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot,
-                      int n_sms, cudaStream_t s) {
+template <int THREADS>
+static int launch_walk_fused_t(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot,
+                               int n_sms, cudaStream_t s) {
   const size_t smem = fused_smem_bytes(m, n_hot);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  uint32_t blocks = (b.n_chunks + FUSED_THREADS - 1) / FUSED_THREADS;
+  uint32_t blocks = (b.n_chunks + THREADS - 1) / THREADS;
   if (blocks > (uint32_t)n_sms) blocks = (uint32_t)n_sms;
-  walk_fused_kernel<<<blocks, FUSED_THREADS, smem, s>>>(m, b, start_state, n_hot);
+  walk_fused_kernel<THREADS><<<blocks, THREADS, smem, s>>>(m, b, start_state, n_hot);
   return (int)cudaGetLastError();
+}
+
+int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot,
+                      int n_sms, cudaStream_t s) {
+  switch (fused_threads()) {
+    case 256: return launch_walk_fused_t<256>(m, b, start_state, n_hot, n_sms, s);
+    case 768: return launch_walk_fused_t<768>(m, b, start_state, n_hot, n_sms, s);
+    case 512: return launch_walk_fused_t<512>(m, b, start_state, n_hot, n_sms, s);
+    default: return launch_walk_fused_t<1024>(m, b, start_state, n_hot, n_sms, s);
+  }
 }
 
 // Calibration: visits per state on a sample, walked speculatively chunk by chunk
@@ -248,9 +273,9 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_emit_kernel(CompactCt
   }
 }
 
-__global__ void compact_finalize_kernel(CompactCtx c, CompactBuffers cb, bool text_end_in) {
+__global__ void compact_finalize_kernel(CompactCtx c, CompactBuffers cb, bool text_end_in, bool final_input) {
   Agg tot = cb.total[0];
-  finalize_stream(c, tot, text_end_in);
+  if (final_input) finalize_stream(c, tot, text_end_in);
   cb.total[1] = tot;
 }
 
@@ -263,8 +288,9 @@ void launch_compact_scan(const CompactCtx& c, const CompactBuffers& cb, bool sen
 void launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
   compact_emit_kernel<<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
 }
-void launch_compact_finalize(const CompactCtx& c, const CompactBuffers& cb, bool text_end_in, cudaStream_t s) {
-  compact_finalize_kernel<<<1, 1, 0, s>>>(c, cb, text_end_in);
+void launch_compact_finalize(const CompactCtx& c, const CompactBuffers& cb, bool text_end_in, bool final_input,
+                             cudaStream_t s) {
+  compact_finalize_kernel<<<1, 1, 0, s>>>(c, cb, text_end_in, final_input);
 }
 
 }  // namespace datok

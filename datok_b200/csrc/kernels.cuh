@@ -15,8 +15,8 @@ struct CompactBuffers {
   uint32_t n_blocks;
 };
 
-constexpr int COMPACT_THREADS = 256;
-constexpr int COMPACT_WPT = 4;  // bitmap words per thread
+constexpr int COMPACT_THREADS = 512;
+constexpr int COMPACT_WPT = 2;  // bitmap words per thread
 
 // fused classify + speculative walk; returns a cudaError_t value
 int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot, int n_sms,
@@ -34,6 +34,7 @@ void launch_collect_errors(const WalkBuffers& b, cudaStream_t s);
 void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
 void launch_compact_scan(const CompactCtx& c, const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s);
 void launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
-void launch_compact_finalize(const CompactCtx& c, const CompactBuffers& cb, bool text_end_in, cudaStream_t s);
+void launch_compact_finalize(const CompactCtx& c, const CompactBuffers& cb, bool text_end_in, bool final_input,
+                             cudaStream_t s);
 
 }  // namespace datok

@@ -199,6 +199,7 @@ struct WalkCtx {
   uint32_t* b_sent;
   uint32_t* b_tend;
   uint32_t* hist;         // optional: visits per state (calibration of the hot-row order)
+  uint32_t final_input;   // 0: the stream continues in a later call: no end-of-input processing (matrix.go:650-695)
 };
 
 DATOK_HD uint32_t cls_at(const WalkCtx& c, uint32_t pos) {
@@ -298,6 +299,7 @@ DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, Spe
     stepped = true;
     if (STOP_REWIND && SPEC && !first_window) break;
     if (pos >= N) {
+      if (!c.final_input) { flags |= WS_DONE; break; }  // shard of a longer stream: stop at the loop top
       // ---- EOF tail (matrix.go:650-678) ----
       if (N > 0 && hw < N - 1) hw = N - 1;
       uint32_t e = c.table[(t << c.row_shift) | K_CLS_EPS];

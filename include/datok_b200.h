@@ -31,7 +31,12 @@ enum {
   /* Not a reference flag: the caller's TokenWriter has already received a Token
    * call (token_writer.go:42,70: `init` is false), i.e. the writer is being
    * reused across Transduce calls as in token_writer_test.go:52-56. */
-  DATOK_WRITER_USED = 256
+  DATOK_WRITER_USED = 256,
+  /* Not a reference flag: the input is a shard of a longer stream that continues in a
+   * later call (another GPU, the next batch).  End-of-input processing (matrix.go:650-695:
+   * final token flush, final SentenceEnd/TextEnd) is skipped; the input must end at a
+   * text boundary (right after an EOT), else DATOK_ERR_NOT_AT_BOUNDARY. */
+  DATOK_NOT_FINAL = 512
 };
 
 /* Error codes.  1..6 mirror inputs on which the Go reference panics (they are
@@ -50,7 +55,8 @@ enum {
   DATOK_ERR_NO_DEVICE = 19,      /* no CUDA device / wrong architecture */
   DATOK_ERR_CUDA = 20,           /* a CUDA call failed; see datok_last_error() */
   DATOK_ERR_TOO_LARGE = 21,      /* input >= 2^32 - 2^20 bytes in one call (split at EOT) */
-  DATOK_ERR_INVALID_ARG = 22
+  DATOK_ERR_INVALID_ARG = 22,
+  DATOK_ERR_NOT_AT_BOUNDARY = 23 /* DATOK_NOT_FINAL input ends inside a token / pending epsilon point */
 };
 
 typedef struct datok_model datok_model;

@@ -66,6 +66,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   WalkBuffers b;
   std::memset(&b, 0, sizeof b);
   b.in = in; b.N = N; b.chunk = chunk;
+  b.final_input = (flags & 512u) ? 0u : 1u;
   b.n_chunks = N / chunk + 1;
   b.n_words = b.n_chunks * (chunk / 32);
   uint32_t counters[8] = {0};
@@ -147,7 +148,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   std::memset(&c, 0, sizeof c);
   c.in = in; c.N = N; c.n_words = b.n_words; c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip;
   c.b_sent = b.b_sent; c.b_tend = b.b_tend; c.flags = flags; c.err_key = &err_key;
-  const uint32_t TPB = 256, WPT = 4, WPB = TPB * WPT;
+  const uint32_t TPB = 512, WPT = 2, WPB = TPB * WPT;
   const uint32_t nblk = (b.n_words + WPB - 1) / WPB;
   std::vector<Agg> block_agg(nblk), block_carry(nblk);
   for (uint32_t blk = 0; blk < nblk; blk++) {
@@ -189,7 +190,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       }
     }
   }
-  finalize_stream(c, total, text_end_in != 0);
+  if (b.final_input) finalize_stream(c, total, text_end_in != 0);
   R->n_tokens = total.n_tok; R->n_sentences = total.n_sent; R->n_texts = total.n_text; R->n_sent_pos = total.n_sentpos;
   if (err_key != ~0ull) R->status = (int)(err_key & 0xFF);
   return R;

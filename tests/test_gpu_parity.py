@@ -214,3 +214,31 @@ def test_device_resident_path(gpu_models, oracle_models):
     cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
     assert cudart.cudaMemcpy(host.ctypes.data, r.device_ptr("tok_pos"), host.nbytes, 2) == 0  # cudaMemcpyDeviceToHost
     np.testing.assert_array_equal(host, o.tok_pos)
+
+
+def test_shards_equal_one_stream(gpu_models, oracle_models):
+    """EOT-aligned shards walked independently (DATOK_NOT_FINAL + carry), concatenated with
+    their index bases, equal the single-stream result (the multi-GPU path, on one GPU)."""
+    import datok_b200 as d
+    from datok_b200 import corpus, shard
+    a = corpus.generate(corpus.GERMAN, 2 << 20, seed=9)
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
+    tok = gpu_models["tokenizer_de.matok"]
+    plan = shard.plan_shards(a, 4)
+    parts, carry, seen = [], None, False
+    for r, (lo, hi) in enumerate(plan):
+        f = 15 | (0 if r == len(plan) - 1 else d.NOT_FINAL) | (d.WRITER_USED if seen else 0)
+        res = tok.transduce_arrays(a[lo:hi], f, carry=carry)
+        parts.append(res)
+        carry = d.Carry(res.carry_state, 1, 1, 0)
+        seen = seen or res.n_tokens > 0
+    tb = np.concatenate([p.tok_bytes.astype(np.int64) + lo for p, (lo, _) in zip(parts, plan)])
+    np.testing.assert_array_equal(tb[0::2], o.tok_byte_start)
+    np.testing.assert_array_equal(tb[1::2], o.tok_byte_end)
+    np.testing.assert_array_equal(np.concatenate([p.tok_pos for p in parts]), o.tok_pos)
+    np.testing.assert_array_equal(np.concatenate([p.sent_pos for p in parts]), o.sent_pos)
+    assert sum(p.n_texts for p in parts) == o.n_texts
+    # a non-final input that stops inside a token is refused
+    with pytest.raises(d.DatokError) as ei:
+        tok.transduce_arrays(b"mitten im Wor", 15 | d.NOT_FINAL)
+    assert ei.value.code == 23
