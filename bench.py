@@ -38,6 +38,18 @@ MODEL = os.path.join(ROOT, "testdata", "tokenizer_de.matok")
 METRIC = "GB/s input tokenized+sentence-split (de .matok)"
 
 
+def measured_traffic(n_bytes):
+    """DRAM bytes (read+write) of one step from the committed ncu --set full capture of the same
+    workload (profiles/r1_traffic.json, written by scripts/ncu_traffic.py); None if absent"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if int(t["input_bytes"]) == int(n_bytes):
+            return float(t["dram_bytes_per_step"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -260,10 +272,11 @@ def main():
                        "bytes_per_gpu": N, "documents_per_gpu": D, "tokens_per_gpu": T, "sentences_per_gpu": S,
                        "l2": "input (>= 1 GiB) and outputs exceed the 126 MB L2; no flush needed",
                        "chunk_bytes": int(os.environ.get("DATOK_CHUNK", "256")),
+                       "calibration": "state order specialised once on the first 8 MiB of the corpus (untimed warm-up)",
                        "timing": "CUDA events on the library's stream around the whole device path, max over ranks",
                        "ms_per_step_wall": ms_wall},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic(N), "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "formula": "N + 8*tokens + 8*sentences + 8*documents",
                          "kernel": "whole device path (all kernels of one step); per-kernel ms in kernel_ms",
                          "kernel_ms": kt},

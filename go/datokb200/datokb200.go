@@ -1,0 +1,157 @@
+// Package datokb200 is the Go side of the drop-in boundary: a type that implements
+// datok.Tokenizer (fomafile.go:29-33) on top of libdatok_b200.so, the B200-native
+// implementation of MatrixTokenizer.TransduceTokenWriter (matrix.go:348-698).
+//
+// NOTE: this file cannot be compiled in the build image (no Go toolchain); it is the
+// binding a Datok maintainer would add.  Everything it needs from the native side is
+// declared in include/datok_b200.h and exercised through the same C ABI by the Python
+// host mirror (datok_b200/tokenizer.py) and the -m gpu parity tests.
+package datokb200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../datok_b200 -ldatok_b200
+#include <stdlib.h>
+#include "datok_b200.h"
+
+// cgo cannot call Go closures from C directly; the replay goes through these
+// exported trampolines (see //export below).
+extern void goDatokToken(void *user, const uint8_t *buf, size_t bufBytes, size_t offBytes, int32_t offRunes);
+extern void goDatokSentenceEnd(void *user);
+extern void goDatokTextEnd(void *user);
+
+static int datok_replay_go(const datok_result *r, const uint8_t *in, size_t n, void *user) {
+  datok_callbacks cb = { user, goDatokToken, goDatokSentenceEnd, goDatokTextEnd };
+  return datok_replay(r, in, n, &cb);
+}
+*/
+import "C"
+
+import (
+	"errors"
+	"io"
+	"log"
+	"runtime/cgo"
+	"unsafe"
+
+	datok "github.com/KorAP/datok"
+)
+
+// Tokenizer implements datok.Tokenizer for .matok models on one B200.
+type Tokenizer struct {
+	model *C.datok_model
+}
+
+// compile-time check: same interface as the reference (fomafile.go:29-33)
+var _ datok.Tokenizer = (*Tokenizer)(nil)
+
+// LoadTokenizerFile mirrors datok.LoadTokenizerFile (fomafile.go:452-484) for the
+// MATOK magic: nil on any error, the reason is logged.
+func LoadTokenizerFile(file string, device int) *Tokenizer {
+	cs := C.CString(file)
+	defer C.free(unsafe.Pointer(cs))
+	var rc C.int
+	m := C.datok_load(cs, C.int(device), &rc)
+	if m == nil {
+		log.Println(C.GoString(C.datok_last_error()))
+		return nil
+	}
+	return &Tokenizer{model: m}
+}
+
+// Close releases the GPU resident model.
+func (t *Tokenizer) Close() { C.datok_free(t.model); t.model = nil }
+
+// Type is "MATOK" (matrix.go:102-104).
+func (t *Tokenizer) Type() string { return C.GoString(C.datok_type()) }
+
+// Transduce mirrors matrix.go:340-342.
+func (t *Tokenizer) Transduce(r io.Reader, w io.Writer) bool {
+	return t.TransduceTokenWriter(r, datok.NewTokenWriter(w, datok.SIMPLE))
+}
+
+// TransduceTokenWriter mirrors matrix.go:348-698: the input is transduced on the GPU
+// and the event stream (Token / SentenceEnd / TextEnd, in the reference's order and
+// with the reference's arguments) is replayed into the caller's TokenWriter, so custom
+// writers (token_writer.go:27-33) keep working.  Inputs on which the reference panics
+// make this function panic with the same cause.
+func (t *Tokenizer) TransduceTokenWriter(r io.Reader, w *datok.TokenWriter) bool {
+	defer w.Flush() // matrix.go:374
+	in, err := io.ReadAll(r)
+	if err != nil {
+		log.Fatalln(err) // matrix.go:401
+		return false
+	}
+	var p *C.uint8_t
+	if len(in) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&in[0]))
+	}
+	var res *C.datok_result
+	rc := C.datok_transduce(t.model, p, C.size_t(len(in)), C.uint32_t(C.DATOK_TOKENS|C.DATOK_SENTENCES), nil, &res)
+	if rc != C.DATOK_OK {
+		if rc <= C.DATOK_ERR_DEGENERATE {
+			panic(errors.New(C.GoString(C.datok_strerror(rc)))) // the reference panics here too
+		}
+		log.Println(C.GoString(C.datok_last_error()))
+		return false
+	}
+	defer C.datok_result_free(res)
+	h := cgo.NewHandle(w)
+	defer h.Delete()
+	C.datok_replay_go(res, p, C.size_t(len(in)), unsafe.Pointer(&h))
+	return true
+}
+
+//export goDatokToken
+func goDatokToken(user unsafe.Pointer, buf *C.uint8_t, bufBytes C.size_t, offBytes C.size_t, offRunes C.int32_t) {
+	w := (*cgo.Handle)(user).Value().(*datok.TokenWriter)
+	// []rune(string(bytes)) decodes exactly like bufio.Reader.ReadRune: one U+FFFD per bad byte
+	runes := []rune(string(C.GoBytes(unsafe.Pointer(buf), C.int(bufBytes))))
+	w.Token(int(offRunes), runes)
+}
+
+//export goDatokSentenceEnd
+func goDatokSentenceEnd(user unsafe.Pointer) {
+	(*cgo.Handle)(user).Value().(*datok.TokenWriter).SentenceEnd(0)
+}
+
+//export goDatokTextEnd
+func goDatokTextEnd(user unsafe.Pointer) {
+	(*cgo.Handle)(user).Value().(*datok.TokenWriter).TextEnd(0)
+}
+
+// Offsets is the array-level result for callers that do not need the closure replay:
+// the TokenWriter's pos / sent lists and the token byte spans, straight from the GPU.
+type Offsets struct {
+	TokBytes []uint32 // 2 per token: surface = in[TokBytes[2k]:TokBytes[2k+1]]
+	TokPos   []int32  // 2 per token: text-relative rune offsets (TokenWriter.pos)
+	SentPos  []int32  // TokenWriter.sent entries
+	TextTok  []uint32 // per TextEnd: tokens emitted so far
+}
+
+// TransduceOffsets runs the path and copies the offset arrays out of the pinned result.
+func (t *Tokenizer) TransduceOffsets(in []byte, flags datok.Bits) (*Offsets, error) {
+	var p *C.uint8_t
+	if len(in) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&in[0]))
+	}
+	var res *C.datok_result
+	if rc := C.datok_transduce(t.model, p, C.size_t(len(in)), C.uint32_t(flags), nil, &res); rc != C.DATOK_OK {
+		return nil, errors.New(C.GoString(C.datok_strerror(rc)))
+	}
+	defer C.datok_result_free(res)
+	v := C.datok_result_view(res)
+	nt, ns, nx := int(v.n_tokens), int(v.n_sent_pos), int(v.n_texts)
+	o := &Offsets{}
+	if v.tok_bytes != nil {
+		o.TokBytes = append(o.TokBytes, unsafe.Slice((*uint32)(unsafe.Pointer(v.tok_bytes)), 2*nt)...)
+	}
+	if v.tok_pos != nil {
+		o.TokPos = append(o.TokPos, unsafe.Slice((*int32)(unsafe.Pointer(v.tok_pos)), 2*nt)...)
+	}
+	if v.sent_pos != nil {
+		o.SentPos = append(o.SentPos, unsafe.Slice((*int32)(unsafe.Pointer(v.sent_pos)), ns)...)
+	}
+	o.TextTok = append(o.TextTok, unsafe.Slice((*uint32)(unsafe.Pointer(v.text_tok_end)), nx)...)
+	return o, nil
+}
