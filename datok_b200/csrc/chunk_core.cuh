@@ -140,9 +140,13 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   st.pos = st.tstart = st.base = st.hw = 0;
   st.eps_pos = 0; st.eps_state = 0; st.flags = 0; st.t = (uint16_t)start_state;
   FastLane L;
-  L.pos = L.tstart = L.base = L.eps_pos = L.eps_b = L.hw_med = L.first_hw = 0;
-  L.t = start_state;
+  L.pos = L.tstart = L.base = L.eps_p = L.eps_rec = L.hw_med = L.first_hw = 0;
+  L.stale_end = L.raw_from = 0;
+  L.u_in = 1;
+  L.trow = start_state * FT.row_bytes;
   L.first_window = (i != 0 && !rewalk);  // a guessed start: the first window's overflow check is deferred (SpecInfo)
+  RawBits R;
+  R.c1 = R.c2 = R.nt = 0;
   bool started = (i == 0) || rewalk, fast = true, halted = false;
   uint32_t sync = (i == 0) ? 0u : K_NOPOS;
   uint32_t err = 0;
@@ -158,9 +162,9 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
 
   for (uint32_t seg_start = first_seg; seg_start < hi; seg_start += SEG) {
     const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
-    uint32_t rs;
+    uint32_t rs, eotm;
     bool inv = false;
-    classify_segment(b.in, N, seg_start, m.cls, seg_cls, &rs, &inv);
+    classify_segment(b.in, N, seg_start, m.cls, seg_cls, &rs, &eotm, &inv);
     if (!rewalk) {
       b.rstart[w] = rs;
       if (inv) note_invalid_utf8(b);
@@ -170,8 +174,9 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       sync = find_sync(b.in, N, m.sync_ascii, seg_start, seg_end < hi ? seg_end : hi);
       if (sync == K_NOPOS) continue;
       started = true;
-      L.pos = L.tstart = L.base = L.hw_med = sync;
-      L.t = m.start;
+      L.pos = L.tstart = L.base = L.hw_med = L.raw_from = sync;
+      L.u_in = 1;
+      L.trow = m.start * FT.row_bytes;
     }
     B.end = B.skip = B.sent = B.tend = 0;
     bool in_regs = true;  // the segment's boundary words live in B (else in memory)
@@ -184,12 +189,15 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       fast = false;
     }
     bool must_walk_exact = false;  // the fast path just gave up at st.pos: the exact walker has to move first
+    const uint32_t limit = seg_end < N ? seg_end : N;
     for (;;) {
       if (fast) {
-        int rc = FAST_OK;
-        while (L.pos < seg_end && L.pos < N) {
-          rc = fast_step(L, FT, seg_cls, seg_start, B);
-          if (rc != FAST_OK) break;
+        const int rc = fast_run(L, R, FT, seg_cls, seg_start, limit, eotm, B);
+        if (!fast_flush(L, R, B, eotm, seg_start)) {  // two SentenceEnds at one position
+          err = E_DEGENERATE;
+          st = wstate_invalid(E_DEGENERATE);
+          halted = true;
+          break;
         }
         if (rc == FAST_OK && L.pos >= seg_end) break;  // segment done, stay fast
         lane_note_first_rewind(L, B, seg_start);
@@ -203,7 +211,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
           seg_end - st.base < FAST_WINDOW_GUARD) {
         if (!in_regs) { load_seg_bits(b, w, B); in_regs = true; }
         if (st.flags & WS_PEND) { B.end |= 1u << (st.pos - seg_start); st.flags &= ~WS_PEND; }
-        to_fast(st, L);
+        to_fast(st, FT, L, R);
         fast = true;
         continue;
       }
@@ -220,7 +228,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       if (err || (st.flags & WS_DONE)) { halted = true; break; }
       must_walk_exact = false;
     }
-    if (fast) {
+    if (fast && !halted) {
       lane_note_first_rewind(L, B, seg_start);
       L.base = lane_base(L, B, seg_start);
     }

@@ -5,13 +5,17 @@
 //      into a small class buffer (shared memory in the kernel) and produces the
 //      rune-start word,
 //   2. steps through the classes with ONE fused-table lookup per byte
-//      (model.hpp: T2 folds "fail -> epsilon at this position -> re-read",
-//      matrix.go:472-497,563-576), accumulating the boundary bits of the segment
-//      in registers,
-//   3. stores the four boundary words of the segment.
+//      (model.hpp: T3 folds "fail -> epsilon at this position -> re-read",
+//      matrix.go:472-497,563-576).  A step only records what the table entry says
+//      about its byte in three RAW masks (boundaries before the byte: >= 1, == 2;
+//      consumed by a non-token transition) and remembers the latest epsilon point,
+//   3. derives the four boundary words of the segment from the raw masks with
+//      word-parallel logic (derive_bits): the reference's bufft/"token pending"
+//      bookkeeping (matrix.go:563-591) is a carry chain over the segment, evaluated
+//      with one 64-bit addition instead of per-byte branches.
 // Real backtracks (to an epsilon point recorded at an earlier byte, matrix.go:487-497)
-// are handled in place when the point lies in the current segment; anything else
-// that is rare -- far backtracks, hard fails, stale buffer offsets, the window-limit
+// are handled in place when the point lies in the raw range of the current segment;
+// anything else that is rare -- far backtracks, hard fails, the window-limit
 // vicinity, chunk hand-off, EOF -- drops to the exact walker walk_run() for the rest
 // of the segment.  Both walkers are step-equivalent, so a lane can switch between
 // them at any loop top.
@@ -22,43 +26,64 @@
 namespace datok {
 
 constexpr uint32_t SEG = 32;                 // bytes per segment = bits per bitmap word
-constexpr uint32_t T2K_SHIFT = 16;
-constexpr uint32_t T2_EPS = 1u << 18;
-constexpr uint32_t T2_SLOWMARK = 1u << 31;
+// fused table entry (model.hpp)
+constexpr uint32_t T3_NT = 1u;               // the consuming transition is a non-token one (FIRSTBIT)
+constexpr uint32_t T3_EA = 2u;               // the state that consumes the byte has an epsilon transition
+constexpr uint32_t T3_OFF = 0x03FFFFFCu;     // byte offset of the target state's row
+constexpr uint32_t T3_K1 = 1u << 26, T3_K2 = 1u << 27, T3_KANY = T3_K1 | T3_K2;  // epsilon steps before the byte: 1, 2
+constexpr uint32_t T3_KSHIFT = 26;
+constexpr uint32_t T3_SLOWMARK = 1u << 31;
 constexpr uint32_t FAST_WINDOW_GUARD = 960;  // stay exact when the buffer window could reach 1024 runes
 
 struct FastTables {
-  const uint32_t* hot;     // fused rows of states 0..n_hot-1 (shared memory in the kernel)
+  const uint32_t* hot;     // fused rows of the hottest states (shared memory in the kernel)
   const uint32_t* cold;    // the full fused table (global memory)
-  uint32_t n_hot;
-  uint32_t stride;         // entries per row (odd)
+  uint32_t hot_bytes;      // rows with byte offset < hot_bytes are in `hot`
+  uint32_t row_bytes;      // bytes per row
+  uint32_t hot_saddr;      // device only: shared-window address of `hot`
 };
 
-DATOK_HD uint32_t t2_lookup(const FastTables& T, uint32_t t, uint32_t cl) {
-  const uint32_t idx = t * T.stride + cl;
-  return t < T.n_hot ? T.hot[idx] : T.cold[idx];
-}
-
-// eps_b: [14:0] state at the loop top where the point was recorded, [17:16] epsilon
-// steps taken there before the byte was consumed, [18] a token was pending, [19] valid
-constexpr uint32_t EB_PENDING = 1u << 18, EB_VALID = 1u << 19;
-
-#if defined(__CUDACC__)
-#define DATOK_UNLIKELY(x) __builtin_expect(!!(x), 0)
+// entry at byte offset `off` (= row offset + 4 * class)
+DATOK_HD uint32_t t3_load(const FastTables& T, uint32_t off) {
+#if defined(__CUDA_ARCH__)
+  // both loads predicated instead of a divergent branch: lanes on cold rows do not split the warp
+  uint32_t e;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.lt.u32 p, %1, %2;\n\t"
+      "@p ld.shared.u32 %0, [%3];\n\t"
+      "@!p ld.global.nc.u32 %0, [%4];\n\t}"
+      : "=r"(e)
+      : "r"(off), "r"(T.hot_bytes), "r"(T.hot_saddr + off), "l"(reinterpret_cast<const uint8_t*>(T.cold) + off));
+  return e;
 #else
-#define DATOK_UNLIKELY(x) __builtin_expect(!!(x), 0)
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(off < T.hot_bytes ? T.hot : T.cold);
+  return *reinterpret_cast<const uint32_t*>(base + off);
 #endif
+}
+// target row of the epsilon transition of the state at row `row` (0: none)
+DATOK_HD uint32_t t3_eps(const FastTables& T, uint32_t row) { return t3_load(T, row + 4u * K_CLS_EPS) & T3_OFF; }
 
 struct FastLane {
-  uint32_t pos, tstart;
-  uint32_t base;                 // last rewind point known at the START of the current segment;
-                                 // rewinds inside the segment are read off the END/TEND bits (lane_base)
-  uint32_t t;
-  uint32_t eps_pos, eps_b;
-  uint32_t hw_med;               // furthest failing position seen by an in-place backtrack (never reset:
-                                 // an over-estimate from an older window cannot fake an overflow, see to_exact)
-  uint32_t first_hw;             // SpecInfo of a guessed start: hw at the first rewind
-  uint32_t first_window;         // 1 until the first rewind of a guessed start
+  uint32_t pos;
+  uint32_t trow;           // row byte offset of the current state
+  uint32_t tstart;         // token start (base + bufft) as of raw_from
+  uint32_t base;           // last rewind point known at the START of the current segment
+  uint32_t eps_p, eps_rec; // latest epsilon point: position, row at that loop top | the entry's k bits (0: none).
+                           // Checked lazily: a later boundary or EOT kills it (eps_alive)
+  uint32_t hw_med;         // furthest failing position seen by an in-place backtrack (never reset:
+                           // an over-estimate from an older window cannot fake an overflow, see to_exact)
+  uint32_t first_hw;       // SpecInfo of a guessed start: hw at the first rewind
+  uint32_t first_window;   // 1 until the first rewind of a guessed start
+  uint32_t stale_end;      // bufft is stale (> buffc) below this position (SentenceEnd backtrack over skipped runes)
+  uint32_t raw_from;       // the raw masks cover [raw_from, pos)
+  uint32_t u_in;           // 1: tstart == raw_from at raw_from (nothing pending there)
+};
+
+// what the steps of the current segment recorded, one bit per byte position
+struct RawBits {
+  uint32_t c1, c2;         // >= 1 / == 2 boundaries (epsilon transitions) taken before the byte was consumed
+  uint32_t nt;             // consumed by a non-token transition (or inside a stale-bufft zone)
 };
 
 struct SegBits {
@@ -66,6 +91,70 @@ struct SegBits {
 };
 
 enum { FAST_OK = 0, FAST_SLOW = 1 };
+
+#define DATOK_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+#define DATOK_STAT(x) ((x)++)
+#else
+#define DATOK_STAT(x) ((void)0)
+#endif
+
+// Boundary words of the positions [ro, po) of a segment from the raw masks.
+//   u[p] = "bufft == buffc at the loop top of p" obeys  u[p+1] = ((u[p] | c1[p]) & nt[p]) | eot[p]
+// (matrix.go:584-588: a leading non-token rune moves bufft along; :565-572,:601-603: Token and
+// EOT rewind), i.e. a carry chain with generate (c1 & nt) | eot and propagate nt.
+//   END  = c1 & ~u          first boundary with something pending: Token      (:565-572)
+//   SENT = (c1 & u) | c2    boundary with nothing pending: SentenceEnd        (:573-576)
+//   SKIP = (u | c1) & nt    leading non-token rune                            (:584-588)
+// deg: two SentenceEnds at one position (not representable, walk_run reports it the same way).
+struct Derived {
+  uint32_t u;              // bits [ro, po)
+  uint32_t end, sent, skip, tend, deg;
+  uint32_t u_at_pos;       // u at position po
+};
+DATOK_HD Derived derive_bits(const RawBits& R, uint32_t eotm, uint32_t ro, uint32_t po, uint32_t u_in) {
+  Derived D;
+  const uint32_t lim = mask_below(po) & mask_from(ro);
+  const uint32_t eot = eotm & lim;
+  const uint32_t x = R.nt | eot, g = (R.c1 & R.nt) | eot;
+  const unsigned long long s = (unsigned long long)x + g + ((unsigned long long)(u_in & 1u) << ro);
+  const uint32_t carries = (uint32_t)s ^ x ^ g;
+  D.u_at_pos = po < 32 ? ((carries >> po) & 1u) : (uint32_t)(s >> 32);
+  D.u = carries & lim;
+  D.end = R.c1 & ~D.u;
+  D.sent = (R.c1 & D.u) | R.c2;
+  D.skip = (D.u | R.c1) & R.nt;
+  D.tend = eot;
+  D.deg = R.c2 & D.u;
+  return D;
+}
+
+// token start at position po given the derived words (L.tstart if it was not moved in [ro, po))
+DATOK_HD uint32_t derived_tstart(const FastLane& L, const RawBits& R, const Derived& D, uint32_t seg_start, uint32_t po) {
+  uint32_t ts;
+  if (D.u_at_pos) ts = seg_start + po;
+  else {
+    const uint32_t m = (D.u | R.c1) & ~R.nt;  // bufft was set here and the byte was not skipped
+    ts = m ? seg_start + 31u - clz32(m) : L.tstart;
+  }
+  if (seg_start + po < L.stale_end) ts = L.stale_end;
+  return ts;
+}
+
+// is the recorded epsilon point still the reference's epsilonState?  A Token/SentenceEnd
+// boundary after it (matrix.go:608-627 clears it on rewind; a SentenceEnd consumes it) or a
+// consumed EOT at or after it (:601-603) kills it.
+DATOK_HD bool eps_alive(const FastLane& L, const RawBits& R, uint32_t eotm, uint32_t seg_start, uint32_t po) {
+  if (!L.eps_rec) return false;
+  uint32_t above = 0xFFFFFFFFu, from = 0xFFFFFFFFu;
+  if (L.eps_p >= seg_start) {
+    const uint32_t qo = L.eps_p - seg_start;
+    from = mask_from(qo);
+    above = mask_from(qo + 1);
+  }
+  const uint32_t consumed = mask_below(po) & mask_from(L.raw_from > seg_start ? L.raw_from - seg_start : 0);
+  return ((R.c1 & above) | (eotm & from & consumed)) == 0;
+}
 
 // last rewind point, taking the boundary bits of the current segment into account
 DATOK_HD uint32_t lane_base(const FastLane& L, const SegBits& B, uint32_t seg_start) {
@@ -84,24 +173,47 @@ DATOK_HD void lane_note_first_rewind(FastLane& L, const SegBits& B, uint32_t seg
 DATOK_HD bool can_go_fast(const WState& st) {
   return (st.flags & ~WS_PEND) == 0 && st.tstart <= st.pos;
 }
-DATOK_HD void to_fast(const WState& st, FastLane& L) {
-  L.pos = st.pos; L.tstart = st.tstart; L.base = st.base; L.t = st.t;
-  L.eps_pos = st.eps_pos;
-  L.eps_b = st.eps_state ? (EB_VALID | st.eps_state | (st.eps_pos > st.tstart ? EB_PENDING : 0)) : 0;
+DATOK_HD void to_fast(const WState& st, const FastTables& T, FastLane& L, RawBits& R) {
+  L.pos = st.pos; L.tstart = st.tstart; L.base = st.base; L.trow = (uint32_t)st.t * T.row_bytes;
+  L.eps_p = st.eps_pos;
+  L.eps_rec = st.eps_state ? (uint32_t)st.eps_state * T.row_bytes : 0;  // k = 0: the state itself has the transition
   L.hw_med = st.hw;
+  L.stale_end = 0;
+  L.raw_from = st.pos;
+  L.u_in = st.tstart == st.pos ? 1u : 0u;
+  R.c1 = R.c2 = R.nt = 0;
 }
-// fast lane -> exact state (resolves the lazily stored epsilon point and window base)
+
+// Closes the raw range [raw_from, pos) of the segment: merges its boundary words into B and
+// moves the lane's token start / unstarted flag to pos.  Returns false on a degenerate event
+// sequence.  Afterwards the raw masks are empty and raw_from == pos.
+DATOK_HD bool fast_flush(FastLane& L, RawBits& R, SegBits& B, uint32_t eotm, uint32_t seg_start) {
+  const uint32_t po = L.pos - seg_start;
+  const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
+  const Derived D = derive_bits(R, eotm, ro, po, L.u_in);
+  const bool alive = eps_alive(L, R, eotm, seg_start, po);
+  B.end |= D.end; B.sent |= D.sent; B.skip |= D.skip; B.tend |= D.tend;
+  L.tstart = derived_tstart(L, R, D, seg_start, po);
+  L.u_in = (L.tstart == L.pos) ? 1u : 0u;
+  if (!alive) L.eps_rec = 0;
+  L.raw_from = L.pos;
+  R.c1 = R.c2 = R.nt = 0;
+  return D.deg == 0;
+}
+
+// fast lane (flushed: raw range empty) -> exact state
 DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, const FastTables& T, WState& st) {
   const uint32_t base = lane_base(L, B, seg_start);
-  st.pos = L.pos; st.tstart = L.tstart; st.base = base; st.t = (uint16_t)L.t;
+  st.pos = L.pos; st.tstart = L.tstart; st.base = base; st.t = (uint16_t)(L.trow / T.row_bytes);
   st.flags = 0;
   uint32_t es = 0;
-  if (L.eps_b & EB_VALID) {
-    es = L.eps_b & 0x7FFFu;
-    for (uint32_t k = (L.eps_b >> T2K_SHIFT) & 3u; k; k--) es = t2_lookup(T, es, K_CLS_EPS) & 0x7FFFu;
+  if (L.eps_rec) {
+    es = L.eps_rec & T3_OFF;
+    for (uint32_t k = (L.eps_rec >> T3_KSHIFT) & 3u; k; k--) es = t3_eps(T, es);
+    es /= T.row_bytes;
   }
   st.eps_state = (uint16_t)es;
-  st.eps_pos = es ? L.eps_pos : 0;
+  st.eps_pos = es ? L.eps_p : 0;
   // hw: furthest byte read in the current buffer window.  hw_med may stem from an older window;
   // it was a real read then, [base, hw_med] is contained in that older window, so counting its
   // runes can never exceed what the reference itself had buffered.
@@ -111,87 +223,103 @@ DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, 
   st.hw = hw;
 }
 
-// In-place backtrack to the epsilon point recorded in this segment (matrix.go:487-497),
-// or FAST_SLOW (nothing changed) when the exact walker has to take over.
-DATOK_HD int fast_backtrack(FastLane& L, const FastTables& T, uint32_t seg_start, SegBits& B) {
-#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
-  if (!(L.eps_b & EB_VALID)) g_hard++; else if (L.eps_pos < seg_start) g_far++;
-#endif
-  if (!(L.eps_b & EB_VALID) || L.eps_pos < seg_start) return FAST_SLOW;  // hard fail / far backtrack
-  const uint32_t bbit = 1u << (L.eps_pos - seg_start);
-  const bool pending = (L.eps_b & EB_PENDING) != 0;
-  if (!pending && (B.sent & bbit)) return FAST_SLOW;  // second SentenceEnd at one position
-  uint32_t cur = L.eps_b & 0x7FFFu;
-  for (uint32_t k = (L.eps_b >> T2K_SHIFT) & 3u; k; k--) cur = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
-  const uint32_t tgt = t2_lookup(T, cur, K_CLS_EPS) & 0x7FFFu;
+// In-place backtrack to the epsilon point recorded in the raw range of this segment
+// (matrix.go:487-497), or FAST_SLOW (nothing changed) when the exact walker has to take over.
+// Bprev: boundary words of the segment's positions before raw_from.
+DATOK_HD int fast_backtrack(FastLane& L, RawBits& R, const FastTables& T, const uint8_t* seg_cls, uint32_t seg_start,
+                            uint32_t eotm, const SegBits& Bprev) {
+  if (!L.eps_rec) { DATOK_STAT(g_bt_hard); return FAST_SLOW; }                                 // hard fail
+  if (L.eps_p < L.raw_from || L.eps_p < seg_start) { DATOK_STAT(g_bt_far); return FAST_SLOW; }  // far backtrack
+  const uint32_t po = L.pos - seg_start, qo = L.eps_p - seg_start, qb = 1u << qo;
+  if (!eps_alive(L, R, eotm, seg_start, po)) { DATOK_STAT(g_bt_dead); return FAST_SLOW; }  // the point is dead: hard fail
+  if (R.c2 & qb) { DATOK_STAT(g_bt_third); return FAST_SLOW; }                             // third boundary at one position
+  const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
+  const Derived D = derive_bits(R, eotm, ro, po, L.u_in);
+  // epsilon transition(s) from the recorded loop-top state
+  uint32_t es = L.eps_rec & T3_OFF;
+  for (uint32_t k = (L.eps_rec >> T3_KSHIFT) & 3u; k; k--) es = t3_eps(T, es);
+  const uint32_t tgt = t3_eps(T, es);
   if (L.hw_med < L.pos) L.hw_med = L.pos;
-  if (pending) {  // Token + rewind (:565-572)
-    if (L.first_window) {
-      const uint32_t m = (B.end | B.tend) & (bbit - 1u);
-      L.first_hw = m ? seg_start + ctz32(m) : L.hw_med;
-      L.first_window = 0;
-    }
-    B.end |= bbit;
-    L.tstart = L.eps_pos;
-  } else {
-    B.sent |= bbit;  // SentenceEnd (:573-576)
+  if (!((D.u | R.c1) & qb) && L.first_window) {  // Token + rewind (:565-572): closes a guessed start's first window
+    const uint32_t m = ((D.end | D.tend) & (qb - 1u)) | Bprev.end | Bprev.tend;
+    L.first_hw = m ? seg_start + ctz32(m) : L.hw_med;
+    L.first_window = 0;
   }
-  L.pos = L.eps_pos;
-  L.eps_b = 0;
-  L.t = tgt;
+  // bytes from q on that the first pass skipped as leading non-token runes stay skipped: bufft is
+  // not reset by a SentenceEnd (:573-576), it is stale until buffc catches up with it
+  uint32_t zone = 0;
+  if (D.skip & qb) {
+    const uint32_t s = D.skip + qb;       // the carry runs through the skip run that starts at q
+    zone = D.skip & ~s & mask_from(qo);
+    L.stale_end = seg_start + qo + popc32(zone);
+    DATOK_STAT(g_zone);
+  }
+  const uint32_t keep = (qb << 1) - 1u;   // positions <= q
+  R.c2 = (R.c2 | (R.c1 & qb)) & keep;
+  R.c1 = (R.c1 | qb) & keep;
+  R.nt = (R.nt & (qb - 1u)) | zone;
+  L.pos = L.eps_p;
+  L.eps_rec = 0;
+  L.trow = tgt;
+  DATOK_STAT(g_bt_ok);
+  // The byte at q is read again from the new state.  Its epsilon steps ADD to the boundaries q already
+  // holds (the plain step only ORs), so this one step is taken here.
+  const uint32_t e = t3_load(T, tgt + 4u * seg_cls[qo]);
+  if ((e & T3_OFF) == 0) return FAST_SLOW;  // fails again or marked: walk_run continues at this loop top
+  if (e & T3_KANY) {
+    if ((R.c2 & qb) || (e & T3_K2)) return FAST_SLOW;  // a third boundary at q
+    R.c2 |= qb;
+  }
+  if (e & T3_NT) R.nt |= qb;
+  if (e & T3_EA) { L.eps_p = L.pos; L.eps_rec = tgt | (e & T3_KANY); }
+  L.trow = e & T3_OFF;
+  L.pos++;
   return FAST_OK;
 }
 
-// One loop-top iteration of the reference at L.pos, which must lie in the segment
-// [seg_start, seg_start+32) whose classes are seg_cls[0..31].  On FAST_SLOW nothing
-// has been changed and the exact walker must take over at L.pos.
-DATOK_HD int fast_step(FastLane& L, const FastTables& T, const uint8_t* seg_cls, uint32_t seg_start, SegBits& B) {
+// Loop-top iterations of the reference from L.pos up to `limit` (<= seg_start + 32) over the
+// classes seg_cls[0..31] of the segment.  On FAST_SLOW nothing has been changed by the failing
+// iteration and the exact walker must take over at L.pos.
+DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_t* seg_cls, uint32_t seg_start,
+                      uint32_t limit, uint32_t eotm, const SegBits& Bprev) {
+  if (L.pos >= limit) return FAST_OK;
+  // positions are tracked as (class pointer, one-hot bit) so that a step needs no index arithmetic
+  const uint32_t lim_off = limit - seg_start;
+  const uint32_t end_bit = lim_off < 32 ? 1u << lim_off : 0u;
+  uint32_t off = L.pos - seg_start;
+  uint32_t bit = 1u << off;
+  uint32_t trow = L.trow, eps_off = L.eps_p - seg_start, eps_rec = L.eps_rec;  // eps_off wraps for older points
+  uint32_t c1 = R.c1, c2 = R.c2, nt = R.nt;
+  int rc = FAST_OK;
+  do {
+    const uint32_t e = t3_load(T, trow + 4u * seg_cls[off]);
+    DATOK_STAT(g_fast);
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
-  g_fast++;
+    if (trow >= T.hot_bytes) g_cold++;
+    if (e & T3_SLOWMARK) g_mark++;
 #endif
-  const uint32_t off = L.pos - seg_start;
-  const uint32_t cl = seg_cls[off];
-  const uint32_t e = t2_lookup(T, L.t, cl);
-  const uint32_t bit = 1u << off;
-  if (DATOK_UNLIKELY((int32_t)e <= 0)) {  // 0: failure without epsilon transition; bit 31: leave to walk_run
-#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
-    g_bt++;
-#endif
-#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
-    if (e != 0) g_mark++;
-#endif
-    if (e != 0) return FAST_SLOW;
-    return fast_backtrack(L, T, seg_start, B);
-  }
-  const uint32_t k = (e >> T2K_SHIFT) & 3u;
-  const bool is_eps = k != 0;
-  const bool pending = L.pos > L.tstart;
-  const bool two = k == 2;
-  // k epsilon steps before the byte is consumed: Token if something is pending, else SentenceEnd
-  {
-    // a second SentenceEnd at one position is left to walk_run (it reports the degenerate case)
-    const uint32_t sent_here = (B.sent & bit) != 0;
-    const uint32_t bad = (uint32_t)is_eps & ((sent_here & (uint32_t)!(pending && !two)) | (uint32_t)(two && !pending));
-    if (DATOK_UNLIKELY(bad)) return FAST_SLOW;
-  }
-  B.end |= (is_eps && pending) ? bit : 0u;
-  B.sent |= ((is_eps && !pending) || two) ? bit : 0u;
-  if (is_eps) { L.tstart = L.pos; L.eps_b = 0; }
-  if (e & T2_EPS) {
-    L.eps_pos = L.pos;
-    L.eps_b = EB_VALID | L.t | (e & (3u << T2K_SHIFT)) | ((!is_eps && pending) ? EB_PENDING : 0u);
-  }
-  const uint32_t next = L.pos + 1;
-  const bool skip = (L.tstart == L.pos) && (e & K_NT);  // :584-588
-  B.skip |= skip ? bit : 0u;
-  L.tstart = skip ? next : L.tstart;
-  if (DATOK_UNLIKELY(cl == K_CLS_EOT)) {  // :593-605 (the forced SentenceEnd is derived by the compaction)
-    B.tend |= bit;
-    L.tstart = next; L.eps_b = 0;
-  }
-  L.t = e & 0x7FFFu;
-  L.pos = next;
-  return FAST_OK;
+    if (DATOK_UNLIKELY((e & T3_OFF) == 0)) {  // 0: failure without epsilon transition; marked: leave to walk_run
+      L.pos = seg_start + off; L.trow = trow; L.eps_p = seg_start + eps_off; L.eps_rec = eps_rec;
+      R.c1 = c1; R.c2 = c2; R.nt = nt;
+      if (e != 0) return FAST_SLOW;
+      rc = fast_backtrack(L, R, T, seg_cls, seg_start, eotm, Bprev);
+      if (rc != FAST_OK) return rc;
+      off = L.pos - seg_start; bit = off < 32 ? 1u << off : 0u;
+      trow = L.trow; eps_off = L.eps_p - seg_start; eps_rec = L.eps_rec;
+      c1 = R.c1; c2 = R.c2; nt = R.nt;
+      continue;
+    }
+    if (e & T3_KANY) c1 |= bit;
+    if (e & T3_K2) c2 |= bit;
+    if (e & T3_NT) nt |= bit;
+    if (e & T3_EA) { eps_off = off; eps_rec = trow | (e & T3_KANY); }
+    trow = e & T3_OFF;
+    off++;
+    bit <<= 1;
+  } while (bit != end_bit);
+  L.pos = seg_start + off; L.trow = trow; L.eps_p = seg_start + eps_off; L.eps_rec = eps_rec;
+  R.c1 = c1; R.c2 = c2; R.nt = nt;
+  return rc;
 }
 
 // loads the 32 raw bytes at `p` (zero padded beyond N) as 8 little-endian words
@@ -224,12 +352,13 @@ DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_sta
 // Classes and rune starts of the 32 bytes at seg_start (bytes >= N: no rune start,
 // class unspecified).  seg_cls must be 4-byte aligned.  ASCII bytes go through the
 // LUT four at a time; the few other bytes are decoded afterwards, one rune each.
+// *eot_word: positions holding the byte 0x04 (matrix.go:13,422).
 DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start, const ClsTables& T,
-                               uint8_t* seg_cls, uint32_t* rstart_word, bool* any_invalid) {
+                               uint8_t* seg_cls, uint32_t* rstart_word, uint32_t* eot_word, bool* any_invalid) {
   uint32_t words[8];
   load_segment_words(in, N, seg_start, words);
   uint32_t* out = reinterpret_cast<uint32_t*>(seg_cls);
-  uint32_t nonascii = 0;
+  uint32_t nonascii = 0, eot_any = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -240,8 +369,17 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
     out[k] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
     const uint32_t h = v & 0x80808080u;
     nonascii |= (((h >> 7) | (h >> 14) | (h >> 21) | (h >> 28)) & 0xFu) << (4 * k);
+    const uint32_t x = v ^ 0x04040404u;
+    eot_any |= (x - 0x01010101u) & ~x & 0x80808080u;  // some byte of v is 0x04 (exact as an "any" test)
   }
   const uint32_t valid = (seg_start + SEG <= N) ? 0xFFFFFFFFu : mask_below(N > seg_start ? N - seg_start : 0);
+  uint32_t eot = 0;
+  if (DATOK_UNLIKELY(eot_any != 0)) {
+    for (int k = 0; k < 8; k++)
+      for (int j = 0; j < 4; j++)
+        if (((words[k] >> (8 * j)) & 0xFFu) == 0x04u) eot |= 1u << (4 * k + j);
+  }
+  *eot_word = eot & valid;
   uint32_t rs = ~nonascii & valid;
   uint32_t m = nonascii & valid;
   while (m) {

@@ -43,7 +43,11 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   lm.cls.ascii_cls = s_lut;
   lm.cls.latin1_cls = s_lut + 128;
   FastTables FT;
-  FT.hot = s_hot; FT.cold = m.table2; FT.n_hot = n_hot; FT.stride = m.stride2;
+  FT.hot = s_hot; FT.cold = m.table2; FT.hot_bytes = n_hot * m.stride2 * 4u; FT.row_bytes = m.stride2 * 4u;
+  {  // opaque to the compiler: otherwise the shared-window base is re-derived in every step of the hot loop
+    const unsigned long long sa = __cvta_generic_to_shared(s_hot);
+    asm volatile("cvt.u32.u64 %0, %1;" : "=r"(FT.hot_saddr) : "l"(sa));
+  }
   uint8_t* my_cls = s_cls + threadIdx.x * LANE_CLS_STRIDE;
   for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * THREADS)
     chunk_spec_fast(lm, b, FT, i, start_state, my_cls);
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(WALK_THREADS) rewalk_kernel(DeviceModel m, Wal
   // n_rewalk is only the launch bound; the list length was counted on the device by stitch_kernel
   if (k >= n_rewalk || k >= b.counters[1]) return;
   FastTables FT;
-  FT.hot = m.table2; FT.cold = m.table2; FT.n_hot = 0; FT.stride = m.stride2;
+  FT.hot = m.table2; FT.cold = m.table2; FT.hot_bytes = 0; FT.row_bytes = m.stride2 * 4u; FT.hot_saddr = 0;
   chunk_rewalk_fast(m, b, FT, b.list_rewalk[k], s_cls + threadIdx.x * LANE_CLS_STRIDE);
 }
 

@@ -235,39 +235,47 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
     if ((m.sync_mask[c >> 5] >> (c & 31)) & 1u) m.sync_ascii[bch >> 5] |= 1u << (bch & 31);
   }
 
-  // --- fused table T2 ---
+  // --- fused table T3 ---
   // At the loop top in state t reading class c the reference (matrix.go:437-497):
   //   records the epsilon point (t, here) if t has an epsilon transition, looks up
   //   (t, c); on failure with that point recorded it backtracks by 0 runes, takes the
   //   epsilon transition (Token or SentenceEnd), and re-reads c from the new state.
-  // T2[t][c] is the transition that finally consumes c, with the number of epsilon
+  // T3[t][c] is the transition that finally consumes c, with the number of epsilon
   // steps before it.  0: failure in a state without epsilon transition (backtrack to an
-  // older point or hard fail).  T2_SLOW: anything else the fast path leaves to walk_run().
+  // older point or hard fail).  T3_SLOW: anything else the fast path leaves to walk_run().
+  // Targets are stored as the BYTE OFFSET of the target state's row, so that a step is
+  // "mask, add class*4, load".
   m.stride2 = m.n_classes | 1u;
+  const size_t row_bytes = (size_t)m.stride2 * 4;
+  if (((size_t)S + 1) * row_bytes > (size_t)T3_OFFMASK) { why = "fused table exceeds 64 MB"; return DATOK_ERR_UNSUPPORTED_MODEL; }
   m.table2.assign(((size_t)S + 1) * m.stride2, 0);
+  // An in-place backtrack can stack the epsilon steps of two lookups at one position; with at most two
+  // chained epsilon transitions in the model that never exceeds the two boundaries a position can hold.
+  const bool fast_ok = m.max_eps_chain <= 2;
   for (int t = 1; t <= S; t++) {
     uint32_t* row2 = &m.table2[(size_t)t * m.stride2];
     const uint16_t* row = &m.table[(size_t)t * R];
-    row2[CLS_EPS] = row[CLS_EPS];
+    row2[CLS_EPS] = (uint32_t)((row[CLS_EPS] & 0x7FFFu) * row_bytes);
     for (uint32_t c = CLS_CONT; c < m.n_classes; c++) {
       uint32_t cur = (uint32_t)t, k = 0, e = 0;
       for (;;) {
         const uint16_t* r = &m.table[(size_t)cur * R];
         if (r[c] != 0) {
-          e = r[c] | (k << T2_K_SHIFT) | (r[CLS_EPS] != 0 ? T2_EPSBIT : 0);
+          e = (uint32_t)((r[c] & 0x7FFFu) * row_bytes) | ((r[c] & NT_BIT) ? T3_NTBIT : 0u) | (k << T3_K_SHIFT) |
+              (r[CLS_EPS] != 0 ? T3_EPSBIT : 0u);
           break;
         }
         if (r[CLS_EPS] == 0) {
           // failure in a state without epsilon transition.  k == 0: the walk backtracks to an
           // OLDER point or fails hard (entry 0).  k > 0: hard fail right after the epsilon steps.
-          if (k) e = T2_SLOW;
+          if (k) e = T3_SLOW;
           break;
         }
-        if (k == 2) { e = T2_SLOW; break; }  // more than two epsilon steps at one position
+        if (k == 2) { e = T3_SLOW; break; }  // more than two epsilon steps at one position
         cur = r[CLS_EPS] & 0x7FFFu;
         k++;
       }
-      row2[c] = e;
+      row2[c] = fast_ok ? e : T3_SLOW;
     }
   }
   return DATOK_OK;

@@ -10,7 +10,7 @@
 //     reference's FIRSTBIT "non-token" flag (datok.go:43), bits 0..14 = target,
 //   * states are renumbered by expected visit frequency, so that the hottest
 //     rows are the ones with the smallest ids (they are kept in shared memory),
-//   * a second, "fused" table T2 (u32) folds the reference's fail -> backtrack to
+//   * a second, "fused" table T3 (u32) folds the reference's fail -> backtrack to
 //     the epsilon recorded at the same position -> take epsilon -> re-read
 //     sequence (matrix.go:472-497,563-576) into one lookup per input byte.
 #pragma once
@@ -25,12 +25,16 @@ constexpr uint32_t CLS_CONT = 1;  // UTF-8 continuation byte of a valid sequence
 constexpr uint32_t CLS_EOT = 2;   // the byte 0x04 (matrix.go:13,422)
 constexpr uint32_t CLS_FIRST = 3; // first ordinary class
 constexpr uint16_t NT_BIT = 0x8000;
-// fused table entry: [14:0] target, [15] non-token, [17:16] number of epsilon
-// transitions taken before the byte is consumed, [18] the state the byte is finally
-// consumed from has an epsilon transition itself.  0 = not decidable locally.
-constexpr uint32_t T2_K_SHIFT = 16;
-constexpr uint32_t T2_EPSBIT = 1u << 18;
-constexpr uint32_t T2_SLOW = 1u << 31;  // leave this (state, class) to the exact walker
+// fused table entry (u32): [25:2] byte offset of the target state's row in the fused table,
+// [0] non-token transition, [1] the state the byte is finally consumed from has an epsilon
+// transition itself, [27:26] number of epsilon transitions taken before the byte is consumed.
+// 0 = not decidable locally (older epsilon point or hard fail).  Column CLS_EPS holds the row
+// offset of the epsilon transition's target (0: none).
+constexpr uint32_t T3_NTBIT = 1u;
+constexpr uint32_t T3_EPSBIT = 2u;
+constexpr uint32_t T3_OFFMASK = 0x03FFFFFCu;
+constexpr uint32_t T3_K_SHIFT = 26;
+constexpr uint32_t T3_SLOW = 1u << 31;  // leave this (state, class) to the exact walker
 
 struct HostModel {
   // --- reference view (ParseMatrix) ---

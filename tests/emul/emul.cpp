@@ -97,8 +97,9 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
     FastTables FT;
     std::vector<uint32_t> hot(em->hm.table2.begin(),
                               em->hm.table2.begin() + std::min<size_t>(em->hm.table2.size(), (size_t)mode * m.stride2));
-    FT.hot = hot.data(); FT.cold = m.table2; FT.n_hot = (uint32_t)std::min<size_t>(mode, em->hm.stateCount + 1);
-    FT.stride = m.stride2;
+    FT.hot = hot.data(); FT.cold = m.table2;
+    FT.hot_bytes = (uint32_t)std::min<size_t>(mode, em->hm.stateCount + 1) * m.stride2 * 4u;
+    FT.row_bytes = m.stride2 * 4u;
     uint8_t seg_cls[32];
     for (uint32_t k = 0; k < b.n_chunks; k++)
       chunk_spec_fast(m, b, FT, order ? b.n_chunks - 1 - k : k, start_state, seg_cls);
@@ -106,7 +107,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   R->has_invalid = counters[2];
 
   FastTables FTr;
-  FTr.hot = m.table2; FTr.cold = m.table2; FTr.n_hot = 0; FTr.stride = m.stride2;
+  FTr.hot = m.table2; FTr.cold = m.table2; FTr.hot_bytes = 0; FTr.row_bytes = m.stride2 * 4u;
   uint8_t seg_cls_r[36];
   // K2b-d fix-up rounds
   std::vector<uint32_t> list, next, rew;
