@@ -235,11 +235,13 @@ int upload_model(datok_model* m) {
   if (m->d_cls_tables) { cudaFree(m->d_cls_tables); m->d_cls_tables = nullptr; }
   if (m->d_rune_key) { cudaFree(m->d_rune_key); m->d_rune_key = nullptr; }
   const size_t t2_bytes = align_up(h.table2.size() * sizeof(uint32_t), 256);
-  const size_t t1_bytes = h.table.size() * sizeof(uint16_t);
-  m->d_tables_bytes = t2_bytes + t1_bytes;
+  const size_t t1_bytes = align_up(h.table.size() * sizeof(uint16_t), 256);
+  const size_t h16_bytes = h.hot16.size() * sizeof(uint16_t);
+  m->d_tables_bytes = t2_bytes + t1_bytes + h16_bytes;
   CUDA_TRY(cudaMalloc(&m->d_tables, m->d_tables_bytes));
   CUDA_TRY(cudaMemcpy(m->d_tables, h.table2.data(), h.table2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(m->d_tables + t2_bytes, h.table.data(), t1_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(m->d_tables + t2_bytes, h.table.data(), h.table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(m->d_tables + t2_bytes + t1_bytes, h.hot16.data(), h16_bytes, cudaMemcpyHostToDevice));
   const size_t nr = h.rune_key.size();
   std::vector<uint8_t> blob(256 + nr + 16, 0);
   std::memcpy(blob.data(), h.ascii_cls, 128);
@@ -252,7 +254,9 @@ int upload_model(datok_model* m) {
   DeviceModel& d = m->dm;
   d.table2 = reinterpret_cast<const uint32_t*>(m->d_tables);
   d.table = reinterpret_cast<const uint16_t*>(m->d_tables + t2_bytes);
+  d.hot16 = reinterpret_cast<const uint16_t*>(m->d_tables + t2_bytes + t1_bytes);
   d.row_shift = h.row_shift; d.start = h.start; d.n_classes = h.n_classes; d.stride2 = h.stride2;
+  d.stride16 = h.stride16; d.hot16_rows = h.hot16_rows;
   d.cls.ascii_cls = m->d_cls_tables;
   d.cls.latin1_cls = m->d_cls_tables + 128;
   d.cls.rune_cls = m->d_cls_tables + 256;

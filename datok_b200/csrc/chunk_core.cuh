@@ -27,8 +27,9 @@ constexpr uint32_t CF_OVERWRITTEN = 2;  // the speculative trace has been replac
 
 struct DeviceModel {
   const uint16_t* table;   // exact table (walk_run)
-  const uint32_t* table2;  // fused table (fast_step), stride2 entries per row
-  uint32_t row_shift, start, n_classes, stride2;
+  const uint32_t* table2;  // fused table T3 (fast_run), stride2 entries per row
+  const uint16_t* hot16;   // compact rows of the first hot16_rows states, stride16 entries per row
+  uint32_t row_shift, start, n_classes, stride2, stride16, hot16_rows;
   ClsTables cls;           // pointers into device memory
   uint32_t sync_ascii[4];  // ASCII bytes the root state skips: a chunk may start right after one
 };
@@ -143,10 +144,10 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   L.pos = L.tstart = L.base = L.eps_p = L.eps_rec = L.hw_med = L.first_hw = 0;
   L.stale_end = L.raw_from = 0;
   L.u_in = 1;
-  L.trow = start_state * FT.row_bytes;
+  L.t = start_state;
   L.first_window = (i != 0 && !rewalk);  // a guessed start: the first window's overflow check is deferred (SpecInfo)
   RawBits R;
-  R.c1 = R.c2 = R.nt = 0;
+  raw_clear(R);
   bool started = (i == 0) || rewalk, fast = true, halted = false;
   uint32_t sync = (i == 0) ? 0u : K_NOPOS;
   uint32_t err = 0;
@@ -164,7 +165,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
     uint32_t rs, eotm;
     bool inv = false;
-    classify_segment(b.in, N, seg_start, m.cls, seg_cls, &rs, &eotm, &inv);
+    classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, seg_cls, &rs, &eotm, &inv);
     if (!rewalk) {
       b.rstart[w] = rs;
       if (inv) note_invalid_utf8(b);
@@ -176,7 +177,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       started = true;
       L.pos = L.tstart = L.base = L.hw_med = L.raw_from = sync;
       L.u_in = 1;
-      L.trow = m.start * FT.row_bytes;
+      L.t = m.start;
     }
     B.end = B.skip = B.sent = B.tend = 0;
     bool in_regs = true;  // the segment's boundary words live in B (else in memory)
@@ -211,7 +212,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
           seg_end - st.base < FAST_WINDOW_GUARD) {
         if (!in_regs) { load_seg_bits(b, w, B); in_regs = true; }
         if (st.flags & WS_PEND) { B.end |= 1u << (st.pos - seg_start); st.flags &= ~WS_PEND; }
-        to_fast(st, FT, L, R);
+        to_fast(st, L, R);
         fast = true;
         continue;
       }

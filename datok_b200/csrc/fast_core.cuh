@@ -26,50 +26,60 @@
 namespace datok {
 
 constexpr uint32_t SEG = 32;                 // bytes per segment = bits per bitmap word
-// fused table entry (model.hpp)
-constexpr uint32_t T3_NT = 1u;               // the consuming transition is a non-token one (FIRSTBIT)
-constexpr uint32_t T3_EA = 2u;               // the state that consumes the byte has an epsilon transition
-constexpr uint32_t T3_OFF = 0x03FFFFFCu;     // byte offset of the target state's row
-constexpr uint32_t T3_K1 = 1u << 26, T3_K2 = 1u << 27, T3_KANY = T3_K1 | T3_K2;  // epsilon steps before the byte: 1, 2
-constexpr uint32_t T3_KSHIFT = 26;
-constexpr uint32_t T3_SLOWMARK = 1u << 31;
+// fused table T3 (u32) and the compact hot rows (u16): see model.hpp
+constexpr uint32_t F3_TGT = 0x7FFFu, F3_NT = 1u << 15, F3_K1 = 1u << 16, F3_K2 = 1u << 17, F3_KANY = F3_K1 | F3_K2,
+                   F3_EA = 1u << 18, F3_SLOWMARK = 1u << 31;
+constexpr uint32_t F16_TGT = 0x0FFFu, F16_NT = 1u << 12, F16_EA = 1u << 13, F16_K1 = 1u << 14, F16_K2 = 1u << 15,
+                   F16_KANY = F16_K1 | F16_K2,
+                   F16_FAIL = F16_NT;  // target 0 + this flag: the full table says 0 (failure without epsilon transition)
+// eps_rec: [14:0] state at the loop top where the point was recorded, [17:16] epsilon steps taken
+// there before the byte was consumed, [19] valid
+constexpr uint32_t ER_VALID = 1u << 19;
 constexpr uint32_t FAST_WINDOW_GUARD = 960;  // stay exact when the buffer window could reach 1024 runes
 
 struct FastTables {
-  const uint32_t* hot;     // fused rows of the hottest states (shared memory in the kernel)
-  const uint32_t* cold;    // the full fused table (global memory)
-  uint32_t hot_bytes;      // rows with byte offset < hot_bytes are in `hot`
-  uint32_t row_bytes;      // bytes per row
-  uint32_t hot_saddr;      // device only: shared-window address of `hot`
+  const uint16_t* hot16;   // compact rows of states 0..n_hot-1, targets >= n_hot already zeroed, plus one all-zero
+                           // row n_hot (shared memory in the kernel)
+  const uint32_t* t3;      // the full fused table (global memory)
+  uint32_t n_hot;
+  uint32_t row16;          // BYTES per compact row
+  uint32_t stride3;        // entries per T3 row
+  uint32_t hot_saddr;      // device only: shared-window address of hot16
+  const uint8_t* ascii_cls2;  // 2 * class of the ASCII bytes (shared memory in the kernel)
 };
 
-// entry at byte offset `off` (= row offset + 4 * class)
-DATOK_HD uint32_t t3_load(const FastTables& T, uint32_t off) {
+// compact entry of hot state t (< n_hot) for the doubled class cl2 = 2 * class
+DATOK_HD uint32_t h16_load(const FastTables& T, uint32_t t, uint32_t cl2) {
 #if defined(__CUDA_ARCH__)
-  // both loads predicated instead of a divergent branch: lanes on cold rows do not split the warp
   uint32_t e;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.lt.u32 p, %1, %2;\n\t"
-      "@p ld.shared.u32 %0, [%3];\n\t"
-      "@!p ld.global.nc.u32 %0, [%4];\n\t}"
-      : "=r"(e)
-      : "r"(off), "r"(T.hot_bytes), "r"(T.hot_saddr + off), "l"(reinterpret_cast<const uint8_t*>(T.cold) + off));
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(T.hot_saddr + t * T.row16 + cl2));
   return e;
 #else
-  const uint8_t* base = reinterpret_cast<const uint8_t*>(off < T.hot_bytes ? T.hot : T.cold);
-  return *reinterpret_cast<const uint32_t*>(base + off);
+  return *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(T.hot16) + t * T.row16 + cl2);
 #endif
 }
-// target row of the epsilon transition of the state at row `row` (0: none)
-DATOK_HD uint32_t t3_eps(const FastTables& T, uint32_t row) { return t3_load(T, row + 4u * K_CLS_EPS) & T3_OFF; }
+DATOK_HD uint32_t t3_load(const FastTables& T, uint32_t t, uint32_t cl) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(T.t3 + t * T.stride3 + cl);
+#else
+  return T.t3[t * T.stride3 + cl];
+#endif
+}
+// target of the epsilon transition of state t (0: none)
+DATOK_HD uint32_t eps_target(const FastTables& T, uint32_t t) {
+  if (t < T.n_hot) {
+    const uint32_t h = h16_load(T, t, 2u * K_CLS_EPS);
+    if (h) return h;
+  }
+  return t3_load(T, t, K_CLS_EPS) & F3_TGT;
+}
 
 struct FastLane {
   uint32_t pos;
-  uint32_t trow;           // row byte offset of the current state
+  uint32_t t;              // current state
   uint32_t tstart;         // token start (base + bufft) as of raw_from
   uint32_t base;           // last rewind point known at the START of the current segment
-  uint32_t eps_p, eps_rec; // latest epsilon point: position, row at that loop top | the entry's k bits (0: none).
+  uint32_t eps_p, eps_rec; // latest epsilon point: position, ER_* record (0: none).
                            // Checked lazily: a later boundary or EOT kills it (eps_alive)
   uint32_t hw_med;         // furthest failing position seen by an in-place backtrack (never reset:
                            // an over-estimate from an older window cannot fake an overflow, see to_exact)
@@ -82,7 +92,8 @@ struct FastLane {
 
 // what the steps of the current segment recorded, one bit per byte position
 struct RawBits {
-  uint32_t c1, c2;         // >= 1 / == 2 boundaries (epsilon transitions) taken before the byte was consumed
+  uint32_t c1, c2;         // >= 1 / == 2 epsilon steps in the lookup that consumed the byte
+  uint32_t cb;             // an in-place backtrack added one boundary before the byte
   uint32_t nt;             // consumed by a non-token transition (or inside a stale-bufft zone)
 };
 
@@ -99,16 +110,18 @@ enum { FAST_OK = 0, FAST_SLOW = 1 };
 #define DATOK_STAT(x) ((void)0)
 #endif
 
-// Boundary words of the positions [ro, po) of a segment from the raw masks.
-//   u[p] = "bufft == buffc at the loop top of p" obeys  u[p+1] = ((u[p] | c1[p]) & nt[p]) | eot[p]
+// Boundary words of the positions [ro, po) of a segment from the raw masks.  With
+//   n1 = c1 | cb   (at least one boundary before the byte),  n2 = c2 | (c1 & cb)  (two),
+//   u[p] = "bufft == buffc at the loop top of p" obeys  u[p+1] = ((u[p] | n1[p]) & nt[p]) | eot[p]
 // (matrix.go:584-588: a leading non-token rune moves bufft along; :565-572,:601-603: Token and
-// EOT rewind), i.e. a carry chain with generate (c1 & nt) | eot and propagate nt.
-//   END  = c1 & ~u          first boundary with something pending: Token      (:565-572)
-//   SENT = (c1 & u) | c2    boundary with nothing pending: SentenceEnd        (:573-576)
-//   SKIP = (u | c1) & nt    leading non-token rune                            (:584-588)
+// EOT rewind), i.e. a carry chain with generate (n1 & nt) | eot and propagate nt.
+//   END  = n1 & ~u          first boundary with something pending: Token      (:565-572)
+//   SENT = (n1 & u) | n2    boundary with nothing pending: SentenceEnd        (:573-576)
+//   SKIP = (u | n1) & nt    leading non-token rune                            (:584-588)
 // deg: two SentenceEnds at one position (not representable, walk_run reports it the same way).
 struct Derived {
   uint32_t u;              // bits [ro, po)
+  uint32_t n1;
   uint32_t end, sent, skip, tend, deg;
   uint32_t u_at_pos;       // u at position po
 };
@@ -116,16 +129,18 @@ DATOK_HD Derived derive_bits(const RawBits& R, uint32_t eotm, uint32_t ro, uint3
   Derived D;
   const uint32_t lim = mask_below(po) & mask_from(ro);
   const uint32_t eot = eotm & lim;
-  const uint32_t x = R.nt | eot, g = (R.c1 & R.nt) | eot;
+  const uint32_t n1 = R.c1 | R.cb, n2 = R.c2 | (R.c1 & R.cb);
+  const uint32_t x = R.nt | eot, g = (n1 & R.nt) | eot;
   const unsigned long long s = (unsigned long long)x + g + ((unsigned long long)(u_in & 1u) << ro);
   const uint32_t carries = (uint32_t)s ^ x ^ g;
   D.u_at_pos = po < 32 ? ((carries >> po) & 1u) : (uint32_t)(s >> 32);
   D.u = carries & lim;
-  D.end = R.c1 & ~D.u;
-  D.sent = (R.c1 & D.u) | R.c2;
-  D.skip = (D.u | R.c1) & R.nt;
+  D.n1 = n1;
+  D.end = n1 & ~D.u;
+  D.sent = (n1 & D.u) | n2;
+  D.skip = (D.u | n1) & R.nt;
   D.tend = eot;
-  D.deg = R.c2 & D.u;
+  D.deg = (n2 & D.u) | (R.c2 & R.cb);
   return D;
 }
 
@@ -134,7 +149,7 @@ DATOK_HD uint32_t derived_tstart(const FastLane& L, const RawBits& R, const Deri
   uint32_t ts;
   if (D.u_at_pos) ts = seg_start + po;
   else {
-    const uint32_t m = (D.u | R.c1) & ~R.nt;  // bufft was set here and the byte was not skipped
+    const uint32_t m = (D.u | D.n1) & ~R.nt;  // bufft was set here and the byte was not skipped
     ts = m ? seg_start + 31u - clz32(m) : L.tstart;
   }
   if (seg_start + po < L.stale_end) ts = L.stale_end;
@@ -153,7 +168,7 @@ DATOK_HD bool eps_alive(const FastLane& L, const RawBits& R, uint32_t eotm, uint
     above = mask_from(qo + 1);
   }
   const uint32_t consumed = mask_below(po) & mask_from(L.raw_from > seg_start ? L.raw_from - seg_start : 0);
-  return ((R.c1 & above) | (eotm & from & consumed)) == 0;
+  return (((R.c1 | R.cb) & above) | (eotm & from & consumed)) == 0;
 }
 
 // last rewind point, taking the boundary bits of the current segment into account
@@ -173,15 +188,16 @@ DATOK_HD void lane_note_first_rewind(FastLane& L, const SegBits& B, uint32_t seg
 DATOK_HD bool can_go_fast(const WState& st) {
   return (st.flags & ~WS_PEND) == 0 && st.tstart <= st.pos;
 }
-DATOK_HD void to_fast(const WState& st, const FastTables& T, FastLane& L, RawBits& R) {
-  L.pos = st.pos; L.tstart = st.tstart; L.base = st.base; L.trow = (uint32_t)st.t * T.row_bytes;
+DATOK_HD void raw_clear(RawBits& R) { R.c1 = R.c2 = R.cb = R.nt = 0; }
+DATOK_HD void to_fast(const WState& st, FastLane& L, RawBits& R) {
+  L.pos = st.pos; L.tstart = st.tstart; L.base = st.base; L.t = st.t;
   L.eps_p = st.eps_pos;
-  L.eps_rec = st.eps_state ? (uint32_t)st.eps_state * T.row_bytes : 0;  // k = 0: the state itself has the transition
+  L.eps_rec = st.eps_state ? (ER_VALID | st.eps_state) : 0;  // k = 0: the state itself has the transition
   L.hw_med = st.hw;
   L.stale_end = 0;
   L.raw_from = st.pos;
   L.u_in = st.tstart == st.pos ? 1u : 0u;
-  R.c1 = R.c2 = R.nt = 0;
+  raw_clear(R);
 }
 
 // Closes the raw range [raw_from, pos) of the segment: merges its boundary words into B and
@@ -197,20 +213,19 @@ DATOK_HD bool fast_flush(FastLane& L, RawBits& R, SegBits& B, uint32_t eotm, uin
   L.u_in = (L.tstart == L.pos) ? 1u : 0u;
   if (!alive) L.eps_rec = 0;
   L.raw_from = L.pos;
-  R.c1 = R.c2 = R.nt = 0;
+  raw_clear(R);
   return D.deg == 0;
 }
 
 // fast lane (flushed: raw range empty) -> exact state
 DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, const FastTables& T, WState& st) {
   const uint32_t base = lane_base(L, B, seg_start);
-  st.pos = L.pos; st.tstart = L.tstart; st.base = base; st.t = (uint16_t)(L.trow / T.row_bytes);
+  st.pos = L.pos; st.tstart = L.tstart; st.base = base; st.t = (uint16_t)L.t;
   st.flags = 0;
   uint32_t es = 0;
   if (L.eps_rec) {
-    es = L.eps_rec & T3_OFF;
-    for (uint32_t k = (L.eps_rec >> T3_KSHIFT) & 3u; k; k--) es = t3_eps(T, es);
-    es /= T.row_bytes;
+    es = L.eps_rec & F3_TGT;
+    for (uint32_t k = (L.eps_rec >> 16) & 3u; k; k--) es = eps_target(T, es);
   }
   st.eps_state = (uint16_t)es;
   st.eps_pos = es ? L.eps_p : 0;
@@ -226,100 +241,149 @@ DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, 
 // In-place backtrack to the epsilon point recorded in the raw range of this segment
 // (matrix.go:487-497), or FAST_SLOW (nothing changed) when the exact walker has to take over.
 // Bprev: boundary words of the segment's positions before raw_from.
-DATOK_HD int fast_backtrack(FastLane& L, RawBits& R, const FastTables& T, const uint8_t* seg_cls, uint32_t seg_start,
-                            uint32_t eotm, const SegBits& Bprev) {
+DATOK_HD int fast_backtrack(FastLane& L, RawBits& R, const FastTables& T, uint32_t seg_start, uint32_t eotm,
+                            const SegBits& Bprev) {
   if (!L.eps_rec) { DATOK_STAT(g_bt_hard); return FAST_SLOW; }                                 // hard fail
   if (L.eps_p < L.raw_from || L.eps_p < seg_start) { DATOK_STAT(g_bt_far); return FAST_SLOW; }  // far backtrack
   const uint32_t po = L.pos - seg_start, qo = L.eps_p - seg_start, qb = 1u << qo;
   if (!eps_alive(L, R, eotm, seg_start, po)) { DATOK_STAT(g_bt_dead); return FAST_SLOW; }  // the point is dead: hard fail
-  if (R.c2 & qb) { DATOK_STAT(g_bt_third); return FAST_SLOW; }                             // third boundary at one position
-  const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
-  const Derived D = derive_bits(R, eotm, ro, po, L.u_in);
+  if ((R.c2 | R.cb) & qb) { DATOK_STAT(g_bt_third); return FAST_SLOW; }                   // would be a third boundary at q
   // epsilon transition(s) from the recorded loop-top state
-  uint32_t es = L.eps_rec & T3_OFF;
-  for (uint32_t k = (L.eps_rec >> T3_KSHIFT) & 3u; k; k--) es = t3_eps(T, es);
-  const uint32_t tgt = t3_eps(T, es);
+  uint32_t es = L.eps_rec & F3_TGT;
+  for (uint32_t k = (L.eps_rec >> 16) & 3u; k; k--) es = eps_target(T, es);
+  const uint32_t tgt = eps_target(T, es);
   if (L.hw_med < L.pos) L.hw_med = L.pos;
-  if (!((D.u | R.c1) & qb) && L.first_window) {  // Token + rewind (:565-572): closes a guessed start's first window
-    const uint32_t m = ((D.end | D.tend) & (qb - 1u)) | Bprev.end | Bprev.tend;
-    L.first_hw = m ? seg_start + ctz32(m) : L.hw_med;
-    L.first_window = 0;
-  }
-  // bytes from q on that the first pass skipped as leading non-token runes stay skipped: bufft is
-  // not reset by a SentenceEnd (:573-576), it is stale until buffc catches up with it
   uint32_t zone = 0;
-  if (D.skip & qb) {
-    const uint32_t s = D.skip + qb;       // the carry runs through the skip run that starts at q
-    zone = D.skip & ~s & mask_from(qo);
-    L.stale_end = seg_start + qo + popc32(zone);
-    DATOK_STAT(g_zone);
+  if (DATOK_UNLIKELY(L.first_window || (R.nt & qb))) {
+    const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
+    const Derived D = derive_bits(R, eotm, ro, po, L.u_in);
+    if (!((D.u | D.n1) & qb) && L.first_window) {  // Token + rewind (:565-572): closes a guessed start's first window
+      const uint32_t m = ((D.end | D.tend) & (qb - 1u)) | Bprev.end | Bprev.tend;
+      L.first_hw = m ? seg_start + ctz32(m) : L.hw_med;
+      L.first_window = 0;
+    }
+    // bytes from q on that the first pass skipped as leading non-token runes stay skipped: bufft is
+    // not reset by a SentenceEnd (:573-576), it is stale until buffc catches up with it
+    if (D.skip & qb) {
+      const uint32_t s = D.skip + qb;       // the carry runs through the skip run that starts at q
+      zone = D.skip & ~s & mask_from(qo);
+      L.stale_end = seg_start + qo + popc32(zone);
+      DATOK_STAT(g_zone);
+    }
   }
-  const uint32_t keep = (qb << 1) - 1u;   // positions <= q
-  R.c2 = (R.c2 | (R.c1 & qb)) & keep;
-  R.c1 = (R.c1 | qb) & keep;
-  R.nt = (R.nt & (qb - 1u)) | zone;
+  const uint32_t keep = (qb << 1) - 1u, below = qb - 1u;   // positions <= q, < q
+  // the byte at q is read again: its own lookup bits are cleared, the boundary taken here is kept in cb.
+  // (c1 at q set: that lookup's epsilon step came first; the chain bound of model.cpp rules out more.)
+  R.c2 &= below;
+  R.c1 &= keep;
+  R.cb = (R.cb & below) | qb;
+  R.nt = (R.nt & below) | zone;
   L.pos = L.eps_p;
   L.eps_rec = 0;
-  L.trow = tgt;
+  L.t = tgt;
   DATOK_STAT(g_bt_ok);
-  // The byte at q is read again from the new state.  Its epsilon steps ADD to the boundaries q already
-  // holds (the plain step only ORs), so this one step is taken here.
-  const uint32_t e = t3_load(T, tgt + 4u * seg_cls[qo]);
-  if ((e & T3_OFF) == 0) return FAST_SLOW;  // fails again or marked: walk_run continues at this loop top
-  if (e & T3_KANY) {
-    if ((R.c2 & qb) || (e & T3_K2)) return FAST_SLOW;  // a third boundary at q
-    R.c2 |= qb;
-  }
-  if (e & T3_NT) R.nt |= qb;
-  if (e & T3_EA) { L.eps_p = L.pos; L.eps_rec = tgt | (e & T3_KANY); }
-  L.trow = e & T3_OFF;
-  L.pos++;
   return FAST_OK;
 }
 
 // Loop-top iterations of the reference from L.pos up to `limit` (<= seg_start + 32) over the
-// classes seg_cls[0..31] of the segment.  On FAST_SLOW nothing has been changed by the failing
-// iteration and the exact walker must take over at L.pos.
+// DOUBLED classes seg_cls[0..31] of the segment.  On FAST_SLOW nothing has been changed by the
+// failing iteration and the exact walker must take over at L.pos.
+//
+// One loop for all lanes of a warp: a lane that needs the rare path (cold state, failure) takes
+// it inside the iteration and rejoins the others at the end of the same iteration.
+// eps_rec inside the loop: [14:0] state at the loop top, [31:30] epsilon steps of that lookup
+// (the compact entry shifted up by 16); converted to the ER_* form on exit.
 DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_t* seg_cls, uint32_t seg_start,
                       uint32_t limit, uint32_t eotm, const SegBits& Bprev) {
   if (L.pos >= limit) return FAST_OK;
-  // positions are tracked as (class pointer, one-hot bit) so that a step needs no index arithmetic
   const uint32_t lim_off = limit - seg_start;
   const uint32_t end_bit = lim_off < 32 ? 1u << lim_off : 0u;
   uint32_t off = L.pos - seg_start;
   uint32_t bit = 1u << off;
-  uint32_t trow = L.trow, eps_off = L.eps_p - seg_start, eps_rec = L.eps_rec;  // eps_off wraps for older points
+  uint32_t t = L.t, eps_off = L.eps_p - seg_start;  // eps_off wraps for older points
+  uint32_t eps_rec = L.eps_rec ? ((L.eps_rec & F3_TGT) | ((L.eps_rec & F3_KANY) << 14)) : 0;
   uint32_t c1 = R.c1, c2 = R.c2, nt = R.nt;
-  int rc = FAST_OK;
-  do {
-    const uint32_t e = t3_load(T, trow + 4u * seg_cls[off]);
-    DATOK_STAT(g_fast);
-#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
-    if (trow >= T.hot_bytes) g_cold++;
-    if (e & T3_SLOWMARK) g_mark++;
+#if defined(__CUDA_ARCH__)
+  const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(seg_cls);
 #endif
-    if (DATOK_UNLIKELY((e & T3_OFF) == 0)) {  // 0: failure without epsilon transition; marked: leave to walk_run
-      L.pos = seg_start + off; L.trow = trow; L.eps_p = seg_start + eps_off; L.eps_rec = eps_rec;
-      R.c1 = c1; R.c2 = c2; R.nt = nt;
-      if (e != 0) return FAST_SLOW;
-      rc = fast_backtrack(L, R, T, seg_cls, seg_start, eotm, Bprev);
-      if (rc != FAST_OK) return rc;
-      off = L.pos - seg_start; bit = off < 32 ? 1u << off : 0u;
-      trow = L.trow; eps_off = L.eps_p - seg_start; eps_rec = L.eps_rec;
-      c1 = R.c1; c2 = R.c2; nt = R.nt;
+  // row of the lookup: the state's own, or the all-zero row n_hot ("see the full table") for a cold state,
+  // which the loop top only sees on entry: the rare path below steps until the state is hot again
+  uint32_t tl = t < T.n_hot ? t : T.n_hot;
+  do {
+    // ---- one compact-row lookup per byte ----
+    uint32_t e;
+#if defined(__CUDA_ARCH__)
+    {
+      uint32_t cl2;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cl2) : "r"(cls_saddr + off));
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(T.hot_saddr + tl * T.row16 + cl2));
+    }
+#else
+    e = h16_load(T, tl, seg_cls[off]);
+#endif
+    if (DATOK_UNLIKELY((e & F16_TGT) == 0)) {
+      // ---- rare: failure (F16_FAIL), or not in the compact rows (0): cold state, target outside
+      // the hot rows, marked entry.  Steps through the full table until the state is hot again ----
+      bool failed = e == F16_FAIL;
+      for (;;) {
+        uint32_t e3 = 0;
+        if (!failed) {
+          DATOK_STAT(g_cold);
+          e3 = t3_load(T, t, (uint32_t)seg_cls[off] >> 1);
+        }
+        if ((e3 & F3_TGT) == 0) {  // 0: failure without epsilon transition; marked: leave to walk_run
+          L.pos = seg_start + off; L.t = t; L.eps_p = seg_start + eps_off;
+          L.eps_rec = eps_rec ? (ER_VALID | (eps_rec & F3_TGT) | ((eps_rec >> 14) & F3_KANY)) : 0;
+          R.c1 = c1; R.c2 = c2; R.nt = nt;
+          if (e3 != 0) { DATOK_STAT(g_mark); return FAST_SLOW; }
+          if (fast_backtrack(L, R, T, seg_start, eotm, Bprev) != FAST_OK) return FAST_SLOW;
+          off = L.pos - seg_start; bit = 1u << off;
+          t = L.t; eps_rec = 0;
+          c1 = R.c1; c2 = R.c2; nt = R.nt;
+          failed = false;
+        } else {
+          DATOK_STAT(g_fast);
+          if (e3 & F3_KANY) c1 |= bit;
+          if (e3 & F3_K2) c2 |= bit;
+          if (e3 & F3_NT) nt |= bit;
+          if (e3 & F3_EA) { eps_off = off; eps_rec = t | ((e3 & F3_KANY) << 14); }
+          t = e3 & F3_TGT;
+          off++;
+          bit += bit;
+        }
+        if (t < T.n_hot || bit == end_bit) break;
+      }
+      tl = t < T.n_hot ? t : T.n_hot;
       continue;
     }
-    if (e & T3_KANY) c1 |= bit;
-    if (e & T3_K2) c2 |= bit;
-    if (e & T3_NT) nt |= bit;
-    if (e & T3_EA) { eps_off = off; eps_rec = trow | (e & T3_KANY); }
-    trow = e & T3_OFF;
+    DATOK_STAT(g_fast);
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred pk, p2, pn, pe;\n\t.reg .b32 x;\n\t"
+        "and.b32 x, %5, 0xC000;\n\tsetp.ne.u32 pk, x, 0;\n\t"
+        "and.b32 x, %5, 0x8000;\n\tsetp.ne.u32 p2, x, 0;\n\t"
+        "and.b32 x, %5, 0x1000;\n\tsetp.ne.u32 pn, x, 0;\n\t"
+        "and.b32 x, %5, 0x2000;\n\tsetp.ne.u32 pe, x, 0;\n\t"
+        "@pk or.b32 %0, %0, %6;\n\t"
+        "@p2 or.b32 %1, %1, %6;\n\t"
+        "@pn or.b32 %2, %2, %6;\n\t"
+        "@pe mov.b32 %3, %7;\n\t"
+        "@pe mad.lo.u32 %4, %5, 65536, %8;\n\t}"
+        : "+r"(c1), "+r"(c2), "+r"(nt), "+r"(eps_off), "+r"(eps_rec)
+        : "r"(e), "r"(bit), "r"(off), "r"(t));
+#else
+    if (e & F16_KANY) c1 |= bit;
+    if (e & F16_K2) c2 |= bit;
+    if (e & F16_NT) nt |= bit;
+    if (e & F16_EA) { eps_off = off; eps_rec = t | (e << 16); }
+#endif
+    t = tl = e & F16_TGT;
     off++;
-    bit <<= 1;
+    bit += bit;
   } while (bit != end_bit);
-  L.pos = seg_start + off; L.trow = trow; L.eps_p = seg_start + eps_off; L.eps_rec = eps_rec;
+  L.pos = seg_start + off; L.t = t; L.eps_p = seg_start + eps_off;
+  L.eps_rec = eps_rec ? (ER_VALID | (eps_rec & F3_TGT) | ((eps_rec >> 14) & F3_KANY)) : 0;
   R.c1 = c1; R.c2 = c2; R.nt = nt;
-  return rc;
+  return FAST_OK;
 }
 
 // loads the 32 raw bytes at `p` (zero padded beyond N) as 8 little-endian words
@@ -349,12 +413,13 @@ DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_sta
   }
 }
 
-// Classes and rune starts of the 32 bytes at seg_start (bytes >= N: no rune start,
-// class unspecified).  seg_cls must be 4-byte aligned.  ASCII bytes go through the
-// LUT four at a time; the few other bytes are decoded afterwards, one rune each.
+// DOUBLED classes (2 * class: the byte offset into a compact table row) and rune starts of the
+// 32 bytes at seg_start (bytes >= N: no rune start, class unspecified).  seg_cls must be 4-byte
+// aligned.  ASCII bytes go through the LUT `ascii_cls2` (2 * class per ASCII byte) four at a
+// time; the few other bytes are decoded afterwards, one rune each.
 // *eot_word: positions holding the byte 0x04 (matrix.go:13,422).
 DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start, const ClsTables& T,
-                               uint8_t* seg_cls, uint32_t* rstart_word, uint32_t* eot_word, bool* any_invalid) {
+                               const uint8_t* ascii_cls2, uint8_t* seg_cls, uint32_t* rstart_word, uint32_t* eot_word, bool* any_invalid) {
   uint32_t words[8];
   load_segment_words(in, N, seg_start, words);
   uint32_t* out = reinterpret_cast<uint32_t*>(seg_cls);
@@ -364,9 +429,9 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
 #endif
   for (int k = 0; k < 8; k++) {
     const uint32_t v = words[k];
-    const uint32_t c0 = T.ascii_cls[v & 0x7Fu], c1 = T.ascii_cls[(v >> 8) & 0x7Fu];
-    const uint32_t c2 = T.ascii_cls[(v >> 16) & 0x7Fu], c3 = T.ascii_cls[(v >> 24) & 0x7Fu];
-    out[k] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+    const uint32_t c0 = ascii_cls2[v & 0x7Fu], c1 = ascii_cls2[(v >> 8) & 0x7Fu];
+    const uint32_t c2 = ascii_cls2[(v >> 16) & 0x7Fu], c3 = ascii_cls2[(v >> 24) & 0x7Fu];
+    out[k] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);  // the LUT already holds 2 * class
     const uint32_t h = v & 0x80808080u;
     nonascii |= (((h >> 7) | (h >> 14) | (h >> 21) | (h >> 28)) & 0xFu) << (4 * k);
     const uint32_t x = v ^ 0x04040404u;
@@ -388,7 +453,7 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
     const uint32_t p = seg_start + j;
     bool st, inv;
     const uint32_t cl = classify_pos(in, N, p, T, &st, &inv);
-    seg_cls[j] = (uint8_t)cl;
+    seg_cls[j] = (uint8_t)(2u * cl);
     if (st) rs |= 1u << j;
     if (inv) *any_invalid = true;
     if (st && !inv) {
@@ -396,7 +461,7 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
       const uint32_t b0 = in[p];
       const uint32_t wdt = b0 >= 0xF0 ? 4u : b0 >= 0xE0 ? 3u : 2u;
       for (uint32_t q = 1; q < wdt && j + q < SEG; q++) {
-        seg_cls[j + q] = (uint8_t)K_CLS_CONT;
+        seg_cls[j + q] = (uint8_t)(2u * K_CLS_CONT);
         m &= ~(1u << (j + q));
       }
     }

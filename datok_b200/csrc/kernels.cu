@@ -22,28 +22,35 @@ namespace datok {
 constexpr int WALK_THREADS = 128;
 constexpr int LANE_CLS_STRIDE = 36;  // bytes of class scratch per lane (9 words: bank spread)
 
-// Persistent kernel, one CTA per SM.  The hottest rows of the fused transition
-// table and the two byte->class LUTs live in shared memory; every lane owns one
-// chunk at a time and walks it segment by segment (chunk_spec_fast).
+// Persistent kernel, one CTA per SM.  The compact (u16) rows of the hottest states and the
+// byte->class LUTs live in shared memory; every lane owns one chunk at a time and walks it
+// segment by segment (chunk_spec_fast).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n_hot) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* s_hot = smem;
-  uint8_t* s_cls = reinterpret_cast<uint8_t*>(s_hot + (size_t)n_hot * m.stride2);
+  uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);
+  const uint32_t hot_entries = n_hot * m.stride16;
+  uint8_t* s_cls = reinterpret_cast<uint8_t*>(smem) + (((hot_entries + m.stride16) * 2u + 15u) & ~15u);
   uint8_t* s_lut = s_cls + THREADS * LANE_CLS_STRIDE;
-  const uint32_t hot_words = n_hot * m.stride2;
-  for (uint32_t k = threadIdx.x; k < hot_words; k += THREADS) s_hot[k] = m.table2[k];
+  for (uint32_t k = threadIdx.x; k < hot_entries; k += THREADS) {
+    uint32_t e = m.hot16[k];
+    if ((e & F16_TGT) >= n_hot) e = 0;  // the target's row is not resident: that step goes through T3
+    s_hot[k] = (uint16_t)e;
+  }
+  for (uint32_t k = threadIdx.x; k < m.stride16; k += THREADS) s_hot[hot_entries + k] = 0;  // row n_hot: "see T3"
   if (threadIdx.x < 128) {
     s_lut[threadIdx.x] = m.cls.ascii_cls[threadIdx.x];
     s_lut[128 + threadIdx.x] = m.cls.latin1_cls[threadIdx.x];
+    s_lut[256 + threadIdx.x] = (uint8_t)(2u * m.cls.ascii_cls[threadIdx.x]);
   }
   __syncthreads();
   DeviceModel lm = m;
   lm.cls.ascii_cls = s_lut;
   lm.cls.latin1_cls = s_lut + 128;
   FastTables FT;
-  FT.hot = s_hot; FT.cold = m.table2; FT.hot_bytes = n_hot * m.stride2 * 4u; FT.row_bytes = m.stride2 * 4u;
+  FT.hot16 = s_hot; FT.t3 = m.table2; FT.n_hot = n_hot; FT.row16 = m.stride16 * 2u; FT.stride3 = m.stride2;
+  FT.ascii_cls2 = s_lut + 256;
   {  // opaque to the compiler: otherwise the shared-window base is re-derived in every step of the hot loop
     const unsigned long long sa = __cvta_generic_to_shared(s_hot);
     asm volatile("cvt.u32.u64 %0, %1;" : "=r"(FT.hot_saddr) : "l"(sa));
@@ -66,14 +73,15 @@ int fused_threads() {
 }
 
 size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot) {
-  return (size_t)n_hot * m.stride2 * 4 + (size_t)fused_threads() * LANE_CLS_STRIDE + 256;
+  return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)fused_threads() * LANE_CLS_STRIDE + 384;
 }
 
 uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states) {
-  const size_t fixed = (size_t)fused_threads() * LANE_CLS_STRIDE + 256 + 1024;
+  const size_t fixed = (size_t)fused_threads() * LANE_CLS_STRIDE + 384 + 16 + 1024 + (size_t)m.stride16 * 2;
   if (smem_limit <= fixed) return 1;
-  size_t rows = (smem_limit - fixed) / ((size_t)m.stride2 * 4);
+  size_t rows = (smem_limit - fixed) / ((size_t)m.stride16 * 2);
   if (rows > (size_t)n_states + 1) rows = (size_t)n_states + 1;
+  if (rows > m.hot16_rows) rows = m.hot16_rows;
   return rows ? (uint32_t)rows : 1u;
 }
 
@@ -140,11 +148,17 @@ __global__ void __launch_bounds__(WALK_THREADS) stitch_kernel(DeviceModel m, Wal
 // Re-walks go through the fast path too (fused table straight from L2: there are few of them).
 __global__ void __launch_bounds__(WALK_THREADS) rewalk_kernel(DeviceModel m, WalkBuffers b, uint32_t n_rewalk) {
   __shared__ __align__(16) uint8_t s_cls[WALK_THREADS * LANE_CLS_STRIDE];
+  __shared__ uint8_t s_lut2[128];
+  __shared__ uint16_t s_zero[136];  // the all-zero compact row: every lookup goes to the full table
+  if (threadIdx.x < 128) s_lut2[threadIdx.x] = (uint8_t)(2u * m.cls.ascii_cls[threadIdx.x]);
+  for (uint32_t k = threadIdx.x; k < 136; k += blockDim.x) s_zero[k] = 0;
+  __syncthreads();
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   // n_rewalk is only the launch bound; the list length was counted on the device by stitch_kernel
   if (k >= n_rewalk || k >= b.counters[1]) return;
   FastTables FT;
-  FT.hot = m.table2; FT.cold = m.table2; FT.hot_bytes = 0; FT.row_bytes = m.stride2 * 4u; FT.hot_saddr = 0;
+  FT.hot16 = s_zero; FT.t3 = m.table2; FT.n_hot = 0; FT.row16 = m.stride16 * 2u; FT.stride3 = m.stride2;
+  FT.hot_saddr = (uint32_t)__cvta_generic_to_shared(s_zero); FT.ascii_cls2 = s_lut2;
   chunk_rewalk_fast(m, b, FT, b.list_rewalk[k], s_cls + threadIdx.x * LANE_CLS_STRIDE);
 }
 

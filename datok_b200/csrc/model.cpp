@@ -243,26 +243,22 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
   // T3[t][c] is the transition that finally consumes c, with the number of epsilon
   // steps before it.  0: failure in a state without epsilon transition (backtrack to an
   // older point or hard fail).  T3_SLOW: anything else the fast path leaves to walk_run().
-  // Targets are stored as the BYTE OFFSET of the target state's row, so that a step is
-  // "mask, add class*4, load".
   m.stride2 = m.n_classes | 1u;
-  const size_t row_bytes = (size_t)m.stride2 * 4;
-  if (((size_t)S + 1) * row_bytes > (size_t)T3_OFFMASK) { why = "fused table exceeds 64 MB"; return DATOK_ERR_UNSUPPORTED_MODEL; }
   m.table2.assign(((size_t)S + 1) * m.stride2, 0);
-  // An in-place backtrack can stack the epsilon steps of two lookups at one position; with at most two
-  // chained epsilon transitions in the model that never exceeds the two boundaries a position can hold.
-  const bool fast_ok = m.max_eps_chain <= 2;
+  // An in-place backtrack stacks the epsilon steps of two lookups and its own at one position; with at
+  // most two chained epsilon transitions in the model that never exceeds the two boundaries a position
+  // can hold.  The fast path keeps 2 * class in one byte.
+  m.fast_ok = m.max_eps_chain <= 2 && m.n_classes <= 128;
   for (int t = 1; t <= S; t++) {
     uint32_t* row2 = &m.table2[(size_t)t * m.stride2];
     const uint16_t* row = &m.table[(size_t)t * R];
-    row2[CLS_EPS] = (uint32_t)((row[CLS_EPS] & 0x7FFFu) * row_bytes);
+    row2[CLS_EPS] = row[CLS_EPS] & 0x7FFFu;
     for (uint32_t c = CLS_CONT; c < m.n_classes; c++) {
       uint32_t cur = (uint32_t)t, k = 0, e = 0;
       for (;;) {
         const uint16_t* r = &m.table[(size_t)cur * R];
         if (r[c] != 0) {
-          e = (uint32_t)((r[c] & 0x7FFFu) * row_bytes) | ((r[c] & NT_BIT) ? T3_NTBIT : 0u) | (k << T3_K_SHIFT) |
-              (r[CLS_EPS] != 0 ? T3_EPSBIT : 0u);
+          e = r[c] | (k << T3_K_SHIFT) | (r[CLS_EPS] != 0 ? T3_EPSBIT : 0u);  // r[c] carries NT_BIT == T3_NTBIT
           break;
         }
         if (r[CLS_EPS] == 0) {
@@ -275,7 +271,22 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
         cur = r[CLS_EPS] & 0x7FFFu;
         k++;
       }
-      row2[c] = fast_ok ? e : T3_SLOW;
+      row2[c] = m.fast_ok ? e : T3_SLOW;
+    }
+  }
+  // --- compact rows of the hottest states ---
+  m.stride16 = ((m.n_classes + 1) / 2 | 1u) * 2;
+  m.hot16_rows = std::min<uint32_t>((uint32_t)S + 1, H16_MAX_ROWS);
+  m.hot16.assign((size_t)m.hot16_rows * m.stride16, 0);
+  for (uint32_t t = 1; t < m.hot16_rows && m.fast_ok; t++) {
+    const uint32_t* row2 = &m.table2[(size_t)t * m.stride2];
+    uint16_t* h = &m.hot16[(size_t)t * m.stride16];
+    for (uint32_t c = 0; c < m.n_classes; c++) {
+      const uint32_t e = row2[c], tgt = e & T3_TGT;
+      if (e == 0 && c != CLS_EPS) { h[c] = (uint16_t)H16_FAIL; continue; }
+      if (e == 0 || (e & T3_SLOW) || tgt >= H16_MAX_ROWS) continue;
+      h[c] = (uint16_t)(tgt | ((e & T3_NTBIT) ? H16_NTBIT : 0u) | ((e & T3_EPSBIT) ? H16_EPSBIT : 0u) |
+                        (((e >> T3_K_SHIFT) & 3u) << H16_K_SHIFT));
     }
   }
   return DATOK_OK;

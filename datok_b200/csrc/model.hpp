@@ -25,16 +25,25 @@ constexpr uint32_t CLS_CONT = 1;  // UTF-8 continuation byte of a valid sequence
 constexpr uint32_t CLS_EOT = 2;   // the byte 0x04 (matrix.go:13,422)
 constexpr uint32_t CLS_FIRST = 3; // first ordinary class
 constexpr uint16_t NT_BIT = 0x8000;
-// fused table entry (u32): [25:2] byte offset of the target state's row in the fused table,
-// [0] non-token transition, [1] the state the byte is finally consumed from has an epsilon
-// transition itself, [27:26] number of epsilon transitions taken before the byte is consumed.
-// 0 = not decidable locally (older epsilon point or hard fail).  Column CLS_EPS holds the row
-// offset of the epsilon transition's target (0: none).
-constexpr uint32_t T3_NTBIT = 1u;
-constexpr uint32_t T3_EPSBIT = 2u;
-constexpr uint32_t T3_OFFMASK = 0x03FFFFFCu;
-constexpr uint32_t T3_K_SHIFT = 26;
-constexpr uint32_t T3_SLOW = 1u << 31;  // leave this (state, class) to the exact walker
+// fused table T3, entry (u32): [14:0] target state, [15] non-token transition, [17:16] number of
+// epsilon transitions taken before the byte is consumed, [18] the state the byte is finally consumed
+// from has an epsilon transition itself.  0 = not decidable locally (older epsilon point or hard
+// fail); T3_SLOW = leave this (state, class) to the exact walker.  Column CLS_EPS holds the target of
+// the state's epsilon transition (0: none).
+constexpr uint32_t T3_TGT = 0x7FFFu;
+constexpr uint32_t T3_NTBIT = 1u << 15;
+constexpr uint32_t T3_K_SHIFT = 16;
+constexpr uint32_t T3_EPSBIT = 1u << 18;
+constexpr uint32_t T3_SLOW = 1u << 31;
+// compact copy of the rows of the hottest states for shared memory, entry (u16): [11:0] target
+// state, [12] non-token, [13] consuming state has an epsilon transition, [15:14] epsilon steps.
+// 0 = look the entry up in T3 (marked, or a target that is not among the hot rows); H16_FAIL = T3 holds 0.
+constexpr uint32_t H16_TGT = 0x0FFFu;
+constexpr uint32_t H16_NTBIT = 1u << 12;
+constexpr uint32_t H16_EPSBIT = 1u << 13;
+constexpr uint32_t H16_K_SHIFT = 14;
+constexpr uint32_t H16_MAX_ROWS = 4096;
+constexpr uint32_t H16_FAIL = H16_NTBIT;  // target 0 with this flag: T3 holds 0 (failure without epsilon transition)
 
 struct HostModel {
   // --- reference view (ParseMatrix) ---
@@ -57,8 +66,12 @@ struct HostModel {
   uint32_t sync_mask[8];  // class c is a sync class iff table[start][c] == (start | NT_BIT)
   uint32_t sync_ascii[4]; // ASCII byte b is a sync byte iff its class is a sync class
   uint32_t max_eps_chain = 0;
-  std::vector<uint32_t> table2;    // fused table, (S+1) * stride2 entries
-  uint32_t stride2 = 0;            // odd (shared-memory bank spread), >= n_classes
+  std::vector<uint32_t> table2;    // fused table T3, (S+1) * stride2 entries
+  uint32_t stride2 = 0;            // >= n_classes
+  std::vector<uint16_t> hot16;     // compact rows of states 0..hot16_rows-1, stride16 entries each
+  uint32_t stride16 = 0;           // entries per compact row; stride16 / 2 is odd (shared-memory bank spread)
+  uint32_t hot16_rows = 0;
+  bool fast_ok = false;            // the fused tables are usable (else every entry is marked T3_SLOW / 0)
 };
 
 // error codes are the DATOK_ERR_* values of include/datok_b200.h

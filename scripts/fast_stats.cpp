@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
   uint32_t chunk = argc > 3 ? atoi(argv[3]) : 256, hot_rows = argc > 4 ? atoi(argv[4]) : 440;
   DeviceModel m; memset(&m, 0, sizeof m);
   m.table = hm.table.data(); m.table2 = hm.table2.data(); m.row_shift = hm.row_shift; m.start = hm.start;
-  m.n_classes = hm.n_classes; m.stride2 = hm.stride2;
+  m.n_classes = hm.n_classes; m.stride2 = hm.stride2; m.hot16 = hm.hot16.data(); m.stride16 = hm.stride16; m.hot16_rows = hm.hot16_rows;
   m.cls.ascii_cls = hm.ascii_cls; m.cls.latin1_cls = hm.latin1_cls; m.cls.rune_key = hm.rune_key.data();
   m.cls.rune_cls = hm.rune_cls.data(); m.cls.n_rune = hm.rune_key.size(); m.cls.identity_cls = hm.identity_cls;
   memcpy(m.sync_ascii, hm.sync_ascii, sizeof hm.sync_ascii);
@@ -34,7 +34,13 @@ int main(int argc, char** argv) {
   std::vector<uint32_t> sync(b.n_chunks), fh(b.n_chunks), cf(b.n_chunks);
   b.E = E.data(); b.exitA = A.data(); b.Enew = En.data(); b.Ytmp = Y.data(); b.sync = sync.data(); b.first_hw = fh.data(); b.cflags = cf.data();
   unsigned long long ek = ~0ull; b.err_key = &ek;
-  FastTables FT; FT.hot = m.table2; FT.cold = m.table2; FT.hot_bytes = hot_rows * m.stride2 * 4; FT.row_bytes = m.stride2 * 4;
+  if (hot_rows > hm.hot16_rows) hot_rows = hm.hot16_rows;
+  std::vector<uint16_t> hot(hm.hot16.begin(), hm.hot16.begin() + (size_t)hot_rows * hm.stride16);
+  for (auto& e : hot) if ((e & F16_TGT) >= hot_rows) e = 0;
+  hot.resize(hot.size() + hm.stride16, 0);
+  uint8_t lut2[128]; for (int i = 0; i < 128; i++) lut2[i] = 2 * hm.ascii_cls[i];
+  FastTables FT; FT.hot16 = hot.data(); FT.t3 = m.table2; FT.n_hot = hot_rows; FT.row16 = hm.stride16 * 2; FT.stride3 = m.stride2;
+  FT.hot_saddr = 0; FT.ascii_cls2 = lut2;
   uint8_t cls[36];
   for (uint32_t i = 0; i < b.n_chunks; i++) chunk_spec_fast(m, b, FT, i, m.start, cls);
   printf("bytes %zu chunks %u\nfast steps %llu (cold %llu = %.3f%%)\nbacktracks in place %llu (%.3f%% of steps), stale zones %llu\n"

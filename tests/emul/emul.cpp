@@ -36,6 +36,19 @@ struct EmulModel {
   DeviceModel dm;
 };
 
+static uint8_t g_ascii_cls2[128];
+// the kernel prologue's job: n_hot compact rows with non-resident targets zeroed
+static void make_fast_tables(const HostModel& hm, const DeviceModel& m, uint32_t n_hot, std::vector<uint16_t>& hot,
+                             FastTables& FT) {
+  if (n_hot > hm.hot16_rows) n_hot = hm.hot16_rows;
+  hot.assign(hm.hot16.begin(), hm.hot16.begin() + (size_t)n_hot * hm.stride16);
+  for (auto& e : hot) if ((e & F16_TGT) >= n_hot) e = 0;
+  hot.resize(hot.size() + hm.stride16, 0);  // the all-zero row n_hot
+  for (int i = 0; i < 128; i++) g_ascii_cls2[i] = (uint8_t)(2 * hm.ascii_cls[i]);
+  FT.hot16 = hot.data(); FT.t3 = m.table2; FT.n_hot = n_hot; FT.row16 = hm.stride16 * 2u; FT.stride3 = m.stride2;
+  FT.hot_saddr = 0; FT.ascii_cls2 = g_ascii_cls2;
+}
+
 EmulModel* emul_load(const char* path, int* err) {
   EmulModel* m = new EmulModel();
   std::string why;
@@ -44,7 +57,9 @@ EmulModel* emul_load(const char* path, int* err) {
   HostModel& h = m->hm;
   m->dm.table = h.table.data();
   m->dm.table2 = h.table2.data();
+  m->dm.hot16 = h.hot16.data();
   m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.n_classes = h.n_classes; m->dm.stride2 = h.stride2;
+  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows;
   m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
   m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
   m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls;
@@ -95,11 +110,8 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   } else {
     // K1+K2a fused fast path
     FastTables FT;
-    std::vector<uint32_t> hot(em->hm.table2.begin(),
-                              em->hm.table2.begin() + std::min<size_t>(em->hm.table2.size(), (size_t)mode * m.stride2));
-    FT.hot = hot.data(); FT.cold = m.table2;
-    FT.hot_bytes = (uint32_t)std::min<size_t>(mode, em->hm.stateCount + 1) * m.stride2 * 4u;
-    FT.row_bytes = m.stride2 * 4u;
+    std::vector<uint16_t> hot;
+    make_fast_tables(em->hm, m, (uint32_t)mode, hot, FT);
     uint8_t seg_cls[32];
     for (uint32_t k = 0; k < b.n_chunks; k++)
       chunk_spec_fast(m, b, FT, order ? b.n_chunks - 1 - k : k, start_state, seg_cls);
@@ -107,7 +119,8 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   R->has_invalid = counters[2];
 
   FastTables FTr;
-  FTr.hot = m.table2; FTr.cold = m.table2; FTr.hot_bytes = 0; FTr.row_bytes = m.stride2 * 4u;
+  std::vector<uint16_t> hot_r;
+  make_fast_tables(em->hm, m, 0, hot_r, FTr);
   uint8_t seg_cls_r[36];
   // K2b-d fix-up rounds
   std::vector<uint32_t> list, next, rew;
