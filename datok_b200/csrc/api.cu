@@ -38,9 +38,9 @@ struct Block {
   bool host = false;
 };
 
-enum { T_CLEAR, T_WALK, T_STITCH, T_REWALK, T_COMMIT, T_REDUCE, T_SCAN, T_EMIT, T_COUNT };
+enum { T_CLEAR, T_WALK, T_STITCH, T_REWALK, T_COMMIT, T_REDUCE, T_SCAN, T_TEXTS, T_EMIT, T_COUNT };
 const char* const kTimerNames[T_COUNT] = {"clear", "walk_fused", "stitch", "rewalk", "commit",
-                                          "compact_reduce", "compact_scan", "compact_emit"};
+                                          "compact_reduce", "compact_scan", "compact_texts", "compact_emit"};
 
 }  // namespace
 
@@ -65,7 +65,7 @@ struct datok_model {
   // cache of result buffers
   std::vector<Block> cache;
   std::mutex mu;
-  uint32_t chunk = 256;
+  uint32_t chunk = 512;
   // instrumentation of the last call
   float t_ms[T_COUNT] = {0};
   int launches = 0;
@@ -185,6 +185,8 @@ size_t carve(uint8_t* base, uint32_t N, uint32_t chunk, bool need_input_copy, Wa
   cb.n_blocks = (b.n_words + wpb - 1) / wpb;
   cb.block_agg = c.take<Agg>(cb.n_blocks);
   cb.block_carry = c.take<Agg>(cb.n_blocks);
+  cb.super_agg = c.take<Agg>(cb.n_blocks / SCAN_THREADS + 1);
+  cb.super_carry = c.take<Agg>(cb.n_blocks / SCAN_THREADS + 1);
   cb.total = c.take<Agg>(2);
   return align_up(c.off, 256);
 }
@@ -463,7 +465,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   launch_compact_reduce(c, cb, s);
   pt.end();
   pt.begin(T_SCAN);
-  launch_compact_scan(c, cb, sentence_end_in, s);
+  launch_compact_scan(cb, sentence_end_in, s);
   pt.end();
   m->launches += 2;
   struct { Agg tot; unsigned long long err; uint32_t invalid; } hdr;
@@ -490,9 +492,10 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
   struct Out { size_t bytes; bool want; void** dev; Block d, h; };
   void *d_tok_bytes = nullptr, *d_tok_pos = nullptr, *d_sent_pos = nullptr, *d_sent_tok = nullptr, *d_text = nullptr;
+  // the per-text arrays are followed by the DocRec table (device scratch, not copied back)
   Out outs[5] = {{2 * nt * 4, want_bytes, &d_tok_bytes, {}, {}}, {2 * nt * 4, want_pos, &d_tok_pos, {}, {}},
                  {np * 4, want_spos, &d_sent_pos, {}, {}},       {ns * 4, want_stok, &d_sent_tok, {}, {}},
-                 {nx * 4 * 4, true, &d_text, {}, {}}};
+                 {nx * 4 * 4 + (nx + 1) * sizeof(DocRec), true, &d_text, {}, {}}};
   for (auto& o : outs) {
     if (!o.want) continue;
     o.d = acquire(m, o.bytes, false, &rc);
@@ -510,13 +513,20 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   c.text_sent_end = c.text_tok_end + nx;
   c.text_sentpos_end = c.text_tok_end + 2 * nx;
   c.text_byte_end = c.text_tok_end + 3 * nx;
+  c.docs = reinterpret_cast<DocRec*>(c.text_tok_end + 4 * nx);
+  pt.begin(T_TEXTS);
+  launch_compact_texts(c, cb, s);
+  pt.end();
   pt.begin(T_EMIT);
-  launch_compact_emit(c, cb, s);
+  {
+    const int e = launch_compact_emit(c, cb, s);
+    if (e != 0) { g_last_error = std::string("compact_emit launch: ") + cudaGetErrorString((cudaError_t)e); free_result_locked(r); return DATOK_ERR_CUDA; }
+  }
   launch_compact_finalize(c, cb, text_end_in, final_input, s);
   pt.end();
-  m->launches += 2;
-  struct { Agg fin; unsigned long long err; WState last; } tail;
-  CUDA_TRY(cudaMemcpyAsync(&tail.fin, cb.total + 1, sizeof(Agg), cudaMemcpyDeviceToHost, s));
+  m->launches += 3;
+  struct { StreamTotals fin; unsigned long long err; WState last; } tail;
+  CUDA_TRY(cudaMemcpyAsync(&tail.fin, cb.total + 1, sizeof(StreamTotals), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(&tail.err, b.err_key, sizeof tail.err, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(&tail.last, b.E + (b.n_chunks - 1), sizeof(WState), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaEventRecord(m->ev[2], s));
@@ -547,7 +557,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
     }
     const uint32_t lk = tail.fin.last_kind;
     v.carry_out.sentence_end = (lk == EV_SENT || lk == EV_TEND) ? 1u : 0u;
-    v.carry_out.text_end = (tail.fin.n_text > 0 && tail.fin.n_tok == tail.fin.doc_tok) ? 1u : (text_end_in ? 1u : 0u);
+    v.carry_out.text_end = (tail.fin.n_text > 0 && tail.fin.tokless) ? 1u : (text_end_in ? 1u : 0u);
   }
   // ---- D2H ----
   for (auto& o : outs) {
@@ -556,6 +566,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
     if (o.dev == &d_tok_bytes || o.dev == &d_tok_pos) bytes = 2 * (size_t)v.n_tokens * 4;
     else if (o.dev == &d_sent_pos) bytes = (size_t)v.n_sent_pos * 4;
     else if (o.dev == &d_sent_tok) bytes = (size_t)v.n_sentences * 4;
+    else if (o.dev == &d_text) bytes = nx * 4 * 4;
     if (bytes) CUDA_TRY(cudaMemcpyAsync(o.h.p, o.d.p, bytes, cudaMemcpyDeviceToHost, s));
   }
   CUDA_TRY(cudaEventRecord(m->ev[3], s));

@@ -4,10 +4,17 @@
 // the closures' captured state (posC, pos, sent, sentB, init) and the walk's
 // sentenceEnd/textEnd flags (matrix.go:360-363,595-605,683-695) become an
 // associative summary (Agg) that is scanned over 32-position words of the
-// boundary bitmaps written by walk_run() (walk_core.cuh).
+// boundary bitmaps written by the walk (walk_core.cuh, fast_core.cuh).
 //
 // Stream order of events: by byte position, and at one position
 //     END (token ends here)  <  SENT (SentenceEnd)  <  TEND (EOT at this byte fired TextEnd).
+//
+// Everything about a word is computed with word-parallel logic: which TextEnds force a
+// SentenceEnd (matrix.go:595-598) and which tokens open a sentence (token_writer.go:76) depend on
+// the kind of the preceding event, a fill-forward over the word done with one addition
+// (word_masks); the output index of every event is then a popcount.  Per-text state (posC reset,
+// NEWLINE_AFTER_EOT shift, `init`) lives in a table of DocRec written by a pass over the TextEnds
+// (emit_texts) before tokens and sentences are emitted (emit_tokens, emit_sentences).
 #pragma once
 #include "walk_core.cuh"
 
@@ -24,33 +31,37 @@ constexpr uint32_t EV_START0 = 4;  // stream start with sentenceEnd=false (matri
 constexpr uint32_t F_TOKENS = 1, F_SENTENCES = 2, F_TOKEN_POS = 4, F_SENTENCE_POS = 8, F_NL_AFTER_EOT = 16,
                    F_WRITER_USED = 256;
 
-// Summary of a contiguous span of positions.  Ranks are rune counts relative to
-// the span start; positions are absolute bytes.
+// Summary of a contiguous span of positions.
 struct Agg {
   uint32_t n_rune;     // rune starts in the span
   uint32_t n_tok;      // Token events
   uint32_t n_sent;     // SentenceEnd events (regular + forced ones already decidable)
   uint32_t n_text;     // TextEnd events
   uint32_t n_sentpos;  // entries appended to TokenWriter.sent (token_writer.go:76-79,108)
-  uint32_t first_kind; // kind of the first event (its forced/opener decision needs the predecessor)
-  uint32_t last_kind;
+  uint32_t kinds;      // kind of the first event | kind of the last event << 8 (EV_NONE: no event)
   uint32_t last_end_pos;   // byte position of the last END (K_NOPOS = none)
-  uint32_t last_end_rank;  // runes from span start to that position
   uint32_t doc_start;      // byte after the last TEND (K_NOPOS = no TEND in span)
-  uint32_t doc_rank;       // runes from span start to doc_start
-  uint32_t doc_adj;        // NEWLINE_AFTER_EOT shift of the text starting at doc_start
-  uint32_t doc_tok;        // tokens in the span before doc_start
 };
-constexpr int AGG_WORDS = 13;
+constexpr int AGG_WORDS = 8;
+
+// State of the TokenWriter at the start of a text (token_writer.go:130-167 resets posC, pos, sent).
+struct DocRec {
+  uint32_t start;      // first byte of the text
+  uint32_t rank;       // runes before `start`
+  uint32_t adj;        // NEWLINE_AFTER_EOT shift of the text (token_writer.go:66-68)
+  uint32_t tok;        // tokens before `start`
+};
 
 DATOK_HD Agg agg_zero() {
   Agg a;
   a.n_rune = a.n_tok = a.n_sent = a.n_text = a.n_sentpos = 0;
-  a.first_kind = a.last_kind = EV_NONE;
-  a.last_end_pos = K_NOPOS; a.last_end_rank = 0;
-  a.doc_start = K_NOPOS; a.doc_rank = 0; a.doc_adj = 0; a.doc_tok = 0;
+  a.kinds = 0;
+  a.last_end_pos = K_NOPOS;
+  a.doc_start = K_NOPOS;
   return a;
 }
+DATOK_HD uint32_t agg_first(const Agg& a) { return a.kinds & 0xFFu; }
+DATOK_HD uint32_t agg_last(const Agg& a) { return a.kinds >> 8; }
 
 // does a TextEnd following an event of kind `k` force a SentenceEnd? (matrix.go:595-598)
 DATOK_HD bool forces_sentence(uint32_t k) { return k == EV_END || k == EV_START0; }
@@ -60,25 +71,20 @@ DATOK_HD bool opens_sentence(uint32_t k) { return k == EV_SENT || k == EV_TEND |
 // R = A followed by B
 DATOK_HD Agg agg_combine(const Agg& A, const Agg& B) {
   Agg R;
+  const uint32_t al = agg_last(A), bf = agg_first(B);
   uint32_t extra_sent = 0, extra_open = 0;
-  if (A.last_kind != EV_NONE) {
-    if (B.first_kind == EV_TEND && forces_sentence(A.last_kind)) extra_sent = 1;
-    if (B.first_kind == EV_END && opens_sentence(A.last_kind)) extra_open = 1;
+  if (al != EV_NONE) {
+    if (bf == EV_TEND && forces_sentence(al)) extra_sent = 1;
+    if (bf == EV_END && opens_sentence(al)) extra_open = 1;
   }
   R.n_rune = A.n_rune + B.n_rune;
   R.n_tok = A.n_tok + B.n_tok;
   R.n_sent = A.n_sent + B.n_sent + extra_sent;
   R.n_text = A.n_text + B.n_text;
   R.n_sentpos = A.n_sentpos + B.n_sentpos + extra_sent + extra_open;
-  R.first_kind = A.first_kind != EV_NONE ? A.first_kind : B.first_kind;
-  R.last_kind = B.last_kind != EV_NONE ? B.last_kind : A.last_kind;
-  if (B.last_end_pos != K_NOPOS) { R.last_end_pos = B.last_end_pos; R.last_end_rank = A.n_rune + B.last_end_rank; }
-  else { R.last_end_pos = A.last_end_pos; R.last_end_rank = A.last_end_rank; }
-  if (B.doc_start != K_NOPOS) {
-    R.doc_start = B.doc_start; R.doc_rank = A.n_rune + B.doc_rank; R.doc_adj = B.doc_adj; R.doc_tok = A.n_tok + B.doc_tok;
-  } else {
-    R.doc_start = A.doc_start; R.doc_rank = A.doc_rank; R.doc_adj = A.doc_adj; R.doc_tok = A.doc_tok;
-  }
+  R.kinds = (agg_first(A) != EV_NONE ? agg_first(A) : bf) | ((agg_last(B) != EV_NONE ? agg_last(B) : al) << 8);
+  R.last_end_pos = B.last_end_pos != K_NOPOS ? B.last_end_pos : A.last_end_pos;
+  R.doc_start = B.doc_start != K_NOPOS ? B.doc_start : A.doc_start;
   return R;
 }
 
@@ -92,7 +98,7 @@ struct CompactCtx {
   const uint32_t* b_sent;
   const uint32_t* b_tend;
   uint32_t flags;          // TokenWriter Bits (+ F_WRITER_USED)
-  // outputs (device); any may be null
+  // outputs (device); any of the first four may be null
   uint32_t* tok_bytes;     // 2 per token
   int32_t* tok_pos;        // 2 per token
   int32_t* sent_pos;
@@ -101,6 +107,7 @@ struct CompactCtx {
   uint32_t* text_sent_end;
   uint32_t* text_sentpos_end;
   uint32_t* text_byte_end;
+  DocRec* docs;            // docs[d]: the text that TextEnd d closes; docs[0] = stream start
   unsigned long long* err_key;  // min over (position << 8 | code), ~0 = none
 };
 
@@ -156,129 +163,222 @@ DATOK_HD void report_error(const CompactCtx& c, uint32_t pos, uint32_t code) {
 #endif
 }
 
-// Walks the events of bitmap word `w` in stream order.
-//   EMIT == false: returns the word's Agg (relative ranks), `carry` unused.
-//   EMIT == true : `carry` is the absolute summary of everything before the word
-//                  (including the stream-start pseudo event); writes the outputs and
-//                  returns the absolute summary including the word.
-template <bool EMIT>
-DATOK_HD Agg process_word(const CompactCtx& c, uint32_t w, const Agg& carry) {
-  const uint32_t rs = c.rstart[w], we = c.b_end[w], ws = c.b_sent[w], wt = c.b_tend[w];
-  Agg a = agg_zero();
-  a.n_rune = popc32(rs);
-  uint32_t m = we | ws | wt;
-  if (m == 0) {
-    if (EMIT) { a = carry; a.n_rune = carry.n_rune + popc32(rs); }
-    return a;
-  }
-  // running absolute state (EMIT) / relative state (!EMIT)
-  uint32_t lk = EMIT ? carry.last_kind : EV_NONE;
-  uint32_t tok = EMIT ? carry.n_tok : 0, sent = EMIT ? carry.n_sent : 0, text = EMIT ? carry.n_text : 0;
-  uint32_t sentpos = EMIT ? carry.n_sentpos : 0;
-  const uint32_t rank0 = EMIT ? carry.n_rune : 0;  // rank of the word's first position
-  uint32_t last_end_pos = EMIT ? carry.last_end_pos : K_NOPOS, last_end_rank = EMIT ? carry.last_end_rank : 0;
-  uint32_t doc_start = EMIT ? carry.doc_start : K_NOPOS, doc_rank = EMIT ? carry.doc_rank : 0;
-  uint32_t doc_adj = EMIT ? carry.doc_adj : 0, doc_tok = EMIT ? carry.doc_tok : 0;
-  const bool writer_used = (c.flags & F_WRITER_USED) != 0;
+// the five bitmap words of positions [32w, 32w+32)
+struct WordBits {
+  uint32_t rs, e, k, s, t;  // rune starts, END, SKIP, SENT, TEND
+};
+DATOK_HD WordBits word_load(const CompactCtx& c, uint32_t w) {
+  WordBits b;
+  b.rs = c.rstart[w]; b.e = c.b_end[w]; b.k = c.b_skip[w]; b.s = c.b_sent[w]; b.t = c.b_tend[w];
+  return b;
+}
 
-  while (m) {
-    const uint32_t b = ctz32(m);
-    m &= m - 1;
-    const uint32_t p = (w << 5) + b;
-    if ((we >> b) & 1u) {  // ---- Token (token_writer.go:59-88) ----
-      const uint32_t rank_e = rank0 + popc32(rs & mask_below(b));
-      if (a.first_kind == EV_NONE) a.first_kind = EV_END;
-      const bool opener = (lk != EV_NONE) && opens_sentence(lk);
-      if (EMIT) {
-        const uint32_t D = doc_start == K_NOPOS ? 0u : doc_start;
-        uint32_t bufstart = D;
-        if (last_end_pos != K_NOPOS && last_end_pos > bufstart) bufstart = last_end_pos;
-        const uint32_t s = next_clear(c.b_skip, c.n_words, bufstart);  // offset = leading non-token runes
-        const uint32_t rank_s = rank_e - count_range(c.rstart, s, p);
-        // `init` (token_writer.go:42,66,70): the text holding the stream's first token is never shifted
-        const int32_t adj = (!writer_used && doc_tok == 0) ? 0 : (int32_t)doc_adj;
-        const int32_t ps = (int32_t)(rank_s - doc_rank) - adj, pe = (int32_t)(rank_e - doc_rank) - adj;
-        if (c.tok_bytes) { c.tok_bytes[2 * (size_t)tok] = s; c.tok_bytes[2 * (size_t)tok + 1] = p; }
-        if (c.tok_pos) { c.tok_pos[2 * (size_t)tok] = ps; c.tok_pos[2 * (size_t)tok + 1] = pe; }
-        if (opener && c.sent_pos) c.sent_pos[sentpos] = ps;
-      }
-      if (opener) sentpos++;
-      tok++;
-      lk = EV_END;
-      last_end_pos = p;
-      last_end_rank = rank_e;
-    }
-    if ((ws >> b) & 1u) {  // ---- SentenceEnd (token_writer.go:103-127) ----
-      if (a.first_kind == EV_NONE) a.first_kind = EV_SENT;
-      if (EMIT) {
-        const int32_t adj = (!writer_used && doc_tok == 0) ? 0 : (int32_t)doc_adj;
-        if (c.sent_tok) c.sent_tok[sent] = tok;
-        if (tok == doc_tok) { if (c.flags & F_SENTENCE_POS) report_error(c, p, E_SENT_NO_TOKEN); }
-        else if (c.sent_pos) c.sent_pos[sentpos] = (int32_t)(last_end_rank - doc_rank) - adj;
-      }
-      sent++;
-      sentpos++;
-      lk = EV_SENT;
-    }
-    if ((wt >> b) & 1u) {  // ---- EOT: forced SentenceEnd + TextEnd (matrix.go:593-605) ----
-      if (a.first_kind == EV_NONE) a.first_kind = EV_TEND;
-      if (lk != EV_NONE && forces_sentence(lk)) {
-        if (EMIT) {
-          const int32_t adj = (!writer_used && doc_tok == 0) ? 0 : (int32_t)doc_adj;
-          if (c.sent_tok) c.sent_tok[sent] = tok;
-          if (tok == doc_tok) { if (c.flags & F_SENTENCE_POS) report_error(c, p, E_SENT_NO_TOKEN); }
-          else if (c.sent_pos) c.sent_pos[sentpos] = (int32_t)(last_end_rank - doc_rank) - adj;
-        }
-        sent++;
-        sentpos++;
-      }
-      if (EMIT) {
-        if (tok == doc_tok) {  // token-less text (token_writer.go:135,145)
-          if (c.flags & F_TOKEN_POS) report_error(c, p, E_TEXT_NO_TOKEN);
-          else if (c.flags & F_SENTENCE_POS) report_error(c, p, E_TEXT_NO_SENT);
-        }
-        c.text_tok_end[text] = tok;
-        c.text_sent_end[text] = sent;
-        c.text_sentpos_end[text] = sentpos;
-        c.text_byte_end[text] = p + 1;
-      }
-      text++;
-      lk = EV_TEND;
-      doc_start = p + 1;
-      doc_rank = rank0 + popc32(rs & mask_below(b + 1));
-      doc_adj = newline_adjust(c, p + 1);
-      doc_tok = tok;
-    }
+// "was the last event before position p a Token?" for every p of the word, given the answer
+// `cin` for the word's first position: positions whose last event is END generate, SENT/TEND kill,
+// the others propagate -- the carries of one addition.
+DATOK_HD uint32_t prev_is_end(const WordBits& b, uint32_t cin) {
+  const uint32_t g = b.e & ~(b.s | b.t);
+  const uint32_t x = g | ~(b.e | b.s | b.t);
+  return (x + g + (cin & 1u)) ^ x ^ g;
+}
+
+struct WordMasks {
+  uint32_t forced;  // TextEnds that force a SentenceEnd first (matrix.go:595-598)
+  uint32_t opener;  // Tokens that open a sentence span (token_writer.go:76-79)
+  uint32_t se;      // all SentenceEnd events: SENT | forced
+};
+// last_kind: kind of the last event before the word (EV_NONE only for a relative summary, where the
+// decisions about the word's first event are left to agg_combine)
+DATOK_HD WordMasks word_masks(const WordBits& b, uint32_t last_kind) {
+  WordMasks m;
+  const uint32_t pf = prev_is_end(b, forces_sentence(last_kind) ? 1u : 0u);
+  // START0 both forces and opens; the two chains only differ up to the first event
+  const uint32_t po = last_kind == EV_START0 ? prev_is_end(b, 0u) : pf;
+  m.forced = b.t & ~b.s & (b.e | pf);
+  m.opener = b.e & ~po;
+  if (last_kind == EV_NONE) {
+    const uint32_t any = b.e | b.s | b.t;
+    if (any) m.opener &= ~(any & (0u - any));  // a first-event Token is decided by the predecessor
   }
-  if (EMIT) { a.n_rune = rank0 + popc32(rs); a.first_kind = carry.first_kind; }
-  a.n_tok = tok; a.n_sent = sent; a.n_text = text; a.n_sentpos = sentpos;
-  a.last_kind = lk;
-  a.last_end_pos = last_end_pos; a.last_end_rank = last_end_rank;
-  a.doc_start = doc_start; a.doc_rank = doc_rank; a.doc_adj = doc_adj; a.doc_tok = doc_tok;
+  m.se = b.s | m.forced;
+  return m;
+}
+
+// relative summary of word w
+DATOK_HD Agg word_agg(uint32_t w, const WordBits& b) {
+  Agg a = agg_zero();
+  a.n_rune = popc32(b.rs);
+  const uint32_t any = b.e | b.s | b.t;
+  if (any == 0) return a;
+  const WordMasks m = word_masks(b, EV_NONE);
+  const uint32_t fb = any & (0u - any), lb = 0x80000000u >> clz32(any);
+  const uint32_t first = (b.e & fb) ? EV_END : (b.s & fb) ? EV_SENT : EV_TEND;
+  const uint32_t last = (b.t & lb) ? EV_TEND : (b.s & lb) ? EV_SENT : EV_END;
+  a.n_tok = popc32(b.e);
+  a.n_text = popc32(b.t);
+  a.n_sent = popc32(m.se);
+  a.n_sentpos = a.n_sent + popc32(m.opener);
+  a.kinds = first | (last << 8);
+  if (b.e) a.last_end_pos = (w << 5) + 31u - clz32(b.e);
+  if (b.t) a.doc_start = (w << 5) + 32u - clz32(b.t);
   return a;
 }
 
-// The pseudo span that precedes position 0: the walk's initial sentenceEnd flag
-// and, for a reused TokenWriter, the shift of the first text.
-DATOK_HD Agg agg_stream_start(const CompactCtx& c, bool sentence_end) {
-  Agg a = agg_zero();
-  a.first_kind = a.last_kind = sentence_end ? EV_SENT : EV_START0;
-  if (c.flags & F_WRITER_USED) { a.doc_start = 0; a.doc_adj = newline_adjust(c, 0); }
-  return a;
+DATOK_HD int32_t doc_shift(const CompactCtx& c, const DocRec& d) {
+  // `init` (token_writer.go:42,66,70): the text holding the stream's first token is never shifted
+  return (!(c.flags & F_WRITER_USED) && d.tok == 0) ? 0 : (int32_t)d.adj;
 }
 
-// End of input (matrix.go:680-695): the final SentenceEnd / TextEnd.  `tot` is the
-// absolute summary of the whole stream.  Returns the final counts in `tot`.
-DATOK_HD void finalize_stream(const CompactCtx& c, Agg& tot, bool text_end_in) {
-  const bool writer_used = (c.flags & F_WRITER_USED) != 0;
-  const int32_t adj = (!writer_used && tot.doc_tok == 0) ? 0 : (int32_t)tot.doc_adj;
-  const bool have_tok = tot.n_tok != tot.doc_tok;
-  if (forces_sentence(tot.last_kind)) {  // :683 if !sentenceEnd
-    if (c.sent_tok) c.sent_tok[tot.n_sent] = tot.n_tok;
+// Texts pass: the TextEnd events of word w (token_writer.go:130-167).  A: absolute summary of
+// everything before the word (including the stream-start pseudo event).
+DATOK_HD void emit_texts(const CompactCtx& c, uint32_t w, const WordBits& b, const Agg& A) {
+  if (b.t == 0) return;
+  const WordMasks m = word_masks(b, agg_last(A));
+  uint32_t t = b.t;
+  uint32_t doc_start = A.doc_start == K_NOPOS ? 0u : A.doc_start;
+  while (t) {
+    const uint32_t bp = ctz32(t);
+    t &= t - 1;
+    const uint32_t le = mask_below(bp + 1), p = (w << 5) + bp;
+    const uint32_t text = A.n_text + popc32(b.t & mask_below(bp));
+    const uint32_t tok = A.n_tok + popc32(b.e & le);
+    const uint32_t sent = A.n_sent + popc32(m.se & le);
+    const uint32_t sentpos = A.n_sentpos + popc32(m.opener & le) + popc32(m.se & le);
+    // token-less text (token_writer.go:135,145): no END since the text started
+    uint32_t last_end = A.last_end_pos;
+    if (b.e & le) last_end = (w << 5) + 31u - clz32(b.e & le);
+    if (last_end == K_NOPOS || last_end <= doc_start) {
+      if (c.flags & F_TOKEN_POS) report_error(c, p, E_TEXT_NO_TOKEN);
+      else if (c.flags & F_SENTENCE_POS) report_error(c, p, E_TEXT_NO_SENT);
+    }
+    c.text_tok_end[text] = tok;
+    c.text_sent_end[text] = sent;
+    c.text_sentpos_end[text] = sentpos;
+    c.text_byte_end[text] = p + 1;
+    DocRec d;
+    d.start = p + 1;
+    d.rank = A.n_rune + popc32(b.rs & le);
+    d.adj = newline_adjust(c, p + 1);
+    d.tok = tok;
+    c.docs[text + 1] = d;
+    doc_start = p + 1;
+  }
+}
+
+// The SentenceEnd events of word w (token_writer.go:103-127), regular and forced.
+DATOK_HD void emit_sentences(const CompactCtx& c, uint32_t w, const WordBits& b, const WordMasks& m, const Agg& A) {
+  uint32_t se = m.se;
+  while (se) {
+    const uint32_t bp = ctz32(se);
+    se &= se - 1;
+    const uint32_t lt = mask_below(bp), le = mask_below(bp + 1), p = (w << 5) + bp;
+    const uint32_t sent = A.n_sent + popc32(m.se & lt);
+    const uint32_t tok = A.n_tok + popc32(b.e & le);
+    const uint32_t sentpos = A.n_sentpos + popc32(m.opener & le) + popc32(m.se & lt);
+    if (c.sent_tok) c.sent_tok[sent] = tok;
+    if (!(c.flags & F_SENTENCE_POS) && !c.sent_pos) continue;
+    const DocRec d = c.docs[A.n_text + popc32(b.t & lt)];
+    if (tok == d.tok) {  // no token in this text yet (token_writer.go:108)
+      if (c.flags & F_SENTENCE_POS) report_error(c, p, E_SENT_NO_TOKEN);
+      continue;
+    }
+    if (!c.sent_pos) continue;
+    // end of the last token: TokenWriter.pos[len(pos)-1]
+    uint32_t rank;
+    if (b.e & le) rank = A.n_rune + popc32(b.rs & mask_below(31u - clz32(b.e & le)));
+    else rank = A.n_rune - count_range(c.rstart, A.last_end_pos, w << 5);
+    c.sent_pos[sentpos] = (int32_t)(rank - d.rank) - doc_shift(c, d);
+  }
+}
+
+// The Token events of word w (token_writer.go:59-95).  Token k goes to tok_bytes/tok_pos[2 * (k - tok_base)]
+// (the kernel stages a block's tokens in shared memory); sentence openers go to c.sent_pos.
+DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, const WordMasks& m, const Agg& A,
+                          uint32_t* tok_bytes, int32_t* tok_pos, uint32_t tok_base) {
+  uint32_t e = b.e;
+  if (e == 0) return;
+  const uint32_t w0 = w << 5;
+  uint32_t tok = A.n_tok - tok_base;
+  uint32_t prev_end = A.last_end_pos;
+  uint32_t doc_id = A.n_text;
+  DocRec d = c.docs[doc_id];
+  int32_t shift = doc_shift(c, d);
+  while (e) {
+    const uint32_t bp = ctz32(e);
+    e &= e - 1;
+    const uint32_t lt = mask_below(bp), p = w0 + bp;
+    if (b.t & lt) {  // a TextEnd earlier in this word
+      const uint32_t id = A.n_text + popc32(b.t & lt);
+      if (id != doc_id) { doc_id = id; d = c.docs[id]; shift = doc_shift(c, d); }
+    }
+    // the Token call's buffer starts at the previous rewind point; offset = leading non-token runes
+    uint32_t bufstart = d.start;
+    if (prev_end != K_NOPOS && prev_end > bufstart) bufstart = prev_end;
+    uint32_t s, runes;  // token start, runes in [s, p)
+    const uint32_t cl = ~b.k & lt & mask_from(bufstart >= w0 ? bufstart - w0 : 32u);
+    if (bufstart >= w0 && cl) {  // within the word
+      s = w0 + ctz32(cl);
+      runes = popc32(b.rs & lt & mask_from(s - w0));
+    } else {
+      s = next_clear(c.b_skip, c.n_words, bufstart);
+      runes = count_range(c.rstart, s, p);
+    }
+    const uint32_t rank_e = A.n_rune + popc32(b.rs & lt);
+    const int32_t pe = (int32_t)(rank_e - d.rank) - shift, ps = pe - (int32_t)runes;
+    if (tok_bytes) { tok_bytes[2 * (size_t)tok] = s; tok_bytes[2 * (size_t)tok + 1] = p; }
+    if (tok_pos) { tok_pos[2 * (size_t)tok] = ps; tok_pos[2 * (size_t)tok + 1] = pe; }
+    if ((m.opener >> bp) & 1u) {
+      if (c.sent_pos) c.sent_pos[A.n_sentpos + popc32(m.opener & lt) + popc32(m.se & lt)] = ps;
+    }
+    tok++;
+    prev_end = p;
+  }
+}
+
+// The pseudo span that precedes position 0: the walk's initial sentenceEnd flag.
+DATOK_HD Agg agg_stream_start(bool sentence_end) {
+  Agg a = agg_zero();
+  const uint32_t k = sentence_end ? EV_SENT : EV_START0;
+  a.kinds = k | (k << 8);
+  return a;
+}
+// docs[0]: the text the stream starts in; for a reused TokenWriter, its shift
+DATOK_HD DocRec doc_stream_start(const CompactCtx& c) {
+  DocRec d;
+  d.start = 0; d.rank = 0; d.tok = 0;
+  d.adj = (c.flags & F_WRITER_USED) ? newline_adjust(c, 0) : 0;
+  return d;
+}
+
+// what the host needs to know about the whole stream
+struct StreamTotals {
+  uint32_t n_rune, n_tok, n_sent, n_text, n_sentpos;
+  uint32_t last_kind;
+  uint32_t tokless;    // no Token since the last TextEnd (or since the stream start)
+  uint32_t reserved;
+};
+
+// End of input (matrix.go:680-695): the final SentenceEnd / TextEnd.  `tot` is the absolute
+// summary of the whole stream.
+DATOK_HD StreamTotals finalize_stream(const CompactCtx& c, const Agg& tot, bool text_end_in, bool final_input) {
+  StreamTotals r;
+  r.n_rune = tot.n_rune; r.n_tok = tot.n_tok; r.n_sent = tot.n_sent; r.n_text = tot.n_text; r.n_sentpos = tot.n_sentpos;
+  r.last_kind = agg_last(tot);
+  r.reserved = 0;
+  const uint32_t doc_start = tot.doc_start == K_NOPOS ? 0u : tot.doc_start;
+  const bool have_tok = tot.last_end_pos != K_NOPOS && tot.last_end_pos > doc_start;
+  r.tokless = have_tok ? 0u : 1u;
+  if (!final_input) return r;
+  const DocRec d = c.docs[tot.n_text];
+  if (forces_sentence(r.last_kind)) {  // :683 if !sentenceEnd
+    if (c.sent_tok) c.sent_tok[r.n_sent] = r.n_tok;
     if (!have_tok) { if (c.flags & F_SENTENCE_POS) report_error(c, c.N, E_SENT_NO_TOKEN); }
-    else if (c.sent_pos) c.sent_pos[tot.n_sentpos] = (int32_t)(tot.last_end_rank - tot.doc_rank) - adj;
-    tot.n_sent++;
-    tot.n_sentpos++;
+    else if (c.sent_pos) {
+      const uint32_t rank = tot.n_rune - count_range(c.rstart, tot.last_end_pos, c.n_words << 5);
+      c.sent_pos[r.n_sentpos] = (int32_t)(rank - d.rank) - doc_shift(c, d);
+    }
+    r.n_sent++;
+    r.n_sentpos++;
   }
   // textEnd (:363): true after a TextEnd with no Token since
   bool text_end;
@@ -290,12 +390,13 @@ DATOK_HD void finalize_stream(const CompactCtx& c, Agg& tot, bool text_end_in) {
       if (c.flags & F_TOKEN_POS) report_error(c, c.N, E_TEXT_NO_TOKEN);
       else if (c.flags & F_SENTENCE_POS) report_error(c, c.N, E_TEXT_NO_SENT);
     }
-    c.text_tok_end[tot.n_text] = tot.n_tok;
-    c.text_sent_end[tot.n_text] = tot.n_sent;
-    c.text_sentpos_end[tot.n_text] = tot.n_sentpos;
-    c.text_byte_end[tot.n_text] = c.N;
-    tot.n_text++;
+    c.text_tok_end[r.n_text] = r.n_tok;
+    c.text_sent_end[r.n_text] = r.n_sent;
+    c.text_sentpos_end[r.n_text] = r.n_sentpos;
+    c.text_byte_end[r.n_text] = c.N;
+    r.n_text++;
   }
+  return r;
 }
 
 }  // namespace datok

@@ -207,6 +207,7 @@ union AggWords {
   uint32_t w[AGG_WORDS];
 };
 static_assert(sizeof(Agg) == AGG_WORDS * 4, "Agg layout");
+static_assert(sizeof(StreamTotals) == sizeof(Agg), "totals share the Agg slots");
 
 __device__ __forceinline__ Agg agg_shfl_up(const Agg& v, int delta) {
   AggWords in, out;
@@ -215,11 +216,18 @@ __device__ __forceinline__ Agg agg_shfl_up(const Agg& v, int delta) {
   for (int k = 0; k < AGG_WORDS; k++) out.w[k] = __shfl_up_sync(0xFFFFFFFFu, in.w[k], delta);
   return out.a;
 }
+__device__ __forceinline__ Agg agg_shfl_down(const Agg& v, int delta) {
+  AggWords in, out;
+  in.a = v;
+#pragma unroll
+  for (int k = 0; k < AGG_WORDS; k++) out.w[k] = __shfl_down_sync(0xFFFFFFFFu, in.w[k], delta);
+  return out.a;
+}
 
 // Ordered (non-commutative) block scan.  Returns the exclusive prefix of `mine`
-// within the block combined after `seed`; *block_total = all threads' values combined.
+// within the block combined after `seed`.
 template <int THREADS>
-__device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& seed, Agg* block_total) {
+__device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& seed) {
   __shared__ Agg s_warp[THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Agg incl = mine;
@@ -232,79 +240,177 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& 
   __syncthreads();
   Agg prefix = seed;
   for (int wi = 0; wi < warp; wi++) prefix = agg_combine(prefix, s_warp[wi]);
-  if (block_total) {
-    Agg tot = s_warp[0];
-    for (int wi = 1; wi < THREADS / 32; wi++) tot = agg_combine(tot, s_warp[wi]);
-    *block_total = tot;
-  }
   Agg prev = agg_shfl_up(incl, 1);
   if (lane > 0) prefix = agg_combine(prefix, prev);
   __syncthreads();
   return prefix;
 }
 
-__global__ void __launch_bounds__(COMPACT_THREADS) compact_reduce_kernel(CompactCtx c, CompactBuffers cb) {
+// Ordered block reduction; the result is valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ Agg block_reduce(const Agg& mine) {
+  __shared__ Agg s_warp[THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Agg v = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Agg o = agg_shfl_down(v, d);
+    if ((lane & (2 * d - 1)) == 0) v = agg_combine(v, o);  // lanes lane..lane+2d-1, in order
+  }
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  Agg tot = s_warp[0];
+  if (threadIdx.x == 0)
+    for (int wi = 1; wi < THREADS / 32; wi++) tot = agg_combine(tot, s_warp[wi]);
+  return tot;
+}
+
+enum { K3_REDUCE = 0, K3_TEXTS = 1, K3_EMIT = 2 };
+
+// One pass over the bitmaps, COMPACT_WPT words per thread.
+//   K3_REDUCE  block summaries
+//   K3_TEXTS   TextEnd events: per-text bounds and the DocRec table
+//   K3_EMIT    Token and SentenceEnd events; a block's tokens are staged in shared memory and
+//              written out as contiguous 8-byte pairs
+template <int MODE>
+__global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, CompactBuffers cb) {
+  extern __shared__ __align__(16) uint32_t s_stage[];
+  if (MODE == K3_TEXTS) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) c.docs[0] = doc_stream_start(c);
+    if (cb.block_agg[blockIdx.x].n_text == 0) return;  // no TextEnd in this block
+  }
   const uint32_t w0 = (blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
+  WordBits wb[COMPACT_WPT];
+  Agg wa[COMPACT_WPT];
   Agg ta = agg_zero();
 #pragma unroll
   for (int k = 0; k < COMPACT_WPT; k++) {
     const uint32_t w = w0 + k;
-    if (w < c.n_words) ta = agg_combine(ta, process_word<false>(c, w, ta));
+    if (w < c.n_words) {
+      wb[k] = word_load(c, w);
+      wa[k] = word_agg(w, wb[k]);
+      ta = agg_combine(ta, wa[k]);
+    }
   }
-  Agg tot;
-  block_exclusive_scan<COMPACT_THREADS>(ta, agg_zero(), &tot);
-  if (threadIdx.x == 0) cb.block_agg[blockIdx.x] = tot;
+  if (MODE == K3_REDUCE) {
+    const Agg tot = block_reduce<COMPACT_THREADS>(ta);
+    if (threadIdx.x == 0) cb.block_agg[blockIdx.x] = tot;
+    return;
+  }
+  // summary of everything before this block: (groups of 1024 blocks before) + (blocks before, in the group)
+  const Agg block_start = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
+  Agg carry = block_exclusive_scan<COMPACT_THREADS>(ta, block_start);
+  if (MODE == K3_TEXTS) {
+#pragma unroll
+    for (int k = 0; k < COMPACT_WPT; k++) {
+      const uint32_t w = w0 + k;
+      if (w < c.n_words) {
+        emit_texts(c, w, wb[k], carry);
+        carry = agg_combine(carry, wa[k]);
+      }
+    }
+    return;
+  }
+  // K3_EMIT
+  const uint32_t blk_tok0 = block_start.n_tok, blk_ntok = cb.block_agg[blockIdx.x].n_tok;
+  const bool staged = blk_ntok <= STAGE_TOKENS;
+  uint32_t* s_tb = s_stage;
+  int32_t* s_tp = reinterpret_cast<int32_t*>(s_stage + 2 * STAGE_TOKENS);
+  // two copies of the loop so that the staged one addresses shared memory directly
+  if (staged) {
+#pragma unroll
+    for (int k = 0; k < COMPACT_WPT; k++) {
+      const uint32_t w = w0 + k;
+      if (w < c.n_words) {
+        if (wb[k].e | wb[k].s | wb[k].t) {
+          const WordMasks m = word_masks(wb[k], agg_last(carry));
+          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes ? s_tb : nullptr, c.tok_pos ? s_tp : nullptr, blk_tok0);
+          emit_sentences(c, w, wb[k], m, carry);
+        }
+        carry = agg_combine(carry, wa[k]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < COMPACT_WPT; k++) {
+      const uint32_t w = w0 + k;
+      if (w < c.n_words) {
+        if (wb[k].e | wb[k].s | wb[k].t) {
+          const WordMasks m = word_masks(wb[k], agg_last(carry));
+          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes, c.tok_pos, 0u);
+          emit_sentences(c, w, wb[k], m, carry);
+        }
+        carry = agg_combine(carry, wa[k]);
+      }
+    }
+  }
+  if (!staged) return;
+  __syncthreads();
+  if (c.tok_bytes) {
+    uint2* dst = reinterpret_cast<uint2*>(c.tok_bytes) + blk_tok0;
+    const uint2* src = reinterpret_cast<const uint2*>(s_tb);
+    for (uint32_t i = threadIdx.x; i < blk_ntok; i += COMPACT_THREADS) dst[i] = src[i];
+  }
+  if (c.tok_pos) {
+    uint2* dst = reinterpret_cast<uint2*>(c.tok_pos) + blk_tok0;
+    const uint2* src = reinterpret_cast<const uint2*>(s_tp);
+    for (uint32_t i = threadIdx.x; i < blk_ntok; i += COMPACT_THREADS) dst[i] = src[i];
+  }
 }
 
-// Single block: thread t owns a contiguous run of block summaries.
-constexpr int SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(SCAN_THREADS) compact_scan_kernel(CompactCtx c, CompactBuffers cb,
-                                                                     bool sentence_end_in) {
-  const uint32_t per = (cb.n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
+// Scan of the block summaries, two levels: groups of SCAN_THREADS block summaries are scanned by one
+// block each (compact_scan_groups), then the group totals by a single block (compact_scan_top).  A
+// consumer block combines super_carry[group] with block_carry[block].
+__global__ void __launch_bounds__(SCAN_THREADS) compact_scan_groups_kernel(CompactBuffers cb) {
+  const uint32_t i = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  const Agg mine = i < cb.n_blocks ? cb.block_agg[i] : agg_zero();
+  const Agg excl = block_exclusive_scan<SCAN_THREADS>(mine, agg_zero());
+  if (i < cb.n_blocks) cb.block_carry[i] = excl;
+  if (threadIdx.x == SCAN_THREADS - 1) cb.super_agg[blockIdx.x] = agg_combine(excl, mine);
+}
+__global__ void __launch_bounds__(SCAN_THREADS) compact_scan_top_kernel(CompactBuffers cb, bool sentence_end_in) {
+  const uint32_t n = (cb.n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t lo = threadIdx.x * per;
-  const uint32_t hi = lo + per < cb.n_blocks ? lo + per : cb.n_blocks;
+  const uint32_t hi = lo + per < n ? lo + per : n;
   Agg mine = agg_zero();
-  for (uint32_t i = lo; i < hi; i++) mine = agg_combine(mine, cb.block_agg[i]);
-  Agg tot;
-  const Agg start = agg_stream_start(c, sentence_end_in);
-  Agg run = block_exclusive_scan<SCAN_THREADS>(mine, start, &tot);
+  for (uint32_t i = lo; i < hi; i++) mine = agg_combine(mine, cb.super_agg[i]);
+  const Agg start = agg_stream_start(sentence_end_in);
+  Agg run = block_exclusive_scan<SCAN_THREADS>(mine, start);
   for (uint32_t i = lo; i < hi; i++) {
-    cb.block_carry[i] = run;
-    run = agg_combine(run, cb.block_agg[i]);
+    cb.super_carry[i] = run;
+    run = agg_combine(run, cb.super_agg[i]);
   }
-  if (threadIdx.x == 0) cb.total[0] = agg_combine(start, tot);
-}
-
-__global__ void __launch_bounds__(COMPACT_THREADS) compact_emit_kernel(CompactCtx c, CompactBuffers cb) {
-  const uint32_t w0 = (blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
-  Agg ta = agg_zero();
-#pragma unroll
-  for (int k = 0; k < COMPACT_WPT; k++) {
-    const uint32_t w = w0 + k;
-    if (w < c.n_words) ta = agg_combine(ta, process_word<false>(c, w, ta));
-  }
-  Agg carry = block_exclusive_scan<COMPACT_THREADS>(ta, cb.block_carry[blockIdx.x], nullptr);
-#pragma unroll 1
-  for (int k = 0; k < COMPACT_WPT; k++) {
-    const uint32_t w = w0 + k;
-    if (w < c.n_words) carry = process_word<true>(c, w, carry);
-  }
+  // the thread that owns the last group holds the stream summary
+  if ((lo < hi && hi == n) || (n == 0 && threadIdx.x == 0)) cb.total[0] = run;
 }
 
 __global__ void compact_finalize_kernel(CompactCtx c, CompactBuffers cb, bool text_end_in, bool final_input) {
-  Agg tot = cb.total[0];
-  if (final_input) finalize_stream(c, tot, text_end_in);
-  cb.total[1] = tot;
+  const StreamTotals t = finalize_stream(c, cb.total[0], text_end_in, final_input);
+  *reinterpret_cast<StreamTotals*>(&cb.total[1]) = t;
 }
 
 void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
-  compact_reduce_kernel<<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
+  compact_kernel<K3_REDUCE><<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
 }
-void launch_compact_scan(const CompactCtx& c, const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s) {
-  compact_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(c, cb, sentence_end_in);
+void launch_compact_scan(const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s) {
+  const uint32_t groups = (cb.n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
+  if (groups) compact_scan_groups_kernel<<<groups, SCAN_THREADS, 0, s>>>(cb);
+  compact_scan_top_kernel<<<1, SCAN_THREADS, 0, s>>>(cb, sentence_end_in);
 }
-void launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
-  compact_emit_kernel<<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
+void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
+  compact_kernel<K3_TEXTS><<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
+}
+int launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
+  const int smem = 4 * STAGE_TOKENS * (int)sizeof(uint32_t);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(compact_kernel<K3_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  compact_kernel<K3_EMIT><<<cb.n_blocks, COMPACT_THREADS, smem, s>>>(c, cb);
+  return (int)cudaGetLastError();
 }
 void launch_compact_finalize(const CompactCtx& c, const CompactBuffers& cb, bool text_end_in, bool final_input,
                              cudaStream_t s) {

@@ -11,12 +11,16 @@ namespace datok {
 struct CompactBuffers {
   Agg* block_agg;
   Agg* block_carry;
-  Agg* total;              // [0] stream total after finalize
+  Agg* super_agg;          // one per group of SCAN_THREADS blocks
+  Agg* super_carry;
+  Agg* total;              // [0] stream summary after the scan, [1] StreamTotals after finalize
   uint32_t n_blocks;
 };
 
-constexpr int COMPACT_THREADS = 512;
-constexpr int COMPACT_WPT = 2;  // bitmap words per thread
+constexpr int COMPACT_THREADS = 256;
+constexpr int COMPACT_WPT = 2;     // bitmap words per thread
+constexpr int SCAN_THREADS = 1024;
+constexpr int STAGE_TOKENS = 4096;  // tokens of one block staged in shared memory (else written directly)
 
 // fused classify + speculative walk; returns a cudaError_t value
 int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot, int n_sms,
@@ -32,8 +36,9 @@ void launch_commit(const WalkBuffers& b, const uint32_t* list, uint32_t n_list, 
 void launch_collect_errors(const WalkBuffers& b, cudaStream_t s);
 
 void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
-void launch_compact_scan(const CompactCtx& c, const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s);
-void launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
+void launch_compact_scan(const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s);
+void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
+int launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
 void launch_compact_finalize(const CompactCtx& c, const CompactBuffers& cb, bool text_end_in, bool final_input,
                              cudaStream_t s);
 

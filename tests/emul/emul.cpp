@@ -157,12 +157,12 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   if (!(last.flags & WS_DONE)) { R->status = 0xFE; return R; }
   R->carry_state = em->hm.old_of_new[last.t];
 
-  // K3 compaction: per-thread aggs -> block aggs -> scan -> emit
+  // K3 compaction: per-thread aggs -> block aggs -> scan -> texts pass -> emit
   CompactCtx c;
   std::memset(&c, 0, sizeof c);
   c.in = in; c.N = N; c.n_words = b.n_words; c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip;
   c.b_sent = b.b_sent; c.b_tend = b.b_tend; c.flags = flags; c.err_key = &err_key;
-  const uint32_t TPB = 512, WPT = 2, WPB = TPB * WPT;
+  const uint32_t TPB = 256, WPT = 2, WPB = TPB * WPT;
   const uint32_t nblk = (b.n_words + WPB - 1) / WPB;
   std::vector<Agg> block_agg(nblk), block_carry(nblk);
   for (uint32_t blk = 0; blk < nblk; blk++) {
@@ -171,15 +171,15 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       Agg ta = agg_zero();
       for (uint32_t k = 0; k < WPT; k++) {
         uint32_t w = blk * WPB + t * WPT + k;
-        if (w < b.n_words) ta = agg_combine(ta, process_word<false>(c, w, ta));
+        if (w < b.n_words) ta = agg_combine(ta, word_agg(w, word_load(c, w)));
       }
       acc = agg_combine(acc, ta);
     }
     block_agg[blk] = acc;
   }
-  Agg run = agg_stream_start(c, sentence_end_in != 0);
+  Agg run = agg_stream_start(sentence_end_in != 0);
   for (uint32_t blk = 0; blk < nblk; blk++) { block_carry[blk] = run; run = agg_combine(run, block_agg[blk]); }
-  Agg total = run;
+  const Agg total = run;
   R->n_runes = total.n_rune;
   size_t nt = total.n_tok, ns = total.n_sent + 1, nx = total.n_text + 1, np = total.n_sentpos + 1;
   R->tok_bytes = (uint32_t*)std::calloc(2 * nt + 2, 4);
@@ -190,22 +190,44 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   R->text_sent_end = (uint32_t*)std::calloc(nx + 1, 4);
   R->text_sentpos_end = (uint32_t*)std::calloc(nx + 1, 4);
   R->text_byte_end = (uint32_t*)std::calloc(nx + 1, 4);
+  std::vector<DocRec> docs(nx + 1);
   c.tok_bytes = R->tok_bytes; c.tok_pos = R->tok_pos; c.sent_pos = R->sent_pos; c.sent_tok = R->sent_tok;
   c.text_tok_end = R->text_tok_end; c.text_sent_end = R->text_sent_end;
   c.text_sentpos_end = R->text_sentpos_end; c.text_byte_end = R->text_byte_end;
-  for (uint32_t kb = 0; kb < nblk; kb++) {
-    uint32_t blk = order ? nblk - 1 - kb : kb;
-    Agg carry = block_carry[blk];
-    for (uint32_t t = 0; t < TPB; t++) {
-      for (uint32_t k = 0; k < WPT; k++) {
-        uint32_t w = blk * WPB + t * WPT + k;
-        if (w >= b.n_words) continue;
-        carry = process_word<true>(c, w, carry);
+  c.docs = docs.data();
+  docs[0] = doc_stream_start(c);
+  for (int pass = 0; pass < 2; pass++) {  // 0: texts, 1: tokens + sentences
+    for (uint32_t kb = 0; kb < nblk; kb++) {
+      uint32_t blk = order ? nblk - 1 - kb : kb;
+      Agg carry = block_carry[blk];
+      // like the kernel: a block's tokens are staged block-relative when they fit
+      const uint32_t blk_tok0 = carry.n_tok, blk_ntok = block_agg[blk].n_tok;
+      const bool staged = blk_ntok <= 64;
+      std::vector<uint32_t> s_tb(2 * 64 + 2);
+      std::vector<int32_t> s_tp(2 * 64 + 2);
+      for (uint32_t t = 0; t < TPB; t++) {
+        for (uint32_t k = 0; k < WPT; k++) {
+          uint32_t w = blk * WPB + t * WPT + k;
+          if (w >= b.n_words) continue;
+          const WordBits wb = word_load(c, w);
+          if (pass == 0) emit_texts(c, w, wb, carry);
+          else if (wb.e | wb.s | wb.t) {
+            const WordMasks wm = word_masks(wb, agg_last(carry));
+            emit_tokens(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
+                        staged ? blk_tok0 : 0u);
+            emit_sentences(c, w, wb, wm, carry);
+          }
+          carry = agg_combine(carry, word_agg(w, wb));
+        }
+      }
+      if (pass == 1 && staged) {
+        std::memcpy(c.tok_bytes + 2 * (size_t)blk_tok0, s_tb.data(), 8 * (size_t)blk_ntok);
+        std::memcpy(c.tok_pos + 2 * (size_t)blk_tok0, s_tp.data(), 8 * (size_t)blk_ntok);
       }
     }
   }
-  if (b.final_input) finalize_stream(c, total, text_end_in != 0);
-  R->n_tokens = total.n_tok; R->n_sentences = total.n_sent; R->n_texts = total.n_text; R->n_sent_pos = total.n_sentpos;
+  const StreamTotals fin = finalize_stream(c, total, text_end_in != 0, b.final_input != 0);
+  R->n_tokens = fin.n_tok; R->n_sentences = fin.n_sent; R->n_texts = fin.n_text; R->n_sent_pos = fin.n_sentpos;
   if (err_key != ~0ull) R->status = (int)(err_key & 0xFF);
   return R;
 }
