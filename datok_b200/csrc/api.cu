@@ -30,6 +30,15 @@ static thread_local std::string g_last_error;
     }                                                                                       \
   } while (0)
 
+#define CUDA_TRYF(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      g_last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+      return fail(DATOK_ERR_CUDA);                                                          \
+    }                                                                                       \
+  } while (0)
+
 namespace {
 
 struct Block {
@@ -72,6 +81,14 @@ struct datok_model {
   uint32_t last_rounds = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> tev;
+  // pipelined host path: copy streams and double-buffered device staging
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr},
+              ev_out[2] = {nullptr, nullptr};
+  Block d_in[2];                 // input pieces
+  Block d_out[2][5];             // per slot: tok_bytes, tok_pos, sent_pos, sent_tok, text arrays + DocRec
+  size_t piece_bytes = (size_t)128 << 20;
+  bool pipelined = true;
   // results hold pooled buffers of their model: the model outlives them
   int live_results = 0;
   bool freed_by_user = false;
@@ -135,6 +152,13 @@ void destroy_model(datok_model* m) {
   if (m->d_cls_tables) cudaFree(m->d_cls_tables);
   if (m->d_rune_key) cudaFree(m->d_rune_key);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; i++) {
+    for (cudaEvent_t e : {m->ev_in[i], m->ev_free[i], m->ev_emit[i], m->ev_out[i]}) if (e) cudaEventDestroy(e);
+    if (m->d_in[i].p) cudaFree(m->d_in[i].p);
+    for (auto& blk : m->d_out[i]) if (blk.p) cudaFree(blk.p);
+  }
+  if (m->s_h2d) cudaStreamDestroy(m->s_h2d);
+  if (m->s_d2h) cudaStreamDestroy(m->s_d2h);
   for (auto& e : m->tev) cudaEventDestroy(e);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -348,6 +372,19 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
     return nullptr;
   }
   for (auto& e : m->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking);
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->ev_emit[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming);
+  }
+  if (const char* s = std::getenv("DATOK_NO_PIPELINE")) m->pipelined = !(s[0] == '1');
+  if (const char* s = std::getenv("DATOK_PIECE_MB")) {
+    long v = std::atol(s);
+    if (v >= 1 && v <= 2048) m->piece_bytes = (size_t)v << 20;
+  }
   m->n_sms = prop.multiProcessorCount;
   m->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   if (const char* s = std::getenv("DATOK_NO_CALIBRATE")) m->auto_calibrate = !(s[0] == '1');
@@ -361,6 +398,359 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
   *err = DATOK_OK;
   return m;
 }
+
+// K1+K2: clear, fused walk, fix-up rounds (host-synchronised on the round counters), error collection
+int do_walk(datok_model* m, WalkBuffers& b, uint32_t start_state, PhaseTimer& pt) {
+  cudaStream_t s = m->stream;
+  pt.begin(T_CLEAR);
+  CUDA_TRY(cudaMemsetAsync(b.b_end, 0, (size_t)b.n_words * 4 * sizeof(uint32_t), s));
+  CUDA_TRY(cudaMemsetAsync(b.counters, 0, 8 * sizeof(uint32_t), s));
+  CUDA_TRY(cudaMemsetAsync(b.err_key, 0xFF, sizeof(unsigned long long), s));
+  pt.end();
+  pt.begin(T_WALK);
+  {
+    const int e = launch_walk_fused(m->dm, b, start_state, m->n_hot, m->n_sms, s);
+    if (e != 0) { g_last_error = std::string("walk_fused launch: ") + cudaGetErrorString((cudaError_t)e); return DATOK_ERR_CUDA; }
+  }
+  pt.end();
+  m->launches += 1;
+  uint32_t n_list = b.n_chunks - 1;
+  const uint32_t* list = nullptr;  // round 1: every chunk but the first
+  uint32_t* cur = b.list_cur;
+  uint32_t* nxt = b.list_next;
+  while (n_list) {
+    m->last_rounds++;
+    b.list_next = nxt;
+    pt.begin(T_STITCH);
+    launch_stitch(m->dm, b, list, n_list, s);
+    pt.end();
+    pt.begin(T_REWALK);
+    launch_rewalk(m->dm, b, n_list, s);
+    pt.end();
+    pt.begin(T_COMMIT);
+    launch_commit(b, list, n_list, s);
+    pt.end();
+    m->launches += 3;
+    uint32_t counts[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(counts, b.counters, sizeof counts, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemsetAsync(b.counters, 0, 2 * sizeof(uint32_t), s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    n_list = counts[0];
+    std::swap(cur, nxt);
+    list = cur;
+  }
+  launch_collect_errors(b, s);
+  m->launches++;
+  return DATOK_OK;
+}
+
+struct PieceHead {
+  Agg tot;
+  unsigned long long err;
+  uint32_t invalid;
+  WState last;
+};
+
+// K3 reduce + scan, then the stream summary, the walk's error key and its final state come back
+int do_count(datok_model* m, const WalkBuffers& b, CompactCtx& c, const CompactBuffers& cb, uint32_t flags,
+             bool sentence_end_in, PhaseTimer& pt, PieceHead& h) {
+  cudaStream_t s = m->stream;
+  std::memset(&c, 0, sizeof c);
+  c.in = b.in; c.N = b.N; c.n_words = b.n_words;
+  c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
+  c.flags = flags; c.err_key = b.err_key;
+  pt.begin(T_REDUCE);
+  launch_compact_reduce(c, cb, s);
+  pt.end();
+  pt.begin(T_SCAN);
+  launch_compact_scan(cb, sentence_end_in, s);
+  pt.end();
+  m->launches += 3;
+  CUDA_TRY(cudaMemcpyAsync(&h.tot, cb.total, sizeof(Agg), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&h.err, b.err_key, sizeof h.err, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&h.invalid, b.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&h.last, b.E + (b.n_chunks - 1), sizeof(WState), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (h.err != ~0ull) {  // the walk itself hit a reference panic
+    const int code = (int)(h.err & 0xFF);
+    g_last_error = std::string("reference would panic: ") + datok_strerror(code);
+    return code >= 0xF0 ? DATOK_ERR_CUDA : code;
+  }
+  return DATOK_OK;
+}
+
+// the walk of a non-final input stopped at the loop top at N: it must be at a rewind point with nothing pending
+bool at_text_boundary(const WState& last, uint32_t N) {
+  return last.tstart == N && last.base == N && last.eps_state == 0 && !(last.flags & WS_PEND);
+}
+
+bool grow_block(Block& b, size_t bytes, bool host) {
+  if (b.p && b.bytes >= bytes) return true;
+  if (b.p) { if (host) cudaFreeHost(b.p); else cudaFree(b.p); }
+  b.p = nullptr;
+  b.bytes = bytes + bytes / 4 + 4096;
+  b.host = host;
+  cudaError_t e = host ? cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) : cudaMalloc(&b.p, b.bytes);
+  if (e != cudaSuccess) { b.p = nullptr; b.bytes = 0; cudaGetLastError(); return false; }
+  return true;
+}
+
+// Host-to-host path for large inputs: the stream is cut after EOT bytes into pieces that are copied in,
+// transduced and copied out in a software pipeline (copy engines in both directions overlap the
+// kernels).  A piece after an EOT starts a new text: only the walk state and "a token was seen"
+// carry over (matrix.go:593-605).  Returns -1 if the input cannot be cut (the caller then runs it in
+// one pass).
+int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, const datok_carry* carry_in,
+                  datok_result** out) {
+  // ---- cut points: the last EOT before each multiple of piece_bytes ----
+  std::vector<size_t> cut;  // piece k = [cut[k], cut[k+1])
+  cut.push_back(0);
+  while (n - cut.back() > m->piece_bytes + m->piece_bytes / 2) {
+    const size_t lo = cut.back(), want = lo + m->piece_bytes;
+    const void* q = memrchr(in + lo, 0x04, want - lo);
+    if (!q) return -1;
+    const size_t c = (size_t)((const uint8_t*)q - in) + 1;
+    if (c - lo < m->piece_bytes / 2) return -1;  // texts longer than half a piece: not worth cutting
+    cut.push_back(c);
+  }
+  cut.push_back(n);
+  const size_t np = cut.size() - 1;
+  if (np < 2) return -1;
+
+  std::lock_guard<std::mutex> lock(m->mu);
+  CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  std::memset(m->t_ms, 0, sizeof m->t_ms);
+  m->launches = 0;
+  m->last_rounds = 0;
+  const bool call_final = !(flags & DATOK_NOT_FINAL);
+
+  size_t max_piece = 0;
+  for (size_t k = 0; k < np; k++) max_piece = std::max(max_piece, cut[k + 1] - cut[k]);
+  for (int i = 0; i < 2; i++)
+    if (!grow_block(m->d_in[i], max_piece + 64, false)) { g_last_error = "cudaMalloc (input piece) failed"; return DATOK_ERR_CUDA; }
+  WalkBuffers b;
+  CompactBuffers cb;
+  std::memset(&b, 0, sizeof b);
+  std::memset(&cb, 0, sizeof cb);
+  int rc = ensure_workspace(m, carve(nullptr, (uint32_t)max_piece, m->chunk, false, b, cb));
+  if (rc) return rc;
+
+  const bool want_bytes = (flags & DATOK_TOKENS) != 0, want_pos = (flags & DATOK_TOKEN_POS) != 0;
+  const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
+  const bool want[5] = {want_bytes, want_pos, want_spos, want_stok, true};
+
+  // first pieces on their way
+  auto issue_h2d = [&](size_t k) -> int {
+    const int slot = (int)(k & 1);
+    CUDA_TRY(cudaStreamWaitEvent(m->s_h2d, m->ev_free[slot], 0));  // the piece that used this buffer is done
+    CUDA_TRY(cudaMemcpyAsync(m->d_in[slot].p, in + cut[k], cut[k + 1] - cut[k], cudaMemcpyHostToDevice, m->s_h2d));
+    CUDA_TRY(cudaEventRecord(m->ev_in[slot], m->s_h2d));
+    return DATOK_OK;
+  };
+  CUDA_TRY(cudaEventRecord(m->ev[0], s));
+
+  if (m->auto_calibrate && !m->calibrated && cut[1] >= (256u << 10)) {
+    // one-time specialisation of the table layout to the caller's text
+    carve(m->ws, (uint32_t)cut[1], m->chunk, false, b, cb);
+    b.in = (const uint8_t*)m->d_in[0].p;
+    b.final_input = 0;
+    CUDA_TRY(cudaMemcpyAsync(m->d_in[0].p, in, std::min<size_t>(cut[1], 8u << 20), cudaMemcpyHostToDevice, s));
+    rc = calibrate_locked(m, b);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventRecord(m->ev_free[i], s)); CUDA_TRY(cudaEventRecord(m->ev_out[i], s)); }
+  if ((rc = issue_h2d(0))) return rc;
+  if ((rc = issue_h2d(1))) return rc;
+
+  datok_result* r = new datok_result();
+  r->model = m;
+  m->live_results++;
+  r->device = false;
+  std::memset(&r->view, 0, sizeof r->view);
+  datok_view& v = r->view;
+  Block host[8];  // tok_bytes, tok_pos, sent_pos, sent_tok, text_tok_end, text_sent_end, text_sentpos_end, text_byte_end
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(m->s_h2d); cudaStreamSynchronize(m->s_d2h); cudaStreamSynchronize(s);
+    for (auto& hb : host) release(m, hb);
+    free_result_locked(r);
+    return code;
+  };
+  // makes room for `need` bytes in host array i, keeping what is there (rare after the first piece)
+  auto host_room = [&](int i, size_t need, size_t used) -> bool {
+    if (host[i].p && host[i].bytes >= need) return true;
+    int rc2 = DATOK_OK;
+    Block nb = acquire(m, need + need / 8, true, &rc2);
+    if (!nb.p) return false;
+    if (host[i].p) {
+      cudaStreamSynchronize(m->s_d2h);
+      std::memcpy(nb.p, host[i].p, used);
+      release(m, host[i]);
+    }
+    host[i] = nb;
+    return true;
+  };
+
+  PhaseTimer pt{m};
+  uint32_t state = m->hm.start;
+  bool sentence_end_in = false, text_end_in = false;
+  if (carry_in) {
+    if (carry_in->state) {
+      if (carry_in->state > (uint32_t)m->hm.stateCount) { g_last_error = "carry state out of range"; return fail(DATOK_ERR_INVALID_ARG); }
+      state = m->hm.new_of_old[carry_in->state];
+    }
+    sentence_end_in = carry_in->sentence_end != 0;
+    text_end_in = carry_in->text_end != 0;
+  }
+  uint64_t base_tok = 0, base_sent = 0, base_sentpos = 0, base_text = 0, runes = 0;
+  uint32_t invalid = 0;
+  float ms_kernels = 0;
+  std::vector<cudaEvent_t> kev;
+
+  for (size_t k = 0; k < np; k++) {
+    const int slot = (int)(k & 1);
+    const uint32_t N = (uint32_t)(cut[k + 1] - cut[k]);
+    const bool last_piece = k + 1 == np;
+    const bool final_input = last_piece && call_final;
+    uint32_t pflags = flags | (final_input ? 0u : (uint32_t)DATOK_NOT_FINAL);
+    if (base_tok > 0) pflags |= DATOK_WRITER_USED;
+    carve(m->ws, N, m->chunk, false, b, cb);
+    b.in = (const uint8_t*)m->d_in[slot].p;
+    b.final_input = final_input ? 1u : 0u;
+    CUDA_TRYF(cudaStreamWaitEvent(s, m->ev_in[slot], 0));
+    cudaEvent_t k0 = pt.next(), k1 = pt.next();
+    CUDA_TRYF(cudaEventRecord(k0, s));
+    if ((rc = do_walk(m, b, state, pt))) return fail(rc);
+    CompactCtx c;
+    PieceHead h;
+    if ((rc = do_count(m, b, c, cb, pflags, sentence_end_in, pt, h))) { pt.collect(); return fail(rc); }
+    if (!final_input && !at_text_boundary(h.last, N)) {
+      g_last_error = last_piece ? "DATOK_NOT_FINAL input does not end at a text boundary"
+                                : "internal: piece does not end at a text boundary";
+      return fail(DATOK_ERR_NOT_AT_BOUNDARY);
+    }
+    // ---- room for this piece's results: device slot and the host arrays ----
+    const size_t nt = h.tot.n_tok, ns = (size_t)h.tot.n_sent + 1, nx = (size_t)h.tot.n_text + 1,
+                 nsp = (size_t)h.tot.n_sentpos + 1;
+    const size_t dev_bytes[5] = {2 * nt * 4, 2 * nt * 4, nsp * 4, ns * 4, nx * 16 + (nx + 1) * sizeof(DocRec)};
+    CUDA_TRYF(cudaStreamWaitEvent(s, m->ev_out[slot], 0));  // the slot's previous results have left the device
+    for (int i = 0; i < 5; i++) {
+      if (!want[i]) continue;
+      if (m->d_out[slot][i].bytes < dev_bytes[i]) CUDA_TRYF(cudaEventSynchronize(m->ev_out[slot]));
+      if (!grow_block(m->d_out[slot][i], dev_bytes[i], false)) { g_last_error = "cudaMalloc (results) failed"; return fail(DATOK_ERR_CUDA); }
+    }
+    {
+      // estimate for the whole stream from what has been seen so far (+12 %), exact for the last piece
+      const double done = (double)cut[k + 1], scale = last_piece ? 1.0 : 1.12 * (double)n / done;
+      auto est = [&](uint64_t have, size_t add) { return (size_t)((double)(have + add) * scale) + 4096; };
+      const size_t need8[8] = {est(base_tok, nt) * 8, est(base_tok, nt) * 8, est(base_sentpos, nsp) * 4, est(base_sent, ns) * 4,
+                               est(base_text, nx) * 4, est(base_text, nx) * 4, est(base_text, nx) * 4, est(base_text, nx) * 4};
+      const size_t used8[8] = {base_tok * 8, base_tok * 8, base_sentpos * 4, base_sent * 4, base_text * 4, base_text * 4,
+                               base_text * 4, base_text * 4};
+      const bool want8[8] = {want_bytes, want_pos, want_spos, want_stok, true, true, true, true};
+      for (int i = 0; i < 8; i++)
+        if (want8[i] && !host_room(i, need8[i], used8[i])) { g_last_error = "cudaHostAlloc (results) failed"; return fail(DATOK_ERR_CUDA); }
+    }
+    c.base_tok = (uint32_t)base_tok; c.base_sent = (uint32_t)base_sent; c.base_sentpos = (uint32_t)base_sentpos;
+    c.base_byte = (uint32_t)cut[k];
+    c.tok_bytes = want_bytes ? (uint32_t*)m->d_out[slot][0].p : nullptr;
+    c.tok_pos = want_pos ? (int32_t*)m->d_out[slot][1].p : nullptr;
+    c.sent_pos = want_spos ? (int32_t*)m->d_out[slot][2].p : nullptr;
+    c.sent_tok = want_stok ? (uint32_t*)m->d_out[slot][3].p : nullptr;
+    c.text_tok_end = (uint32_t*)m->d_out[slot][4].p;
+    c.text_sent_end = c.text_tok_end + nx;
+    c.text_sentpos_end = c.text_tok_end + 2 * nx;
+    c.text_byte_end = c.text_tok_end + 3 * nx;
+    c.docs = reinterpret_cast<DocRec*>(c.text_tok_end + 4 * nx);
+    pt.begin(T_TEXTS);
+    launch_compact_texts(c, cb, s);
+    pt.end();
+    pt.begin(T_EMIT);
+    {
+      const int e = launch_compact_emit(c, cb, s);
+      if (e != 0) { g_last_error = std::string("compact_emit launch: ") + cudaGetErrorString((cudaError_t)e); return fail(DATOK_ERR_CUDA); }
+    }
+    launch_compact_finalize(c, cb, text_end_in, final_input, s);
+    pt.end();
+    m->launches += 3;
+    struct { StreamTotals fin; unsigned long long err; } tail;
+    CUDA_TRYF(cudaMemcpyAsync(&tail.fin, cb.total + 1, sizeof(StreamTotals), cudaMemcpyDeviceToHost, s));
+    CUDA_TRYF(cudaMemcpyAsync(&tail.err, b.err_key, sizeof tail.err, cudaMemcpyDeviceToHost, s));
+    CUDA_TRYF(cudaEventRecord(k1, s));
+    CUDA_TRYF(cudaEventRecord(m->ev_emit[slot], s));
+    CUDA_TRYF(cudaEventRecord(m->ev_free[slot], s));
+    CUDA_TRYF(cudaStreamSynchronize(s));
+    kev.push_back(k0); kev.push_back(k1);
+    if (tail.err != ~0ull) {
+      pt.collect();
+      const int code = (int)(tail.err & 0xFF);
+      g_last_error = std::string("reference would panic: ") + datok_strerror(code);
+      return fail(code);
+    }
+    // the input buffer of this slot is free again: next piece but one
+    if (k + 2 < np && (rc = issue_h2d(k + 2))) return fail(rc);
+    // ---- results out, behind the kernels of the following pieces ----
+    CUDA_TRYF(cudaStreamWaitEvent(m->s_d2h, m->ev_emit[slot], 0));
+    const uint32_t* dtx = (const uint32_t*)m->d_out[slot][4].p;
+    struct Cp { int hi; const void* src; size_t off, bytes; };
+    const Cp cps[8] = {{0, m->d_out[slot][0].p, base_tok * 8, (size_t)tail.fin.n_tok * 8},
+                       {1, m->d_out[slot][1].p, base_tok * 8, (size_t)tail.fin.n_tok * 8},
+                       {2, m->d_out[slot][2].p, base_sentpos * 4, (size_t)tail.fin.n_sentpos * 4},
+                       {3, m->d_out[slot][3].p, base_sent * 4, (size_t)tail.fin.n_sent * 4},
+                       {4, dtx, base_text * 4, (size_t)tail.fin.n_text * 4},
+                       {5, dtx + nx, base_text * 4, (size_t)tail.fin.n_text * 4},
+                       {6, dtx + 2 * nx, base_text * 4, (size_t)tail.fin.n_text * 4},
+                       {7, dtx + 3 * nx, base_text * 4, (size_t)tail.fin.n_text * 4}};
+    const bool want8[8] = {want_bytes, want_pos, want_spos, want_stok, true, true, true, true};
+    for (const Cp& cp : cps)
+      if (want8[cp.hi] && cp.bytes)
+        CUDA_TRYF(cudaMemcpyAsync((uint8_t*)host[cp.hi].p + cp.off, cp.src, cp.bytes, cudaMemcpyDeviceToHost, m->s_d2h));
+    CUDA_TRYF(cudaEventRecord(m->ev_out[slot], m->s_d2h));
+    // ---- carry to the next piece ----
+    base_tok += tail.fin.n_tok; base_sent += tail.fin.n_sent; base_sentpos += tail.fin.n_sentpos;
+    base_text += tail.fin.n_text; runes += tail.fin.n_rune;
+    invalid |= h.invalid;
+    state = h.last.t;
+    v.carry_out.state = m->hm.old_of_new[h.last.t];
+    v.carry_out.sentence_end = 1;
+    v.carry_out.text_end = 1;
+    if (!final_input) {
+      const uint32_t lk = tail.fin.last_kind;
+      v.carry_out.sentence_end = (lk == EV_SENT || lk == EV_TEND) ? 1u : 0u;
+      v.carry_out.text_end = (tail.fin.n_text > 0 && tail.fin.tokless) ? 1u : (text_end_in ? 1u : 0u);
+    }
+    sentence_end_in = v.carry_out.sentence_end != 0;
+    text_end_in = v.carry_out.text_end != 0;
+  }
+  CUDA_TRYF(cudaStreamSynchronize(m->s_d2h));
+  CUDA_TRYF(cudaEventRecord(m->ev[3], s));
+  CUDA_TRYF(cudaStreamSynchronize(s));
+  pt.collect();
+  for (size_t i = 0; i + 1 < kev.size(); i += 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, kev[i], kev[i + 1]) == cudaSuccess) ms_kernels += ms;
+  }
+  v.n_tokens = base_tok; v.n_sentences = base_sent; v.n_texts = base_text; v.n_sent_pos = base_sentpos; v.n_runes = runes;
+  v.has_invalid_utf8 = invalid;
+  v.tok_bytes = want_bytes ? (const uint32_t*)host[0].p : nullptr;
+  v.tok_pos = want_pos ? (const int32_t*)host[1].p : nullptr;
+  v.sent_pos = want_spos ? (const int32_t*)host[2].p : nullptr;
+  v.sent_tok = want_stok ? (const uint32_t*)host[3].p : nullptr;
+  v.text_tok_end = (const uint32_t*)host[4].p;
+  v.text_sent_end = (const uint32_t*)host[5].p;
+  v.text_sentpos_end = (const uint32_t*)host[6].p;
+  v.text_byte_end = (const uint32_t*)host[7].p;
+  // overlapped: only the wall time of the whole call and the summed kernel time are meaningful
+  float total_ms = 0;
+  cudaEventElapsedTime(&total_ms, m->ev[0], m->ev[3]);
+  v.ms_kernels = ms_kernels;
+  v.ms_h2d = 0;
+  v.ms_d2h = total_ms > ms_kernels ? total_ms - ms_kernels : 0;
+  for (auto& hb : host) if (hb.p) r->blocks.push_back(hb);
+  *out = r;
+  return DATOK_OK;
+}
+
 
 int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n, uint32_t flags,
                  const datok_carry* carry_in, bool device_out, datok_result** out) {
@@ -412,73 +802,10 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   if (!in_is_device && N) CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(b.in), in, N, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaEventRecord(m->ev[1], s));
 
-  // ---- K1+K2a: fused classify + speculative walk ----
-  pt.begin(T_CLEAR);
-  CUDA_TRY(cudaMemsetAsync(b.b_end, 0, (size_t)b.n_words * 4 * sizeof(uint32_t), s));
-  CUDA_TRY(cudaMemsetAsync(b.counters, 0, 8 * sizeof(uint32_t), s));
-  CUDA_TRY(cudaMemsetAsync(b.err_key, 0xFF, sizeof(unsigned long long), s));
-  pt.end();
-  pt.begin(T_WALK);
-  {
-    const int e = launch_walk_fused(m->dm, b, start_state, m->n_hot, m->n_sms, s);
-    if (e != 0) { g_last_error = std::string("walk_fused launch: ") + cudaGetErrorString((cudaError_t)e); return DATOK_ERR_CUDA; }
-  }
-  pt.end();
-  m->launches += 1;
-
-  // ---- K2b-d fix-up rounds ----
-  uint32_t n_list = b.n_chunks - 1;
-  const uint32_t* list = nullptr;  // round 1: every chunk but the first
-  uint32_t* cur = b.list_cur;
-  uint32_t* nxt = b.list_next;
-  while (n_list) {
-    m->last_rounds++;
-    b.list_next = nxt;
-    pt.begin(T_STITCH);
-    launch_stitch(m->dm, b, list, n_list, s);
-    pt.end();
-    pt.begin(T_REWALK);
-    launch_rewalk(m->dm, b, n_list, s);
-    pt.end();
-    pt.begin(T_COMMIT);
-    launch_commit(b, list, n_list, s);
-    pt.end();
-    m->launches += 3;
-    uint32_t counts[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(counts, b.counters, sizeof counts, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemsetAsync(b.counters, 0, 2 * sizeof(uint32_t), s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    n_list = counts[0];
-    std::swap(cur, nxt);
-    list = cur;
-  }
-  launch_collect_errors(b, s);
-  m->launches++;
-
-  // ---- K3 compaction ----
+  if ((rc = do_walk(m, b, start_state, pt))) return rc;
   CompactCtx c;
-  std::memset(&c, 0, sizeof c);
-  c.in = b.in; c.N = N; c.n_words = b.n_words;
-  c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
-  c.flags = flags; c.err_key = b.err_key;
-  pt.begin(T_REDUCE);
-  launch_compact_reduce(c, cb, s);
-  pt.end();
-  pt.begin(T_SCAN);
-  launch_compact_scan(cb, sentence_end_in, s);
-  pt.end();
-  m->launches += 2;
-  struct { Agg tot; unsigned long long err; uint32_t invalid; } hdr;
-  CUDA_TRY(cudaMemcpyAsync(&hdr.tot, cb.total, sizeof(Agg), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&hdr.err, b.err_key, sizeof hdr.err, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&hdr.invalid, b.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  if (hdr.err != ~0ull) {  // the walk itself hit a reference panic
-    pt.collect();
-    const int code = (int)(hdr.err & 0xFF);
-    g_last_error = std::string("reference would panic: ") + datok_strerror(code);
-    return code >= 0xF0 ? DATOK_ERR_CUDA : code;
-  }
+  PieceHead hdr;
+  if ((rc = do_count(m, b, c, cb, flags, sentence_end_in, pt, hdr))) { pt.collect(); return rc; }
 
   // output arrays: sized from the scan totals (+1 for the end-of-stream events)
   datok_result* r = new datok_result();
@@ -526,9 +853,9 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   pt.end();
   m->launches += 3;
   struct { StreamTotals fin; unsigned long long err; WState last; } tail;
+  tail.last = hdr.last;
   CUDA_TRY(cudaMemcpyAsync(&tail.fin, cb.total + 1, sizeof(StreamTotals), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(&tail.err, b.err_key, sizeof tail.err, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&tail.last, b.E + (b.n_chunks - 1), sizeof(WState), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaEventRecord(m->ev[2], s));
   CUDA_TRY(cudaStreamSynchronize(s));
   pt.collect();
@@ -550,7 +877,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   v.carry_out.text_end = 1;
   if (!final_input) {
     // the walk stopped at the loop top at N: it must be at a rewind point with nothing pending
-    if (tail.last.tstart != N || tail.last.base != N || tail.last.eps_state != 0 || (tail.last.flags & WS_PEND)) {
+    if (!at_text_boundary(tail.last, N)) {
       g_last_error = "DATOK_NOT_FINAL input does not end at a text boundary";
       free_result_locked(r);
       return DATOK_ERR_NOT_AT_BOUNDARY;
@@ -645,6 +972,10 @@ int datok_model_info(const datok_model* m, uint32_t* state_count, uint32_t* sigm
 
 int datok_transduce(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, const datok_carry* carry_in,
                     datok_result** out) {
+  if (m && out && in && n < 0xFFFFFFFFull - (1u << 20) && n >= 2 * m->piece_bytes && m->pipelined) {
+    const int rc = run_pipelined(m, in, n, flags, carry_in, out);
+    if (rc != -1) return rc;  // -1: no EOT to cut at
+  }
   return run_pipeline(m, in, false, n, flags, carry_in, false, out);
 }
 

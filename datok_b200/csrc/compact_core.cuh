@@ -98,6 +98,9 @@ struct CompactCtx {
   const uint32_t* b_sent;
   const uint32_t* b_tend;
   uint32_t flags;          // TokenWriter Bits (+ F_WRITER_USED)
+  // this input is a piece of a longer stream: what the pieces before it produced (added to every
+  // index / byte offset written to the outputs; DocRec and Agg stay piece-relative)
+  uint32_t base_tok, base_sent, base_sentpos, base_byte;
   // outputs (device); any of the first four may be null
   uint32_t* tok_bytes;     // 2 per token
   int32_t* tok_pos;        // 2 per token
@@ -251,10 +254,10 @@ DATOK_HD void emit_texts(const CompactCtx& c, uint32_t w, const WordBits& b, con
       if (c.flags & F_TOKEN_POS) report_error(c, p, E_TEXT_NO_TOKEN);
       else if (c.flags & F_SENTENCE_POS) report_error(c, p, E_TEXT_NO_SENT);
     }
-    c.text_tok_end[text] = tok;
-    c.text_sent_end[text] = sent;
-    c.text_sentpos_end[text] = sentpos;
-    c.text_byte_end[text] = p + 1;
+    c.text_tok_end[text] = c.base_tok + tok;
+    c.text_sent_end[text] = c.base_sent + sent;
+    c.text_sentpos_end[text] = c.base_sentpos + sentpos;
+    c.text_byte_end[text] = c.base_byte + p + 1;
     DocRec d;
     d.start = p + 1;
     d.rank = A.n_rune + popc32(b.rs & le);
@@ -275,7 +278,7 @@ DATOK_HD void emit_sentences(const CompactCtx& c, uint32_t w, const WordBits& b,
     const uint32_t sent = A.n_sent + popc32(m.se & lt);
     const uint32_t tok = A.n_tok + popc32(b.e & le);
     const uint32_t sentpos = A.n_sentpos + popc32(m.opener & le) + popc32(m.se & lt);
-    if (c.sent_tok) c.sent_tok[sent] = tok;
+    if (c.sent_tok) c.sent_tok[sent] = c.base_tok + tok;
     if (!(c.flags & F_SENTENCE_POS) && !c.sent_pos) continue;
     const DocRec d = c.docs[A.n_text + popc32(b.t & lt)];
     if (tok == d.tok) {  // no token in this text yet (token_writer.go:108)
@@ -325,7 +328,7 @@ DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, co
     }
     const uint32_t rank_e = A.n_rune + popc32(b.rs & lt);
     const int32_t pe = (int32_t)(rank_e - d.rank) - shift, ps = pe - (int32_t)runes;
-    if (tok_bytes) { tok_bytes[2 * (size_t)tok] = s; tok_bytes[2 * (size_t)tok + 1] = p; }
+    if (tok_bytes) { tok_bytes[2 * (size_t)tok] = c.base_byte + s; tok_bytes[2 * (size_t)tok + 1] = c.base_byte + p; }
     if (tok_pos) { tok_pos[2 * (size_t)tok] = ps; tok_pos[2 * (size_t)tok + 1] = pe; }
     if ((m.opener >> bp) & 1u) {
       if (c.sent_pos) c.sent_pos[A.n_sentpos + popc32(m.opener & lt) + popc32(m.se & lt)] = ps;
@@ -371,7 +374,7 @@ DATOK_HD StreamTotals finalize_stream(const CompactCtx& c, const Agg& tot, bool 
   if (!final_input) return r;
   const DocRec d = c.docs[tot.n_text];
   if (forces_sentence(r.last_kind)) {  // :683 if !sentenceEnd
-    if (c.sent_tok) c.sent_tok[r.n_sent] = r.n_tok;
+    if (c.sent_tok) c.sent_tok[r.n_sent] = c.base_tok + r.n_tok;
     if (!have_tok) { if (c.flags & F_SENTENCE_POS) report_error(c, c.N, E_SENT_NO_TOKEN); }
     else if (c.sent_pos) {
       const uint32_t rank = tot.n_rune - count_range(c.rstart, tot.last_end_pos, c.n_words << 5);
@@ -390,10 +393,10 @@ DATOK_HD StreamTotals finalize_stream(const CompactCtx& c, const Agg& tot, bool 
       if (c.flags & F_TOKEN_POS) report_error(c, c.N, E_TEXT_NO_TOKEN);
       else if (c.flags & F_SENTENCE_POS) report_error(c, c.N, E_TEXT_NO_SENT);
     }
-    c.text_tok_end[r.n_text] = r.n_tok;
-    c.text_sent_end[r.n_text] = r.n_sent;
-    c.text_sentpos_end[r.n_text] = r.n_sentpos;
-    c.text_byte_end[r.n_text] = c.N;
+    c.text_tok_end[r.n_text] = c.base_tok + r.n_tok;
+    c.text_sent_end[r.n_text] = c.base_sent + r.n_sent;
+    c.text_sentpos_end[r.n_text] = c.base_sentpos + r.n_sentpos;
+    c.text_byte_end[r.n_text] = c.base_byte + c.N;
     r.n_text++;
   }
   return r;

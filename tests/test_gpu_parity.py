@@ -242,3 +242,38 @@ def test_shards_equal_one_stream(gpu_models, oracle_models):
     with pytest.raises(d.DatokError) as ei:
         tok.transduce_arrays(b"mitten im Wor", 15 | d.NOT_FINAL)
     assert ei.value.code == 23
+
+
+@pytest.mark.parametrize("model,kind", [("tokenizer_de.matok", 2), ("tokenizer_en.matok", 3)])
+def test_pipelined_host_path(model, kind, testdata, oracle_models, monkeypatch):
+    """large host inputs are cut after EOT bytes into pieces whose copies overlap the kernels
+    (api.cu run_pipelined): same arrays as the oracle's single stream, for every flag set"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    a = corpus.generate(kind, 6 << 20, seed=21)
+    monkeypatch.setenv("DATOK_PIECE_MB", "1")
+    tok = d.LoadTokenizerFile(os.path.join(testdata, model))
+    for flags in (15, 31, 3, 12, 5):
+        o = oracle_models[model].transduce_np(a, flags)
+        r = tok.transduce_arrays(a, flags)
+        P.assert_matches_oracle(r, o, flags, f"pipelined flags={flags}")
+        assert tok.format(r, a, flags) == o.text
+    # a reused TokenWriter and a carried state behave like in the single-pass path
+    head = "Vorspann ohne Ende.\n\x04".encode()
+    oa = oracle_models[model].transduce(head, 31)
+    ob = oracle_models[model].transduce(a.tobytes(), 31 | 256, carry_in=dict(state=oa.carry_out["state"], ok=0, sentence_end=1, text_end=1))
+    rb = tok.transduce_arrays(a, 31 | 256, carry=d.Carry(oa.carry_out["state"], 1, 1, 0))
+    P.assert_matches_oracle(rb, ob, 31, "pipelined, writer used")
+    # no EOT to cut at: falls back to one pass
+    one = corpus.generate(4, 3 << 20, seed=2)
+    P.assert_matches_oracle(tok.transduce_arrays(one, 15), oracle_models[model].transduce_np(one, 15), 15, "uncuttable")
+    tok.close()
+    monkeypatch.setenv("DATOK_NO_PIPELINE", "1")
+    tok1 = d.LoadTokenizerFile(os.path.join(testdata, model))
+    r1 = tok1.transduce_arrays(a, 31)
+    monkeypatch.delenv("DATOK_NO_PIPELINE")
+    tok2 = d.LoadTokenizerFile(os.path.join(testdata, model))
+    r2 = tok2.transduce_arrays(a, 31)
+    for f in ("tok_bytes", "tok_pos", "sent_pos", "sent_tok", "text_tok_end", "text_sent_end", "text_sentpos_end", "text_byte_end"):
+        np.testing.assert_array_equal(getattr(r1, f), getattr(r2, f), err_msg=f)
+    tok1.close(); tok2.close()
