@@ -14,11 +14,13 @@ TOKENS, SENTENCES, TOKEN_POS, SENTENCE_POS, NEWLINE_AFTER_EOT = 1, 2, 4, 8, 16
 SIMPLE = TOKENS | SENTENCES
 WRITER_USED = 256
 NOT_FINAL = 512
+COMPACT = 1024
 
 OK = 0
 ERR_BUFFER_OVERFLOW, ERR_SENT_NO_TOKEN, ERR_TEXT_NO_TOKEN, ERR_TEXT_NO_SENT, ERR_DEGENERATE = 1, 2, 3, 4, 5
 ERR_IO, ERR_FORMAT, ERR_UNSUPPORTED_MODEL, ERR_NO_DEVICE, ERR_CUDA, ERR_TOO_LARGE, ERR_INVALID_ARG = 16, 17, 18, 19, 20, 21, 22
 ERR_NOT_AT_BOUNDARY = 23
+ERR_COMPACT_RANGE = 24
 
 
 class Carry(C.Structure):
@@ -37,6 +39,7 @@ class View(C.Structure):
         ("carry_out", Carry),
         ("has_invalid_utf8", C.c_uint32),
         ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float),
+        ("tok_delta", C.POINTER(C.c_uint16)),
     ]
 
 
@@ -50,7 +53,7 @@ class Callbacks(C.Structure):
 
 # every symbol include/datok_b200.h declares
 EXPORTS = ["datok_load", "datok_load_image", "datok_free", "datok_type", "datok_model_info", "datok_transduce",
-           "datok_transduce_device", "datok_result_view", "datok_result_free", "datok_format", "datok_replay",
+           "datok_transduce_device", "datok_result_view", "datok_result_free", "datok_expand", "datok_format", "datok_replay",
            "datok_last_kernel_times", "datok_last_launch_count", "datok_host_alloc", "datok_host_free",
            "datok_last_error", "datok_strerror"]
 
@@ -79,6 +82,8 @@ def lib():
     L.datok_result_view.restype = C.POINTER(View)
     L.datok_result_view.argtypes = [C.c_void_p]
     L.datok_result_free.argtypes = [C.c_void_p]
+    L.datok_expand.restype = C.c_int
+    L.datok_expand.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.datok_format.restype = C.c_size_t
     L.datok_format.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t]
     L.datok_replay.restype = C.c_int

@@ -85,9 +85,11 @@ struct datok_model {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr},
               ev_out[2] = {nullptr, nullptr};
+  uint32_t* h_mail = nullptr;    // mapped pinned host memory the kernels report small results through
+  uint32_t* d_mail = nullptr;    // its device address
   Block d_in[2];                 // input pieces
   Block d_out[2][5];             // per slot: tok_bytes, tok_pos, sent_pos, sent_tok, text arrays + DocRec
-  size_t piece_bytes = (size_t)128 << 20;
+  size_t piece_bytes = (size_t)64 << 20;
   bool pipelined = true;
   // results hold pooled buffers of their model: the model outlives them
   int live_results = 0;
@@ -157,6 +159,7 @@ void destroy_model(datok_model* m) {
     if (m->d_in[i].p) cudaFree(m->d_in[i].p);
     for (auto& blk : m->d_out[i]) if (blk.p) cudaFree(blk.p);
   }
+  if (m->h_mail) cudaFreeHost(m->h_mail);
   if (m->s_h2d) cudaStreamDestroy(m->s_h2d);
   if (m->s_d2h) cudaStreamDestroy(m->s_d2h);
   for (auto& e : m->tev) cudaEventDestroy(e);
@@ -372,6 +375,13 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
     return nullptr;
   }
   for (auto& e : m->ev) cudaEventCreate(&e);
+  if (cudaHostAlloc((void**)&m->h_mail, 4096, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&m->d_mail, m->h_mail, 0) != cudaSuccess) {
+    g_last_error = "cudaHostAlloc (mailbox) failed";
+    *err = DATOK_ERR_CUDA;
+    datok_free(m);
+    return nullptr;
+  }
   cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking);
   for (int i = 0; i < 2; i++) {
@@ -431,11 +441,15 @@ int do_walk(datok_model* m, WalkBuffers& b, uint32_t start_state, PhaseTimer& pt
     launch_commit(b, list, n_list, s);
     pt.end();
     m->launches += 3;
-    uint32_t counts[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(counts, b.counters, sizeof counts, cudaMemcpyDeviceToHost, s));
+    {
+      MailSrc ms;
+      std::memset(&ms, 0, sizeof ms);
+      ms.p[0] = b.counters; ms.words[0] = 2; ms.off[0] = 0;
+      launch_mail(ms, m->d_mail, s);
+    }
     CUDA_TRY(cudaMemsetAsync(b.counters, 0, 2 * sizeof(uint32_t), s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    n_list = counts[0];
+    n_list = m->h_mail[0];
     std::swap(cur, nxt);
     list = cur;
   }
@@ -466,11 +480,20 @@ int do_count(datok_model* m, const WalkBuffers& b, CompactCtx& c, const CompactB
   launch_compact_scan(cb, sentence_end_in, s);
   pt.end();
   m->launches += 3;
-  CUDA_TRY(cudaMemcpyAsync(&h.tot, cb.total, sizeof(Agg), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&h.err, b.err_key, sizeof h.err, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&h.invalid, b.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&h.last, b.E + (b.n_chunks - 1), sizeof(WState), cudaMemcpyDeviceToHost, s));
+  {
+    MailSrc ms;
+    static_assert(sizeof(Agg) == 32 && sizeof(WState) % 4 == 0 && sizeof(WState) <= 32, "mailbox layout");
+    ms.p[0] = reinterpret_cast<const uint32_t*>(cb.total); ms.words[0] = 8; ms.off[0] = 0;
+    ms.p[1] = reinterpret_cast<const uint32_t*>(b.err_key); ms.words[1] = 2; ms.off[1] = 8;
+    ms.p[2] = b.counters + 2; ms.words[2] = 1; ms.off[2] = 10;
+    ms.p[3] = reinterpret_cast<const uint32_t*>(b.E + (b.n_chunks - 1)); ms.words[3] = sizeof(WState) / 4; ms.off[3] = 12;
+    launch_mail(ms, m->d_mail, s);
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
+  std::memcpy(&h.tot, m->h_mail, sizeof(Agg));
+  std::memcpy(&h.err, m->h_mail + 8, sizeof h.err);
+  h.invalid = m->h_mail[10];
+  std::memcpy(&h.last, m->h_mail + 12, sizeof(WState));
   if (h.err != ~0ull) {  // the walk itself hit a reference panic
     const int code = (int)(h.err & 0xFF);
     g_last_error = std::string("reference would panic: ") + datok_strerror(code);
@@ -536,7 +559,10 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   int rc = ensure_workspace(m, carve(nullptr, (uint32_t)max_piece, m->chunk, false, b, cb));
   if (rc) return rc;
 
-  const bool want_bytes = (flags & DATOK_TOKENS) != 0, want_pos = (flags & DATOK_TOKEN_POS) != 0;
+  // in compact mode the token slot 0 holds the 8-byte deltas and slot 1 is unused
+  const bool compact = (flags & DATOK_COMPACT) != 0;
+  const bool want_bytes = compact ? (flags & (DATOK_TOKENS | DATOK_TOKEN_POS)) != 0 : (flags & DATOK_TOKENS) != 0;
+  const bool want_pos = !compact && (flags & DATOK_TOKEN_POS) != 0;
   const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
   const bool want[5] = {want_bytes, want_pos, want_spos, want_stok, true};
 
@@ -653,7 +679,8 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     }
     c.base_tok = (uint32_t)base_tok; c.base_sent = (uint32_t)base_sent; c.base_sentpos = (uint32_t)base_sentpos;
     c.base_byte = (uint32_t)cut[k];
-    c.tok_bytes = want_bytes ? (uint32_t*)m->d_out[slot][0].p : nullptr;
+    c.tok_bytes = (want_bytes && !compact) ? (uint32_t*)m->d_out[slot][0].p : nullptr;
+    c.tok_delta = (want_bytes && compact) ? (uint16_t*)m->d_out[slot][0].p : nullptr;
     c.tok_pos = want_pos ? (int32_t*)m->d_out[slot][1].p : nullptr;
     c.sent_pos = want_spos ? (int32_t*)m->d_out[slot][2].p : nullptr;
     c.sent_tok = want_stok ? (uint32_t*)m->d_out[slot][3].p : nullptr;
@@ -674,12 +701,19 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     pt.end();
     m->launches += 3;
     struct { StreamTotals fin; unsigned long long err; } tail;
-    CUDA_TRYF(cudaMemcpyAsync(&tail.fin, cb.total + 1, sizeof(StreamTotals), cudaMemcpyDeviceToHost, s));
-    CUDA_TRYF(cudaMemcpyAsync(&tail.err, b.err_key, sizeof tail.err, cudaMemcpyDeviceToHost, s));
+    {
+      MailSrc ms;
+      std::memset(&ms, 0, sizeof ms);
+      ms.p[0] = reinterpret_cast<const uint32_t*>(cb.total + 1); ms.words[0] = 8; ms.off[0] = 0;
+      ms.p[1] = reinterpret_cast<const uint32_t*>(b.err_key); ms.words[1] = 2; ms.off[1] = 8;
+      launch_mail(ms, m->d_mail, s);
+    }
     CUDA_TRYF(cudaEventRecord(k1, s));
     CUDA_TRYF(cudaEventRecord(m->ev_emit[slot], s));
     CUDA_TRYF(cudaEventRecord(m->ev_free[slot], s));
     CUDA_TRYF(cudaStreamSynchronize(s));
+    std::memcpy(&tail.fin, m->h_mail, sizeof(StreamTotals));
+    std::memcpy(&tail.err, m->h_mail + 8, sizeof tail.err);
     kev.push_back(k0); kev.push_back(k1);
     if (tail.err != ~0ull) {
       pt.collect();
@@ -732,7 +766,8 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   }
   v.n_tokens = base_tok; v.n_sentences = base_sent; v.n_texts = base_text; v.n_sent_pos = base_sentpos; v.n_runes = runes;
   v.has_invalid_utf8 = invalid;
-  v.tok_bytes = want_bytes ? (const uint32_t*)host[0].p : nullptr;
+  v.tok_bytes = (want_bytes && !compact) ? (const uint32_t*)host[0].p : nullptr;
+  v.tok_delta = (want_bytes && compact) ? (const uint16_t*)host[0].p : nullptr;
   v.tok_pos = want_pos ? (const int32_t*)host[1].p : nullptr;
   v.sent_pos = want_spos ? (const int32_t*)host[2].p : nullptr;
   v.sent_tok = want_stok ? (const uint32_t*)host[3].p : nullptr;
@@ -815,14 +850,18 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   std::memset(&r->view, 0, sizeof r->view);
   const size_t nt = hdr.tot.n_tok, ns = (size_t)hdr.tot.n_sent + 1, nx = (size_t)hdr.tot.n_text + 1,
                np = (size_t)hdr.tot.n_sentpos + 1;
-  const bool want_bytes = (flags & DATOK_TOKENS) != 0, want_pos = (flags & DATOK_TOKEN_POS) != 0;
+  const bool compact = (flags & DATOK_COMPACT) != 0;
+  const bool want_delta = compact && (flags & (DATOK_TOKENS | DATOK_TOKEN_POS)) != 0;
+  const bool want_bytes = !compact && (flags & DATOK_TOKENS) != 0, want_pos = !compact && (flags & DATOK_TOKEN_POS) != 0;
   const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
   struct Out { size_t bytes; bool want; void** dev; Block d, h; };
-  void *d_tok_bytes = nullptr, *d_tok_pos = nullptr, *d_sent_pos = nullptr, *d_sent_tok = nullptr, *d_text = nullptr;
+  void *d_tok_bytes = nullptr, *d_tok_pos = nullptr, *d_sent_pos = nullptr, *d_sent_tok = nullptr, *d_text = nullptr,
+       *d_delta = nullptr;
   // the per-text arrays are followed by the DocRec table (device scratch, not copied back)
-  Out outs[5] = {{2 * nt * 4, want_bytes, &d_tok_bytes, {}, {}}, {2 * nt * 4, want_pos, &d_tok_pos, {}, {}},
+  Out outs[6] = {{2 * nt * 4, want_bytes, &d_tok_bytes, {}, {}}, {2 * nt * 4, want_pos, &d_tok_pos, {}, {}},
                  {np * 4, want_spos, &d_sent_pos, {}, {}},       {ns * 4, want_stok, &d_sent_tok, {}, {}},
-                 {nx * 4 * 4 + (nx + 1) * sizeof(DocRec), true, &d_text, {}, {}}};
+                 {nx * 4 * 4 + (nx + 1) * sizeof(DocRec), true, &d_text, {}, {}},
+                 {nt * 8, want_delta, &d_delta, {}, {}}};
   for (auto& o : outs) {
     if (!o.want) continue;
     o.d = acquire(m, o.bytes, false, &rc);
@@ -834,6 +873,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   if (rc) { free_result_locked(r); return rc; }
   c.tok_bytes = (uint32_t*)d_tok_bytes;
   c.tok_pos = (int32_t*)d_tok_pos;
+  c.tok_delta = (uint16_t*)d_delta;
   c.sent_pos = (int32_t*)d_sent_pos;
   c.sent_tok = (uint32_t*)d_sent_tok;
   c.text_tok_end = (uint32_t*)d_text;
@@ -854,10 +894,17 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   m->launches += 3;
   struct { StreamTotals fin; unsigned long long err; WState last; } tail;
   tail.last = hdr.last;
-  CUDA_TRY(cudaMemcpyAsync(&tail.fin, cb.total + 1, sizeof(StreamTotals), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&tail.err, b.err_key, sizeof tail.err, cudaMemcpyDeviceToHost, s));
+  {
+    MailSrc ms;
+    std::memset(&ms, 0, sizeof ms);
+    ms.p[0] = reinterpret_cast<const uint32_t*>(cb.total + 1); ms.words[0] = 8; ms.off[0] = 0;
+    ms.p[1] = reinterpret_cast<const uint32_t*>(b.err_key); ms.words[1] = 2; ms.off[1] = 8;
+    launch_mail(ms, m->d_mail, s);
+  }
   CUDA_TRY(cudaEventRecord(m->ev[2], s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  std::memcpy(&tail.fin, m->h_mail, sizeof(StreamTotals));
+  std::memcpy(&tail.err, m->h_mail + 8, sizeof tail.err);
   pt.collect();
   if (tail.err != ~0ull) {
     const int code = (int)(tail.err & 0xFF);
@@ -890,7 +937,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   for (auto& o : outs) {
     if (!o.want || device_out) continue;
     size_t bytes = o.bytes;
-    if (o.dev == &d_tok_bytes || o.dev == &d_tok_pos) bytes = 2 * (size_t)v.n_tokens * 4;
+    if (o.dev == &d_tok_bytes || o.dev == &d_tok_pos || o.dev == &d_delta) bytes = 2 * (size_t)v.n_tokens * 4;
     else if (o.dev == &d_sent_pos) bytes = (size_t)v.n_sent_pos * 4;
     else if (o.dev == &d_sent_tok) bytes = (size_t)v.n_sentences * 4;
     else if (o.dev == &d_text) bytes = nx * 4 * 4;
@@ -903,6 +950,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   v.tok_pos = (const int32_t*)pick(1);
   v.sent_pos = (const int32_t*)pick(2);
   v.sent_tok = (const uint32_t*)pick(3);
+  v.tok_delta = (const uint16_t*)pick(5);
   const uint32_t* tx = (const uint32_t*)pick(4);
   v.text_tok_end = tx;
   v.text_sent_end = tx + nx;
@@ -1035,6 +1083,7 @@ const char* datok_strerror(int code) {
     case DATOK_ERR_TOO_LARGE: return "input too large for one call";
     case DATOK_ERR_INVALID_ARG: return "invalid argument";
     case DATOK_ERR_NOT_AT_BOUNDARY: return "non-final input does not end at a text boundary";
+    case DATOK_ERR_COMPACT_RANGE: return "DATOK_COMPACT: a token delta does not fit 16 bits";
     default: return "unknown error";
   }
 }

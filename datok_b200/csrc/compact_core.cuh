@@ -104,6 +104,7 @@ struct CompactCtx {
   // outputs (device); any of the first four may be null
   uint32_t* tok_bytes;     // 2 per token
   int32_t* tok_pos;        // 2 per token
+  uint16_t* tok_delta;     // DATOK_COMPACT: 4 per token, instead of the two above
   int32_t* sent_pos;
   uint32_t* sent_tok;
   uint32_t* text_tok_end;
@@ -294,10 +295,13 @@ DATOK_HD void emit_sentences(const CompactCtx& c, uint32_t w, const WordBits& b,
   }
 }
 
-// The Token events of word w (token_writer.go:59-95).  Token k goes to tok_bytes/tok_pos[2 * (k - tok_base)]
-// (the kernel stages a block's tokens in shared memory); sentence openers go to c.sent_pos.
+constexpr uint32_t E_COMPACT_RANGE = 24;  // DATOK_ERR_COMPACT_RANGE
+
+// The Token events of word w (token_writer.go:59-95).  Token k goes to slot k - tok_base of
+// tok_bytes/tok_pos (2 values each) or of tok_delta (4 values; the kernel stages a block's tokens in
+// shared memory); sentence openers go to c.sent_pos.
 DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, const WordMasks& m, const Agg& A,
-                          uint32_t* tok_bytes, int32_t* tok_pos, uint32_t tok_base) {
+                          uint32_t* tok_bytes, int32_t* tok_pos, uint16_t* tok_delta, uint32_t tok_base) {
   uint32_t e = b.e;
   if (e == 0) return;
   const uint32_t w0 = w << 5;
@@ -316,20 +320,32 @@ DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, co
     }
     // the Token call's buffer starts at the previous rewind point; offset = leading non-token runes
     uint32_t bufstart = d.start;
-    if (prev_end != K_NOPOS && prev_end > bufstart) bufstart = prev_end;
-    uint32_t s, runes;  // token start, runes in [s, p)
-    const uint32_t cl = ~b.k & lt & mask_from(bufstart >= w0 ? bufstart - w0 : 32u);
+    bool first = true;  // first token of its text
+    if (prev_end != K_NOPOS && prev_end > bufstart) { bufstart = prev_end; first = false; }
+    uint32_t s, runes, skipped;  // token start, runes in [s, p), runes in [bufstart, s)
+    const uint32_t from = mask_from(bufstart >= w0 ? bufstart - w0 : 32u);
+    const uint32_t cl = ~b.k & lt & from;
     if (bufstart >= w0 && cl) {  // within the word
-      s = w0 + ctz32(cl);
-      runes = popc32(b.rs & lt & mask_from(s - w0));
+      const uint32_t sb = ctz32(cl);
+      s = w0 + sb;
+      runes = popc32(b.rs & lt & mask_from(sb));
+      skipped = popc32(b.rs & from & mask_below(sb));
     } else {
       s = next_clear(c.b_skip, c.n_words, bufstart);
       runes = count_range(c.rstart, s, p);
+      skipped = tok_delta ? count_range(c.rstart, bufstart, s) : 0;
     }
     const uint32_t rank_e = A.n_rune + popc32(b.rs & lt);
     const int32_t pe = (int32_t)(rank_e - d.rank) - shift, ps = pe - (int32_t)runes;
     if (tok_bytes) { tok_bytes[2 * (size_t)tok] = c.base_byte + s; tok_bytes[2 * (size_t)tok + 1] = c.base_byte + p; }
     if (tok_pos) { tok_pos[2 * (size_t)tok] = ps; tok_pos[2 * (size_t)tok + 1] = pe; }
+    if (tok_delta) {
+      const int32_t rskip = (int32_t)skipped - (first ? shift : 0);
+      const uint32_t bskip = s - bufstart, blen = p - s;
+      if ((bskip | blen | runes | (uint32_t)rskip) > 0xFFFFu) report_error(c, p, E_COMPACT_RANGE);
+      uint16_t* o = tok_delta + 4 * (size_t)tok;
+      o[0] = (uint16_t)bskip; o[1] = (uint16_t)blen; o[2] = (uint16_t)rskip; o[3] = (uint16_t)runes;
+    }
     if ((m.opener >> bp) & 1u) {
       if (c.sent_pos) c.sent_pos[A.n_sentpos + popc32(m.opener & lt) + popc32(m.se & lt)] = ps;
     }

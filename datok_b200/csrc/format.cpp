@@ -5,6 +5,7 @@
 // computed on the GPU.
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../include/datok_b200.h"
 #include "model.hpp"
@@ -46,27 +47,76 @@ void put_surface(Sink& s, const uint8_t* in, size_t lo, size_t hi, bool reencode
   }
 }
 
+// Token spans of a result in stream order, from the absolute arrays or from the DATOK_COMPACT deltas.
+struct TokenCursor {
+  const datok_view* v;
+  uint64_t k = 0, text = 0;
+  uint64_t byte_end = 0;   // end of the previous token of this text, or the start of the text
+  int64_t rune_end = 0;
+  uint32_t lo = 0, hi = 0;
+  int32_t ps = 0, pe = 0;
+  explicit TokenCursor(const datok_view* view) : v(view) {}
+  void next() {  // token k
+    if (v->tok_delta) {
+      while (text < v->n_texts && k >= v->text_tok_end[text]) {  // a new text: both cursors restart
+        byte_end = v->text_byte_end[text];
+        rune_end = 0;
+        text++;
+      }
+      const uint16_t* d = v->tok_delta + 4 * k;
+      lo = (uint32_t)(byte_end + d[0]); hi = lo + d[1];
+      ps = (int32_t)(rune_end + d[2]); pe = ps + d[3];
+      byte_end = hi; rune_end = pe;
+    } else {
+      if (v->tok_bytes) { lo = v->tok_bytes[2 * k]; hi = v->tok_bytes[2 * k + 1]; }
+      if (v->tok_pos) { ps = v->tok_pos[2 * k]; pe = v->tok_pos[2 * k + 1]; }
+    }
+    k++;
+  }
+};
+
 }  // namespace
 
 extern "C" {
+
+int datok_expand(const datok_result* r, uint32_t* tok_bytes, int32_t* tok_pos) {
+  const datok_view* v = datok_result_view(r);
+  if (!v || (!v->tok_delta && v->n_tokens)) return DATOK_ERR_INVALID_ARG;
+  TokenCursor c(v);
+  for (uint64_t k = 0; k < v->n_tokens; k++) {
+    c.next();
+    if (tok_bytes) { tok_bytes[2 * k] = c.lo; tok_bytes[2 * k + 1] = c.hi; }
+    if (tok_pos) { tok_pos[2 * k] = c.ps; tok_pos[2 * k + 1] = c.pe; }
+  }
+  return DATOK_OK;
+}
 
 size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t flags, uint8_t* dst, size_t cap) {
   const datok_view* v = datok_result_view(r);
   if (!v) return (size_t)-1;
   const bool tokens = flags & DATOK_TOKENS, sentences = flags & DATOK_SENTENCES;
   const bool tpos = flags & DATOK_TOKEN_POS, spos = flags & DATOK_SENTENCE_POS;
-  if ((tokens && !v->tok_bytes) || (sentences && !v->sent_tok && v->n_sentences) || (tpos && !v->tok_pos) ||
-      (spos && !v->sent_pos))
+  if ((tokens && !v->tok_bytes && !v->tok_delta) || (sentences && !v->sent_tok && v->n_sentences) ||
+      (tpos && !v->tok_pos && !v->tok_delta) || (spos && !v->sent_pos))
     return (size_t)-1;  // the array was not requested at transduce time
   (void)n;
   Sink s{dst, dst ? cap : 0};
   const bool re = v->has_invalid_utf8 != 0;
   uint64_t tok = 0, sen = 0, sp = 0;
+  TokenCursor cur(v);
+  // rune offsets of the current text's tokens, for the `pos` line (token_writer.go:131-143); the
+  // compact form is decoded once, while the surfaces are written
+  std::vector<int32_t> text_pos;
+  const bool keep_pos = tpos && v->tok_delta;
   auto emit_tokens = [&](uint64_t upto) {
-    if (tokens)
+    if (tokens || keep_pos)
       for (; tok < upto; tok++) {
-        put_surface(s, in, v->tok_bytes[2 * tok], v->tok_bytes[2 * tok + 1], re);
-        s.byte('\n');
+        cur.next();
+        if (keep_pos) { text_pos.push_back(cur.ps); text_pos.push_back(cur.pe); }
+        if (tokens) {
+          put_surface(s, in, cur.lo, cur.hi, re);
+          s.byte('\n');
+        }
       }
     tok = upto;
   };
@@ -87,9 +137,10 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
       if (tpos) {
         for (uint64_t k = 2 * t0; k < 2 * t1; k++) {
           if (k != 2 * t0) s.byte(' ');
-          s.itoa(v->tok_pos[k]);
+          s.itoa(keep_pos ? text_pos[k - 2 * t0] : v->tok_pos[k]);
         }
         s.byte('\n');
+        text_pos.clear();
       }
       if (spos) {
         const uint64_t p1 = v->text_sentpos_end[d];
@@ -111,13 +162,15 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
 int datok_replay(const datok_result* r, const uint8_t* in, size_t n, const datok_callbacks* cb) {
   const datok_view* v = datok_result_view(r);
   if (!v || !cb) return DATOK_ERR_INVALID_ARG;
-  if ((v->n_tokens && !v->tok_bytes) || (v->n_sentences && !v->sent_tok)) return DATOK_ERR_INVALID_ARG;
+  if ((v->n_tokens && !v->tok_bytes && !v->tok_delta) || (v->n_sentences && !v->sent_tok)) return DATOK_ERR_INVALID_ARG;
   (void)n;
   uint64_t tok = 0, sen = 0;
   size_t bufstart = 0;  // the reference's buffer[0]: the last rewind point (matrix.go:608-622)
+  TokenCursor cur(v);
   auto emit_tokens = [&](uint64_t upto) {
     for (; tok < upto; tok++) {
-      const size_t lo = v->tok_bytes[2 * tok], hi = v->tok_bytes[2 * tok + 1];
+      cur.next();
+      const size_t lo = cur.lo, hi = cur.hi;
       int32_t runes = 0;
       for (size_t p = bufstart; p < lo;) { int w; datok::decode_rune(in + p, lo - p, &w); p += (size_t)w; runes++; }
       if (cb->token) cb->token(cb->user, in + bufstart, hi - bufstart, lo - bufstart, runes);

@@ -200,6 +200,18 @@ void launch_collect_errors(const WalkBuffers& b, cudaStream_t s) {
   collect_errors_kernel<<<(b.n_chunks + 255) / 256, 256, 0, s>>>(b);
 }
 
+// ------------------------------------------------------------------ host mailbox
+
+// Small results the host waits for (round counters, stream summary, error key, last walk state) are
+// written by this kernel straight into mapped pinned host memory.  A cudaMemcpy would queue on the
+// device-to-host copy engine behind the result arrays of the previous piece and stall the pipeline.
+__global__ void mail_kernel(MailSrc src, uint32_t* dst) {
+  for (int k = 0; k < 4; k++)
+    for (uint32_t i = threadIdx.x; i < src.words[k]; i += blockDim.x) dst[src.off[k] + i] = src.p[k][i];
+  __threadfence_system();
+}
+void launch_mail(const MailSrc& src, uint32_t* dst_mapped, cudaStream_t s) { mail_kernel<<<1, 32, 0, s>>>(src, dst_mapped); }
+
 // ------------------------------------------------------------------ K3
 
 union AggWords {
@@ -314,8 +326,10 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   // K3_EMIT
   const uint32_t blk_tok0 = block_start.n_tok, blk_ntok = cb.block_agg[blockIdx.x].n_tok;
   const bool staged = blk_ntok <= STAGE_TOKENS;
+  // staging layout: absolute form tok_bytes | tok_pos (2 + 2 words per token), compact form 2 words per token
   uint32_t* s_tb = s_stage;
   int32_t* s_tp = reinterpret_cast<int32_t*>(s_stage + 2 * STAGE_TOKENS);
+  uint16_t* s_td = reinterpret_cast<uint16_t*>(s_stage);
   // two copies of the loop so that the staged one addresses shared memory directly
   if (staged) {
 #pragma unroll
@@ -324,7 +338,8 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
       if (w < c.n_words) {
         if (wb[k].e | wb[k].s | wb[k].t) {
           const WordMasks m = word_masks(wb[k], agg_last(carry));
-          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes ? s_tb : nullptr, c.tok_pos ? s_tp : nullptr, blk_tok0);
+          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes ? s_tb : nullptr, c.tok_pos ? s_tp : nullptr,
+                      c.tok_delta ? s_td : nullptr, blk_tok0);
           emit_sentences(c, w, wb[k], m, carry);
         }
         carry = agg_combine(carry, wa[k]);
@@ -337,7 +352,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
       if (w < c.n_words) {
         if (wb[k].e | wb[k].s | wb[k].t) {
           const WordMasks m = word_masks(wb[k], agg_last(carry));
-          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes, c.tok_pos, 0u);
+          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes, c.tok_pos, c.tok_delta, 0u);
           emit_sentences(c, w, wb[k], m, carry);
         }
         carry = agg_combine(carry, wa[k]);
@@ -354,6 +369,11 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   if (c.tok_pos) {
     uint2* dst = reinterpret_cast<uint2*>(c.tok_pos) + blk_tok0;
     const uint2* src = reinterpret_cast<const uint2*>(s_tp);
+    for (uint32_t i = threadIdx.x; i < blk_ntok; i += COMPACT_THREADS) dst[i] = src[i];
+  }
+  if (c.tok_delta) {
+    uint2* dst = reinterpret_cast<uint2*>(c.tok_delta) + blk_tok0;
+    const uint2* src = reinterpret_cast<const uint2*>(s_td);
     for (uint32_t i = threadIdx.x; i < blk_ntok; i += COMPACT_THREADS) dst[i] = src[i];
   }
 }
@@ -402,10 +422,11 @@ void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStr
   compact_kernel<K3_TEXTS><<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
 }
 int launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
-  const int smem = 4 * STAGE_TOKENS * (int)sizeof(uint32_t);
+  const int smem_max = 4 * STAGE_TOKENS * (int)sizeof(uint32_t);
+  const int smem = (c.tok_delta ? 2 : 4) * STAGE_TOKENS * (int)sizeof(uint32_t);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(compact_kernel<K3_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(compact_kernel<K3_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }

@@ -35,6 +35,14 @@ void launch_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk
 void launch_commit(const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
 void launch_collect_errors(const WalkBuffers& b, cudaStream_t s);
 
+// up to four small device regions (32-bit words) -> mapped host memory at word offsets off[k]
+struct MailSrc {
+  const uint32_t* p[4];
+  uint32_t words[4];
+  uint32_t off[4];
+};
+void launch_mail(const MailSrc& src, uint32_t* dst_mapped, cudaStream_t s);
+
 void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);
 void launch_compact_scan(const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s);
 void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s);

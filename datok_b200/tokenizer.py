@@ -13,7 +13,7 @@ import sys
 import numpy as np
 
 from . import _lib
-from ._lib import (NEWLINE_AFTER_EOT, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Callbacks,
+from ._lib import (COMPACT, NEWLINE_AFTER_EOT, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Callbacks,
                    Carry, EVENT_CB, TOKEN_CB)
 
 
@@ -110,12 +110,26 @@ class Result:
                 return np.ctypeslib.as_array(p, shape=(int(n),))
             self.tok_bytes = arr(v.tok_bytes, 2 * v.n_tokens)
             self.tok_pos = arr(v.tok_pos, 2 * v.n_tokens)
+            self.tok_delta = arr(v.tok_delta, 4 * v.n_tokens) if v.tok_delta else None
+            if self.tok_delta is not None:  # DATOK_COMPACT: the absolute arrays are rebuilt on the host on demand
+                self.tok_bytes = self.tok_pos = None
             self.sent_pos = arr(v.sent_pos, v.n_sent_pos)
             self.sent_tok = arr(v.sent_tok, v.n_sentences)
             self.text_tok_end = arr(v.text_tok_end, v.n_texts)
             self.text_sent_end = arr(v.text_sent_end, v.n_texts)
             self.text_sentpos_end = arr(v.text_sentpos_end, v.n_texts)
             self.text_byte_end = arr(v.text_byte_end, v.n_texts)
+
+    def expand(self):
+        """datok_expand(): absolute tok_bytes / tok_pos of a DATOK_COMPACT result (host-side decode)"""
+        if self.tok_delta is not None and self.tok_bytes is None:
+            tb = np.empty(2 * self.n_tokens, dtype=np.uint32)
+            tp = np.empty(2 * self.n_tokens, dtype=np.int32)
+            rc = _lib.lib().datok_expand(self._h, tb.ctypes.data, tp.ctypes.data)
+            if rc:
+                _raise(rc)
+            self.tok_bytes, self.tok_pos = tb, tp
+        return self
 
     def device_ptr(self, name):
         p = self._ptrs[name]
@@ -183,7 +197,8 @@ class MatrixTokenizer:
         addr, n, keep = _as_buffer(data)
         if w._stock is not None:
             st = w._stock
-            flags = st["flags"] | (0 if st["init"] else WRITER_USED)
+            # the formatter reads the delta-coded spans directly: half the bytes over PCIe
+            flags = st["flags"] | (0 if st["init"] else WRITER_USED) | COMPACT
             res = self.transduce_arrays_raw(addr, n, flags)
             try:
                 if res.n_tokens:
@@ -197,7 +212,7 @@ class MatrixTokenizer:
             w.Flush()  # matrix.go:374 defer w.Flush()
             return True
         # custom TokenWriter: replay the events into its callables
-        res = self.transduce_arrays_raw(addr, n, TOKENS | SENTENCES)
+        res = self.transduce_arrays_raw(addr, n, TOKENS | SENTENCES | COMPACT)
         try:
             def on_token(_u, buf, buf_bytes, _off_bytes, off_runes):
                 w.Token(off_runes, list(_go_runes(C.string_at(buf, buf_bytes))))

@@ -36,7 +36,12 @@ enum {
    * later call (another GPU, the next batch).  End-of-input processing (matrix.go:650-695:
    * final token flush, final SentenceEnd/TextEnd) is skipped; the input must end at a
    * text boundary (right after an EOT), else DATOK_ERR_NOT_AT_BOUNDARY. */
-  DATOK_NOT_FINAL = 512
+  DATOK_NOT_FINAL = 512,
+  /* Not a reference flag: token spans come back delta-encoded (view.tok_delta, 8 bytes per token
+   * instead of 16 over PCIe) in place of tok_bytes / tok_pos; see datok_view.tok_delta.  The
+   * TokenWriter itself only ever sees such deltas: Token(offset, buf) gets the runes since the
+   * previous token end (token_writer.go:59-95). */
+  DATOK_COMPACT = 1024
 };
 
 /* Error codes.  1..6 mirror inputs on which the Go reference panics (they are
@@ -56,7 +61,8 @@ enum {
   DATOK_ERR_CUDA = 20,           /* a CUDA call failed; see datok_last_error() */
   DATOK_ERR_TOO_LARGE = 21,      /* input >= 2^32 - 2^20 bytes in one call (split at EOT) */
   DATOK_ERR_INVALID_ARG = 22,
-  DATOK_ERR_NOT_AT_BOUNDARY = 23 /* DATOK_NOT_FINAL input ends inside a token / pending epsilon point */
+  DATOK_ERR_NOT_AT_BOUNDARY = 23, /* DATOK_NOT_FINAL input ends inside a token / pending epsilon point */
+  DATOK_ERR_COMPACT_RANGE = 24    /* DATOK_COMPACT: a delta does not fit 16 bits (ask for the absolute arrays) */
 };
 
 typedef struct datok_model datok_model;
@@ -98,6 +104,13 @@ typedef struct {
   uint32_t has_invalid_utf8; /* some input byte decodes to U+FFFD (surface re-encoding needed) */
   /* timing of the last call, milliseconds (CUDA events on the call's stream) */
   float ms_h2d, ms_kernels, ms_d2h;
+  /* DATOK_COMPACT: per token k four 16-bit values, relative to the end of the previous token of the
+   * same text (or to the start of the text: byte text_byte_end[d-1], rune 0):
+   *   tok_delta[4k+0] bytes skipped before the token     tok_delta[4k+1] bytes of the token
+   *   tok_delta[4k+2] runes skipped before the token     tok_delta[4k+3] runes of the token
+   * (the rune skip of a text's first token already includes the NEWLINE_AFTER_EOT shift).
+   * tok_bytes / tok_pos are NULL then; datok_expand() rebuilds them. */
+  const uint16_t *tok_delta;
 } datok_view;
 
 /* LoadTokenizerFile (fomafile.go:452-484) for the MATOK magic / LoadMatrixFile
@@ -132,6 +145,10 @@ int datok_transduce_device(datok_model *m, const uint8_t *d_in, size_t n, uint32
 
 const datok_view *datok_result_view(const datok_result *r);
 void datok_result_free(datok_result *r);
+
+/* Rebuilds the absolute token arrays of a DATOK_COMPACT result on the host: tok_bytes (2 per token)
+ * and / or tok_pos (2 per token); either may be NULL. */
+int datok_expand(const datok_result *r, uint32_t *tok_bytes, int32_t *tok_pos);
 
 /* Host half of the TokenWriter (token_writer.go:36-175): formats a host-resident
  * result exactly as NewTokenWriter(w, flags) would have written it.  Returns the

@@ -29,6 +29,7 @@ struct EmulResult {
   uint32_t *text_tok_end, *text_sent_end, *text_sentpos_end, *text_byte_end;
   uint32_t carry_state, has_invalid;
   uint32_t rounds, n_rewalks, n_stitch_mismatch;
+  uint16_t* tok_delta;
 };
 
 struct EmulModel {
@@ -184,6 +185,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   size_t nt = total.n_tok, ns = total.n_sent + 1, nx = total.n_text + 1, np = total.n_sentpos + 1;
   R->tok_bytes = (uint32_t*)std::calloc(2 * nt + 2, 4);
   R->tok_pos = (int32_t*)std::calloc(2 * nt + 2, 4);
+  R->tok_delta = (uint16_t*)std::calloc(4 * nt + 4, 2);
   R->sent_pos = (int32_t*)std::calloc(np + 1, 4);
   R->sent_tok = (uint32_t*)std::calloc(ns + 1, 4);
   R->text_tok_end = (uint32_t*)std::calloc(nx + 1, 4);
@@ -191,7 +193,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   R->text_sentpos_end = (uint32_t*)std::calloc(nx + 1, 4);
   R->text_byte_end = (uint32_t*)std::calloc(nx + 1, 4);
   std::vector<DocRec> docs(nx + 1);
-  c.tok_bytes = R->tok_bytes; c.tok_pos = R->tok_pos; c.sent_pos = R->sent_pos; c.sent_tok = R->sent_tok;
+  c.tok_bytes = R->tok_bytes; c.tok_pos = R->tok_pos; c.tok_delta = R->tok_delta; c.sent_pos = R->sent_pos; c.sent_tok = R->sent_tok;
   c.text_tok_end = R->text_tok_end; c.text_sent_end = R->text_sent_end;
   c.text_sentpos_end = R->text_sentpos_end; c.text_byte_end = R->text_byte_end;
   c.docs = docs.data();
@@ -205,6 +207,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       const bool staged = blk_ntok <= 64;
       std::vector<uint32_t> s_tb(2 * 64 + 2);
       std::vector<int32_t> s_tp(2 * 64 + 2);
+      std::vector<uint16_t> s_td(4 * 64 + 4);
       for (uint32_t t = 0; t < TPB; t++) {
         for (uint32_t k = 0; k < WPT; k++) {
           uint32_t w = blk * WPB + t * WPT + k;
@@ -214,7 +217,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
           else if (wb.e | wb.s | wb.t) {
             const WordMasks wm = word_masks(wb, agg_last(carry));
             emit_tokens(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
-                        staged ? blk_tok0 : 0u);
+                        staged ? s_td.data() : c.tok_delta, staged ? blk_tok0 : 0u);
             emit_sentences(c, w, wb, wm, carry);
           }
           carry = agg_combine(carry, word_agg(w, wb));
@@ -223,6 +226,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       if (pass == 1 && staged) {
         std::memcpy(c.tok_bytes + 2 * (size_t)blk_tok0, s_tb.data(), 8 * (size_t)blk_ntok);
         std::memcpy(c.tok_pos + 2 * (size_t)blk_tok0, s_tp.data(), 8 * (size_t)blk_ntok);
+        std::memcpy(c.tok_delta + 4 * (size_t)blk_tok0, s_td.data(), 8 * (size_t)blk_ntok);
       }
     }
   }
@@ -234,7 +238,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
 
 void emul_result_free(EmulResult* r) {
   if (!r) return;
-  std::free(r->tok_bytes); std::free(r->tok_pos); std::free(r->sent_pos); std::free(r->sent_tok);
+  std::free(r->tok_bytes); std::free(r->tok_pos); std::free(r->tok_delta); std::free(r->sent_pos); std::free(r->sent_tok);
   std::free(r->text_tok_end); std::free(r->text_sent_end); std::free(r->text_sentpos_end); std::free(r->text_byte_end);
   std::free(r);
 }

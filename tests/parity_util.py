@@ -30,7 +30,8 @@ class _Res(C.Structure):
                 ("text_tok_end", C.POINTER(C.c_uint32)), ("text_sent_end", C.POINTER(C.c_uint32)),
                 ("text_sentpos_end", C.POINTER(C.c_uint32)), ("text_byte_end", C.POINTER(C.c_uint32)),
                 ("carry_state", C.c_uint32), ("has_invalid", C.c_uint32),
-                ("rounds", C.c_uint32), ("n_rewalks", C.c_uint32), ("n_stitch_mismatch", C.c_uint32)]
+                ("rounds", C.c_uint32), ("n_rewalks", C.c_uint32), ("n_stitch_mismatch", C.c_uint32),
+                ("tok_delta", C.POINTER(C.c_uint16))]
 
 
 _lib = None
@@ -93,8 +94,30 @@ class EmulModel:
             s.text_byte_end = _arr(r.text_byte_end, r.n_texts, np.uint32)
             s.carry_state = r.carry_state
             s.has_invalid = r.has_invalid
+            s.tok_delta = _arr(r.tok_delta, 4 * r.n_tokens, np.uint16)
         lib().emul_result_free(rp)
         return s
+
+
+def expand_delta(tok_delta, text_tok_end, text_byte_end):
+    """numpy restatement of datok_expand() (format.cpp): DATOK_COMPACT deltas -> absolute (tok_bytes, tok_pos)"""
+    d = tok_delta.astype(np.int64).reshape(-1, 4)
+    n = d.shape[0]
+    tb, tp = np.zeros(2 * n, np.int64), np.zeros(2 * n, np.int64)
+    lo = 0
+    for t in range(len(text_tok_end)):
+        hi = int(text_tok_end[t])
+        if hi > lo:
+            seg = d[lo:hi]
+            byte0 = int(text_byte_end[t - 1]) if t else 0
+            ends = byte0 + np.cumsum(seg[:, 0] + seg[:, 1])
+            tb[2 * lo:2 * hi:2] = ends - seg[:, 1]
+            tb[2 * lo + 1:2 * hi:2] = ends
+            rends = np.cumsum(seg[:, 2] + seg[:, 3])
+            tp[2 * lo:2 * hi:2] = rends - seg[:, 3]
+            tp[2 * lo + 1:2 * hi:2] = rends
+        lo = hi
+    return tb, tp
 
 
 # oracle status -> DATOK_ERR_* code
@@ -127,3 +150,9 @@ def assert_matches_oracle(s, o, flags, ctx=""):
             np.testing.assert_array_equal(s.text_sentpos_end, o.text_sentpos_end.astype(np.uint32),
                                           err_msg=f"{ctx}: text sent-list bounds")
     assert s.carry_state == o.carry_out["state"], f"{ctx}: carry-out state"
+    delta = getattr(s, "tok_delta", None)
+    if delta is not None and delta.size and (flags & 12):  # the emulation also fills the DATOK_COMPACT form
+        tb, tp = expand_delta(delta, s.text_tok_end, s.text_byte_end)
+        np.testing.assert_array_equal(tb[0::2], o.tok_byte_start, err_msg=f"{ctx}: delta-coded byte starts")
+        np.testing.assert_array_equal(tb[1::2], o.tok_byte_end, err_msg=f"{ctx}: delta-coded byte ends")
+        np.testing.assert_array_equal(tp, o.tok_pos, err_msg=f"{ctx}: delta-coded rune offsets")

@@ -258,6 +258,10 @@ def test_pipelined_host_path(model, kind, testdata, oracle_models, monkeypatch):
         r = tok.transduce_arrays(a, flags)
         P.assert_matches_oracle(r, o, flags, f"pipelined flags={flags}")
         assert tok.format(r, a, flags) == o.text
+        rc = tok.transduce_arrays(a, flags | d.COMPACT)
+        assert rc.tok_bytes is None and rc.tok_delta is not None
+        assert tok.format(rc, a, flags) == o.text
+        P.assert_matches_oracle(rc.expand(), o, flags, f"pipelined compact flags={flags}")
     # a reused TokenWriter and a carried state behave like in the single-pass path
     head = "Vorspann ohne Ende.\n\x04".encode()
     oa = oracle_models[model].transduce(head, 31)
@@ -277,3 +281,32 @@ def test_pipelined_host_path(model, kind, testdata, oracle_models, monkeypatch):
     for f in ("tok_bytes", "tok_pos", "sent_pos", "sent_tok", "text_tok_end", "text_sent_end", "text_sentpos_end", "text_byte_end"):
         np.testing.assert_array_equal(getattr(r1, f), getattr(r2, f), err_msg=f)
     tok1.close(); tok2.close()
+
+
+@pytest.mark.parametrize("model,kind", [("tokenizer_de.matok", 2), ("tokenizer_en.matok", 3), ("tokenizer_de.matok", 4),
+                                        ("simpletok.matok", 1)])
+def test_compact_token_deltas(model, kind, gpu_models, oracle_models):
+    """DATOK_COMPACT: 8-byte delta-coded token spans; datok_expand / datok_format / datok_replay decode them"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    tok = gpu_models[model]
+    a = corpus.generate(kind, 3 << 20, seed=33)
+    for flags in (15, 31, 1, 4, 5 | 16):
+        o = oracle_models[model].transduce_np(a, flags)
+        r = tok.transduce_arrays(a, flags | d.COMPACT)
+        assert r.tok_delta is not None and r.tok_delta.size == 4 * r.n_tokens
+        assert tok.format(r, a, flags) == o.text
+        P.assert_matches_oracle(r.expand(), o, flags, f"compact {model} flags={flags}")
+    # numpy restatement of the decode agrees with the library's
+    r = tok.transduce_arrays(a, 15 | d.COMPACT)
+    tb, tp = P.expand_delta(r.tok_delta, r.text_tok_end, r.text_byte_end)
+    r.expand()
+    np.testing.assert_array_equal(tb, r.tok_bytes)
+    np.testing.assert_array_equal(tp, r.tok_pos)
+    for data in (b"", b"abc", b"a.\x04b.\x04c", "ä ö ü ß „Zitat“ – …".encode(), b"\nThis.\n\x04\nAnd.\n\x04\n"):
+        for flags in (3, 31):
+            o = oracle_models[model].transduce(data, flags)
+            if o.status:
+                continue
+            r = tok.transduce_arrays(data, flags | d.COMPACT)
+            assert tok.format(r, data, flags) == o.text
