@@ -199,9 +199,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident leg -------------------------------------------------
+    # ---- device-resident leg (the form the Tokenizer shim asks for: delta-coded token spans) ----
+    DFLAGS = FLAGS | d.COMPACT
     for _ in range(args.warmup):
-        tok.transduce_device(d_in.data_ptr(), N, FLAGS).close()
+        tok.transduce_device(d_in.data_ptr(), N, DFLAGS).close()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -209,7 +210,7 @@ def main():
     dev_ms, ktimes, launches = [], {}, 0
     T = S = D = 0
     for _ in range(args.steps):
-        r = tok.transduce_device(d_in.data_ptr(), N, FLAGS)
+        r = tok.transduce_device(d_in.data_ptr(), N, DFLAGS)
         dev_ms.append(r.ms_kernels)
         T, S, D = r.n_tokens, r.n_sentences, r.n_texts
         for k, v in tok.kernel_times().items():
@@ -273,7 +274,7 @@ def main():
                 cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         kt = {k: round(v / args.steps, 4) for k, v in ktimes.items()}
         # per-kernel algorithmic traffic of one launch: bytes each kernel must move
-        out_b = 16 * T + 8 * S + 16 * D
+        out_b = 8 * T + 8 * S + 16 * D  # delta-coded token spans, sentence entries, per-text bounds
         kalg = {"walk_fused": N + 5 * N // 8, "compact_reduce": 4 * N // 8, "compact_texts": 4 * N // 8,
                 "compact_emit": 5 * N // 8 + out_b}
         kroof = {k: {"ms": kt[k], "alg_bytes": b, "gbps": b / (kt[k] * 1e-3) / 1e9,
@@ -284,7 +285,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"C2: tokenizer_de.matok, {N} B synthetic German corpus per GPU, ~10 KB "
-                                   "EOT-separated documents, flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS",
+                                   "EOT-separated documents, flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS (|DATOK_COMPACT: "
+                                   "8-byte delta-coded token spans)",
                        "bytes_per_gpu": N, "documents_per_gpu": D, "tokens_per_gpu": T, "sentences_per_gpu": S,
                        "l2": "input (>= 1 GiB) and outputs exceed the 126 MB L2; no flush needed",
                        "chunk_bytes": int(os.environ.get("DATOK_CHUNK", "512")),

@@ -20,6 +20,8 @@
 
 namespace datok {
 
+#define DATOK_RARE(x) __builtin_expect(!!(x), 0)
+
 // event kinds (last_kind / first_kind)
 constexpr uint32_t EV_NONE = 0;    // empty span
 constexpr uint32_t EV_END = 1;     // Token              -> sentenceEnd=false, textEnd=false (matrix.go:571-572)
@@ -298,8 +300,9 @@ DATOK_HD void emit_sentences(const CompactCtx& c, uint32_t w, const WordBits& b,
 constexpr uint32_t E_COMPACT_RANGE = 24;  // DATOK_ERR_COMPACT_RANGE
 
 // The Token events of word w (token_writer.go:59-95).  Token k goes to slot k - tok_base of
-// tok_bytes/tok_pos (2 values each) or of tok_delta (4 values; the kernel stages a block's tokens in
-// shared memory); sentence openers go to c.sent_pos.
+// tok_bytes/tok_pos (2 values each, ABS) or of tok_delta (4 values, !ABS; the kernel stages a block's
+// tokens in shared memory); sentence openers go to c.sent_pos.
+template <bool ABS>
 DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, const WordMasks& m, const Agg& A,
                           uint32_t* tok_bytes, int32_t* tok_pos, uint16_t* tok_delta, uint32_t tok_base) {
   uint32_t e = b.e;
@@ -314,7 +317,7 @@ DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, co
     const uint32_t bp = ctz32(e);
     e &= e - 1;
     const uint32_t lt = mask_below(bp), p = w0 + bp;
-    if (b.t & lt) {  // a TextEnd earlier in this word
+    if (DATOK_RARE(b.t & lt)) {  // a TextEnd earlier in this word
       const uint32_t id = A.n_text + popc32(b.t & lt);
       if (id != doc_id) { doc_id = id; d = c.docs[id]; shift = doc_shift(c, d); }
     }
@@ -322,32 +325,38 @@ DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, co
     uint32_t bufstart = d.start;
     bool first = true;  // first token of its text
     if (prev_end != K_NOPOS && prev_end > bufstart) { bufstart = prev_end; first = false; }
-    uint32_t s, runes, skipped;  // token start, runes in [s, p), runes in [bufstart, s)
+    uint32_t s, runes, skipped = 0;  // token start, runes in [s, p), runes in [bufstart, s)
     const uint32_t from = mask_from(bufstart >= w0 ? bufstart - w0 : 32u);
     const uint32_t cl = ~b.k & lt & from;
     if (bufstart >= w0 && cl) {  // within the word
       const uint32_t sb = ctz32(cl);
       s = w0 + sb;
       runes = popc32(b.rs & lt & mask_from(sb));
-      skipped = popc32(b.rs & from & mask_below(sb));
+      if (!ABS) skipped = popc32(b.rs & from & mask_below(sb));
     } else {
       s = next_clear(c.b_skip, c.n_words, bufstart);
       runes = count_range(c.rstart, s, p);
-      skipped = tok_delta ? count_range(c.rstart, bufstart, s) : 0;
+      if (!ABS) skipped = count_range(c.rstart, bufstart, s);
     }
-    const uint32_t rank_e = A.n_rune + popc32(b.rs & lt);
-    const int32_t pe = (int32_t)(rank_e - d.rank) - shift, ps = pe - (int32_t)runes;
-    if (tok_bytes) { tok_bytes[2 * (size_t)tok] = c.base_byte + s; tok_bytes[2 * (size_t)tok + 1] = c.base_byte + p; }
-    if (tok_pos) { tok_pos[2 * (size_t)tok] = ps; tok_pos[2 * (size_t)tok + 1] = pe; }
-    if (tok_delta) {
+    if (ABS) {
+      const uint32_t rank_e = A.n_rune + popc32(b.rs & lt);
+      const int32_t pe = (int32_t)(rank_e - d.rank) - shift, ps = pe - (int32_t)runes;
+      if (tok_bytes) { tok_bytes[2 * tok] = c.base_byte + s; tok_bytes[2 * tok + 1] = c.base_byte + p; }
+      if (tok_pos) { tok_pos[2 * tok] = ps; tok_pos[2 * tok + 1] = pe; }
+    } else {
       const int32_t rskip = (int32_t)skipped - (first ? shift : 0);
       const uint32_t bskip = s - bufstart, blen = p - s;
-      if ((bskip | blen | runes | (uint32_t)rskip) > 0xFFFFu) report_error(c, p, E_COMPACT_RANGE);
-      uint16_t* o = tok_delta + 4 * (size_t)tok;
-      o[0] = (uint16_t)bskip; o[1] = (uint16_t)blen; o[2] = (uint16_t)rskip; o[3] = (uint16_t)runes;
+      if (DATOK_RARE((bskip | blen | runes | (uint32_t)rskip) > 0xFFFFu)) report_error(c, p, E_COMPACT_RANGE);
+      uint32_t* o = reinterpret_cast<uint32_t*>(tok_delta) + 2 * tok;  // {skip bytes, bytes}, {skip runes, runes}
+      o[0] = bskip | (blen << 16);
+      o[1] = ((uint32_t)rskip & 0xFFFFu) | (runes << 16);
     }
-    if ((m.opener >> bp) & 1u) {
-      if (c.sent_pos) c.sent_pos[A.n_sentpos + popc32(m.opener & lt) + popc32(m.se & lt)] = ps;
+    if (DATOK_RARE((m.opener >> bp) & 1u)) {
+      if (c.sent_pos) {
+        const uint32_t rank_e = A.n_rune + popc32(b.rs & lt);
+        const int32_t ps = (int32_t)(rank_e - d.rank) - shift - (int32_t)runes;
+        c.sent_pos[A.n_sentpos + popc32(m.opener & lt) + popc32(m.se & lt)] = ps;
+      }
     }
     tok++;
     prev_end = p;

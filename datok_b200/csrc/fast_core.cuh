@@ -325,6 +325,29 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
       // ---- rare: failure (F16_FAIL), or not in the compact rows (0): cold state, target outside
       // the hot rows, marked entry.  Steps through the full table until the state is hot again ----
       bool failed = e == F16_FAIL;
+      if (failed) {
+        // The common backtrack, inline: the point was recorded in this raw range by a lookup without
+        // epsilon steps of its own, both states are hot, q holds no boundary or skipped rune yet and
+        // nothing killed the point.  Everything else goes through fast_backtrack() below.
+        const uint32_t qo = eps_off, es = eps_rec & F3_TGT;
+        const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
+        if (eps_rec != 0 && (eps_rec >> 30) == 0 && qo < 32 && qo >= ro && !L.first_window && es < T.n_hot) {
+          const uint32_t qb = 1u << qo, below = qb - 1u, keep = below | qb;
+          const uint32_t tgt = h16_load(T, es, 2u * K_CLS_EPS);
+          const uint32_t cb = R.cb;
+          const uint32_t dead = ((c1 | cb) & ~keep) | (eotm & ~below & mask_below(off)) | ((c1 | c2 | cb | nt) & qb);
+          if (tgt != 0 && dead == 0) {
+            DATOK_STAT(g_bt_ok); DATOK_STAT(g_bt_inline);
+            const uint32_t pos = seg_start + off;
+            if (L.hw_med < pos) L.hw_med = pos;
+            c1 &= below; c2 &= below; nt &= below;
+            R.cb = (cb & below) | qb;
+            off = qo; bit = qb;
+            t = tl = tgt; eps_rec = 0;
+            continue;
+          }
+        }
+      }
       for (;;) {
         uint32_t e3 = 0;
         if (!failed) {
@@ -343,6 +366,9 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
           failed = false;
         } else {
           DATOK_STAT(g_fast);
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+          g_hist[t]++;
+#endif
           if (e3 & F3_KANY) c1 |= bit;
           if (e3 & F3_K2) c2 |= bit;
           if (e3 & F3_NT) nt |= bit;
@@ -357,6 +383,9 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
       continue;
     }
     DATOK_STAT(g_fast);
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+    g_hist[t]++;
+#endif
 #if defined(__CUDA_ARCH__)
     asm("{\n\t.reg .pred pk, p2, pn, pe;\n\t.reg .b32 x;\n\t"
         "and.b32 x, %5, 0xC000;\n\tsetp.ne.u32 pk, x, 0;\n\t"
@@ -451,6 +480,22 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
     const uint32_t j = ctz32(m);
     m &= m - 1;
     const uint32_t p = seg_start + j;
+    {
+      // the common case first: a well-formed two-byte rune below U+0100 (lead C2/C3: the Latin-1 letters)
+      const uint32_t b0 = in[p];
+      if ((b0 & 0xFEu) == 0xC2u && p + 1 < N) {
+        const uint32_t b1 = in[p + 1];
+        if ((b1 & 0xC0u) == 0x80u) {
+          seg_cls[j] = (uint8_t)(2u * T.latin1_cls[((b0 & 1u) << 6) | (b1 & 0x3Fu)]);
+          rs |= 1u << j;
+          if (j + 1 < SEG) {
+            seg_cls[j + 1] = (uint8_t)(2u * K_CLS_CONT);
+            m &= ~(1u << (j + 1));
+          }
+          continue;
+        }
+      }
+    }
     bool st, inv;
     const uint32_t cl = classify_pos(in, N, p, T, &st, &inv);
     seg_cls[j] = (uint8_t)(2u * cl);

@@ -330,35 +330,27 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   uint32_t* s_tb = s_stage;
   int32_t* s_tp = reinterpret_cast<int32_t*>(s_stage + 2 * STAGE_TOKENS);
   uint16_t* s_td = reinterpret_cast<uint16_t*>(s_stage);
-  // two copies of the loop so that the staged one addresses shared memory directly
-  if (staged) {
-#pragma unroll
-    for (int k = 0; k < COMPACT_WPT; k++) {
-      const uint32_t w = w0 + k;
-      if (w < c.n_words) {
-        if (wb[k].e | wb[k].s | wb[k].t) {
-          const WordMasks m = word_masks(wb[k], agg_last(carry));
-          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes ? s_tb : nullptr, c.tok_pos ? s_tp : nullptr,
-                      c.tok_delta ? s_td : nullptr, blk_tok0);
-          emit_sentences(c, w, wb[k], m, carry);
-        }
-        carry = agg_combine(carry, wa[k]);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < COMPACT_WPT; k++) {
-      const uint32_t w = w0 + k;
-      if (w < c.n_words) {
-        if (wb[k].e | wb[k].s | wb[k].t) {
-          const WordMasks m = word_masks(wb[k], agg_last(carry));
-          emit_tokens(c, w, wb[k], m, carry, c.tok_bytes, c.tok_pos, c.tok_delta, 0u);
-          emit_sentences(c, w, wb[k], m, carry);
-        }
-        carry = agg_combine(carry, wa[k]);
-      }
-    }
+  // specialised copies of the loop: staged ones address shared memory directly, compact / absolute form
+#define DATOK_EMIT_LOOP(ABS, TB, TP, TD, BASE)                                                   \
+  _Pragma("unroll") for (int k = 0; k < COMPACT_WPT; k++) {                                      \
+    const uint32_t w = w0 + k;                                                                   \
+    if (w < c.n_words) {                                                                         \
+      if (wb[k].e | wb[k].s | wb[k].t) {                                                         \
+        const WordMasks m = word_masks(wb[k], agg_last(carry));                                  \
+        emit_tokens<ABS>(c, w, wb[k], m, carry, TB, TP, TD, BASE);                               \
+        emit_sentences(c, w, wb[k], m, carry);                                                   \
+      }                                                                                          \
+      carry = agg_combine(carry, wa[k]);                                                         \
+    }                                                                                            \
   }
+  if (c.tok_delta) {
+    if (staged) { DATOK_EMIT_LOOP(false, nullptr, nullptr, s_td, blk_tok0) }
+    else { DATOK_EMIT_LOOP(false, nullptr, nullptr, c.tok_delta, 0u) }
+  } else {
+    if (staged) { DATOK_EMIT_LOOP(true, c.tok_bytes ? s_tb : nullptr, c.tok_pos ? s_tp : nullptr, nullptr, blk_tok0) }
+    else { DATOK_EMIT_LOOP(true, c.tok_bytes, c.tok_pos, nullptr, 0u) }
+  }
+#undef DATOK_EMIT_LOOP
   if (!staged) return;
   __syncthreads();
   if (c.tok_bytes) {

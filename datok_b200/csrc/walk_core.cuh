@@ -63,10 +63,18 @@ DATOK_HD uint32_t clz32(uint32_t x) {  // x != 0
   return (uint32_t)__builtin_clz(x);
 #endif
 }
-// mask of bits [lo, 32)
-DATOK_HD uint32_t mask_from(uint32_t lo) { return lo >= 32 ? 0u : (0xFFFFFFFFu << lo); }
 // mask of bits [0, hi)
-DATOK_HD uint32_t mask_below(uint32_t hi) { return hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u); }
+DATOK_HD uint32_t mask_below(uint32_t hi) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0u), "r"(hi));  // one instruction, widths >= 32 clamp to all ones
+  return r;
+#else
+  return hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+#endif
+}
+// mask of bits [lo, 32)
+DATOK_HD uint32_t mask_from(uint32_t lo) { return ~mask_below(lo); }
 
 // number of set bits of bitmap `w` at positions [lo, hi)
 DATOK_HD uint32_t count_range(const uint32_t* w, uint32_t lo, uint32_t hi) {

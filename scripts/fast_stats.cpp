@@ -9,13 +9,23 @@
 #include <string>
 #include <vector>
 static unsigned long long g_exact_calls, g_exact_steps, g_guard, g_fast, g_bt_ok, g_bt_hard, g_bt_far, g_bt_dead,
-    g_bt_third, g_zone, g_mark, g_cold;
+    g_bt_third, g_zone, g_mark, g_cold, g_bt_inline;
+static unsigned long long g_hist[65536];
 #include "../datok_b200/csrc/chunk_core.cuh"
 #include "../datok_b200/csrc/model.hpp"
 using namespace datok;
+int run(int argc, char** argv, HostModel& hm, bool report);
 int main(int argc, char** argv) {
   HostModel hm; std::string why;
   if (load_matok_file(argv[1], hm, why)) { fprintf(stderr, "%s\n", why.c_str()); return 1; }
+  run(argc, argv, hm, false);  // calibration pass: visits per state
+  std::vector<uint64_t> hist_old(hm.stateCount + 1, 0);
+  for (int t = 1; t <= hm.stateCount; t++) hist_old[hm.old_of_new[t]] = g_hist[t];
+  if (build_layout(hm, why, hist_old.data())) return 1;
+  g_exact_calls = g_exact_steps = g_guard = g_fast = g_bt_ok = g_bt_hard = g_bt_far = g_bt_dead = g_bt_third = g_zone = g_mark = g_cold = g_bt_inline = 0;
+  return run(argc, argv, hm, true);
+}
+int run(int argc, char** argv, HostModel& hm, bool report) {
   FILE* f = fopen(argv[2], "rb"); fseek(f, 0, SEEK_END); size_t n = ftell(f); fseek(f, 0, SEEK_SET);
   std::vector<uint8_t> in(n + 64); if (fread(in.data(), 1, n, f) != n) return 1; fclose(f);
   uint32_t chunk = argc > 3 ? atoi(argv[3]) : 256, hot_rows = argc > 4 ? atoi(argv[4]) : 440;
@@ -43,9 +53,9 @@ int main(int argc, char** argv) {
   FT.hot_saddr = 0; FT.ascii_cls2 = lut2;
   uint8_t cls[36];
   for (uint32_t i = 0; i < b.n_chunks; i++) chunk_spec_fast(m, b, FT, i, m.start, cls);
-  printf("bytes %zu chunks %u\nfast steps %llu (cold %llu = %.3f%%)\nbacktracks in place %llu (%.3f%% of steps), stale zones %llu\n"
+  if (report) printf("bytes %zu chunks %u\nfast steps %llu (cold %llu = %.3f%%)\nbacktracks in place %llu (%.3f%% of steps), stale zones %llu, inline %llu\n"
          "slow: marks %llu, hard %llu, far %llu, dead %llu, third %llu; guard %llu\nexact calls %llu steps %llu (%.3f%% of bytes)\n",
-         n, b.n_chunks, g_fast, g_cold, 100.0 * g_cold / g_fast, g_bt_ok, 100.0 * g_bt_ok / g_fast, g_zone, g_mark, g_bt_hard, g_bt_far,
+         n, b.n_chunks, g_fast, g_cold, 100.0 * g_cold / g_fast, g_bt_ok, 100.0 * g_bt_ok / g_fast, g_zone, g_bt_inline, g_mark, g_bt_hard, g_bt_far,
          g_bt_dead, g_bt_third, g_guard, g_exact_calls, g_exact_steps, 100.0 * g_exact_steps / n);
   return 0;
 }

@@ -11,6 +11,6 @@ tok = d.LoadTokenizerFile("testdata/tokenizer_de.matok")
 d_in = torch.from_numpy(a).cuda()
 torch.cuda.synchronize()
 for i in range(2):
-    r = tok.transduce_device(d_in.data_ptr(), size, 15)
+    r = tok.transduce_device(d_in.data_ptr(), size, 15 | d.COMPACT)
     print(i, r.n_tokens, r.ms_kernels, tok.kernel_times(), flush=True)
     r.close()

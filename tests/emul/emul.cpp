@@ -216,8 +216,10 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
           if (pass == 0) emit_texts(c, w, wb, carry);
           else if (wb.e | wb.s | wb.t) {
             const WordMasks wm = word_masks(wb, agg_last(carry));
-            emit_tokens(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
-                        staged ? s_td.data() : c.tok_delta, staged ? blk_tok0 : 0u);
+            emit_tokens<true>(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
+                              nullptr, staged ? blk_tok0 : 0u);
+            emit_tokens<false>(c, w, wb, wm, carry, nullptr, nullptr, staged ? s_td.data() : c.tok_delta,
+                               staged ? blk_tok0 : 0u);
             emit_sentences(c, w, wb, wm, carry);
           }
           carry = agg_combine(carry, word_agg(w, wb));
