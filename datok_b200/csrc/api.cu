@@ -212,6 +212,7 @@ size_t carve(uint8_t* base, uint32_t N, uint32_t chunk, bool need_input_copy, Wa
   cb.n_blocks = (b.n_words + wpb - 1) / wpb;
   cb.block_agg = c.take<Agg>(cb.n_blocks);
   cb.block_carry = c.take<Agg>(cb.n_blocks);
+  cb.warp_agg = c.take<Agg>((size_t)cb.n_blocks * (COMPACT_THREADS / 32));
   cb.super_agg = c.take<Agg>(cb.n_blocks / SCAN_THREADS + 1);
   cb.super_carry = c.take<Agg>(cb.n_blocks / SCAN_THREADS + 1);
   cb.total = c.take<Agg>(2);
@@ -435,7 +436,10 @@ int do_walk(datok_model* m, WalkBuffers& b, uint32_t start_state, PhaseTimer& pt
     launch_stitch(m->dm, b, list, n_list, s);
     pt.end();
     pt.begin(T_REWALK);
-    launch_rewalk(m->dm, b, n_list, s);
+    {
+      const int e = launch_rewalk_fused(m->dm, b, n_list, m->n_hot, m->n_sms, s);
+      if (e != 0) { g_last_error = std::string("rewalk launch: ") + cudaGetErrorString((cudaError_t)e); return DATOK_ERR_CUDA; }
+    }
     pt.end();
     pt.begin(T_COMMIT);
     launch_commit(b, list, n_list, s);

@@ -25,10 +25,12 @@ constexpr int LANE_CLS_STRIDE = 36;  // bytes of class scratch per lane (9 words
 // Persistent kernel, one CTA per SM.  The compact (u16) rows of the hottest states and the
 // byte->class LUTs live in shared memory; every lane owns one chunk at a time and walks it
 // segment by segment (chunk_spec_fast).
-template <int THREADS>
+// REWALK: the same tables, but the lanes re-walk the chunks of list_rewalk (K2c) from their true states.
+template <int THREADS, bool REWALK>
 __global__ void __launch_bounds__(THREADS, 1)
 walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n_hot) {
   extern __shared__ __align__(16) uint32_t smem[];
+  if (REWALK && blockIdx.x * THREADS >= b.counters[1]) return;  // the list length is only known on the device
   uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);
   const uint32_t hot_entries = n_hot * m.stride16;
   uint8_t* s_cls = reinterpret_cast<uint8_t*>(smem) + (((hot_entries + m.stride16) * 2u + 15u) & ~15u);
@@ -56,8 +58,14 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
     asm volatile("cvt.u32.u64 %0, %1;" : "=r"(FT.hot_saddr) : "l"(sa));
   }
   uint8_t* my_cls = s_cls + threadIdx.x * LANE_CLS_STRIDE;
-  for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * THREADS)
-    chunk_spec_fast(lm, b, FT, i, start_state, my_cls);
+  if (REWALK) {
+    const uint32_t n = b.counters[1];
+    for (uint32_t k = blockIdx.x * THREADS + threadIdx.x; k < n; k += gridDim.x * THREADS)
+      chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls);
+  } else {
+    for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * THREADS)
+      chunk_spec_fast(lm, b, FT, i, start_state, my_cls);
+  }
 }
 
 static int g_fused_threads = 0;
@@ -72,9 +80,10 @@ int fused_threads() {
   return g_fused_threads;
 }
 
-size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot) {
-  return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)fused_threads() * LANE_CLS_STRIDE + 384;
+static size_t fused_smem_bytes_t(const DeviceModel& m, uint32_t n_hot, int threads) {
+  return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)threads * LANE_CLS_STRIDE + 384;
 }
+size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot) { return fused_smem_bytes_t(m, n_hot, fused_threads()); }
 
 uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states) {
   const size_t fixed = (size_t)fused_threads() * LANE_CLS_STRIDE + 384 + 16 + 1024 + (size_t)m.stride16 * 2;
@@ -91,13 +100,32 @@ static int launch_walk_fused_t(const DeviceModel& m, const WalkBuffers& b, uint3
   const size_t smem = fused_smem_bytes(m, n_hot);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
   uint32_t blocks = (b.n_chunks + THREADS - 1) / THREADS;
   if (blocks > (uint32_t)n_sms) blocks = (uint32_t)n_sms;
-  walk_fused_kernel<THREADS><<<blocks, THREADS, smem, s>>>(m, b, start_state, n_hot);
+  walk_fused_kernel<THREADS, false><<<blocks, THREADS, smem, s>>>(m, b, start_state, n_hot);
+  return (int)cudaGetLastError();
+}
+
+// K2c: the mismatched chunks, with the hot rows in shared memory like the first walk
+constexpr int REWALK_THREADS = 256;
+int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk_max, uint32_t n_hot, int n_sms,
+                        cudaStream_t s) {
+  if (!n_rewalk_max) return 0;
+  const size_t smem = fused_smem_bytes_t(m, n_hot, REWALK_THREADS);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel<REWALK_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  uint32_t blocks = (n_rewalk_max + REWALK_THREADS - 1) / REWALK_THREADS;
+  if (blocks > (uint32_t)n_sms) blocks = (uint32_t)n_sms;
+  walk_fused_kernel<REWALK_THREADS, true><<<blocks, REWALK_THREADS, smem, s>>>(m, b, 0, n_hot);
   return (int)cudaGetLastError();
 }
 
@@ -134,7 +162,7 @@ void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cud
 
 // ------------------------------------------------------------------ K2b-d
 
-__global__ void __launch_bounds__(WALK_THREADS) stitch_kernel(DeviceModel m, WalkBuffers b, const uint32_t* list,
+__global__ void __launch_bounds__(WALK_THREADS, 6) stitch_kernel(DeviceModel m, WalkBuffers b, const uint32_t* list,
                                                               uint32_t n_list) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_list) return;
@@ -143,23 +171,6 @@ __global__ void __launch_bounds__(WALK_THREADS) stitch_kernel(DeviceModel m, Wal
     const uint32_t slot = atomicAdd(&b.counters[1], 1u);
     b.list_rewalk[slot] = i;
   }
-}
-
-// Re-walks go through the fast path too (fused table straight from L2: there are few of them).
-__global__ void __launch_bounds__(WALK_THREADS) rewalk_kernel(DeviceModel m, WalkBuffers b, uint32_t n_rewalk) {
-  __shared__ __align__(16) uint8_t s_cls[WALK_THREADS * LANE_CLS_STRIDE];
-  __shared__ uint8_t s_lut2[128];
-  __shared__ uint16_t s_zero[136];  // the all-zero compact row: every lookup goes to the full table
-  if (threadIdx.x < 128) s_lut2[threadIdx.x] = (uint8_t)(2u * m.cls.ascii_cls[threadIdx.x]);
-  for (uint32_t k = threadIdx.x; k < 136; k += blockDim.x) s_zero[k] = 0;
-  __syncthreads();
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  // n_rewalk is only the launch bound; the list length was counted on the device by stitch_kernel
-  if (k >= n_rewalk || k >= b.counters[1]) return;
-  FastTables FT;
-  FT.hot16 = s_zero; FT.t3 = m.table2; FT.n_hot = 0; FT.row16 = m.stride16 * 2u; FT.stride3 = m.stride2;
-  FT.hot_saddr = (uint32_t)__cvta_generic_to_shared(s_zero); FT.ascii_cls2 = s_lut2;
-  chunk_rewalk_fast(m, b, FT, b.list_rewalk[k], s_cls + threadIdx.x * LANE_CLS_STRIDE);
 }
 
 __global__ void __launch_bounds__(256) commit_kernel(WalkBuffers b, const uint32_t* list, uint32_t n_list) {
@@ -187,10 +198,6 @@ __global__ void __launch_bounds__(256) collect_errors_kernel(WalkBuffers b) {
 void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s) {
   if (!n_list) return;
   stitch_kernel<<<(n_list + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, list, n_list);
-}
-void launch_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk, cudaStream_t s) {
-  if (!n_rewalk) return;
-  rewalk_kernel<<<(n_rewalk + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, n_rewalk);
 }
 void launch_commit(const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s) {
   if (!n_list) return;
@@ -258,9 +265,10 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& 
   return prefix;
 }
 
-// Ordered block reduction; the result is valid in thread 0.
+// Ordered block reduction; the result is valid in thread 0.  warp_out (optional): the block's
+// THREADS / 32 warp totals.
 template <int THREADS>
-__device__ __forceinline__ Agg block_reduce(const Agg& mine) {
+__device__ __forceinline__ Agg block_reduce(const Agg& mine, Agg* warp_out) {
   __shared__ Agg s_warp[THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Agg v = mine;
@@ -269,12 +277,28 @@ __device__ __forceinline__ Agg block_reduce(const Agg& mine) {
     Agg o = agg_shfl_down(v, d);
     if ((lane & (2 * d - 1)) == 0) v = agg_combine(v, o);  // lanes lane..lane+2d-1, in order
   }
-  if (lane == 0) s_warp[warp] = v;
+  if (lane == 0) {
+    s_warp[warp] = v;
+    if (warp_out) warp_out[warp] = v;
+  }
   __syncthreads();
   Agg tot = s_warp[0];
   if (threadIdx.x == 0)
     for (int wi = 1; wi < THREADS / 32; wi++) tot = agg_combine(tot, s_warp[wi]);
   return tot;
+}
+
+// Ordered exclusive scan within one warp, combined after `seed`.
+__device__ __forceinline__ Agg warp_exclusive_scan(const Agg& mine, const Agg& seed) {
+  const int lane = threadIdx.x & 31;
+  Agg incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Agg o = agg_shfl_up(incl, d);
+    if (lane >= d) incl = agg_combine(o, incl);
+  }
+  Agg prev = agg_shfl_up(incl, 1);
+  return lane > 0 ? agg_combine(seed, prev) : seed;
 }
 
 enum { K3_REDUCE = 0, K3_TEXTS = 1, K3_EMIT = 2 };
@@ -288,8 +312,38 @@ template <int MODE>
 __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, CompactBuffers cb) {
   extern __shared__ __align__(16) uint32_t s_stage[];
   if (MODE == K3_TEXTS) {
+    // TextEnds are rare (one per text): warps work on their own and leave when their words hold none
     if (blockIdx.x == 0 && threadIdx.x == 0) c.docs[0] = doc_stream_start(c);
-    if (cb.block_agg[blockIdx.x].n_text == 0) return;  // no TextEnd in this block
+    const uint32_t wt0 = (blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
+    uint32_t anyt = 0;
+#pragma unroll
+    for (int k = 0; k < COMPACT_WPT; k++)
+      if (wt0 + k < c.n_words) anyt |= c.b_tend[wt0 + k];
+    if (!__any_sync(0xFFFFFFFFu, anyt != 0)) return;
+    const int warp = threadIdx.x >> 5;
+    Agg seed = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
+    const Agg* wagg = cb.warp_agg + (size_t)blockIdx.x * (COMPACT_THREADS / 32);
+    for (int wi = 0; wi < warp; wi++) seed = agg_combine(seed, wagg[wi]);
+    WordBits tb[COMPACT_WPT];
+    Agg tw[COMPACT_WPT];
+    Agg mine = agg_zero();
+#pragma unroll
+    for (int k = 0; k < COMPACT_WPT; k++) {
+      if (wt0 + k < c.n_words) {
+        tb[k] = word_load(c, wt0 + k);
+        tw[k] = word_agg(wt0 + k, tb[k]);
+        mine = agg_combine(mine, tw[k]);
+      }
+    }
+    Agg run = warp_exclusive_scan(mine, seed);
+#pragma unroll
+    for (int k = 0; k < COMPACT_WPT; k++) {
+      if (wt0 + k < c.n_words) {
+        emit_texts(c, wt0 + k, tb[k], run);
+        run = agg_combine(run, tw[k]);
+      }
+    }
+    return;
   }
   const uint32_t w0 = (blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
   WordBits wb[COMPACT_WPT];
@@ -305,24 +359,13 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
     }
   }
   if (MODE == K3_REDUCE) {
-    const Agg tot = block_reduce<COMPACT_THREADS>(ta);
+    const Agg tot = block_reduce<COMPACT_THREADS>(ta, cb.warp_agg + (size_t)blockIdx.x * (COMPACT_THREADS / 32));
     if (threadIdx.x == 0) cb.block_agg[blockIdx.x] = tot;
     return;
   }
   // summary of everything before this block: (groups of 1024 blocks before) + (blocks before, in the group)
   const Agg block_start = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
   Agg carry = block_exclusive_scan<COMPACT_THREADS>(ta, block_start);
-  if (MODE == K3_TEXTS) {
-#pragma unroll
-    for (int k = 0; k < COMPACT_WPT; k++) {
-      const uint32_t w = w0 + k;
-      if (w < c.n_words) {
-        emit_texts(c, w, wb[k], carry);
-        carry = agg_combine(carry, wa[k]);
-      }
-    }
-    return;
-  }
   // K3_EMIT
   const uint32_t blk_tok0 = block_start.n_tok, blk_ntok = cb.block_agg[blockIdx.x].n_tok;
   const bool staged = blk_ntok <= STAGE_TOKENS;

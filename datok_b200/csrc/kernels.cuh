@@ -11,6 +11,7 @@ namespace datok {
 struct CompactBuffers {
   Agg* block_agg;
   Agg* block_carry;
+  Agg* warp_agg;           // COMPACT_THREADS / 32 warp totals per block (for the texts pass)
   Agg* super_agg;          // one per group of SCAN_THREADS blocks
   Agg* super_carry;
   Agg* total;              // [0] stream summary after the scan, [1] StreamTotals after finalize
@@ -31,7 +32,8 @@ uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_
 void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cudaStream_t s);
 // one fix-up round over `n_list` chunks (list == nullptr: all chunks 1..n_chunks-1)
 void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
-void launch_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk, cudaStream_t s);
+int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk_max, uint32_t n_hot, int n_sms,
+                        cudaStream_t s);
 void launch_commit(const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
 void launch_collect_errors(const WalkBuffers& b, cudaStream_t s);
 
