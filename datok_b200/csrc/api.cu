@@ -413,8 +413,7 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
 // K1+K2: clear, fused walk, fix-up rounds (host-synchronised on the round counters), error collection
 int do_walk(datok_model* m, WalkBuffers& b, uint32_t start_state, PhaseTimer& pt) {
   cudaStream_t s = m->stream;
-  pt.begin(T_CLEAR);
-  CUDA_TRY(cudaMemsetAsync(b.b_end, 0, (size_t)b.n_words * 4 * sizeof(uint32_t), s));
+  pt.begin(T_CLEAR);  // (the boundary bitmaps are fully written by the walk itself)
   CUDA_TRY(cudaMemsetAsync(b.counters, 0, 8 * sizeof(uint32_t), s));
   CUDA_TRY(cudaMemsetAsync(b.err_key, 0xFF, sizeof(unsigned long long), s));
   pt.end();

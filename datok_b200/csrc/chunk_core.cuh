@@ -127,7 +127,7 @@ DATOK_HD void load_seg_bits(const WalkBuffers& b, uint32_t w, SegBits& B) {
 // K1+K2a fused: classification and speculative walk of chunk i, segment by segment
 // (fast_core.cuh).  Produces exactly what chunk_spec() produces, plus the rune-start
 // words of the chunk.  seg_cls: 32 bytes of lane-private scratch (shared memory in
-// the kernel).  The boundary bitmaps of the chunk must be zero on entry.
+// the kernel).  Every boundary word of the chunk is written here: no clearing pass is needed.
 //
 // from == nullptr: speculative walk (K2a).  from != nullptr: re-walk (K2c) of the chunk from the
 // known state *from (its position lies in the chunk); the result goes to Enew[i] instead and the
@@ -170,10 +170,12 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       b.rstart[w] = rs;
       if (inv) note_invalid_utf8(b);
     }
-    if (halted) continue;
+    // (the speculative walk writes every boundary word of its chunk, so the bitmaps need no clearing pass)
+    B.end = B.skip = B.sent = B.tend = 0;
+    if (halted) { if (!rewalk) store_seg_bits(b, w, B); continue; }
     if (!started) {
       sync = find_sync(b.in, N, m.sync_ascii, seg_start, seg_end < hi ? seg_end : hi);
-      if (sync == K_NOPOS) continue;
+      if (sync == K_NOPOS) { store_seg_bits(b, w, B); continue; }
       started = true;
       L.pos = L.tstart = L.base = L.hw_med = L.raw_from = sync;
       L.u_in = 1;

@@ -365,7 +365,14 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   }
   // summary of everything before this block: (groups of 1024 blocks before) + (blocks before, in the group)
   const Agg block_start = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
-  Agg carry = block_exclusive_scan<COMPACT_THREADS>(ta, block_start);
+  // prefix of this thread: warps before it in the block (totals left by the reduce pass), lanes before it
+  Agg seed = block_start;
+  {
+    const Agg* wagg = cb.warp_agg + (size_t)blockIdx.x * (COMPACT_THREADS / 32);
+    const int warp = threadIdx.x >> 5;
+    for (int wi = 0; wi < warp; wi++) seed = agg_combine(seed, wagg[wi]);
+  }
+  Agg carry = warp_exclusive_scan(ta, seed);
   // K3_EMIT
   const uint32_t blk_tok0 = block_start.n_tok, blk_ntok = cb.block_agg[blockIdx.x].n_tok;
   const bool staged = blk_ntok <= STAGE_TOKENS;

@@ -109,7 +109,8 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
     }
     for (uint32_t k = 0; k < b.n_chunks; k++) chunk_spec(m, b, order ? b.n_chunks - 1 - k : k, start_state);
   } else {
-    // K1+K2a fused fast path
+    // K1+K2a fused fast path (it has to write every boundary word itself: start from garbage)
+    for (auto* v : {&bend, &bskip, &bsent, &btend}) std::fill(v->begin(), v->end(), 0xDEADBEEFu);
     FastTables FT;
     std::vector<uint16_t> hot;
     make_fast_tables(em->hm, m, (uint32_t)mode, hot, FT);
