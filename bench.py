@@ -244,9 +244,34 @@ def main():
     wall_e2e, d2h = e2e_leg(FLAGS | d.COMPACT)
     h2d = N
 
+    # ---- the same call followed by the host half of the TokenWriter: the exact text
+    # NewTokenWriter(w, flags) writes (datok_format, all host cores) ----
+    import ctypes as C
+    import numpy as np
+    # (single-GPU runs only: the text is ~2.7x the input and every rank would hold its own copy)
+    fmt_bytes, wall_fmt = 0, float("nan")
+    if world == 1:
+        fmt_buf = np.empty(4 * N + (1 << 20), dtype=np.uint8)
+
+        def fmt_once():
+            r = tok.transduce_arrays(arr, FLAGS | d.COMPACT)
+            need = L.datok_format(r._h, arr.ctypes.data, N, FLAGS, fmt_buf.ctypes.data, fmt_buf.size)
+            r.close()
+            return int(need)
+
+        fmt_once()
+        barrier()
+        t0 = time.perf_counter()
+        fmt_steps = max(1, min(args.steps, 2))
+        for _ in range(fmt_steps):
+            fmt_bytes = fmt_once()
+        barrier()
+        wall_fmt = (time.perf_counter() - t0) / fmt_steps
+        del fmt_buf
+
     # ---- reduce over ranks (max time; counts summed via the per-shard count exchange) -
     ms_step = sum(dev_ms) / len(dev_ms)
-    stats = torch.tensor([ms_step, wall_dev / args.steps * 1e3, wall_e2e * 1e3, wall_abs * 1e3], dtype=torch.float64,
+    stats = torch.tensor([ms_step, wall_dev / args.steps * 1e3, wall_e2e * 1e3, wall_abs * 1e3, wall_fmt * 1e3], dtype=torch.float64,
                          device="cuda")
     counts = torch.tensor([N, T, S, D], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -258,7 +283,7 @@ def main():
         bases = torch.cumsum(allc, 0) - allc
         counts = allc.sum(0)
         _ = bases
-    ms_step, ms_wall, ms_e2e, ms_abs = [float(x) for x in stats.tolist()]
+    ms_step, ms_wall, ms_e2e, ms_abs, ms_fmt = [float(x) for x in stats.tolist()]
     Ntot, Ttot, Stot, Dtot = [int(x) for x in counts.tolist()]
 
     if rank == 0:
@@ -266,7 +291,7 @@ def main():
         alg_bytes = N + 8 * T + 8 * S + 8 * D  # per launch (one GPU's shard)
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
         cpu = None
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world == 1:
             try:
                 cpu = cpu_reference_rate(arr)
                 cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -307,6 +332,10 @@ def main():
             "e2e_absolute": {"value": Ntot / (ms_abs * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                              "d2h_bytes_per_step": d2h_abs, "ms_per_step": ms_abs,
                              "path": "same call without DATOK_COMPACT: absolute (byte, rune) offset pairs, 16 B/token"},
+            "e2e_formatted": None if world > 1 else {"value": Ntot / (ms_fmt * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_fmt,
+                              "text_bytes_per_step": fmt_bytes, "host_threads": os.cpu_count(),
+                              "path": "datok_transduce(DATOK_COMPACT) + datok_format(): the text NewTokenWriter(w, TOKENS|SENTENCES|"
+                                      "TOKEN_POS|SENTENCE_POS) writes, formatted on the host cores"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -133,7 +133,7 @@ void release(datok_model* m, const Block& b) {
   if (!b.p) return;
   size_t cached = 0;
   for (auto& c : m->cache) cached += c.bytes;
-  if (m->cache.size() < 64 && cached < ((size_t)24 << 30)) { m->cache.push_back(b); return; }
+  if (m->cache.size() < 64 && cached < ((size_t)8 << 30)) { m->cache.push_back(b); return; }
   if (b.host) cudaFreeHost(b.p); else cudaFree(b.p);
 }
 

@@ -117,8 +117,22 @@ DATOK_HD void note_invalid_utf8(const WalkBuffers& b) {
 #endif
 }
 
+// A lane fills a 32-byte sector of each bitmap with 8 word stores spread over 8 segments; the partly
+// written sectors are asked to stay in L2 until then (evict_last) instead of going to DRAM piecemeal.
+DATOK_HD void store_word_keep(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile(
+      "{\n\t.reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+      "st.global.L2::cache_hint.u32 [%0], %1, pol;\n\t}"
+      :: "l"(p), "r"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
 DATOK_HD void store_seg_bits(const WalkBuffers& b, uint32_t w, const SegBits& B) {
-  b.b_end[w] = B.end; b.b_skip[w] = B.skip; b.b_sent[w] = B.sent; b.b_tend[w] = B.tend;
+  store_word_keep(b.b_end + w, B.end); store_word_keep(b.b_skip + w, B.skip);
+  store_word_keep(b.b_sent + w, B.sent); store_word_keep(b.b_tend + w, B.tend);
 }
 DATOK_HD void load_seg_bits(const WalkBuffers& b, uint32_t w, SegBits& B) {
   B.end = b.b_end[w]; B.skip = b.b_skip[w]; B.sent = b.b_sent[w]; B.tend = b.b_tend[w];
@@ -167,7 +181,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     bool inv = false;
     classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, seg_cls, &rs, &eotm, &inv);
     if (!rewalk) {
-      b.rstart[w] = rs;
+      store_word_keep(b.rstart + w, rs);
       if (inv) note_invalid_utf8(b);
     }
     // (the speculative walk writes every boundary word of its chunk, so the bitmaps need no clearing pass)

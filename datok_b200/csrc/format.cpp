@@ -4,7 +4,9 @@
 // token_writer.go:27-33).  Pure formatting: all boundaries and offsets were
 // computed on the GPU.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/datok_b200.h"
@@ -13,11 +15,16 @@
 namespace {
 
 struct Sink {
-  uint8_t* dst;
+  uint8_t* dst;      // nullptr: only count
   size_t cap, n = 0;
   inline void put(const uint8_t* p, size_t len) {
-    if (n + len <= cap) std::memcpy(dst + n, p, len);
-    else if (n < cap) std::memcpy(dst + n, p, cap - n);
+    if (n + len <= cap) {
+      uint8_t* d = dst + n;
+      if (len <= 16) { for (size_t i = 0; i < len; i++) d[i] = p[i]; }  // token surfaces are short
+      else std::memcpy(d, p, len);
+    } else if (n < cap) {
+      std::memcpy(dst + n, p, cap - n);
+    }
     n += len;
   }
   inline void byte(uint8_t b) {
@@ -25,9 +32,14 @@ struct Sink {
     n++;
   }
   inline void itoa(int32_t v) {  // strconv.Itoa
+    uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    if (!dst) {  // counting pass: digits only
+      n += (v < 0) + 1 + (u >= 10) + (u >= 100) + (u >= 1000) + (u >= 10000) + (u >= 100000) + (u >= 1000000) +
+           (u >= 10000000) + (u >= 100000000) + (u >= 1000000000);
+      return;
+    }
     uint8_t tmp[12];
     int i = 12;
-    uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
     do { tmp[--i] = (uint8_t)('0' + u % 10); u /= 10; } while (u);
     if (v < 0) tmp[--i] = '-';
     put(tmp + i, (size_t)(12 - i));
@@ -91,22 +103,24 @@ int datok_expand(const datok_result* r, uint32_t* tok_bytes, int32_t* tok_pos) {
   return DATOK_OK;
 }
 
-size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t flags, uint8_t* dst, size_t cap) {
-  const datok_view* v = datok_result_view(r);
-  if (!v) return (size_t)-1;
+}  // extern "C"
+
+namespace {
+
+// Output of the texts [d0, d1) (and, for the last range, of the events after the last TextEnd).
+// Texts are independent: token, sentence and `sent` indices restart from the per-text bounds.
+void format_range(const datok_view* v, const uint8_t* in, uint32_t flags, uint64_t d0, uint64_t d1, bool tail, Sink& s) {
   const bool tokens = flags & DATOK_TOKENS, sentences = flags & DATOK_SENTENCES;
   const bool tpos = flags & DATOK_TOKEN_POS, spos = flags & DATOK_SENTENCE_POS;
-  if ((tokens && !v->tok_bytes && !v->tok_delta) || (sentences && !v->sent_tok && v->n_sentences) ||
-      (tpos && !v->tok_pos && !v->tok_delta) || (spos && !v->sent_pos))
-    return (size_t)-1;  // the array was not requested at transduce time
-  (void)n;
-  Sink s{dst, dst ? cap : 0};
   const bool re = v->has_invalid_utf8 != 0;
-  uint64_t tok = 0, sen = 0, sp = 0;
+  uint64_t tok = d0 ? v->text_tok_end[d0 - 1] : 0, sen = d0 ? v->text_sent_end[d0 - 1] : 0,
+           sp = d0 ? v->text_sentpos_end[d0 - 1] : 0;
   TokenCursor cur(v);
+  cur.k = tok; cur.text = d0; cur.byte_end = d0 ? v->text_byte_end[d0 - 1] : 0;
   // rune offsets of the current text's tokens, for the `pos` line (token_writer.go:131-143); the
   // compact form is decoded once, while the surfaces are written
   std::vector<int32_t> text_pos;
+  text_pos.reserve(4096);
   const bool keep_pos = tpos && v->tok_delta;
   auto emit_tokens = [&](uint64_t upto) {
     if (tokens || keep_pos)
@@ -129,7 +143,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
     }
     sen = upto;
   };
-  for (uint64_t d = 0; d < v->n_texts; d++) {
+  for (uint64_t d = d0; d < d1; d++) {
     const uint64_t t0 = tok, t1 = v->text_tok_end[d];
     emit_sentences(v->text_sent_end[d]);
     emit_tokens(t1);
@@ -155,8 +169,66 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
       s.byte('\n');  // token_writer.go:163-166
     }
   }
-  emit_sentences(v->n_sentences);  // SentenceEnd events after the last TextEnd
-  return s.n;
+  if (tail) emit_sentences(v->n_sentences);  // SentenceEnd events after the last TextEnd
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t flags, uint8_t* dst, size_t cap) {
+  const datok_view* v = datok_result_view(r);
+  if (!v) return (size_t)-1;
+  const bool tokens = flags & DATOK_TOKENS, sentences = flags & DATOK_SENTENCES;
+  const bool tpos = flags & DATOK_TOKEN_POS, spos = flags & DATOK_SENTENCE_POS;
+  if ((tokens && !v->tok_bytes && !v->tok_delta) || (sentences && !v->sent_tok && v->n_sentences) ||
+      (tpos && !v->tok_pos && !v->tok_delta) || (spos && !v->sent_pos))
+    return (size_t)-1;  // the array was not requested at transduce time
+  (void)n;
+  // ---- ranges of texts, one per worker thread ----
+  unsigned workers = std::thread::hardware_concurrency();
+  if (const char* e = std::getenv("DATOK_FORMAT_THREADS")) workers = (unsigned)std::atoi(e);
+  if (workers > 64) workers = 64;
+  if (v->n_texts < 64 || workers < 2) workers = 1;
+  if (workers == 1) {
+    Sink s{dst, dst ? cap : 0};
+    format_range(v, in, flags, 0, v->n_texts, true, s);
+    return s.n;
+  }
+  std::vector<uint64_t> lo(workers + 1);
+  for (unsigned i = 0; i <= workers; i++) lo[i] = v->n_texts * i / workers;
+  // pass 1: sizes
+  std::vector<size_t> size(workers, 0);
+  {
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < workers; i++)
+      th.emplace_back([&, i] {
+        Sink s{nullptr, 0};
+        format_range(v, in, flags, lo[i], lo[i + 1], i + 1 == workers, s);
+        size[i] = s.n;
+      });
+    for (auto& t : th) t.join();
+  }
+  size_t total = 0;
+  std::vector<size_t> off(workers);
+  for (unsigned i = 0; i < workers; i++) { off[i] = total; total += size[i]; }
+  if (!dst) return total;
+  if (cap < total) {  // truncated output: the plain sequential writer handles the cut
+    Sink s{dst, cap};
+    format_range(v, in, flags, 0, v->n_texts, true, s);
+    return s.n;
+  }
+  // pass 2: every range writes at its offset
+  {
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < workers; i++)
+      th.emplace_back([&, i] {
+        Sink s{dst + off[i], size[i]};
+        format_range(v, in, flags, lo[i], lo[i + 1], i + 1 == workers, s);
+      });
+    for (auto& t : th) t.join();
+  }
+  return total;
 }
 
 int datok_replay(const datok_result* r, const uint8_t* in, size_t n, const datok_callbacks* cb) {

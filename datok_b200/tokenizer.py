@@ -99,6 +99,7 @@ class Result:
         self.n_sent_pos, self.n_runes = v.n_sent_pos, v.n_runes
         self.has_invalid_utf8 = bool(v.has_invalid_utf8)
         self.carry_state = v.carry_out.state
+        self.carry = Carry(v.carry_out.state, v.carry_out.sentence_end, v.carry_out.text_end, 0)
         self.ms_h2d, self.ms_kernels, self.ms_d2h = v.ms_h2d, v.ms_kernels, v.ms_d2h
         self._ptrs = dict(tok_bytes=v.tok_bytes, tok_pos=v.tok_pos, sent_pos=v.sent_pos, sent_tok=v.sent_tok,
                           text_tok_end=v.text_tok_end, text_sent_end=v.text_sent_end,
@@ -188,18 +189,31 @@ class MatrixTokenizer:
         """matrix.go:340-342"""
         return self.TransduceTokenWriter(r, NewTokenWriter(w, SIMPLE))
 
-    def TransduceTokenWriter(self, r, w: TokenWriter):
-        """matrix.go:348-698.  `r`: bytes-like or binary file-like (.read())."""
+    def TransduceTokenWriter(self, r, w: TokenWriter, batch_bytes=None):
+        """matrix.go:348-698.  `r`: bytes-like or binary file-like (.read()).
+
+        batch_bytes: stream a file-like `r` in batches of about that many bytes, each cut after its last EOT
+        (the stream front-end: bounded memory; state, sentenceEnd/textEnd and the writer's `init` flag are
+        carried from batch to batch through the C ABI's carry / DATOK_NOT_FINAL / DATOK_WRITER_USED)."""
+        if batch_bytes and hasattr(r, "read"):
+            return self._transduce_stream(r, w, int(batch_bytes))
         data = r.read() if hasattr(r, "read") else r
         if isinstance(data, str):
             data = data.encode("utf-8")
+        self._transduce_batch(data, w, None, True)
+        w.Flush()  # matrix.go:374 defer w.Flush()
+        return True
+
+    def _transduce_batch(self, data, w, carry, final):
+        """one datok_transduce call + the host half of the TokenWriter; returns the carry for the next batch"""
         L = _lib.lib()
         addr, n, keep = _as_buffer(data)
+        extra = COMPACT | (0 if final else _lib.NOT_FINAL)
         if w._stock is not None:
             st = w._stock
             # the formatter reads the delta-coded spans directly: half the bytes over PCIe
-            flags = st["flags"] | (0 if st["init"] else WRITER_USED) | COMPACT
-            res = self.transduce_arrays_raw(addr, n, flags)
+            flags = st["flags"] | (0 if st["init"] else WRITER_USED) | extra
+            res = self.transduce_arrays_raw(addr, n, flags, carry)
             try:
                 if res.n_tokens:
                     st["init"] = False
@@ -207,12 +221,11 @@ class MatrixTokenizer:
                 out = C.create_string_buffer(max(1, need))
                 L.datok_format(res._h, addr, n, st["flags"], out, need)
                 st["w"].write(out.raw[:need])
+                return res.carry
             finally:
                 res.close()
-            w.Flush()  # matrix.go:374 defer w.Flush()
-            return True
         # custom TokenWriter: replay the events into its callables
-        res = self.transduce_arrays_raw(addr, n, TOKENS | SENTENCES | COMPACT)
+        res = self.transduce_arrays_raw(addr, n, TOKENS | SENTENCES | extra, carry)
         try:
             def on_token(_u, buf, buf_bytes, _off_bytes, off_runes):
                 w.Token(off_runes, list(_go_runes(C.string_at(buf, buf_bytes))))
@@ -221,9 +234,25 @@ class MatrixTokenizer:
             rc = L.datok_replay(res._h, addr, n, C.byref(cb))
             if rc:
                 _raise(rc)
+            return res.carry
         finally:
             res.close()
-        w.Flush()
+
+    def _transduce_stream(self, r, w, batch_bytes):
+        pending = b""
+        carry = None
+        while True:
+            block = r.read(batch_bytes)
+            if not block:
+                break
+            pending += block
+            cut = pending.rfind(b"\x04") + 1  # batches end right after an EOT: a text boundary (matrix.go:593-605)
+            if cut == 0:
+                continue                        # no text ends in here yet: keep reading
+            carry = self._transduce_batch(pending[:cut], w, carry, False)
+            pending = pending[cut:]
+        self._transduce_batch(pending, w, carry, True)
+        w.Flush()  # matrix.go:374 defer w.Flush()
         return True
 
     # -- offset-array API ---------------------------------------------------------

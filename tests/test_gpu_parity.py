@@ -310,3 +310,73 @@ def test_compact_token_deltas(model, kind, gpu_models, oracle_models):
                 continue
             r = tok.transduce_arrays(data, flags | d.COMPACT)
             assert tok.format(r, data, flags) == o.text
+
+
+def test_full_size_corpus_properties(gpu_models, oracle_models, testdata, monkeypatch):
+    """BASELINE.json's C2 size (1 GiB, ~10 KB EOT-separated documents): the pipelined host path against
+    size-independent properties, against the single-pass path, and against the oracle on sampled documents."""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    n = 1 << 30
+    a = np.empty(n, dtype=np.uint8)
+    docs = corpus.generate_blocks_into(corpus.GERMAN, corpus.SEED, a, block=16 << 20)
+    tok = gpu_models["tokenizer_de.matok"]
+    r = tok.transduce_arrays(a, 15 | d.COMPACT)          # >= 128 MiB: pieces, copies overlapped with the kernels
+    assert r.n_texts == docs == int((a == 4).sum())
+    assert r.tok_delta.size == 4 * r.n_tokens and r.n_sent_pos == 2 * r.n_sentences
+    tte = r.text_tok_end.astype(np.int64)
+    assert (np.diff(tte) > 0).all() and tte[-1] == r.n_tokens and r.text_sent_end[-1] == r.n_sentences
+    assert int(r.text_byte_end[-1]) == n and (np.diff(r.text_byte_end.astype(np.int64)) > 0).all()
+    dl = r.tok_delta.reshape(-1, 4).astype(np.int64)
+    # every byte of a text is either skipped before a token or part of one, up to the trailing skip
+    used = np.add.reduceat(dl[:, 0] + dl[:, 1], np.concatenate(([0], tte[:-1])))
+    text_len = np.diff(np.concatenate(([0], r.text_byte_end.astype(np.int64))))
+    assert (used <= text_len).all() and (text_len - used <= 4).all()
+    assert (dl[:, 1] > 0).all() and (dl[:, 3] > 0).all() and (dl[:, 3] <= dl[:, 1]).all()
+    r.expand()
+    tb, tp = r.tok_bytes.copy(), r.tok_pos.copy()
+    sp, st = r.sent_pos.copy(), r.sent_tok.copy()
+    tbe = r.text_byte_end.copy()
+    r.close()
+    # the single-pass path (absolute arrays) gives the same stream
+    monkeypatch.setenv("DATOK_NO_PIPELINE", "1")
+    tok1 = d.LoadTokenizerFile(os.path.join(testdata, "tokenizer_de.matok"))
+    r1 = tok1.transduce_arrays(a, 15)
+    np.testing.assert_array_equal(r1.tok_bytes, tb)
+    np.testing.assert_array_equal(r1.tok_pos, tp)
+    np.testing.assert_array_equal(r1.sent_pos, sp)
+    np.testing.assert_array_equal(r1.sent_tok, st)
+    np.testing.assert_array_equal(r1.text_byte_end, tbe)
+    r1.close(); tok1.close()
+    # oracle on sampled documents (each starts in the root state: checked through the carry of its predecessor)
+    om = oracle_models["tokenizer_de.matok"]
+    rng = np.random.default_rng(7)
+    starts = np.concatenate(([0], tbe[:-1].astype(np.int64)))
+    for k in rng.integers(1, docs, 24):
+        lo, hi = int(starts[k]), int(tbe[k])
+        o = om.transduce_np(a[lo:hi], 15 | 256)
+        t0, t1 = int(tte[k - 1]), int(tte[k])
+        np.testing.assert_array_equal(tb[2 * t0:2 * t1:2].astype(np.int64) - lo, o.tok_byte_start)
+        np.testing.assert_array_equal(tb[2 * t0 + 1:2 * t1:2].astype(np.int64) - lo, o.tok_byte_end)
+        np.testing.assert_array_equal(tp[2 * t0:2 * t1], o.tok_pos)
+
+
+def test_stream_front_end(gpu_models, oracle_models):
+    """TransduceTokenWriter over a file-like reader in EOT-aligned batches (bounded memory): the same text
+    as one call, for the stock writer and for a custom TokenWriter"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    tok = gpu_models["tokenizer_de.matok"]
+    a = corpus.generate(2, 2 << 20, seed=77).tobytes() + "Schluss ohne EOT. Noch ein Satz".encode()
+    for flags in (3, 15, 31):
+        o = oracle_models["tokenizer_de.matok"].transduce(a, flags)
+        for batch in (64 << 10, 300_000, 8 << 20):
+            w = io.BytesIO()
+            assert tok.TransduceTokenWriter(io.BytesIO(a), d.NewTokenWriter(w, flags), batch_bytes=batch)
+            assert w.getvalue() == o.text, (flags, batch)
+    events, ref = [], []
+    mk = lambda ev: d.TokenWriter(Token=lambda off, buf: ev.append(("T", off, "".join(buf))),
+                                  SentenceEnd=lambda n: ev.append("S"), TextEnd=lambda n: ev.append("X"))
+    tok.TransduceTokenWriter(io.BytesIO(a), mk(events), batch_bytes=128 << 10)
+    tok.TransduceTokenWriter(a, mk(ref))
+    assert events == ref and len(events) > 1000
