@@ -418,24 +418,20 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
 // loads the 32 raw bytes at `p` (zero padded beyond N) as 8 little-endian words
 DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_start, uint32_t* words) {
   const uint8_t* p = in + seg_start;
+  if (seg_start + SEG <= N && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
 #if defined(__CUDA_ARCH__)
-  if (seg_start + SEG <= N && (reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
-    // one 256-bit load: the lane's whole 32-byte sector in a single request
-    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(words[0]), "=r"(words[1]), "=r"(words[2]), "=r"(words[3]), "=r"(words[4]), "=r"(words[5]),
-                   "=r"(words[6]), "=r"(words[7])
-                 : "l"(p));
-    return;
-  }
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint4 c = *reinterpret_cast<const uint4*>(p + 16);
+    words[0] = a.x; words[1] = a.y; words[2] = a.z; words[3] = a.w;
+    words[4] = c.x; words[5] = c.y; words[6] = c.z; words[7] = c.w;
 #else
-  if (seg_start + SEG <= N) {
     for (int k = 0; k < 8; k++) {
       words[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
                  ((uint32_t)p[4 * k + 3] << 24);
     }
+#endif
     return;
   }
-#endif
   for (int k = 0; k < 8; k++) {
     uint32_t v = 0;
     for (int j = 0; j < 4; j++) {
@@ -473,10 +469,9 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
   const uint32_t valid = (seg_start + SEG <= N) ? 0xFFFFFFFFu : mask_below(N > seg_start ? N - seg_start : 0);
   uint32_t eot = 0;
   if (DATOK_UNLIKELY(eot_any != 0)) {
-    // exact positions from the class bytes just written (0x04 is ASCII: its class byte is final here);
-    // no dynamic indexing of words[], which would push the array into local memory for every segment
-    for (uint32_t j = 0; j < SEG; j++)
-      if (seg_cls[j] == 2u * K_CLS_EOT && !((nonascii >> j) & 1u)) eot |= 1u << j;
+    for (int k = 0; k < 8; k++)
+      for (int j = 0; j < 4; j++)
+        if (((words[k] >> (8 * j)) & 0xFFu) == 0x04u) eot |= 1u << (4 * k + j);
   }
   *eot_word = eot & valid;
   uint32_t rs = ~nonascii & valid;
