@@ -172,6 +172,47 @@ void format_range(const datok_view* v, const uint8_t* in, uint32_t flags, uint64
   if (tail) emit_sentences(v->n_sentences);  // SentenceEnd events after the last TextEnd
 }
 
+// Size of format_range()'s output without touching the text: token lengths, digit counts and
+// separators only (valid UTF-8: surfaces are copied verbatim).
+inline size_t digits10(int32_t v) {
+  uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+  return (v < 0) + 1 + (u >= 10) + (u >= 100) + (u >= 1000) + (u >= 10000) + (u >= 100000) + (u >= 1000000) +
+         (u >= 10000000) + (u >= 100000000) + (u >= 1000000000);
+}
+size_t count_range(const datok_view* v, uint32_t flags, uint64_t d0, uint64_t d1, bool tail) {
+  const bool tokens = flags & DATOK_TOKENS, sentences = flags & DATOK_SENTENCES;
+  const bool tpos = flags & DATOK_TOKEN_POS, spos = flags & DATOK_SENTENCE_POS;
+  const uint64_t t0 = d0 ? v->text_tok_end[d0 - 1] : 0, t1 = d1 ? v->text_tok_end[d1 - 1] : 0;
+  const uint64_t s0 = d0 ? v->text_sent_end[d0 - 1] : 0, s1 = d1 ? v->text_sent_end[d1 - 1] : 0;
+  const uint64_t p0 = d0 ? v->text_sentpos_end[d0 - 1] : 0, p1 = d1 ? v->text_sentpos_end[d1 - 1] : 0;
+  size_t n = 0;
+  // tokens of the range's texts (+ those emitted by trailing SentenceEnd events)
+  const uint64_t t_hi = (tail && sentences && v->n_sentences > s1) ? v->sent_tok[v->n_sentences - 1] : t1;
+  if (tokens || tpos) {
+    TokenCursor cur(v);
+    cur.k = t0; cur.text = d0; cur.byte_end = d0 ? v->text_byte_end[d0 - 1] : 0;
+    for (uint64_t k = t0; k < (t_hi > t1 ? t_hi : t1); k++) {
+      cur.next();
+      if (tokens) n += (size_t)(cur.hi - cur.lo) + 1;
+      if (tpos && k < t1) n += digits10(cur.ps) + digits10(cur.pe) + 2;  // each number is followed by ' ' or '\n'
+    }
+  }
+  if (sentences) n += (tail ? v->n_sentences : s1) - s0;
+  if (tpos || spos) {
+    for (uint64_t d = d0; d < d1; d++) {
+      if (tpos && v->text_tok_end[d] == (d ? v->text_tok_end[d - 1] : 0)) n += 1;  // empty list: just the newline
+      if (spos) {
+        const uint64_t a = d ? v->text_sentpos_end[d - 1] : 0, b = v->text_sentpos_end[d];
+        if (a == b) n += 1;
+      }
+    }
+    if (spos) for (uint64_t k = p0; k < p1; k++) n += digits10(v->sent_pos[k]) + 1;
+  } else {
+    n += d1 - d0;
+  }
+  return n;
+}
+
 }  // namespace
 
 extern "C" {
@@ -203,6 +244,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
     std::vector<std::thread> th;
     for (unsigned i = 0; i < workers; i++)
       th.emplace_back([&, i] {
+        if (!v->has_invalid_utf8) { size[i] = count_range(v, flags, lo[i], lo[i + 1], i + 1 == workers); return; }
         Sink s{nullptr, 0};
         format_range(v, in, flags, lo[i], lo[i + 1], i + 1 == workers, s);
         size[i] = s.n;
@@ -219,15 +261,23 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
     return s.n;
   }
   // pass 2: every range writes at its offset
+  std::vector<size_t> wrote(workers, 0);
   {
     std::vector<std::thread> th;
     for (unsigned i = 0; i < workers; i++)
       th.emplace_back([&, i] {
         Sink s{dst + off[i], size[i]};
         format_range(v, in, flags, lo[i], lo[i + 1], i + 1 == workers, s);
+        wrote[i] = s.n;
       });
     for (auto& t : th) t.join();
   }
+  for (unsigned i = 0; i < workers; i++)
+    if (wrote[i] != size[i]) {  // the two passes disagree: never hand out a torn buffer
+      Sink s{dst, cap};
+      format_range(v, in, flags, 0, v->n_texts, true, s);
+      return s.n;
+    }
   return total;
 }
 
