@@ -66,6 +66,7 @@ struct datok_model {
   int n_sms = 148;
   size_t smem_optin = 0;
   uint32_t n_hot = 1;
+  int fused_threads = 1024;
   bool calibrated = false;
   bool auto_calibrate = true;
   // workspace (grow only)
@@ -294,7 +295,7 @@ int upload_model(datok_model* m) {
   d.cls.n_rune = (uint32_t)nr;
   d.cls.identity_cls = h.identity_cls;
   std::memcpy(d.sync_ascii, h.sync_ascii, sizeof d.sync_ascii);
-  m->n_hot = fused_max_hot_rows(d, m->smem_optin, (uint32_t)h.stateCount);
+  m->n_hot = fused_max_hot_rows(d, m->smem_optin, (uint32_t)h.stateCount, m->fused_threads);
   if (const char* s = std::getenv("DATOK_HOT_ROWS")) {
     long v = std::atol(s);
     if (v >= 1 && (uint32_t)v < m->n_hot) m->n_hot = (uint32_t)v;
@@ -398,6 +399,7 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
   }
   m->n_sms = prop.multiProcessorCount;
   m->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  m->fused_threads = fused_threads_from_env();
   if (const char* s = std::getenv("DATOK_NO_CALIBRATE")) m->auto_calibrate = !(s[0] == '1');
   int rc = upload_model(m);
   if (rc) { *err = rc; datok_free(m); return nullptr; }
@@ -419,7 +421,7 @@ int do_walk(datok_model* m, WalkBuffers& b, uint32_t start_state, PhaseTimer& pt
   pt.end();
   pt.begin(T_WALK);
   {
-    const int e = launch_walk_fused(m->dm, b, start_state, m->n_hot, m->n_sms, s);
+    const int e = launch_walk_fused(m->dm, b, start_state, m->n_hot, m->n_sms, s, m->fused_threads);
     if (e != 0) { g_last_error = std::string("walk_fused launch: ") + cudaGetErrorString((cudaError_t)e); return DATOK_ERR_CUDA; }
   }
   pt.end();
@@ -443,7 +445,7 @@ int do_walk(datok_model* m, WalkBuffers& b, uint32_t start_state, PhaseTimer& pt
     pt.begin(T_COMMIT);
     launch_commit(b, list, n_list, s);
     pt.end();
-    m->launches += 3;
+    m->launches += 4;  // stitch, re-walk, commit, mailbox
     {
       MailSrc ms;
       std::memset(&ms, 0, sizeof ms);
@@ -482,7 +484,7 @@ int do_count(datok_model* m, const WalkBuffers& b, CompactCtx& c, const CompactB
   pt.begin(T_SCAN);
   launch_compact_scan(cb, sentence_end_in, s);
   pt.end();
-  m->launches += 3;
+  m->launches += 4;  // reduce, two scan levels, mailbox
   {
     MailSrc ms;
     static_assert(sizeof(Agg) == 32 && sizeof(WState) % 4 == 0 && sizeof(WState) <= 32, "mailbox layout");
@@ -702,7 +704,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     }
     launch_compact_finalize(c, cb, text_end_in, final_input, s);
     pt.end();
-    m->launches += 3;
+    m->launches += 4;  // texts, emit, finalize, mailbox
     struct { StreamTotals fin; unsigned long long err; } tail;
     {
       MailSrc ms;
@@ -894,7 +896,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   }
   launch_compact_finalize(c, cb, text_end_in, final_input, s);
   pt.end();
-  m->launches += 3;
+  m->launches += 4;  // texts, emit, finalize, mailbox
   struct { StreamTotals fin; unsigned long long err; WState last; } tail;
   tail.last = hdr.last;
   {

@@ -68,25 +68,22 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   }
 }
 
-static int g_fused_threads = 0;
-int fused_threads() {
-  if (!g_fused_threads) {
-    g_fused_threads = 1024;
-    if (const char* s = std::getenv("DATOK_FUSED_THREADS")) {
-      const long v = std::atol(s);
-      if (v == 256 || v == 512 || v == 768 || v == 1024) g_fused_threads = (int)v;
-    }
+int fused_threads_from_env() {
+  int t = 1024;
+  if (const char* s = std::getenv("DATOK_FUSED_THREADS")) {
+    const long v = std::atol(s);
+    if (v == 256 || v == 512 || v == 768 || v == 1024) t = (int)v;
   }
-  return g_fused_threads;
+  return t;
 }
 
 static size_t fused_smem_bytes_t(const DeviceModel& m, uint32_t n_hot, int threads) {
   return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)threads * LANE_CLS_STRIDE + 384;
 }
-size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot) { return fused_smem_bytes_t(m, n_hot, fused_threads()); }
+size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot, int threads) { return fused_smem_bytes_t(m, n_hot, threads); }
 
-uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states) {
-  const size_t fixed = (size_t)fused_threads() * LANE_CLS_STRIDE + 384 + 16 + 1024 + (size_t)m.stride16 * 2;
+uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states, int threads) {
+  const size_t fixed = (size_t)threads * LANE_CLS_STRIDE + 384 + 16 + 1024 + (size_t)m.stride16 * 2;
   if (smem_limit <= fixed) return 1;
   size_t rows = (smem_limit - fixed) / ((size_t)m.stride16 * 2);
   if (rows > (size_t)n_states + 1) rows = (size_t)n_states + 1;
@@ -97,7 +94,7 @@ uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_
 template <int THREADS>
 static int launch_walk_fused_t(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot,
                                int n_sms, cudaStream_t s) {
-  const size_t smem = fused_smem_bytes(m, n_hot);
+  const size_t smem = fused_smem_bytes_t(m, n_hot, THREADS);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -130,8 +127,8 @@ int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_r
 }
 
 int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot,
-                      int n_sms, cudaStream_t s) {
-  switch (fused_threads()) {
+                      int n_sms, cudaStream_t s, int threads) {
+  switch (threads) {
     case 256: return launch_walk_fused_t<256>(m, b, start_state, n_hot, n_sms, s);
     case 768: return launch_walk_fused_t<768>(m, b, start_state, n_hot, n_sms, s);
     case 512: return launch_walk_fused_t<512>(m, b, start_state, n_hot, n_sms, s);

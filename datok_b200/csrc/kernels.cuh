@@ -24,10 +24,12 @@ constexpr int SCAN_THREADS = 1024;
 constexpr int STAGE_TOKENS = 4096;  // tokens of one block staged in shared memory (else written directly)
 
 // fused classify + speculative walk; returns a cudaError_t value
+// `threads`: lanes per CTA of the fused walk (256, 512, 768 or 1024; DATOK_FUSED_THREADS, default 1024)
+int fused_threads_from_env();
 int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot, int n_sms,
-                      cudaStream_t s);
-size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot);
-uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states);
+                      cudaStream_t s, int threads);
+size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot, int threads);
+uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states, int threads);
 // calibration histogram (visits per state, GPU numbering)
 void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cudaStream_t s);
 // one fix-up round over `n_list` chunks (list == nullptr: all chunks 1..n_chunks-1)

@@ -380,3 +380,32 @@ def test_stream_front_end(gpu_models, oracle_models):
     tok.TransduceTokenWriter(io.BytesIO(a), mk(events), batch_bytes=128 << 10)
     tok.TransduceTokenWriter(a, mk(ref))
     assert events == ref and len(events) > 1000
+
+
+@pytest.mark.parametrize("hot_rows,chunk,threads", [("8", "64", "256"), ("40", "96", "768"), ("300", "2048", "512")])
+def test_stress_configurations(hot_rows, chunk, threads, testdata, oracle_models, monkeypatch):
+    """few resident rows (most steps take the cold path through the full table), small and odd chunk sizes,
+    other CTA sizes: the rare paths of the real kernels under load"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    monkeypatch.setenv("DATOK_HOT_ROWS", hot_rows)
+    monkeypatch.setenv("DATOK_CHUNK", chunk)
+    monkeypatch.setenv("DATOK_FUSED_THREADS", threads)
+    rng = random.Random(int(hot_rows) * 7919 + int(chunk))
+    for model, kinds in (("tokenizer_de.matok", (2, 4)), ("tokenizer_en.matok", (3,))):
+        tok = d.LoadTokenizerFile(os.path.join(testdata, model))
+        for kind in kinds:
+            a = corpus.generate(kind, 1 << 20, seed=int(chunk) + kind)
+            for flags in (15, 31 | d.COMPACT):
+                o = oracle_models[model].transduce_np(a, flags & 31)
+                r = tok.transduce_arrays(a, flags)
+                if flags & d.COMPACT:
+                    assert tok.format(r, a, flags & 31) == o.text
+                    r.expand()
+                P.assert_matches_oracle(r, o, flags & 31, f"{model} kind={kind} hot={hot_rows} chunk={chunk}")
+        for it in range(60):
+            data = _fuzz_text(rng, rng.choice((33, 200, 1500, 5000)))
+            flags = rng.choice((3, 15, 31))
+            o = oracle_models[model].transduce(data, flags)
+            P.assert_matches_oracle(gpu_arrays(tok, data, flags), o, flags, f"{model} fuzz it={it} {data[:40]!r}")
+        tok.close()
