@@ -180,6 +180,10 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     uint32_t rs, eotm;
     bool inv = false;
     classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, seg_cls, &rs, &eotm, &inv);
+#if defined(__CUDA_ARCH__)
+    // the next segment's sector on its way while this one is walked (no registers held)
+    if (seg_end < hi && seg_end + SEG <= N) asm volatile("prefetch.global.L1 [%0];" :: "l"(b.in + seg_end));
+#endif
     if (!rewalk) {
       store_word_keep(b.rstart + w, rs);
       if (inv) note_invalid_utf8(b);

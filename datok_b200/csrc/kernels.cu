@@ -95,11 +95,9 @@ template <int THREADS>
 static int launch_walk_fused_t(const DeviceModel& m, const WalkBuffers& b, uint32_t start_state, uint32_t n_hot,
                                int n_sms, cudaStream_t s) {
   const size_t smem = fused_smem_bytes_t(m, n_hot, THREADS);
-  static size_t configured = 0;
-  if (smem > configured) {
+  {  // per launch: the attribute belongs to the current device, and a process may drive several
     cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
   }
   uint32_t blocks = (b.n_chunks + THREADS - 1) / THREADS;
   if (blocks > (uint32_t)n_sms) blocks = (uint32_t)n_sms;
@@ -113,12 +111,10 @@ int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_r
                         cudaStream_t s) {
   if (!n_rewalk_max) return 0;
   const size_t smem = fused_smem_bytes_t(m, n_hot, REWALK_THREADS);
-  static size_t configured = 0;
-  if (smem > configured) {
+  {
     cudaError_t e = cudaFuncSetAttribute(walk_fused_kernel<REWALK_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
   }
   uint32_t blocks = (n_rewalk_max + REWALK_THREADS - 1) / REWALK_THREADS;
   if (blocks > (uint32_t)n_sms) blocks = (uint32_t)n_sms;
@@ -463,11 +459,9 @@ void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStr
 int launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
   const int smem_max = 4 * STAGE_TOKENS * (int)sizeof(uint32_t);
   const int smem = (c.tok_delta ? 2 : 4) * STAGE_TOKENS * (int)sizeof(uint32_t);
-  static bool configured = false;
-  if (!configured) {
+  {
     cudaError_t e = cudaFuncSetAttribute(compact_kernel<K3_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
   }
   compact_kernel<K3_EMIT><<<cb.n_blocks, COMPACT_THREADS, smem, s>>>(c, cb);
   return (int)cudaGetLastError();
