@@ -199,7 +199,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident leg (the form the Tokenizer shim asks for: delta-coded token spans) ----
+    # ---- device-resident leg: delta-coded token spans, two bytes per value (the one-byte form of the
+    # host legs only pays off across PCIe) ----
     DFLAGS = FLAGS | d.COMPACT
     for _ in range(args.warmup):
         tok.transduce_device(d_in.data_ptr(), N, DFLAGS).close()
@@ -222,7 +223,7 @@ def main():
     clocks = sampler.summary()
 
     # ---- end-to-end legs (host buffers through the C ABI) ----------------------
-    # e2e: what the Tokenizer shim calls -- DATOK_COMPACT, 8-byte delta-coded token spans that the
+    # e2e: what the Tokenizer shim calls -- DATOK_COMPACT8, 4-byte delta-coded token spans that the
     # host formatter / replay decode while they walk the tokens anyway.  e2e_absolute: the same call
     # returning absolute (byte, rune) offset pairs, 16 bytes per token.
     def e2e_leg(flags):
@@ -234,14 +235,14 @@ def main():
         out_bytes = 0
         for _ in range(steps):
             r = tok.transduce_arrays(arr, flags)
-            per_tok = 8 if r.tok_delta is not None else 16
+            per_tok = 4 if r.tok_delta8 is not None else 8 if r.tok_delta is not None else 16
             out_bytes = per_tok * r.n_tokens + 4 * (r.n_sent_pos + r.n_sentences + 4 * r.n_texts)
             r.close()
         barrier()
         return (time.perf_counter() - t0) / steps, out_bytes
 
     wall_abs, d2h_abs = e2e_leg(FLAGS)
-    wall_e2e, d2h = e2e_leg(FLAGS | d.COMPACT)
+    wall_e2e, d2h = e2e_leg(FLAGS | d.COMPACT8)
     h2d = N
 
     # ---- the same call followed by the host half of the TokenWriter: the exact text
@@ -254,7 +255,7 @@ def main():
         fmt_buf = np.empty(4 * N + (1 << 20), dtype=np.uint8)
 
         def fmt_once():
-            r = tok.transduce_arrays(arr, FLAGS | d.COMPACT)
+            r = tok.transduce_arrays(arr, FLAGS | d.COMPACT8)
             need = L.datok_format(r._h, arr.ctypes.data, N, FLAGS, fmt_buf.ctypes.data, fmt_buf.size)
             r.close()
             return int(need)
@@ -310,8 +311,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"C2: tokenizer_de.matok, {N} B synthetic German corpus per GPU, ~10 KB "
-                                   "EOT-separated documents, flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS (|DATOK_COMPACT: "
-                                   "8-byte delta-coded token spans)",
+                                   "EOT-separated documents, flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS (device leg: DATOK_COMPACT, "
+                                   "8-byte delta-coded token spans; host legs: DATOK_COMPACT8, 4 bytes per token)",
                        "bytes_per_gpu": N, "documents_per_gpu": D, "tokens_per_gpu": T, "sentences_per_gpu": S,
                        "l2": "input (>= 1 GiB) and outputs exceed the 126 MB L2; no flush needed",
                        "chunk_bytes": int(os.environ.get("DATOK_CHUNK", "512")),
@@ -327,14 +328,14 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": Ntot / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                    "path": "datok_transduce(DATOK_COMPACT): pinned host input, EOT-aligned pieces, H2D | kernels | D2H "
-                            "overlapped; token spans delta-coded (8 B/token), decoded by the host formatter"},
+                    "path": "datok_transduce(DATOK_COMPACT8): pinned host input, EOT-aligned pieces, H2D | kernels | D2H "
+                            "overlapped; token spans delta-coded (4 B/token), decoded by the host formatter"},
             "e2e_absolute": {"value": Ntot / (ms_abs * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                              "d2h_bytes_per_step": d2h_abs, "ms_per_step": ms_abs,
-                             "path": "same call without DATOK_COMPACT: absolute (byte, rune) offset pairs, 16 B/token"},
+                             "path": "same call without DATOK_COMPACT8: absolute (byte, rune) offset pairs, 16 B/token"},
             "e2e_formatted": None if world > 1 else {"value": Ntot / (ms_fmt * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_fmt,
                               "text_bytes_per_step": fmt_bytes, "host_threads": os.cpu_count(),
-                              "path": "datok_transduce(DATOK_COMPACT) + datok_format(): the text NewTokenWriter(w, TOKENS|SENTENCES|"
+                              "path": "datok_transduce(DATOK_COMPACT8) + datok_format(): the text NewTokenWriter(w, TOKENS|SENTENCES|"
                                       "TOKEN_POS|SENTENCE_POS) writes, formatted on the host cores"},
             "gpu_launches": launches,
             "clocks": clocks,

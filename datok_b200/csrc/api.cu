@@ -100,6 +100,7 @@ struct datok_model {
 struct datok_result {
   datok_model* model = nullptr;
   datok_view view;
+  std::vector<uint32_t> esc;  // DATOK_COMPACT8 escape pairs, sorted
   std::vector<Block> blocks;
   bool device = false;
 };
@@ -507,6 +508,14 @@ int do_count(datok_model* m, const WalkBuffers& b, CompactCtx& c, const CompactB
   return DATOK_OK;
 }
 
+void sort_escapes(std::vector<uint32_t>& esc) {
+  const size_t n = esc.size() / 2;
+  std::vector<uint64_t> key(n);
+  for (size_t i = 0; i < n; i++) key[i] = ((uint64_t)esc[2 * i] << 32) | esc[2 * i + 1];
+  std::sort(key.begin(), key.end());
+  for (size_t i = 0; i < n; i++) { esc[2 * i] = (uint32_t)(key[i] >> 32); esc[2 * i + 1] = (uint32_t)key[i]; }
+}
+
 // the walk of a non-final input stopped at the loop top at N: it must be at a rewind point with nothing pending
 bool at_text_boundary(const WState& last, uint32_t N) {
   return last.tstart == N && last.base == N && last.eps_state == 0 && !(last.flags & WS_PEND);
@@ -564,12 +573,14 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   int rc = ensure_workspace(m, carve(nullptr, (uint32_t)max_piece, m->chunk, false, b, cb));
   if (rc) return rc;
 
-  // in compact mode the token slot 0 holds the 8-byte deltas and slot 1 is unused
-  const bool compact = (flags & DATOK_COMPACT) != 0;
+  // in the compact modes the token slot 0 holds the deltas (8 or 4 bytes per token); slot 1 is unused by
+  // DATOK_COMPACT and holds the escape list of DATOK_COMPACT8
+  const bool compact8 = (flags & DATOK_COMPACT8) != 0, compact = compact8 || (flags & DATOK_COMPACT) != 0;
+  const size_t tok_rec = compact8 ? 4 : 8;  // bytes per token in slot 0
   const bool want_bytes = compact ? (flags & (DATOK_TOKENS | DATOK_TOKEN_POS)) != 0 : (flags & DATOK_TOKENS) != 0;
   const bool want_pos = !compact && (flags & DATOK_TOKEN_POS) != 0;
   const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
-  const bool want[5] = {want_bytes, want_pos, want_spos, want_stok, true};
+  const bool want[5] = {want_bytes, want_pos || (compact8 && want_bytes), want_spos, want_stok, true};
 
   // first pieces on their way
   auto issue_h2d = [&](size_t k) -> int {
@@ -663,7 +674,9 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     // ---- room for this piece's results: device slot and the host arrays ----
     const size_t nt = h.tot.n_tok, ns = (size_t)h.tot.n_sent + 1, nx = (size_t)h.tot.n_text + 1,
                  nsp = (size_t)h.tot.n_sentpos + 1;
-    const size_t dev_bytes[5] = {2 * nt * 4, 2 * nt * 4, nsp * 4, ns * 4, nx * 16 + (nx + 1) * sizeof(DocRec)};
+    const size_t esc_cap = nt / 16 + 4096;
+    const size_t dev_bytes[5] = {nt * tok_rec + 4, compact8 ? esc_cap * 8 : 2 * nt * 4, nsp * 4, ns * 4,
+                                 nx * 16 + (nx + 1) * sizeof(DocRec)};
     CUDA_TRYF(cudaStreamWaitEvent(s, m->ev_out[slot], 0));  // the slot's previous results have left the device
     for (int i = 0; i < 5; i++) {
       if (!want[i]) continue;
@@ -674,9 +687,9 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       // estimate for the whole stream from what has been seen so far (+12 %), exact for the last piece
       const double done = (double)cut[k + 1], scale = last_piece ? 1.0 : 1.12 * (double)n / done;
       auto est = [&](uint64_t have, size_t add) { return (size_t)((double)(have + add) * scale) + 4096; };
-      const size_t need8[8] = {est(base_tok, nt) * 8, est(base_tok, nt) * 8, est(base_sentpos, nsp) * 4, est(base_sent, ns) * 4,
+      const size_t need8[8] = {est(base_tok, nt) * tok_rec, est(base_tok, nt) * 8, est(base_sentpos, nsp) * 4, est(base_sent, ns) * 4,
                                est(base_text, nx) * 4, est(base_text, nx) * 4, est(base_text, nx) * 4, est(base_text, nx) * 4};
-      const size_t used8[8] = {base_tok * 8, base_tok * 8, base_sentpos * 4, base_sent * 4, base_text * 4, base_text * 4,
+      const size_t used8[8] = {base_tok * tok_rec, base_tok * 8, base_sentpos * 4, base_sent * 4, base_text * 4, base_text * 4,
                                base_text * 4, base_text * 4};
       const bool want8[8] = {want_bytes, want_pos, want_spos, want_stok, true, true, true, true};
       for (int i = 0; i < 8; i++)
@@ -685,7 +698,10 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     c.base_tok = (uint32_t)base_tok; c.base_sent = (uint32_t)base_sent; c.base_sentpos = (uint32_t)base_sentpos;
     c.base_byte = (uint32_t)cut[k];
     c.tok_bytes = (want_bytes && !compact) ? (uint32_t*)m->d_out[slot][0].p : nullptr;
-    c.tok_delta = (want_bytes && compact) ? (uint16_t*)m->d_out[slot][0].p : nullptr;
+    c.tok_delta = (want_bytes && compact && !compact8) ? (uint16_t*)m->d_out[slot][0].p : nullptr;
+    c.tok_delta8 = (want_bytes && compact8) ? (uint8_t*)m->d_out[slot][0].p : nullptr;
+    c.esc = (want_bytes && compact8) ? (uint32_t*)m->d_out[slot][1].p : nullptr;
+    c.esc_count = b.counters + 3; c.esc_cap = (uint32_t)esc_cap;
     c.tok_pos = want_pos ? (int32_t*)m->d_out[slot][1].p : nullptr;
     c.sent_pos = want_spos ? (int32_t*)m->d_out[slot][2].p : nullptr;
     c.sent_tok = want_stok ? (uint32_t*)m->d_out[slot][3].p : nullptr;
@@ -711,6 +727,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       std::memset(&ms, 0, sizeof ms);
       ms.p[0] = reinterpret_cast<const uint32_t*>(cb.total + 1); ms.words[0] = 8; ms.off[0] = 0;
       ms.p[1] = reinterpret_cast<const uint32_t*>(b.err_key); ms.words[1] = 2; ms.off[1] = 8;
+      ms.p[2] = b.counters + 3; ms.words[2] = 1; ms.off[2] = 10;
       launch_mail(ms, m->d_mail, s);
     }
     CUDA_TRYF(cudaEventRecord(k1, s));
@@ -726,13 +743,18 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       g_last_error = std::string("reference would panic: ") + datok_strerror(code);
       return fail(code);
     }
+    if (compact8 && want_bytes && m->h_mail[10]) {  // rare: this piece's escape pairs (a plain, blocking copy)
+      const size_t ne = m->h_mail[10], at = r->esc.size();
+      r->esc.resize(at + 2 * ne);
+      CUDA_TRYF(cudaMemcpy(r->esc.data() + at, m->d_out[slot][1].p, ne * 8, cudaMemcpyDeviceToHost));
+    }
     // the input buffer of this slot is free again: next piece but one
     if (k + 2 < np && (rc = issue_h2d(k + 2))) return fail(rc);
     // ---- results out, behind the kernels of the following pieces ----
     CUDA_TRYF(cudaStreamWaitEvent(m->s_d2h, m->ev_emit[slot], 0));
     const uint32_t* dtx = (const uint32_t*)m->d_out[slot][4].p;
     struct Cp { int hi; const void* src; size_t off, bytes; };
-    const Cp cps[8] = {{0, m->d_out[slot][0].p, base_tok * 8, (size_t)tail.fin.n_tok * 8},
+    const Cp cps[8] = {{0, m->d_out[slot][0].p, base_tok * tok_rec, (size_t)tail.fin.n_tok * tok_rec},
                        {1, m->d_out[slot][1].p, base_tok * 8, (size_t)tail.fin.n_tok * 8},
                        {2, m->d_out[slot][2].p, base_sentpos * 4, (size_t)tail.fin.n_sentpos * 4},
                        {3, m->d_out[slot][3].p, base_sent * 4, (size_t)tail.fin.n_sent * 4},
@@ -772,7 +794,13 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   v.n_tokens = base_tok; v.n_sentences = base_sent; v.n_texts = base_text; v.n_sent_pos = base_sentpos; v.n_runes = runes;
   v.has_invalid_utf8 = invalid;
   v.tok_bytes = (want_bytes && !compact) ? (const uint32_t*)host[0].p : nullptr;
-  v.tok_delta = (want_bytes && compact) ? (const uint16_t*)host[0].p : nullptr;
+  v.tok_delta = (want_bytes && compact && !compact8) ? (const uint16_t*)host[0].p : nullptr;
+  v.tok_delta8 = (want_bytes && compact8) ? (const uint8_t*)host[0].p : nullptr;
+  if (v.tok_delta8) {
+    sort_escapes(r->esc);
+    v.tok_esc = r->esc.data();
+    v.n_esc = r->esc.size() / 2;
+  }
   v.tok_pos = want_pos ? (const int32_t*)host[1].p : nullptr;
   v.sent_pos = want_spos ? (const int32_t*)host[2].p : nullptr;
   v.sent_tok = want_stok ? (const uint32_t*)host[3].p : nullptr;
@@ -855,18 +883,21 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   std::memset(&r->view, 0, sizeof r->view);
   const size_t nt = hdr.tot.n_tok, ns = (size_t)hdr.tot.n_sent + 1, nx = (size_t)hdr.tot.n_text + 1,
                np = (size_t)hdr.tot.n_sentpos + 1;
-  const bool compact = (flags & DATOK_COMPACT) != 0;
-  const bool want_delta = compact && (flags & (DATOK_TOKENS | DATOK_TOKEN_POS)) != 0;
+  const bool compact8 = (flags & DATOK_COMPACT8) != 0, compact = compact8 || (flags & DATOK_COMPACT) != 0;
+  const bool want_tok = (flags & (DATOK_TOKENS | DATOK_TOKEN_POS)) != 0;
+  const bool want_delta = compact && !compact8 && want_tok, want_delta8 = compact8 && want_tok;
   const bool want_bytes = !compact && (flags & DATOK_TOKENS) != 0, want_pos = !compact && (flags & DATOK_TOKEN_POS) != 0;
+  const size_t esc_cap = nt / 16 + 4096;
   const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
   struct Out { size_t bytes; bool want; void** dev; Block d, h; };
   void *d_tok_bytes = nullptr, *d_tok_pos = nullptr, *d_sent_pos = nullptr, *d_sent_tok = nullptr, *d_text = nullptr,
-       *d_delta = nullptr;
+       *d_delta = nullptr, *d_delta8 = nullptr, *d_esc = nullptr;
   // the per-text arrays are followed by the DocRec table (device scratch, not copied back)
-  Out outs[6] = {{2 * nt * 4, want_bytes, &d_tok_bytes, {}, {}}, {2 * nt * 4, want_pos, &d_tok_pos, {}, {}},
+  Out outs[8] = {{2 * nt * 4, want_bytes, &d_tok_bytes, {}, {}}, {2 * nt * 4, want_pos, &d_tok_pos, {}, {}},
                  {np * 4, want_spos, &d_sent_pos, {}, {}},       {ns * 4, want_stok, &d_sent_tok, {}, {}},
                  {nx * 4 * 4 + (nx + 1) * sizeof(DocRec), true, &d_text, {}, {}},
-                 {nt * 8, want_delta, &d_delta, {}, {}}};
+                 {nt * 8, want_delta, &d_delta, {}, {}},         {nt * 4 + 4, want_delta8, &d_delta8, {}, {}},
+                 {esc_cap * 8, want_delta8, &d_esc, {}, {}}};
   for (auto& o : outs) {
     if (!o.want) continue;
     o.d = acquire(m, o.bytes, false, &rc);
@@ -879,6 +910,8 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   c.tok_bytes = (uint32_t*)d_tok_bytes;
   c.tok_pos = (int32_t*)d_tok_pos;
   c.tok_delta = (uint16_t*)d_delta;
+  c.tok_delta8 = (uint8_t*)d_delta8;
+  c.esc = (uint32_t*)d_esc; c.esc_count = b.counters + 3; c.esc_cap = (uint32_t)esc_cap;
   c.sent_pos = (int32_t*)d_sent_pos;
   c.sent_tok = (uint32_t*)d_sent_tok;
   c.text_tok_end = (uint32_t*)d_text;
@@ -897,19 +930,21 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   launch_compact_finalize(c, cb, text_end_in, final_input, s);
   pt.end();
   m->launches += 4;  // texts, emit, finalize, mailbox
-  struct { StreamTotals fin; unsigned long long err; WState last; } tail;
+  struct { StreamTotals fin; unsigned long long err; WState last; uint32_t n_esc; } tail;
   tail.last = hdr.last;
   {
     MailSrc ms;
     std::memset(&ms, 0, sizeof ms);
     ms.p[0] = reinterpret_cast<const uint32_t*>(cb.total + 1); ms.words[0] = 8; ms.off[0] = 0;
     ms.p[1] = reinterpret_cast<const uint32_t*>(b.err_key); ms.words[1] = 2; ms.off[1] = 8;
+    ms.p[2] = b.counters + 3; ms.words[2] = 1; ms.off[2] = 10;
     launch_mail(ms, m->d_mail, s);
   }
   CUDA_TRY(cudaEventRecord(m->ev[2], s));
   CUDA_TRY(cudaStreamSynchronize(s));
   std::memcpy(&tail.fin, m->h_mail, sizeof(StreamTotals));
   std::memcpy(&tail.err, m->h_mail + 8, sizeof tail.err);
+  tail.n_esc = m->h_mail[10];
   pt.collect();
   if (tail.err != ~0ull) {
     const int code = (int)(tail.err & 0xFF);
@@ -943,6 +978,8 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
     if (!o.want || device_out) continue;
     size_t bytes = o.bytes;
     if (o.dev == &d_tok_bytes || o.dev == &d_tok_pos || o.dev == &d_delta) bytes = 2 * (size_t)v.n_tokens * 4;
+    else if (o.dev == &d_delta8) bytes = (size_t)v.n_tokens * 4;
+    else if (o.dev == &d_esc) bytes = (size_t)tail.n_esc * 8;
     else if (o.dev == &d_sent_pos) bytes = (size_t)v.n_sent_pos * 4;
     else if (o.dev == &d_sent_tok) bytes = (size_t)v.n_sentences * 4;
     else if (o.dev == &d_text) bytes = nx * 4 * 4;
@@ -956,6 +993,17 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   v.sent_pos = (const int32_t*)pick(2);
   v.sent_tok = (const uint32_t*)pick(3);
   v.tok_delta = (const uint16_t*)pick(5);
+  v.tok_delta8 = (const uint8_t*)pick(6);
+  if (want_delta8 && !device_out) {  // the escape list is tiny: sorted copy owned by the result
+    const uint32_t* e = (const uint32_t*)outs[7].h.p;
+    r->esc.assign(e, e + 2 * (size_t)tail.n_esc);
+    sort_escapes(r->esc);
+    v.tok_esc = r->esc.data();
+    v.n_esc = tail.n_esc;
+  } else if (want_delta8) {
+    v.tok_esc = (const uint32_t*)outs[7].d.p;  // device-resident and unordered
+    v.n_esc = tail.n_esc;
+  }
   const uint32_t* tx = (const uint32_t*)pick(4);
   v.text_tok_end = tx;
   v.text_sent_end = tx + nx;

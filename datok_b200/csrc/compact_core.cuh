@@ -107,6 +107,10 @@ struct CompactCtx {
   uint32_t* tok_bytes;     // 2 per token
   int32_t* tok_pos;        // 2 per token
   uint16_t* tok_delta;     // DATOK_COMPACT: 4 per token, instead of the two above
+  uint8_t* tok_delta8;     // DATOK_COMPACT8: 4 bytes per token; values >= 255 go to the escape list
+  uint32_t* esc;           // escape list: pairs {token index, field << 16 | value}, unordered on the device
+  uint32_t* esc_count;
+  uint32_t esc_cap;        // pairs
   int32_t* sent_pos;
   uint32_t* sent_tok;
   uint32_t* text_tok_end;
@@ -302,9 +306,22 @@ constexpr uint32_t E_COMPACT_RANGE = 24;  // DATOK_ERR_COMPACT_RANGE
 // The Token events of word w (token_writer.go:59-95).  Token k goes to slot k - tok_base of
 // tok_bytes/tok_pos (2 values each, ABS) or of tok_delta (4 values, !ABS; the kernel stages a block's
 // tokens in shared memory); sentence openers go to c.sent_pos.
-template <bool ABS>
+DATOK_HD void emit_escape(const CompactCtx& c, uint32_t tok, uint32_t field, uint32_t value, uint32_t pos) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t slot = atomicAdd(c.esc_count, 1u);
+#else
+  const uint32_t slot = (*c.esc_count)++;
+#endif
+  if (slot < c.esc_cap) { c.esc[2 * slot] = c.base_tok + tok; c.esc[2 * slot + 1] = (field << 16) | value; }
+  else report_error(c, pos, E_COMPACT_RANGE);
+}
+
+// FORM: 0 absolute pairs (tok_bytes / tok_pos), 1 four u16 deltas per token (tok_delta), 2 four u8 deltas
+// per token (tok_delta is then a byte array) with escapes
+template <int FORM>
 DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, const WordMasks& m, const Agg& A,
                           uint32_t* tok_bytes, int32_t* tok_pos, uint16_t* tok_delta, uint32_t tok_base) {
+  constexpr bool ABS = FORM == 0;
   uint32_t e = b.e;
   if (e == 0) return;
   const uint32_t w0 = w << 5;
@@ -347,9 +364,35 @@ DATOK_HD void emit_tokens(const CompactCtx& c, uint32_t w, const WordBits& b, co
       const int32_t rskip = (int32_t)skipped - (first ? shift : 0);
       const uint32_t bskip = s - bufstart, blen = p - s;
       if (DATOK_RARE((bskip | blen | runes | (uint32_t)rskip) > 0xFFFFu)) report_error(c, p, E_COMPACT_RANGE);
-      uint32_t* o = reinterpret_cast<uint32_t*>(tok_delta) + 2 * tok;  // {skip bytes, bytes}, {skip runes, runes}
-      o[0] = bskip | (blen << 16);
-      o[1] = ((uint32_t)rskip & 0xFFFFu) | (runes << 16);
+      if (FORM == 1) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(tok_delta) + 2 * tok;  // {skip bytes, bytes}, {skip runes, runes}
+        o[0] = bskip | (blen << 16);
+        o[1] = ((uint32_t)rskip & 0xFFFFu) | (runes << 16);
+      } else {
+        // (no array here: dynamic indexing would put it into local memory for every token)
+        const uint32_t v0 = bskip, v1 = blen, v2 = (uint32_t)rskip & 0xFFFFu, v3 = runes;
+        if (DATOK_RARE((v0 | v1 | v2 | v3) >= 255u)) {
+          if (v0 >= 255u) emit_escape(c, tok + tok_base, 0, v0, p);
+          if (v1 >= 255u) emit_escape(c, tok + tok_base, 1, v1, p);
+          if (v2 >= 255u) emit_escape(c, tok + tok_base, 2, v2, p);
+          if (v3 >= 255u) emit_escape(c, tok + tok_base, 3, v3, p);
+        }
+        uint32_t packed;
+#if defined(__CUDA_ARCH__)
+        {  // four values saturated to 255 and packed, two instructions
+          uint32_t hi2;
+          asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(v3), "r"(v2), "r"(0u));
+          asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(packed) : "r"(v1), "r"(v0), "r"(hi2));
+        }
+#else
+        {
+          const uint32_t b0 = v0 < 255u ? v0 : 255u, b1 = v1 < 255u ? v1 : 255u, b2 = v2 < 255u ? v2 : 255u,
+                         b3 = v3 < 255u ? v3 : 255u;
+          packed = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+#endif
+        reinterpret_cast<uint32_t*>(tok_delta)[tok] = packed;
+      }
     }
     if (DATOK_RARE((m.opener >> bp) & 1u)) {
       if (c.sent_pos) {

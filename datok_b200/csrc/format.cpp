@@ -65,19 +65,43 @@ struct TokenCursor {
   uint64_t k = 0, text = 0;
   uint64_t byte_end = 0;   // end of the previous token of this text, or the start of the text
   int64_t rune_end = 0;
+  uint64_t esc = 0;        // next entry of the DATOK_COMPACT8 escape list
   uint32_t lo = 0, hi = 0;
   int32_t ps = 0, pe = 0;
   explicit TokenCursor(const datok_view* view) : v(view) {}
+  // positions the cursor on the first token of text d
+  void seek_text(uint64_t d) {
+    k = d ? v->text_tok_end[d - 1] : 0;
+    text = d;
+    byte_end = d ? v->text_byte_end[d - 1] : 0;
+    rune_end = 0;
+    if (v->tok_delta8) {  // first escape entry of a token >= k
+      uint64_t a = 0, b = v->n_esc;
+      while (a < b) { const uint64_t mid = (a + b) / 2; if (v->tok_esc[2 * mid] < k) a = mid + 1; else b = mid; }
+      esc = a;
+    }
+  }
   void next() {  // token k
-    if (v->tok_delta) {
+    if (v->tok_delta || v->tok_delta8) {
       while (text < v->n_texts && k >= v->text_tok_end[text]) {  // a new text: both cursors restart
         byte_end = v->text_byte_end[text];
         rune_end = 0;
         text++;
       }
-      const uint16_t* d = v->tok_delta + 4 * k;
+      uint32_t d[4];
+      if (v->tok_delta) {
+        const uint16_t* p = v->tok_delta + 4 * k;
+        d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+      } else {
+        const uint8_t* p = v->tok_delta8 + 4 * k;
+        d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+        if ((d[0] == 255) | (d[1] == 255) | (d[2] == 255) | (d[3] == 255)) {  // rare: values from the escape list
+          while (esc < v->n_esc && v->tok_esc[2 * esc] < k) esc++;
+          for (; esc < v->n_esc && v->tok_esc[2 * esc] == k; esc++) d[(v->tok_esc[2 * esc + 1] >> 16) & 3u] = v->tok_esc[2 * esc + 1] & 0xFFFFu;
+        }
+      }
       lo = (uint32_t)(byte_end + d[0]); hi = lo + d[1];
-      ps = (int32_t)(rune_end + d[2]); pe = ps + d[3];
+      ps = (int32_t)(rune_end + d[2]); pe = ps + (int32_t)d[3];
       byte_end = hi; rune_end = pe;
     } else {
       if (v->tok_bytes) { lo = v->tok_bytes[2 * k]; hi = v->tok_bytes[2 * k + 1]; }
@@ -93,7 +117,7 @@ extern "C" {
 
 int datok_expand(const datok_result* r, uint32_t* tok_bytes, int32_t* tok_pos) {
   const datok_view* v = datok_result_view(r);
-  if (!v || (!v->tok_delta && v->n_tokens)) return DATOK_ERR_INVALID_ARG;
+  if (!v || (!v->tok_delta && !v->tok_delta8 && v->n_tokens)) return DATOK_ERR_INVALID_ARG;
   TokenCursor c(v);
   for (uint64_t k = 0; k < v->n_tokens; k++) {
     c.next();
@@ -116,12 +140,12 @@ void format_range(const datok_view* v, const uint8_t* in, uint32_t flags, uint64
   uint64_t tok = d0 ? v->text_tok_end[d0 - 1] : 0, sen = d0 ? v->text_sent_end[d0 - 1] : 0,
            sp = d0 ? v->text_sentpos_end[d0 - 1] : 0;
   TokenCursor cur(v);
-  cur.k = tok; cur.text = d0; cur.byte_end = d0 ? v->text_byte_end[d0 - 1] : 0;
+  cur.seek_text(d0);
   // rune offsets of the current text's tokens, for the `pos` line (token_writer.go:131-143); the
   // compact form is decoded once, while the surfaces are written
   std::vector<int32_t> text_pos;
   text_pos.reserve(4096);
-  const bool keep_pos = tpos && v->tok_delta;
+  const bool keep_pos = tpos && (v->tok_delta || v->tok_delta8);
   auto emit_tokens = [&](uint64_t upto) {
     if (tokens || keep_pos)
       for (; tok < upto; tok++) {
@@ -190,7 +214,7 @@ size_t count_range(const datok_view* v, uint32_t flags, uint64_t d0, uint64_t d1
   const uint64_t t_hi = (tail && sentences && v->n_sentences > s1) ? v->sent_tok[v->n_sentences - 1] : t1;
   if (tokens || tpos) {
     TokenCursor cur(v);
-    cur.k = t0; cur.text = d0; cur.byte_end = d0 ? v->text_byte_end[d0 - 1] : 0;
+    cur.seek_text(d0);
     for (uint64_t k = t0; k < (t_hi > t1 ? t_hi : t1); k++) {
       cur.next();
       if (tokens) n += (size_t)(cur.hi - cur.lo) + 1;
@@ -222,8 +246,9 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
   if (!v) return (size_t)-1;
   const bool tokens = flags & DATOK_TOKENS, sentences = flags & DATOK_SENTENCES;
   const bool tpos = flags & DATOK_TOKEN_POS, spos = flags & DATOK_SENTENCE_POS;
-  if ((tokens && !v->tok_bytes && !v->tok_delta) || (sentences && !v->sent_tok && v->n_sentences) ||
-      (tpos && !v->tok_pos && !v->tok_delta) || (spos && !v->sent_pos))
+  const bool have_delta = v->tok_delta || v->tok_delta8;
+  if ((tokens && !v->tok_bytes && !have_delta) || (sentences && !v->sent_tok && v->n_sentences) ||
+      (tpos && !v->tok_pos && !have_delta) || (spos && !v->sent_pos))
     return (size_t)-1;  // the array was not requested at transduce time
   (void)n;
   // ---- ranges of texts, one per worker thread ----
@@ -284,7 +309,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
 int datok_replay(const datok_result* r, const uint8_t* in, size_t n, const datok_callbacks* cb) {
   const datok_view* v = datok_result_view(r);
   if (!v || !cb) return DATOK_ERR_INVALID_ARG;
-  if ((v->n_tokens && !v->tok_bytes && !v->tok_delta) || (v->n_sentences && !v->sent_tok)) return DATOK_ERR_INVALID_ARG;
+  if ((v->n_tokens && !v->tok_bytes && !v->tok_delta && !v->tok_delta8) || (v->n_sentences && !v->sent_tok)) return DATOK_ERR_INVALID_ARG;
   (void)n;
   uint64_t tok = 0, sen = 0;
   size_t bufstart = 0;  // the reference's buffer[0]: the last rewind point (matrix.go:608-622)

@@ -374,24 +374,28 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   int32_t* s_tp = reinterpret_cast<int32_t*>(s_stage + 2 * STAGE_TOKENS);
   uint16_t* s_td = reinterpret_cast<uint16_t*>(s_stage);
   // specialised copies of the loop: staged ones address shared memory directly, compact / absolute form
-#define DATOK_EMIT_LOOP(ABS, TB, TP, TD, BASE)                                                   \
+#define DATOK_EMIT_LOOP(FORM, TB, TP, TD, BASE)                                                   \
   _Pragma("unroll") for (int k = 0; k < COMPACT_WPT; k++) {                                      \
     const uint32_t w = w0 + k;                                                                   \
     if (w < c.n_words) {                                                                         \
       if (wb[k].e | wb[k].s | wb[k].t) {                                                         \
         const WordMasks m = word_masks(wb[k], agg_last(carry));                                  \
-        emit_tokens<ABS>(c, w, wb[k], m, carry, TB, TP, TD, BASE);                               \
+        emit_tokens<FORM>(c, w, wb[k], m, carry, TB, TP, TD, BASE);                               \
         emit_sentences(c, w, wb[k], m, carry);                                                   \
       }                                                                                          \
       carry = agg_combine(carry, wa[k]);                                                         \
     }                                                                                            \
   }
-  if (c.tok_delta) {
-    if (staged) { DATOK_EMIT_LOOP(false, nullptr, nullptr, s_td, blk_tok0) }
-    else { DATOK_EMIT_LOOP(false, nullptr, nullptr, c.tok_delta, 0u) }
+  if (c.tok_delta8) {
+    uint16_t* g8 = reinterpret_cast<uint16_t*>(c.tok_delta8);
+    if (staged) { DATOK_EMIT_LOOP(2, nullptr, nullptr, s_td, blk_tok0) }
+    else { DATOK_EMIT_LOOP(2, nullptr, nullptr, g8, 0u) }
+  } else if (c.tok_delta) {
+    if (staged) { DATOK_EMIT_LOOP(1, nullptr, nullptr, s_td, blk_tok0) }
+    else { DATOK_EMIT_LOOP(1, nullptr, nullptr, c.tok_delta, 0u) }
   } else {
-    if (staged) { DATOK_EMIT_LOOP(true, c.tok_bytes ? s_tb : nullptr, c.tok_pos ? s_tp : nullptr, nullptr, blk_tok0) }
-    else { DATOK_EMIT_LOOP(true, c.tok_bytes, c.tok_pos, nullptr, 0u) }
+    if (staged) { DATOK_EMIT_LOOP(0, c.tok_bytes ? s_tb : nullptr, c.tok_pos ? s_tp : nullptr, nullptr, blk_tok0) }
+    else { DATOK_EMIT_LOOP(0, c.tok_bytes, c.tok_pos, nullptr, 0u) }
   }
 #undef DATOK_EMIT_LOOP
   if (!staged) return;
@@ -409,6 +413,11 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   if (c.tok_delta) {
     uint2* dst = reinterpret_cast<uint2*>(c.tok_delta) + blk_tok0;
     const uint2* src = reinterpret_cast<const uint2*>(s_td);
+    for (uint32_t i = threadIdx.x; i < blk_ntok; i += COMPACT_THREADS) dst[i] = src[i];
+  }
+  if (c.tok_delta8) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.tok_delta8) + blk_tok0;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_td);
     for (uint32_t i = threadIdx.x; i < blk_ntok; i += COMPACT_THREADS) dst[i] = src[i];
   }
 }
@@ -458,7 +467,7 @@ void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStr
 }
 int launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
   const int smem_max = 4 * STAGE_TOKENS * (int)sizeof(uint32_t);
-  const int smem = (c.tok_delta ? 2 : 4) * STAGE_TOKENS * (int)sizeof(uint32_t);
+  const int smem = (c.tok_delta8 ? 1 : c.tok_delta ? 2 : 4) * STAGE_TOKENS * (int)sizeof(uint32_t);
   {
     cudaError_t e = cudaFuncSetAttribute(compact_kernel<K3_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return (int)e;

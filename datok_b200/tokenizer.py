@@ -13,7 +13,7 @@ import sys
 import numpy as np
 
 from . import _lib
-from ._lib import (COMPACT, NEWLINE_AFTER_EOT, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Callbacks,
+from ._lib import (COMPACT, COMPACT8, NEWLINE_AFTER_EOT, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Callbacks,
                    Carry, EVENT_CB, TOKEN_CB)
 
 
@@ -112,8 +112,10 @@ class Result:
             self.tok_bytes = arr(v.tok_bytes, 2 * v.n_tokens)
             self.tok_pos = arr(v.tok_pos, 2 * v.n_tokens)
             self.tok_delta = arr(v.tok_delta, 4 * v.n_tokens) if v.tok_delta else None
-            if self.tok_delta is not None:  # DATOK_COMPACT: the absolute arrays are rebuilt on the host on demand
-                self.tok_bytes = self.tok_pos = None
+            self.tok_delta8 = arr(v.tok_delta8, 4 * v.n_tokens) if v.tok_delta8 else None
+            self.tok_esc = arr(v.tok_esc, 2 * v.n_esc) if v.tok_delta8 else None
+            if self.tok_delta is not None or self.tok_delta8 is not None:
+                self.tok_bytes = self.tok_pos = None  # DATOK_COMPACT(8): the absolute arrays are rebuilt on demand
             self.sent_pos = arr(v.sent_pos, v.n_sent_pos)
             self.sent_tok = arr(v.sent_tok, v.n_sentences)
             self.text_tok_end = arr(v.text_tok_end, v.n_texts)
@@ -123,7 +125,7 @@ class Result:
 
     def expand(self):
         """datok_expand(): absolute tok_bytes / tok_pos of a DATOK_COMPACT result (host-side decode)"""
-        if self.tok_delta is not None and self.tok_bytes is None:
+        if (self.tok_delta is not None or self.tok_delta8 is not None) and self.tok_bytes is None:
             tb = np.empty(2 * self.n_tokens, dtype=np.uint32)
             tp = np.empty(2 * self.n_tokens, dtype=np.int32)
             rc = _lib.lib().datok_expand(self._h, tb.ctypes.data, tp.ctypes.data)
@@ -208,7 +210,7 @@ class MatrixTokenizer:
         """one datok_transduce call + the host half of the TokenWriter; returns the carry for the next batch"""
         L = _lib.lib()
         addr, n, keep = _as_buffer(data)
-        extra = COMPACT | (0 if final else _lib.NOT_FINAL)
+        extra = COMPACT8 | (0 if final else _lib.NOT_FINAL)  # the smallest transport form: the host decodes it anyway
         if w._stock is not None:
             st = w._stock
             # the formatter reads the delta-coded spans directly: half the bytes over PCIe

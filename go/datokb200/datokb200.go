@@ -87,8 +87,8 @@ func (t *Tokenizer) TransduceTokenWriter(r io.Reader, w *datok.TokenWriter) bool
 		p = (*C.uint8_t)(unsafe.Pointer(&in[0]))
 	}
 	var res *C.datok_result
-	// DATOK_COMPACT: the replay only needs the delta-coded spans (8 bytes per token over PCIe)
-	rc := C.datok_transduce(t.model, p, C.size_t(len(in)), C.uint32_t(C.DATOK_TOKENS|C.DATOK_SENTENCES|C.DATOK_COMPACT), nil, &res)
+	// DATOK_COMPACT8: the replay only needs the delta-coded spans (4 bytes per token over PCIe)
+	rc := C.datok_transduce(t.model, p, C.size_t(len(in)), C.uint32_t(C.DATOK_TOKENS|C.DATOK_SENTENCES|C.DATOK_COMPACT8), nil, &res)
 	if rc != C.DATOK_OK {
 		if rc <= C.DATOK_ERR_DEGENERATE {
 			panic(errors.New(C.GoString(C.datok_strerror(rc)))) // the reference panics here too

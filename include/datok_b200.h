@@ -41,7 +41,10 @@ enum {
    * instead of 16 over PCIe) in place of tok_bytes / tok_pos; see datok_view.tok_delta.  The
    * TokenWriter itself only ever sees such deltas: Token(offset, buf) gets the runes since the
    * previous token end (token_writer.go:59-95). */
-  DATOK_COMPACT = 1024
+  DATOK_COMPACT = 1024,
+  /* Not a reference flag: like DATOK_COMPACT with one byte per value (view.tok_delta8, 4 bytes per
+   * token over PCIe).  A value that does not fit is stored as 255 and listed in view.tok_esc. */
+  DATOK_COMPACT8 = 2048
 };
 
 /* Error codes.  1..6 mirror inputs on which the Go reference panics (they are
@@ -111,6 +114,11 @@ typedef struct {
    * (the rune skip of a text's first token already includes the NEWLINE_AFTER_EOT shift).
    * tok_bytes / tok_pos are NULL then; datok_expand() rebuilds them. */
   const uint16_t *tok_delta;
+  /* DATOK_COMPACT8: the same four values per token as one byte each.  255 means "look it up":
+   * tok_esc holds n_esc pairs {token index, field << 16 | value}, sorted by token index and field. */
+  const uint8_t *tok_delta8;
+  const uint32_t *tok_esc;
+  uint64_t n_esc;
 } datok_view;
 
 /* LoadTokenizerFile (fomafile.go:452-484) for the MATOK magic / LoadMatrixFile
@@ -146,7 +154,7 @@ int datok_transduce_device(datok_model *m, const uint8_t *d_in, size_t n, uint32
 const datok_view *datok_result_view(const datok_result *r);
 void datok_result_free(datok_result *r);
 
-/* Rebuilds the absolute token arrays of a DATOK_COMPACT result on the host: tok_bytes (2 per token)
+/* Rebuilds the absolute token arrays of a DATOK_COMPACT / DATOK_COMPACT8 result on the host: tok_bytes (2 per token)
  * and / or tok_pos (2 per token); either may be NULL. */
 int datok_expand(const datok_result *r, uint32_t *tok_bytes, int32_t *tok_pos);
 

@@ -30,6 +30,9 @@ struct EmulResult {
   uint32_t carry_state, has_invalid;
   uint32_t rounds, n_rewalks, n_stitch_mismatch;
   uint16_t* tok_delta;
+  uint8_t* tok_delta8;
+  uint32_t* esc;
+  uint32_t n_esc;
 };
 
 struct EmulModel {
@@ -187,6 +190,9 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   R->tok_bytes = (uint32_t*)std::calloc(2 * nt + 2, 4);
   R->tok_pos = (int32_t*)std::calloc(2 * nt + 2, 4);
   R->tok_delta = (uint16_t*)std::calloc(4 * nt + 4, 2);
+  R->tok_delta8 = (uint8_t*)std::calloc(4 * nt + 8, 1);
+  R->esc = (uint32_t*)std::calloc(2 * (4 * nt + 4), 4);
+  uint32_t esc_count = 0;
   R->sent_pos = (int32_t*)std::calloc(np + 1, 4);
   R->sent_tok = (uint32_t*)std::calloc(ns + 1, 4);
   R->text_tok_end = (uint32_t*)std::calloc(nx + 1, 4);
@@ -194,7 +200,8 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   R->text_sentpos_end = (uint32_t*)std::calloc(nx + 1, 4);
   R->text_byte_end = (uint32_t*)std::calloc(nx + 1, 4);
   std::vector<DocRec> docs(nx + 1);
-  c.tok_bytes = R->tok_bytes; c.tok_pos = R->tok_pos; c.tok_delta = R->tok_delta; c.sent_pos = R->sent_pos; c.sent_tok = R->sent_tok;
+  c.tok_bytes = R->tok_bytes; c.tok_pos = R->tok_pos; c.tok_delta = R->tok_delta;
+  c.tok_delta8 = R->tok_delta8; c.esc = R->esc; c.esc_count = &esc_count; c.esc_cap = (uint32_t)(4 * nt + 4); c.sent_pos = R->sent_pos; c.sent_tok = R->sent_tok;
   c.text_tok_end = R->text_tok_end; c.text_sent_end = R->text_sent_end;
   c.text_sentpos_end = R->text_sentpos_end; c.text_byte_end = R->text_byte_end;
   c.docs = docs.data();
@@ -208,7 +215,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       const bool staged = blk_ntok <= 64;
       std::vector<uint32_t> s_tb(2 * 64 + 2);
       std::vector<int32_t> s_tp(2 * 64 + 2);
-      std::vector<uint16_t> s_td(4 * 64 + 4);
+      std::vector<uint16_t> s_td(4 * 64 + 4), s_t8(2 * 64 + 4);
       for (uint32_t t = 0; t < TPB; t++) {
         for (uint32_t k = 0; k < WPT; k++) {
           uint32_t w = blk * WPB + t * WPT + k;
@@ -217,10 +224,12 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
           if (pass == 0) emit_texts(c, w, wb, carry);
           else if (wb.e | wb.s | wb.t) {
             const WordMasks wm = word_masks(wb, agg_last(carry));
-            emit_tokens<true>(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
-                              nullptr, staged ? blk_tok0 : 0u);
-            emit_tokens<false>(c, w, wb, wm, carry, nullptr, nullptr, staged ? s_td.data() : c.tok_delta,
-                               staged ? blk_tok0 : 0u);
+            emit_tokens<0>(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
+                           nullptr, staged ? blk_tok0 : 0u);
+            emit_tokens<1>(c, w, wb, wm, carry, nullptr, nullptr, staged ? s_td.data() : c.tok_delta,
+                           staged ? blk_tok0 : 0u);
+            emit_tokens<2>(c, w, wb, wm, carry, nullptr, nullptr,
+                           staged ? s_t8.data() : reinterpret_cast<uint16_t*>(c.tok_delta8), staged ? blk_tok0 : 0u);
             emit_sentences(c, w, wb, wm, carry);
           }
           carry = agg_combine(carry, word_agg(w, wb));
@@ -230,9 +239,11 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
         std::memcpy(c.tok_bytes + 2 * (size_t)blk_tok0, s_tb.data(), 8 * (size_t)blk_ntok);
         std::memcpy(c.tok_pos + 2 * (size_t)blk_tok0, s_tp.data(), 8 * (size_t)blk_ntok);
         std::memcpy(c.tok_delta + 4 * (size_t)blk_tok0, s_td.data(), 8 * (size_t)blk_ntok);
+        std::memcpy(c.tok_delta8 + 4 * (size_t)blk_tok0, s_t8.data(), 4 * (size_t)blk_ntok);
       }
     }
   }
+  R->n_esc = esc_count;
   const StreamTotals fin = finalize_stream(c, total, text_end_in != 0, b.final_input != 0);
   R->n_tokens = fin.n_tok; R->n_sentences = fin.n_sent; R->n_texts = fin.n_text; R->n_sent_pos = fin.n_sentpos;
   if (err_key != ~0ull) R->status = (int)(err_key & 0xFF);
@@ -241,7 +252,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
 
 void emul_result_free(EmulResult* r) {
   if (!r) return;
-  std::free(r->tok_bytes); std::free(r->tok_pos); std::free(r->tok_delta); std::free(r->sent_pos); std::free(r->sent_tok);
+  std::free(r->tok_bytes); std::free(r->tok_pos); std::free(r->tok_delta); std::free(r->tok_delta8); std::free(r->esc); std::free(r->sent_pos); std::free(r->sent_tok);
   std::free(r->text_tok_end); std::free(r->text_sent_end); std::free(r->text_sentpos_end); std::free(r->text_byte_end);
   std::free(r);
 }

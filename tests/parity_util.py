@@ -31,7 +31,8 @@ class _Res(C.Structure):
                 ("text_sentpos_end", C.POINTER(C.c_uint32)), ("text_byte_end", C.POINTER(C.c_uint32)),
                 ("carry_state", C.c_uint32), ("has_invalid", C.c_uint32),
                 ("rounds", C.c_uint32), ("n_rewalks", C.c_uint32), ("n_stitch_mismatch", C.c_uint32),
-                ("tok_delta", C.POINTER(C.c_uint16))]
+                ("tok_delta", C.POINTER(C.c_uint16)), ("tok_delta8", C.POINTER(C.c_uint8)),
+                ("esc", C.POINTER(C.c_uint32)), ("n_esc", C.c_uint32)]
 
 
 _lib = None
@@ -95,8 +96,21 @@ class EmulModel:
             s.carry_state = r.carry_state
             s.has_invalid = r.has_invalid
             s.tok_delta = _arr(r.tok_delta, 4 * r.n_tokens, np.uint16)
+            s.tok_delta8 = _arr(r.tok_delta8, 4 * r.n_tokens, np.uint8)
+            s.tok_esc = _arr(r.esc, 2 * r.n_esc, np.uint32)
         lib().emul_result_free(rp)
         return s
+
+
+def unescape_delta8(tok_delta8, tok_esc):
+    """DATOK_COMPACT8 -> the u16 form: 255 means "see the escape list" ({token, field << 16 | value} pairs, any order)"""
+    d = tok_delta8.astype(np.uint16).reshape(-1, 4).copy()
+    e = tok_esc.reshape(-1, 2)
+    assert int((d == 255).sum()) == e.shape[0], "every 255 has exactly one escape entry"
+    for tok, fv in e:
+        assert d[tok, fv >> 16] == 255
+        d[tok, fv >> 16] = fv & 0xFFFF
+    return d.reshape(-1)
 
 
 def expand_delta(tok_delta, text_tok_end, text_byte_end):
@@ -156,3 +170,6 @@ def assert_matches_oracle(s, o, flags, ctx=""):
         np.testing.assert_array_equal(tb[0::2], o.tok_byte_start, err_msg=f"{ctx}: delta-coded byte starts")
         np.testing.assert_array_equal(tb[1::2], o.tok_byte_end, err_msg=f"{ctx}: delta-coded byte ends")
         np.testing.assert_array_equal(tp, o.tok_pos, err_msg=f"{ctx}: delta-coded rune offsets")
+        d8 = getattr(s, "tok_delta8", None)
+        if d8 is not None and d8.size and not hasattr(s, "expand"):  # the emulation fills the one-byte form as well
+            np.testing.assert_array_equal(unescape_delta8(d8, s.tok_esc), delta, err_msg=f"{ctx}: one-byte deltas")

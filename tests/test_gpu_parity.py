@@ -409,3 +409,33 @@ def test_stress_configurations(hot_rows, chunk, threads, testdata, oracle_models
             o = oracle_models[model].transduce(data, flags)
             P.assert_matches_oracle(gpu_arrays(tok, data, flags), o, flags, f"{model} fuzz it={it} {data[:40]!r}")
         tok.close()
+
+
+@pytest.mark.parametrize("model,kind", [("tokenizer_de.matok", 2), ("tokenizer_en.matok", 3), ("tokenizer_de.matok", 4)])
+def test_compact8_token_deltas(model, kind, gpu_models, oracle_models, testdata, monkeypatch):
+    """DATOK_COMPACT8: one byte per delta, values >= 255 through the escape list (long tokens, long gaps)"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    tok = gpu_models[model]
+    long_bits = ("\n" + "x" * 300 + " " * 400 + "é" * 280 + "\t" * 256 + "kurz " + "-" * 255 + " Ende.\x04").encode()
+    a = np.concatenate([corpus.generate(kind, 2 << 20, seed=41), np.frombuffer(long_bits, dtype=np.uint8),
+                        corpus.generate(kind, 1 << 20, seed=42)])
+    for flags in (15, 31, 1, 4):
+        o = oracle_models[model].transduce_np(a, flags)
+        r = tok.transduce_arrays(a, flags | d.COMPACT8)
+        assert r.tok_delta8 is not None and r.tok_delta8.size == 4 * r.n_tokens and r.tok_bytes is None
+        assert r.tok_esc.size >= 2 * 5 and (r.tok_delta8 == 255).sum() == r.tok_esc.size // 2
+        assert (np.diff(r.tok_esc[0::2].astype(np.int64)) >= 0).all()
+        assert tok.format(r, a, flags) == o.text
+        d16 = P.unescape_delta8(r.tok_delta8, r.tok_esc)
+        r16 = tok.transduce_arrays(a, flags | d.COMPACT)
+        np.testing.assert_array_equal(d16, r16.tok_delta)
+        P.assert_matches_oracle(r.expand(), o, flags, f"compact8 {model} flags={flags}")
+    # the pipelined path: escapes of several pieces, merged and sorted
+    monkeypatch.setenv("DATOK_PIECE_MB", "1")
+    tokp = d.LoadTokenizerFile(os.path.join(testdata, model))
+    o = oracle_models[model].transduce_np(a, 15)
+    rp = tokp.transduce_arrays(a, 15 | d.COMPACT8)
+    assert tokp.format(rp, a, 15) == o.text
+    P.assert_matches_oracle(rp.expand(), o, 15, "compact8 pipelined")
+    tokp.close()
