@@ -14,14 +14,22 @@
 
 namespace {
 
+static const char kDigits2[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+
 struct Sink {
   uint8_t* dst;      // nullptr: only count
   size_t cap, n = 0;
+  const uint8_t* src_end = nullptr;  // end of the input buffer: lets short surfaces be copied as one 16-byte block
   inline void put(const uint8_t* p, size_t len) {
     if (n + len <= cap) {
       uint8_t* d = dst + n;
-      if (len <= 16) { for (size_t i = 0; i < len; i++) d[i] = p[i]; }  // token surfaces are short
-      else std::memcpy(d, p, len);
+      if (len <= 16) {  // token surfaces are short
+        if (n + 16 <= cap && p + 16 <= src_end) std::memcpy(d, p, 16);  // fixed size: two moves; the tail is overwritten next
+        else for (size_t i = 0; i < len; i++) d[i] = p[i];
+      } else {
+        std::memcpy(d, p, len);
+      }
     } else if (n < cap) {
       std::memcpy(dst + n, p, cap - n);
     }
@@ -40,9 +48,13 @@ struct Sink {
     }
     uint8_t tmp[12];
     int i = 12;
-    do { tmp[--i] = (uint8_t)('0' + u % 10); u /= 10; } while (u);
+    while (u >= 100) { const uint32_t q = u / 100, r = u - q * 100; tmp[--i] = (uint8_t)kDigits2[2 * r + 1]; tmp[--i] = (uint8_t)kDigits2[2 * r]; u = q; }
+    if (u >= 10) { tmp[--i] = (uint8_t)kDigits2[2 * u + 1]; tmp[--i] = (uint8_t)kDigits2[2 * u]; }
+    else tmp[--i] = (uint8_t)('0' + u);
     if (v < 0) tmp[--i] = '-';
-    put(tmp + i, (size_t)(12 - i));
+    const size_t len = (size_t)(12 - i);
+    if (n + len <= cap) { for (size_t k = 0; k < len; k++) dst[n + k] = tmp[i + k]; n += len; }
+    else { for (size_t k = 0; k < len; k++) byte(tmp[i + k]); }
   }
 };
 
@@ -133,7 +145,9 @@ namespace {
 
 // Output of the texts [d0, d1) (and, for the last range, of the events after the last TextEnd).
 // Texts are independent: token, sentence and `sent` indices restart from the per-text bounds.
-void format_range(const datok_view* v, const uint8_t* in, uint32_t flags, uint64_t d0, uint64_t d1, bool tail, Sink& s) {
+void format_range(const datok_view* v, const uint8_t* in, size_t n_in, uint32_t flags, uint64_t d0, uint64_t d1, bool tail,
+                  Sink& s) {
+  s.src_end = in + n_in;
   const bool tokens = flags & DATOK_TOKENS, sentences = flags & DATOK_SENTENCES;
   const bool tpos = flags & DATOK_TOKEN_POS, spos = flags & DATOK_SENTENCE_POS;
   const bool re = v->has_invalid_utf8 != 0;
@@ -141,20 +155,15 @@ void format_range(const datok_view* v, const uint8_t* in, uint32_t flags, uint64
            sp = d0 ? v->text_sentpos_end[d0 - 1] : 0;
   TokenCursor cur(v);
   cur.seek_text(d0);
-  // rune offsets of the current text's tokens, for the `pos` line (token_writer.go:131-143); the
-  // compact form is decoded once, while the surfaces are written
-  std::vector<int32_t> text_pos;
-  text_pos.reserve(4096);
-  const bool keep_pos = tpos && (v->tok_delta || v->tok_delta8);
+  // the `pos` line (token_writer.go:131-143) of a delta-coded result: a second cursor decodes the text's
+  // rune offsets again (cheaper than buffering them while the surfaces are written)
+  const bool delta_pos = tpos && (v->tok_delta || v->tok_delta8);
   auto emit_tokens = [&](uint64_t upto) {
-    if (tokens || keep_pos)
+    if (tokens)
       for (; tok < upto; tok++) {
         cur.next();
-        if (keep_pos) { text_pos.push_back(cur.ps); text_pos.push_back(cur.pe); }
-        if (tokens) {
-          put_surface(s, in, cur.lo, cur.hi, re);
-          s.byte('\n');
-        }
+        put_surface(s, in, cur.lo, cur.hi, re);
+        s.byte('\n');
       }
     tok = upto;
   };
@@ -173,12 +182,23 @@ void format_range(const datok_view* v, const uint8_t* in, uint32_t flags, uint64
     emit_tokens(t1);
     if (tpos || spos) {  // token_writer.go:131-159
       if (tpos) {
-        for (uint64_t k = 2 * t0; k < 2 * t1; k++) {
-          if (k != 2 * t0) s.byte(' ');
-          s.itoa(keep_pos ? text_pos[k - 2 * t0] : v->tok_pos[k]);
+        if (delta_pos) {
+          TokenCursor pc(v);
+          pc.seek_text(d);
+          for (uint64_t k = t0; k < t1; k++) {
+            pc.next();
+            if (k != t0) s.byte(' ');
+            s.itoa(pc.ps);
+            s.byte(' ');
+            s.itoa(pc.pe);
+          }
+        } else {
+          for (uint64_t k = 2 * t0; k < 2 * t1; k++) {
+            if (k != 2 * t0) s.byte(' ');
+            s.itoa(v->tok_pos[k]);
+          }
         }
         s.byte('\n');
-        text_pos.clear();
       }
       if (spos) {
         const uint64_t p1 = v->text_sentpos_end[d];
@@ -250,7 +270,6 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
   if ((tokens && !v->tok_bytes && !have_delta) || (sentences && !v->sent_tok && v->n_sentences) ||
       (tpos && !v->tok_pos && !have_delta) || (spos && !v->sent_pos))
     return (size_t)-1;  // the array was not requested at transduce time
-  (void)n;
   // ---- ranges of texts, one per worker thread ----
   unsigned workers = std::thread::hardware_concurrency();
   if (const char* e = std::getenv("DATOK_FORMAT_THREADS")) workers = (unsigned)std::atoi(e);
@@ -258,7 +277,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
   if (v->n_texts < 64 || workers < 2) workers = 1;
   if (workers == 1) {
     Sink s{dst, dst ? cap : 0};
-    format_range(v, in, flags, 0, v->n_texts, true, s);
+    format_range(v, in, n, flags, 0, v->n_texts, true, s);
     return s.n;
   }
   std::vector<uint64_t> lo(workers + 1);
@@ -271,7 +290,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
       th.emplace_back([&, i] {
         if (!v->has_invalid_utf8) { size[i] = count_range(v, flags, lo[i], lo[i + 1], i + 1 == workers); return; }
         Sink s{nullptr, 0};
-        format_range(v, in, flags, lo[i], lo[i + 1], i + 1 == workers, s);
+        format_range(v, in, n, flags, lo[i], lo[i + 1], i + 1 == workers, s);
         size[i] = s.n;
       });
     for (auto& t : th) t.join();
@@ -282,7 +301,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
   if (!dst) return total;
   if (cap < total) {  // truncated output: the plain sequential writer handles the cut
     Sink s{dst, cap};
-    format_range(v, in, flags, 0, v->n_texts, true, s);
+    format_range(v, in, n, flags, 0, v->n_texts, true, s);
     return s.n;
   }
   // pass 2: every range writes at its offset
@@ -292,7 +311,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
     for (unsigned i = 0; i < workers; i++)
       th.emplace_back([&, i] {
         Sink s{dst + off[i], size[i]};
-        format_range(v, in, flags, lo[i], lo[i + 1], i + 1 == workers, s);
+        format_range(v, in, n, flags, lo[i], lo[i + 1], i + 1 == workers, s);
         wrote[i] = s.n;
       });
     for (auto& t : th) t.join();
@@ -300,7 +319,7 @@ size_t datok_format(const datok_result* r, const uint8_t* in, size_t n, uint32_t
   for (unsigned i = 0; i < workers; i++)
     if (wrote[i] != size[i]) {  // the two passes disagree: never hand out a torn buffer
       Sink s{dst, cap};
-      format_range(v, in, flags, 0, v->n_texts, true, s);
+      format_range(v, in, n, flags, 0, v->n_texts, true, s);
       return s.n;
     }
   return total;

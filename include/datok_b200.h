@@ -137,8 +137,10 @@ int datok_model_info(const datok_model *m, uint32_t *state_count, uint32_t *sigm
                      uint32_t *n_classes, uint32_t *epsilon, uint32_t *unknown, uint32_t *identity);
 
 /* TransduceTokenWriter (matrix.go:348-698) over `n` bytes of host memory.
- * `flags` are TokenWriter Bits (plus DATOK_WRITER_USED); they select which arrays
- * are produced and copied back.  carry_in may be NULL (stream start).
+ * `flags` are TokenWriter Bits (plus DATOK_WRITER_USED, DATOK_NOT_FINAL, DATOK_COMPACT,
+ * DATOK_COMPACT8); they select which arrays are produced and copied back.  carry_in may be
+ * NULL (stream start).  Inputs of 128 MiB and more are cut after EOT bytes into pieces whose
+ * host<->device copies overlap the kernels; the result is the same single set of arrays.
  * Synchronous; calls on one model are serialised. Returns DATOK_OK or an error;
  * on reference-panic inputs (codes 1..5) *out is still a valid, partial result
  * holding everything up to the failing event is NOT guaranteed -- treat as failed. */
@@ -146,8 +148,9 @@ int datok_transduce(datok_model *m, const uint8_t *in, size_t n, uint32_t flags,
                     const datok_carry *carry_in, datok_result **out);
 
 /* Same, but `d_in` is a DEVICE pointer (input already resident in HBM) and the
- * offset arrays stay on the device; *view then holds device pointers.  Used by the
- * benchmark's kernel-only leg and by callers that post-process on the GPU. */
+ * offset arrays stay on the device; *view then holds device pointers (under
+ * DATOK_COMPACT8 the escape pairs are left in the order the kernel appended them).
+ * Used by the benchmark's kernel-only leg and by callers that post-process on the GPU. */
 int datok_transduce_device(datok_model *m, const uint8_t *d_in, size_t n, uint32_t flags,
                            const datok_carry *carry_in, datok_result **out);
 
