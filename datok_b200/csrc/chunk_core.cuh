@@ -296,7 +296,9 @@ DATOK_HD void chunk_rewalk_fast(const DeviceModel& m, const WalkBuffers& b, cons
 }
 
 // K2b: returns true if chunk i must be re-walked (state in Ytmp[i]); otherwise Enew[i] is set.
-DATOK_HD bool chunk_stitch(const DeviceModel& m, const WalkBuffers& b, uint32_t i) {
+// first_round: the head [lo, sync) has not been walked yet -- the speculative walk left its bits zero,
+// so there is nothing to clear.
+DATOK_HD bool chunk_stitch(const DeviceModel& m, const WalkBuffers& b, uint32_t i, bool first_round = false) {
   const WState X = b.E[i - 1];
   if (X.flags & (WS_INVALID | WS_DONE)) {  // predecessor not (yet) usable: leave the chunk as it is
     b.Enew[i] = b.E[i];
@@ -306,7 +308,7 @@ DATOK_HD bool chunk_stitch(const DeviceModel& m, const WalkBuffers& b, uint32_t 
   const uint32_t s = b.sync[i];
   if (s == K_NOPOS) { b.Ytmp[i] = X; return true; }
   const WalkCtx c = make_walk_ctx(m, b);
-  clear_chunk_bits(b, lo, s);
+  if (!first_round) clear_chunk_bits(b, lo, s);
   WState Y = X;
   SpecInfo si;
   const uint32_t err = walk_run<false, true, false>(c, Y, s, &si);

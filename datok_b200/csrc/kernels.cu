@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(WALK_THREADS, 6) stitch_kernel(DeviceModel m, 
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_list) return;
   const uint32_t i = list ? list[k] : k + 1;
-  if (chunk_stitch(m, b, i)) {
+  if (chunk_stitch(m, b, i, list == nullptr)) {  // list == nullptr: the first round over all chunks
     const uint32_t slot = atomicAdd(&b.counters[1], 1u);
     b.list_rewalk[slot] = i;
   }

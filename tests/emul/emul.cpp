@@ -135,7 +135,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
     rew.clear(); next.clear();
     for (size_t k = 0; k < list.size(); k++) {
       uint32_t i = list[order ? list.size() - 1 - k : k];
-      if (chunk_stitch(m, b, i)) rew.push_back(i);
+      if (chunk_stitch(m, b, i, R->rounds == 1)) rew.push_back(i);
     }
     R->n_stitch_mismatch += (uint32_t)rew.size();
     for (size_t k = 0; k < rew.size(); k++) {
