@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdatok_b200.so")
+# DATOK_B200_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("DATOK_B200_LIB") or os.path.join(HERE, "libdatok_b200.so")
 
 TOKENS, SENTENCES, TOKEN_POS, SENTENCE_POS, NEWLINE_AFTER_EOT = 1, 2, 4, 8, 16
 SIMPLE = TOKENS | SENTENCES

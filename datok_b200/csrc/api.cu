@@ -84,13 +84,15 @@ struct datok_model {
   std::vector<cudaEvent_t> tev;
   // pipelined host path: copy streams and double-buffered device staging
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr},
+  // (three input buffers: the copy engine runs up to two pieces ahead of the kernels; two result slots)
+  cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_free[3] = {nullptr, nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr},
               ev_out[2] = {nullptr, nullptr};
   uint32_t* h_mail = nullptr;    // mapped pinned host memory the kernels report small results through
   uint32_t* d_mail = nullptr;    // its device address
-  Block d_in[2];                 // input pieces
+  Block d_in[3];                 // input pieces
   Block d_out[2][5];             // per slot: tok_bytes, tok_pos, sent_pos, sent_tok, text arrays + DocRec
-  size_t piece_bytes = (size_t)64 << 20;
+  size_t piece_bytes = (size_t)64 << 20;  // smallest piece; also: inputs >= 2 * piece_bytes are pipelined
+  bool piece_fixed = false;               // DATOK_PIECE_MB: every piece has piece_bytes (else sized per call)
   bool pipelined = true;
   // results hold pooled buffers of their model: the model outlives them
   int live_results = 0;
@@ -156,9 +158,12 @@ void destroy_model(datok_model* m) {
   if (m->d_cls_tables) cudaFree(m->d_cls_tables);
   if (m->d_rune_key) cudaFree(m->d_rune_key);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
-  for (int i = 0; i < 2; i++) {
-    for (cudaEvent_t e : {m->ev_in[i], m->ev_free[i], m->ev_emit[i], m->ev_out[i]}) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 3; i++) {
+    for (cudaEvent_t e : {m->ev_in[i], m->ev_free[i]}) if (e) cudaEventDestroy(e);
     if (m->d_in[i].p) cudaFree(m->d_in[i].p);
+  }
+  for (int i = 0; i < 2; i++) {
+    for (cudaEvent_t e : {m->ev_emit[i], m->ev_out[i]}) if (e) cudaEventDestroy(e);
     for (auto& blk : m->d_out[i]) if (blk.p) cudaFree(blk.p);
   }
   if (m->h_mail) cudaFreeHost(m->h_mail);
@@ -387,16 +392,18 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
   }
   cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming);
+  }
+  for (int i = 0; i < 2; i++) {
     cudaEventCreateWithFlags(&m->ev_emit[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming);
   }
   if (const char* s = std::getenv("DATOK_NO_PIPELINE")) m->pipelined = !(s[0] == '1');
   if (const char* s = std::getenv("DATOK_PIECE_MB")) {
     long v = std::atol(s);
-    if (v >= 1 && v <= 2048) m->piece_bytes = (size_t)v << 20;
+    if (v >= 1 && v <= 2048) { m->piece_bytes = (size_t)v << 20; m->piece_fixed = true; }
   }
   m->n_sms = prop.multiProcessorCount;
   m->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
@@ -540,14 +547,19 @@ bool grow_block(Block& b, size_t bytes, bool host) {
 int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, const datok_carry* carry_in,
                   datok_result** out) {
   // ---- cut points: the last EOT before each multiple of piece_bytes ----
+  // A piece costs the kernels a fixed ~1 ms (fix-up rounds, host round trips) on top of ~7 us per MiB,
+  // the copy engine ~20 us per MiB: pieces of >= 96 MiB keep the call copy-bound.  The first piece is a
+  // third of that, so that the kernels start early.
   std::vector<size_t> cut;  // piece k = [cut[k], cut[k+1])
   cut.push_back(0);
-  while (n - cut.back() > m->piece_bytes + m->piece_bytes / 2) {
-    const size_t lo = cut.back(), want = lo + m->piece_bytes;
+  size_t piece = m->piece_bytes;
+  if (!m->piece_fixed) piece = std::min<size_t>(std::max<size_t>(n / 10, (size_t)64 << 20), (size_t)128 << 20);
+  while (n - cut.back() > piece + piece / 2) {
+    const size_t lo = cut.back(), sz = (cut.size() == 1 && !m->piece_fixed) ? piece / 3 : piece, want = lo + sz;
     const void* q = memrchr(in + lo, 0x04, want - lo);
     if (!q) return -1;
     const size_t c = (size_t)((const uint8_t*)q - in) + 1;
-    if (c - lo < m->piece_bytes / 2) return -1;  // texts longer than half a piece: not worth cutting
+    if (c - lo < sz / 2) return -1;  // texts longer than half a piece: not worth cutting
     cut.push_back(c);
   }
   cut.push_back(n);
@@ -564,7 +576,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
 
   size_t max_piece = 0;
   for (size_t k = 0; k < np; k++) max_piece = std::max(max_piece, cut[k + 1] - cut[k]);
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 3; i++)
     if (!grow_block(m->d_in[i], max_piece + 64, false)) { g_last_error = "cudaMalloc (input piece) failed"; return DATOK_ERR_CUDA; }
   WalkBuffers b;
   CompactBuffers cb;
@@ -582,11 +594,20 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   const bool want_spos = (flags & DATOK_SENTENCE_POS) != 0, want_stok = (flags & DATOK_SENTENCES) != 0;
   const bool want[5] = {want_bytes, want_pos || (compact8 && want_bytes), want_spos, want_stok, true};
 
+  // DATOK_PIPE_TRACE=1: per-piece timeline (copy-in, kernels, copy-out; ms since the call started) on stderr
+  const bool trace = std::getenv("DATOK_PIPE_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;  // 6 per piece: h2d begin/end, kernels begin/end, d2h begin/end
+  if (trace) {
+    tev.resize(6 * np);
+    for (auto& e : tev) cudaEventCreate(&e);
+  }
   // first pieces on their way
   auto issue_h2d = [&](size_t k) -> int {
-    const int slot = (int)(k & 1);
+    const int slot = (int)(k % 3);
     CUDA_TRY(cudaStreamWaitEvent(m->s_h2d, m->ev_free[slot], 0));  // the piece that used this buffer is done
+    if (trace) cudaEventRecord(tev[6 * k], m->s_h2d);
     CUDA_TRY(cudaMemcpyAsync(m->d_in[slot].p, in + cut[k], cut[k + 1] - cut[k], cudaMemcpyHostToDevice, m->s_h2d));
+    if (trace) cudaEventRecord(tev[6 * k + 1], m->s_h2d);
     CUDA_TRY(cudaEventRecord(m->ev_in[slot], m->s_h2d));
     return DATOK_OK;
   };
@@ -601,9 +622,10 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     rc = calibrate_locked(m, b);
     if (rc) return rc;
   }
-  for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventRecord(m->ev_free[i], s)); CUDA_TRY(cudaEventRecord(m->ev_out[i], s)); }
-  if ((rc = issue_h2d(0))) return rc;
-  if ((rc = issue_h2d(1))) return rc;
+  for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventRecord(m->ev_free[i], s));
+  for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventRecord(m->ev_out[i], s));
+  for (size_t k = 0; k < 3 && k < np; k++)
+    if ((rc = issue_h2d(k))) return rc;
 
   datok_result* r = new datok_result();
   r->model = m;
@@ -650,18 +672,21 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   std::vector<cudaEvent_t> kev;
 
   for (size_t k = 0; k < np; k++) {
-    const int slot = (int)(k & 1);
+    const int slot = (int)(k & 1), islot = (int)(k % 3);  // result slot, input buffer
+    // the copy of the piece after next goes out now: its buffer was freed by piece k - 1, whose kernels are done
+    if (k >= 1 && k + 2 < np && (rc = issue_h2d(k + 2))) return fail(rc);
     const uint32_t N = (uint32_t)(cut[k + 1] - cut[k]);
     const bool last_piece = k + 1 == np;
     const bool final_input = last_piece && call_final;
     uint32_t pflags = flags | (final_input ? 0u : (uint32_t)DATOK_NOT_FINAL);
     if (base_tok > 0) pflags |= DATOK_WRITER_USED;
     carve(m->ws, N, m->chunk, false, b, cb);
-    b.in = (const uint8_t*)m->d_in[slot].p;
+    b.in = (const uint8_t*)m->d_in[islot].p;
     b.final_input = final_input ? 1u : 0u;
-    CUDA_TRYF(cudaStreamWaitEvent(s, m->ev_in[slot], 0));
+    CUDA_TRYF(cudaStreamWaitEvent(s, m->ev_in[islot], 0));
     cudaEvent_t k0 = pt.next(), k1 = pt.next();
     CUDA_TRYF(cudaEventRecord(k0, s));
+    if (trace) cudaEventRecord(tev[6 * k + 2], s);
     if ((rc = do_walk(m, b, state, pt))) return fail(rc);
     CompactCtx c;
     PieceHead h;
@@ -731,8 +756,9 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       launch_mail(ms, m->d_mail, s);
     }
     CUDA_TRYF(cudaEventRecord(k1, s));
+    if (trace) cudaEventRecord(tev[6 * k + 3], s);
     CUDA_TRYF(cudaEventRecord(m->ev_emit[slot], s));
-    CUDA_TRYF(cudaEventRecord(m->ev_free[slot], s));
+    CUDA_TRYF(cudaEventRecord(m->ev_free[islot], s));
     CUDA_TRYF(cudaStreamSynchronize(s));
     std::memcpy(&tail.fin, m->h_mail, sizeof(StreamTotals));
     std::memcpy(&tail.err, m->h_mail + 8, sizeof tail.err);
@@ -748,8 +774,6 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       r->esc.resize(at + 2 * ne);
       CUDA_TRYF(cudaMemcpy(r->esc.data() + at, m->d_out[slot][1].p, ne * 8, cudaMemcpyDeviceToHost));
     }
-    // the input buffer of this slot is free again: next piece but one
-    if (k + 2 < np && (rc = issue_h2d(k + 2))) return fail(rc);
     // ---- results out, behind the kernels of the following pieces ----
     CUDA_TRYF(cudaStreamWaitEvent(m->s_d2h, m->ev_emit[slot], 0));
     const uint32_t* dtx = (const uint32_t*)m->d_out[slot][4].p;
@@ -763,9 +787,11 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
                        {6, dtx + 2 * nx, base_text * 4, (size_t)tail.fin.n_text * 4},
                        {7, dtx + 3 * nx, base_text * 4, (size_t)tail.fin.n_text * 4}};
     const bool want8[8] = {want_bytes, want_pos, want_spos, want_stok, true, true, true, true};
+    if (trace) cudaEventRecord(tev[6 * k + 4], m->s_d2h);
     for (const Cp& cp : cps)
       if (want8[cp.hi] && cp.bytes)
         CUDA_TRYF(cudaMemcpyAsync((uint8_t*)host[cp.hi].p + cp.off, cp.src, cp.bytes, cudaMemcpyDeviceToHost, m->s_d2h));
+    if (trace) cudaEventRecord(tev[6 * k + 5], m->s_d2h);
     CUDA_TRYF(cudaEventRecord(m->ev_out[slot], m->s_d2h));
     // ---- carry to the next piece ----
     base_tok += tail.fin.n_tok; base_sent += tail.fin.n_sent; base_sentpos += tail.fin.n_sentpos;
@@ -787,6 +813,15 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   CUDA_TRYF(cudaEventRecord(m->ev[3], s));
   CUDA_TRYF(cudaStreamSynchronize(s));
   pt.collect();
+  if (trace) {
+    for (size_t k = 0; k < np; k++) {
+      float t[6];
+      for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], m->ev[0], tev[6 * k + j]);
+      std::fprintf(stderr, "piece %2zu %9zu B  h2d %7.3f-%7.3f  kernels %7.3f-%7.3f  d2h %7.3f-%7.3f\n", k, cut[k + 1] - cut[k],
+                   t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
   for (size_t i = 0; i + 1 < kev.size(); i += 2) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, kev[i], kev[i + 1]) == cudaSuccess) ms_kernels += ms;

@@ -16,6 +16,9 @@
 // A lane writes boundary bits only inside its own chunk (walk_run's hand-off rule),
 // so no atomics are needed.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+
 #include "compact_core.cuh"
 #include "fast_core.cuh"
 #include "walk_core.cuh"
@@ -130,12 +133,49 @@ DATOK_HD void store_word_keep(uint32_t* p, uint32_t v) {
   *p = v;
 #endif
 }
+#if !defined(__CUDA_ARCH__)
+// host builds (tests/emul): the word a lane is about to store is checked against its chunk -- a store into
+// a neighbour's words is invisible to a sequential emulation but a race on the GPU
+static thread_local uint32_t g_own_lo = 0, g_own_hi = 0xFFFFFFFFu;
+#endif
 DATOK_HD void store_seg_bits(const WalkBuffers& b, uint32_t w, const SegBits& B) {
+#if !defined(__CUDA_ARCH__)
+  if (w < g_own_lo || w >= g_own_hi) { fprintf(stderr, "store_seg_bits: word %u outside [%u, %u)\n", w, g_own_lo, g_own_hi); abort(); }
+#endif
   store_word_keep(b.b_end + w, B.end); store_word_keep(b.b_skip + w, B.skip);
   store_word_keep(b.b_sent + w, B.sent); store_word_keep(b.b_tend + w, B.tend);
 }
 DATOK_HD void load_seg_bits(const WalkBuffers& b, uint32_t w, SegBits& B) {
   B.end = b.b_end[w]; B.skip = b.b_skip[w]; B.sent = b.b_sent[w]; B.tend = b.b_tend[w];
+}
+
+// Short look-ahead of the hand-off: what becomes of the epsilon point at eps_pos < hi that the lane
+// (state t at `hi`) still holds?
+//   LOOK_DEAD   a later state has an epsilon transition of its own and replaces it, or a boundary / a
+//               consumed EOT kills it (walk_run, PROBE): the arrival state stands
+//   LOOK_EXACT  left to the exact probe: a lookup fails within a few bytes of the point (the exact walker
+//               re-walks that short distance at less cost than the lanes of the warp waiting for this one
+//               to repeat whole segments), or a rare case, the window limit, the end of the input
+//   LOOK_PROBE  still alive after LOOK bytes, or a failure far from the point (long tokens: compounds,
+//               markup): the lane reads on through the fast path
+enum { LOOK_DEAD = 0, LOOK_EXACT = 1, LOOK_PROBE = 2 };
+#ifndef DATOK_NEAR_BACKTRACK
+#define DATOK_NEAR_BACKTRACK 8
+#endif
+constexpr uint32_t NEAR_BACKTRACK = DATOK_NEAR_BACKTRACK;  // bytes: up to this distance the exact walker re-walks
+DATOK_HD int look_ahead(const FastTables& FT, const WalkCtx& c, uint32_t t, uint32_t hi, uint32_t base, uint32_t eps_pos) {
+  constexpr uint32_t LOOK = 16;
+  if (eps_target(FT, t) != 0) return LOOK_DEAD;
+  if (hi + LOOK > c.N || hi + LOOK - base >= FAST_WINDOW_GUARD) return LOOK_EXACT;
+  for (uint32_t k = 0; k < LOOK; k++) {
+    const uint32_t cl = cls_at(c, hi + k);
+    const uint32_t e3 = t3_load(FT, t, cl);
+    if (e3 & F3_SLOWMARK) return LOOK_EXACT;
+    if ((e3 & F3_TGT) == 0) return hi + k - eps_pos <= NEAR_BACKTRACK ? LOOK_EXACT : LOOK_PROBE;
+    if ((e3 & (F3_KANY | F3_EA)) || cl == K_CLS_EOT) return LOOK_DEAD;
+    t = e3 & F3_TGT;
+  }
+  return LOOK_PROBE;
 }
 
 // K1+K2a fused: classification and speculative walk of chunk i, segment by segment
@@ -151,6 +191,9 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   const WalkCtx c = make_walk_ctx(m, b);
   const uint32_t lo = i * b.chunk, hi = lo + b.chunk, N = b.N;
   const bool rewalk = from != nullptr;
+#if !defined(__CUDA_ARCH__)
+  g_own_lo = lo >> 5; g_own_hi = hi >> 5;
+#endif
   WState st;
   st.pos = st.tstart = st.base = st.hw = 0;
   st.eps_pos = 0; st.eps_state = 0; st.flags = 0; st.t = (uint16_t)start_state;
@@ -175,7 +218,39 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     if (first_seg < lo) first_seg = lo;
   }
 
-  for (uint32_t seg_start = first_seg; seg_start < hi; seg_start += SEG) {
+  // A backtrack to an epsilon point in an EARLIER segment (matrix.go:487-497) is taken by the exact walker
+  // (one iteration); the lane then goes back to that segment -- first_seg again, its boundary words are in
+  // memory like those of a re-walk's first segment -- and continues from there through the fast path.
+  //
+  // Hand-off through the fast path (the rule of walk_run's PROBE mode): at the chunk end an epsilon point
+  // below `hi` may still be pending.  The lane reads on in the same loop -- `probing`, writing nothing --
+  // until that point is dead: replaced by a newer one, or killed by a boundary / EOT.  If a lookup fails
+  // while the point is alive, the exact walker takes that one backtrack and the lane walks on from the
+  // point, inside its own chunk again.  Anything else (a rare case, the window limit, the end of the
+  // input) is left to the exact probe after the loop, from the arrival state.
+  // (One loop for everything, no jumps back into it: the lanes of a warp stay converged.)
+  // (as few values as possible live across the hot loop: it is very sensitive to register pressure)
+  enum { PH_WALK = 0, PH_PROBE = 1, PH_HANDED_OFF = 2, PH_GAVE_UP = 3 };
+  uint32_t phase = PH_WALK;
+  bool in_regs = !rewalk;  // the segment's boundary words live in B (else in memory: first segment of a re-walk)
+  for (uint32_t seg_start = first_seg;; seg_start += SEG) {
+    if (seg_start >= hi) {
+      if (phase == PH_WALK) {
+        // arrival at the chunk end: st is what the successor starts from, if it stands
+        if (fast && !halted) { B.end = B.skip = B.sent = B.tend = 0; to_exact(L, B, hi, FT, st); }
+        if (!fast || halted || L.first_window || hi >= N) break;  // the exact probe decides
+        const int look = st.eps_state == 0 ? LOOK_DEAD : look_ahead(FT, c, L.t, hi, L.base, st.eps_pos);
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+        g_probe[2]++;
+        if (st.eps_state == 0 || eps_target(FT, L.t) != 0) g_probe[3]++;
+        if (look == LOOK_PROBE) g_probe[0]++;
+#endif
+        if (look == LOOK_DEAD) phase = PH_HANDED_OFF;
+        if (look != LOOK_PROBE) break;
+        phase = PH_PROBE;
+      }
+      if (seg_start - hi >= 1024u || seg_start + SEG > N || seg_start + SEG - L.base >= FAST_WINDOW_GUARD) break;
+    }
     const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
     uint32_t rs, eotm;
     bool inv = false;
@@ -184,7 +259,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     // the next segment's sector on its way while this one is walked (no registers held)
     if (seg_end < hi && seg_end + SEG <= N) asm volatile("prefetch.global.L1 [%0];" :: "l"(b.in + seg_end));
 #endif
-    if (!rewalk) {
+    if (!rewalk && phase == PH_WALK) {
       store_word_keep(b.rstart + w, rs);
       if (inv) note_invalid_utf8(b);
     }
@@ -200,8 +275,6 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       L.t = m.start;
     }
     B.end = B.skip = B.sent = B.tend = 0;
-    bool in_regs = true;  // the segment's boundary words live in B (else in memory)
-    if (rewalk && seg_start == first_seg) in_regs = false;  // the words of the first segment were prepared in memory
     if (fast && seg_end - L.base >= FAST_WINDOW_GUARD) {  // too close to the 1024-rune buffer limit
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
       g_guard++;
@@ -215,12 +288,28 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       if (fast) {
         const int rc = fast_run(L, R, FT, seg_cls, seg_start, limit, eotm, B);
         if (!fast_flush(L, R, B, eotm, seg_start)) {  // two SentenceEnds at one position
+          if (phase == PH_PROBE) { phase = PH_GAVE_UP; break; }
           err = E_DEGENERATE;
           st = wstate_invalid(E_DEGENERATE);
           halted = true;
           break;
         }
         if (rc == FAST_OK && L.pos >= seg_end) break;  // segment done, stay fast
+        if (phase == PH_PROBE) {
+          phase = PH_GAVE_UP;
+          if (rc == FAST_SLOW_FAIL && L.eps_rec && L.eps_p < hi) {
+            // (the flush has just confirmed that the point is alive: the failing iteration is this backtrack)
+            to_exact(L, B, seg_start, FT, st);
+            SpecInfo dummy;
+            err = walk_run<false, false, false>(c, st, st.pos + 1, &dummy, 0);
+            phase = PH_WALK;
+            fast = false;
+            // (stale bufft, matrix.go:573-576: the exact walker takes the lane to the chunk end; as above)
+            if (!err && !can_go_fast(st)) err = walk_run<false, false, false>(c, st, hi, &dummy);
+            if (err) halted = true;  // the stream itself is in error here
+          }
+          break;
+        }
         lane_note_first_rewind(L, B, seg_start);
         to_exact(L, B, seg_start, FT, st);              // rare case, or end of input
         fast = false;
@@ -237,37 +326,73 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
         continue;
       }
       if (st.pos >= seg_end) break;
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+      if (must_walk_exact) g_nf[0]++;
+      else if (st.pos < seg_start || st.pos >= N) g_nf[1]++;
+      else if (st.flags & ~WS_PEND) g_nf[2]++;
+      else if (st.tstart > st.pos) g_nf[3]++;
+      else g_nf[4]++;
+#endif
       if (in_regs) { store_seg_bits(b, w, B); in_regs = false; }
       SpecInfo si;
       si.first_hw = 0; si.had_rewind = 0;
+      // (resume_at 0: back after one iteration, wherever it led)
       if (L.first_window) {
-        err = walk_run<true, false, true>(c, st, seg_end, &si, seg_start);
+        err = walk_run<true, false, true>(c, st, seg_end, &si, 0);
         if (si.had_rewind) { L.first_hw = si.first_hw; L.first_window = 0; }
       } else {
-        err = walk_run<false, false, false>(c, st, seg_end, &si, seg_start);
+        err = walk_run<false, false, false>(c, st, seg_end, &si, 0);
       }
       if (err || (st.flags & WS_DONE)) { halted = true; break; }
       must_walk_exact = false;
+      // far backtrack (this segment's words are in memory).  A lane with a stale bufft (matrix.go:573-576)
+      // stays with the exact walker instead: the skipped runes ahead of it keep the SKIP bits they have there
+      // (a near one is re-walked by the exact walker, iteration by iteration: cheaper than the other lanes of
+      // the warp waiting for this one to repeat whole segments)
+      if (seg_start - st.pos > NEAR_BACKTRACK && st.pos < seg_start && can_go_fast(st)) break;
+    }
+    if (phase == PH_GAVE_UP) break;
+    if (!fast && !halted && st.pos < seg_start && seg_start - st.pos > NEAR_BACKTRACK) {  // back to the segment of the epsilon point: its words are in memory
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+      g_nf[2]++;
+#endif
+      seg_start = (st.pos & ~(SEG - 1)) - SEG;
+      in_regs = false;
+      continue;
+    }
+    if (seg_start >= hi) {  // beyond the chunk end: these words belong to the successor, nothing is stored
+      // (not probing any more: the probe's backtrack led the exact walker to the chunk end again, or into an
+      // error: the loop top deals with this arrival)
+      if (phase != PH_PROBE) continue;
+#if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
+      g_probe[1]++;
+#endif
+      if (!L.eps_rec || L.eps_p >= hi) { phase = PH_HANDED_OFF; break; }
+      L.base = lane_base(L, B, seg_start);
+      continue;
     }
     if (fast && !halted) {
       lane_note_first_rewind(L, B, seg_start);
       L.base = lane_base(L, B, seg_start);
     }
     if (in_regs) store_seg_bits(b, w, B);
+    in_regs = true;
   }
 
-  if (!rewalk) b.sync[i] = sync;
   SpecInfo si;
   si.first_hw = L.first_hw; si.had_rewind = L.first_window ? 0u : 1u;
   if (!started) st = wstate_invalid(0);
   else if (!err && !(halted && (st.flags & WS_DONE))) {
-    if (fast) { B.end = B.skip = B.sent = B.tend = 0; to_exact(L, B, hi, FT, st); }
-    // hand-off at the chunk end (probe, walk_run)
-    if (L.first_window) err = walk_run<true, true, false>(c, st, hi, &si);
-    else { SpecInfo dummy; err = walk_run<false, true, false>(c, st, hi, &dummy); }
+    if (phase == PH_HANDED_OFF) { st.eps_state = 0; st.eps_pos = 0; }
+    else {
+      // hand-off at the chunk end (probe, walk_run) from the arrival state
+      if (L.first_window) err = walk_run<true, true, false>(c, st, hi, &si);
+      else { SpecInfo dummy; err = walk_run<false, true, false>(c, st, hi, &dummy); }
+    }
   } else if (!err && L.first_window) {
     si.first_hw = st.hw; si.had_rewind = 0;
   }
+  if (!rewalk) b.sync[i] = sync;
   if (rewalk) {
     b.Enew[i] = st;
     return;

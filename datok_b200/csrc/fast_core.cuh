@@ -101,7 +101,7 @@ struct SegBits {
   uint32_t end, skip, sent, tend;
 };
 
-enum { FAST_OK = 0, FAST_SLOW = 1 };
+enum { FAST_OK = 0, FAST_SLOW = 1, FAST_SLOW_FAIL = 2 };  // _FAIL: a lookup failed and the backtrack is not for the fast path
 
 #define DATOK_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
@@ -297,14 +297,19 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
                       uint32_t limit, uint32_t eotm, const SegBits& Bprev) {
   if (L.pos >= limit) return FAST_OK;
   const uint32_t lim_off = limit - seg_start;
-  const uint32_t end_bit = lim_off < 32 ? 1u << lim_off : 0u;
+  uint32_t end_bit = lim_off < 32 ? 1u << lim_off : 0u;
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(end_bit));  // opaque: otherwise recomputed (five instructions) in every iteration of the loop below
+#endif
   uint32_t off = L.pos - seg_start;
   uint32_t bit = 1u << off;
   uint32_t t = L.t, eps_off = L.eps_p - seg_start;  // eps_off wraps for older points
   uint32_t eps_rec = L.eps_rec ? ((L.eps_rec & F3_TGT) | ((L.eps_rec & F3_KANY) << 14)) : 0;
   uint32_t c1 = R.c1, c2 = R.c2, nt = R.nt;
 #if defined(__CUDA_ARCH__)
-  const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(seg_cls);
+  uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(seg_cls);
+  uint32_t row16 = T.row16;
+  asm volatile("" : "+r"(cls_saddr), "+r"(row16));  // opaque, like end_bit
 #endif
   // row of the lookup: the state's own, or the all-zero row n_hot ("see the full table") for a cold state,
   // which the loop top only sees on entry: the rare path below steps until the state is hot again
@@ -316,7 +321,7 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
     {
       uint32_t cl2;
       asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cl2) : "r"(cls_saddr + off));
-      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(T.hot_saddr + tl * T.row16 + cl2));
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(T.hot_saddr + tl * row16 + cl2));
     }
 #else
     e = h16_load(T, tl, seg_cls[off]);
@@ -359,7 +364,7 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
           L.eps_rec = eps_rec ? (ER_VALID | (eps_rec & F3_TGT) | ((eps_rec >> 14) & F3_KANY)) : 0;
           R.c1 = c1; R.c2 = c2; R.nt = nt;
           if (e3 != 0) { DATOK_STAT(g_mark); return FAST_SLOW; }
-          if (fast_backtrack(L, R, T, seg_start, eotm, Bprev) != FAST_OK) return FAST_SLOW;
+          if (fast_backtrack(L, R, T, seg_start, eotm, Bprev) != FAST_OK) return FAST_SLOW_FAIL;
           off = L.pos - seg_start; bit = 1u << off;
           t = L.t; eps_rec = 0;
           c1 = R.c1; c2 = R.c2; nt = R.nt;

@@ -18,8 +18,14 @@ struct CompactBuffers {
   uint32_t n_blocks;
 };
 
-constexpr int COMPACT_THREADS = 256;
-constexpr int COMPACT_WPT = 2;     // bitmap words per thread
+#ifndef DATOK_COMPACT_THREADS
+#define DATOK_COMPACT_THREADS 256
+#endif
+#ifndef DATOK_COMPACT_WPT
+#define DATOK_COMPACT_WPT 2
+#endif
+constexpr int COMPACT_THREADS = DATOK_COMPACT_THREADS;
+constexpr int COMPACT_WPT = DATOK_COMPACT_WPT;     // bitmap words per thread
 constexpr int SCAN_THREADS = 1024;
 constexpr int STAGE_TOKENS = 4096;  // tokens of one block staged in shared memory (else written directly)
 

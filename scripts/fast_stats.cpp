@@ -11,6 +11,8 @@
 static unsigned long long g_exact_calls, g_exact_steps, g_guard, g_fast, g_bt_ok, g_bt_hard, g_bt_far, g_bt_dead,
     g_bt_third, g_zone, g_mark, g_cold, g_bt_inline;
 static unsigned long long g_hist[65536];
+static unsigned long long g_probe[4];  // hand-off: probes started, probe segments walked, arrivals, arrivals decided at once
+static unsigned long long g_nf[5];  // exact-walker calls by reason: fast path gave up here, position outside the segment, flags, stale bufft, window guard
 #include "../datok_b200/csrc/chunk_core.cuh"
 #include "../datok_b200/csrc/model.hpp"
 using namespace datok;
@@ -23,6 +25,7 @@ int main(int argc, char** argv) {
   for (int t = 1; t <= hm.stateCount; t++) hist_old[hm.old_of_new[t]] = g_hist[t];
   if (build_layout(hm, why, hist_old.data())) return 1;
   g_exact_calls = g_exact_steps = g_guard = g_fast = g_bt_ok = g_bt_hard = g_bt_far = g_bt_dead = g_bt_third = g_zone = g_mark = g_cold = g_bt_inline = 0;
+  memset(g_nf, 0, sizeof g_nf); memset(g_probe, 0, sizeof g_probe);
   return run(argc, argv, hm, true);
 }
 int run(int argc, char** argv, HostModel& hm, bool report) {
@@ -57,5 +60,9 @@ int run(int argc, char** argv, HostModel& hm, bool report) {
          "slow: marks %llu, hard %llu, far %llu, dead %llu, third %llu; guard %llu\nexact calls %llu steps %llu (%.3f%% of bytes)\n",
          n, b.n_chunks, g_fast, g_cold, 100.0 * g_cold / g_fast, g_bt_ok, 100.0 * g_bt_ok / g_fast, g_zone, g_bt_inline, g_mark, g_bt_hard, g_bt_far,
          g_bt_dead, g_bt_third, g_guard, g_exact_calls, g_exact_steps, 100.0 * g_exact_steps / n);
+  if (report) printf("hand-off: %llu arrivals in the fast path, %llu decided at once, %llu by the look-ahead, %llu probes over %llu segments\n",
+         g_probe[2], g_probe[3], g_probe[2] - g_probe[3] - g_probe[0], g_probe[0], g_probe[1]);
+  if (report) printf("exact calls by reason: gave up here %llu, outside the segment %llu, flags %llu, stale bufft %llu, window guard %llu\n",
+         g_nf[0], g_nf[1], g_nf[2], g_nf[3], g_nf[4]);
   return 0;
 }

@@ -85,6 +85,22 @@ def test_tiny_chunks_on_markup_heavy_text(oracle_models, emul_models, corpus_lib
         assert s.stats["rounds"] > 5
 
 
+@pytest.mark.parametrize("name", ["longdoc_handoff_a.bin", "longdoc_handoff_b.bin"])
+def test_hand_off_with_stale_bufft_at_the_chunk_end(name, oracle_models, emul_models):
+    """regression (16 KiB windows of the C4 corpus): the hand-off probe of the chunk ending at byte 8192
+    backtracks to a SentenceEnd point one byte below the chunk end with a stale bufft (matrix.go:573-576).
+    The lane must not store anything beyond its chunk on the way back (a race on the GPU; the emulation
+    aborts on such a store, chunk_core.cuh store_seg_bits)."""
+    import os
+    a = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", name), dtype=np.uint8)
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
+    assert o.status == 0
+    for chunk, mode in ((512, 886), (512, 64), (256, 886), (1024, 300)):
+        for order in (0, 1):
+            s = emul_models["tokenizer_de.matok"].transduce(a, 15, chunk, order, mode=mode)
+            P.assert_matches_oracle(s, o, 15, f"{name} chunk={chunk} mode={mode} order={order}")
+
+
 def _fuzz_text(rng, n):
     alphabet = [b" ", b" ", b" ", b"\n", b"\t", b".", b",", b"!", b"?", b"\x04", b"<", b">", b"\"", b"'", b"&", b";",
                 b"-", b"/", b":", b"@", b"a", b"e", b"n", b"r", b"S", b"T", b"1", b"9", "ä".encode(), "ß".encode(),

@@ -164,6 +164,36 @@ def test_chunk_size_independence(testdata, oracle_models, monkeypatch):
         tok.close()
 
 
+@pytest.mark.parametrize("name", ["longdoc_handoff_a.bin", "longdoc_handoff_b.bin"])
+def test_hand_off_with_stale_bufft_at_the_chunk_end(name, gpu_models, oracle_models):
+    """regression: see tests/test_emul_parity.py (a lane stored into its successor's words)"""
+    import os
+    a = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", name), dtype=np.uint8)
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
+    for _ in range(20):  # (a race: not every run showed it)
+        s = gpu_arrays(gpu_models["tokenizer_de.matok"], a, 15)
+        P.assert_matches_oracle(s, o, 15, name)
+
+
+def test_long_document_corpus_in_windows(gpu_models, oracle_models):
+    """C4 (one long document, markup- and abbreviation-heavy: far backtracks, hand-off probes over long
+    tokens, fix-up rounds): 256 MiB against the oracle, in 64 MiB windows"""
+    from datok_b200 import corpus
+    n, w = 256 << 20, 64 << 20
+    a = np.empty(n, dtype=np.uint8)
+    corpus.generate_into(corpus.GERMAN_LONGDOC, corpus.SEED + 3, a)
+    tok = gpu_models["tokenizer_de.matok"]
+    for k in range(n // w):
+        part = np.ascontiguousarray(a[k * w:(k + 1) * w])
+        o = oracle_models["tokenizer_de.matok"].transduce_np(part, 3)
+        r = tok.transduce_arrays(part, 3)
+        assert r.n_tokens == o.n_tokens, f"window {k}"
+        np.testing.assert_array_equal(r.tok_bytes[0::2], o.tok_byte_start, err_msg=f"window {k}")
+        np.testing.assert_array_equal(r.tok_bytes[1::2], o.tok_byte_end, err_msg=f"window {k}")
+        np.testing.assert_array_equal(r.sent_tok, o.sent_tok_idx.astype(np.uint32), err_msg=f"window {k}")
+        r.close()
+
+
 def test_large_input_properties(gpu_models, oracle_models):
     """64 MiB German corpus: size-independent properties plus oracle parity on a prefix."""
     from datok_b200 import corpus
