@@ -306,6 +306,17 @@ def main():
         kroof = {k: {"ms": kt[k], "alg_bytes": b, "gbps": b / (kt[k] * 1e-3) / 1e9,
                      "frac": b / (kt[k] * 1e-3) / 1e9 / peak} for k, b in kalg.items() if kt.get(k)}
         dominant = max(kt, key=kt.get)
+        # second bound of the walk (R_gather): the bare dependent shared-memory gather chain
+        # of one byte step in the walk's own configuration, measured on this device (not part of the step)
+        try:
+            gsteps = tok.gather_bound()
+            walk_rate = N / (kt["walk_fused"] * 1e-3)
+            gather = {"peak": gsteps / 1e9, "achieved": walk_rate / 1e9, "unit": "G byte steps/s (= GB/s of input)",
+                      "frac": walk_rate / gsteps,
+                      "what": "peak: one ld.shared.u8 (class) + one dependent ld.shared.u16 (row entry) per byte and lane, "
+                              "1024-thread CTA per SM, nothing else; achieved: input bytes / walk_fused time"}
+        except Exception as e:
+            gather = {"peak": None, "error": str(e)}
         line = {
             "metric": METRIC, "value": Ntot / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -324,7 +335,7 @@ def main():
                          "algorithmic_bytes": alg_bytes, "formula": "N + 8*tokens + 8*sentences + 8*documents",
                          "kernel": "whole device path (all kernels of one step); per-kernel ms in kernel_ms, "
                                    "per-kernel rooflines in kernels",
-                         "dominant_kernel": dominant, "kernel_ms": kt, "kernels": kroof},
+                         "dominant_kernel": dominant, "kernel_ms": kt, "kernels": kroof, "gather": gather},
             "cpu_baseline": cpu,
             "e2e": {"value": Ntot / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,

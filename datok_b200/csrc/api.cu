@@ -1146,6 +1146,34 @@ int datok_last_kernel_times(const datok_model* m, const char** names, float* ms,
 
 int datok_last_launch_count(const datok_model* m) { return m ? m->launches : 0; }
 
+int datok_measure_gather_bound(datok_model* m, double* byte_steps_per_s) {
+  if (!m || !byte_steps_per_s) return DATOK_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(m->mu);
+  CUDA_TRY(cudaSetDevice(m->device));
+  const uint32_t row16 = m->dm.stride16 * 2u, segs = 256;
+  int rc = ensure_workspace(m, 4096);
+  if (rc) return rc;
+  uint32_t* sink = reinterpret_cast<uint32_t*>(m->ws);
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  float best = 0;
+  for (int it = 0; it < 4; it++) {  // the first launch warms up
+    CUDA_TRY(cudaEventRecord(a, m->stream));
+    const int e = launch_gather_bound(m->n_hot, row16, segs, m->n_sms, sink, m->stream);
+    if (e != 0) { g_last_error = std::string("gather_bound launch: ") + cudaGetErrorString((cudaError_t)e); return DATOK_ERR_CUDA; }
+    CUDA_TRY(cudaEventRecord(b, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    if (it > 0 && (best == 0 || ms < best)) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *byte_steps_per_s = (double)m->n_sms * 1024.0 * segs * 32.0 / (best * 1e-3);
+  return DATOK_OK;
+}
+
 void* datok_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }

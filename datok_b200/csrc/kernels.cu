@@ -153,9 +153,60 @@ void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cud
   hist_kernel<<<(b.n_chunks + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, hist);
 }
 
+// ------------------------------------------------------------------ gather bound (measurement only)
+
+// What the hardware allows a lane-per-chunk table walk of this shape: the walk's configuration (one
+// 1024-thread CTA per SM, the compact rows in shared memory) with nothing but the dependent chain of one
+// byte step -- class byte from the lane's scratch, row entry of (state, class), next state -- and one
+// XOR to keep the result.  bench.py reports the fused walk against this figure next to the HBM roofline
+// (R_gather).  The rows hold pseudo-random targets below n_rows.
+__global__ void __launch_bounds__(1024, 1) gather_bound_kernel(uint32_t n_rows, uint32_t row16, uint32_t segs, uint32_t* sink) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);
+  const uint32_t entries = n_rows * (row16 / 2);
+  uint8_t* s_cls = reinterpret_cast<uint8_t*>(smem) + ((entries * 2u + 15u) & ~15u);
+  uint32_t x = 0x9E3779B9u * (blockIdx.x + 1);
+  for (uint32_t k = threadIdx.x; k < entries; k += 1024) {
+    uint32_t h = (k + x) * 2654435761u;
+    h ^= h >> 15;
+    s_hot[k] = (uint16_t)(h % n_rows);
+  }
+  uint8_t* my = s_cls + threadIdx.x * LANE_CLS_STRIDE;
+  for (uint32_t k = 0; k < 32; k++) {
+    uint32_t h = (threadIdx.x * 32 + k + x) * 2246822519u;
+    h ^= h >> 13;
+    my[k] = (uint8_t)(2u * (h % (row16 / 2)));
+  }
+  __syncthreads();
+  const uint32_t hot_saddr = (uint32_t)__cvta_generic_to_shared(s_hot), cls_saddr = (uint32_t)__cvta_generic_to_shared(my);
+  uint32_t t = threadIdx.x % n_rows, acc = 0;
+  for (uint32_t sg = 0; sg < segs; sg++) {
+#pragma unroll 1
+    for (uint32_t off = 0; off < 32; off++) {
+      uint32_t cl2, e;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cl2) : "r"(cls_saddr + off));
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(hot_saddr + t * row16 + cl2));
+      acc ^= e + off;
+      t = e;
+    }
+  }
+  if (acc == 0x12345678u) sink[0] = acc;  // (keeps the chain alive)
+}
+
+int launch_gather_bound(uint32_t n_rows, uint32_t row16, uint32_t segs, int n_sms, uint32_t* sink, cudaStream_t s) {
+  const size_t smem = (((size_t)n_rows * row16 + 15) & ~(size_t)15) + 1024 * LANE_CLS_STRIDE;
+  cudaError_t e = cudaFuncSetAttribute(gather_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  gather_bound_kernel<<<n_sms, 1024, smem, s>>>(n_rows, row16, segs, sink);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ K2b-d
 
-__global__ void __launch_bounds__(WALK_THREADS, 6) stitch_kernel(DeviceModel m, WalkBuffers b, const uint32_t* list,
+#ifndef DATOK_STITCH_MINB
+#define DATOK_STITCH_MINB 6
+#endif
+__global__ void __launch_bounds__(WALK_THREADS, DATOK_STITCH_MINB) stitch_kernel(DeviceModel m, WalkBuffers b, const uint32_t* list,
                                                               uint32_t n_list) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_list) return;
@@ -296,8 +347,26 @@ __device__ __forceinline__ Agg warp_exclusive_scan(const Agg& mine, const Agg& s
 
 enum { K3_REDUCE = 0, K3_TEXTS = 1, K3_EMIT = 2 };
 
+// K3a: a CTA takes one block of THREADS * WPT words after the other (grid-stride) and leaves its summary in
+// block_agg[block] (and the warp totals in warp_agg) -- the same units the texts and emit passes use.
+__global__ void __launch_bounds__(COMPACT_THREADS) compact_reduce_kernel(CompactCtx c, CompactBuffers cb) {
+  for (uint32_t vb = blockIdx.x; vb < cb.n_blocks; vb += gridDim.x) {
+    const uint32_t w0 = (vb * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
+    Agg ta = agg_zero();
+#pragma unroll
+    for (int k = 0; k < COMPACT_WPT; k++) {
+      const uint32_t w = w0 + k;
+      if (w < c.n_words) ta = agg_combine(ta, word_agg(w, word_load(c, w)));
+    }
+    const Agg tot = block_reduce<COMPACT_THREADS>(ta, cb.warp_agg + (size_t)vb * (COMPACT_THREADS / 32));
+    if (threadIdx.x == 0) cb.block_agg[vb] = tot;
+    __syncthreads();  // block_reduce's shared slots are reused by the next block
+  }
+}
+
+
 // One pass over the bitmaps, COMPACT_WPT words per thread.
-//   K3_REDUCE  block summaries
+//   (block summaries: compact_reduce_kernel)
 //   K3_TEXTS   TextEnd events: per-text bounds and the DocRec table
 //   K3_EMIT    Token and SentenceEnd events; a block's tokens are staged in shared memory and
 //              written out as contiguous 8-byte pairs
@@ -305,35 +374,41 @@ template <int MODE>
 __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, CompactBuffers cb) {
   extern __shared__ __align__(16) uint32_t s_stage[];
   if (MODE == K3_TEXTS) {
-    // TextEnds are rare (one per text): warps work on their own and leave when their words hold none
+    // TextEnds are rare (one per text).  A warp takes one warp unit of the reduce pass after
+    // the other (32 * COMPACT_WPT words, whose prefix that pass left behind) and moves on at once when
+    // the unit's TEND words hold none -- the pass is one read of that bitmap.
     if (blockIdx.x == 0 && threadIdx.x == 0) c.docs[0] = doc_stream_start(c);
-    const uint32_t wt0 = (blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
-    uint32_t anyt = 0;
+    constexpr uint32_t UNIT = 32 * COMPACT_WPT, WARPS = COMPACT_THREADS / 32;
+    const uint32_t n_units = (c.n_words + UNIT - 1) / UNIT, lane = threadIdx.x & 31;
+    for (uint32_t u = blockIdx.x * WARPS + (threadIdx.x >> 5); u < n_units; u += gridDim.x * WARPS) {
+      const uint32_t wt0 = u * UNIT + lane * COMPACT_WPT;
+      uint32_t anyt = 0;
 #pragma unroll
-    for (int k = 0; k < COMPACT_WPT; k++)
-      if (wt0 + k < c.n_words) anyt |= c.b_tend[wt0 + k];
-    if (!__any_sync(0xFFFFFFFFu, anyt != 0)) return;
-    const int warp = threadIdx.x >> 5;
-    Agg seed = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
-    const Agg* wagg = cb.warp_agg + (size_t)blockIdx.x * (COMPACT_THREADS / 32);
-    for (int wi = 0; wi < warp; wi++) seed = agg_combine(seed, wagg[wi]);
-    WordBits tb[COMPACT_WPT];
-    Agg tw[COMPACT_WPT];
-    Agg mine = agg_zero();
+      for (int k = 0; k < COMPACT_WPT; k++)
+        if (wt0 + k < c.n_words) anyt |= c.b_tend[wt0 + k];
+      if (!__any_sync(0xFFFFFFFFu, anyt != 0)) continue;
+      const uint32_t blk = u / WARPS, warp = u % WARPS;  // the reduce pass's block and warp of this unit
+      Agg seed = agg_combine(cb.super_carry[blk / SCAN_THREADS], cb.block_carry[blk]);
+      const Agg* wagg = cb.warp_agg + (size_t)blk * WARPS;
+      for (uint32_t wi = 0; wi < warp; wi++) seed = agg_combine(seed, wagg[wi]);
+      WordBits tb[COMPACT_WPT];
+      Agg tw[COMPACT_WPT];
+      Agg mine = agg_zero();
 #pragma unroll
-    for (int k = 0; k < COMPACT_WPT; k++) {
-      if (wt0 + k < c.n_words) {
-        tb[k] = word_load(c, wt0 + k);
-        tw[k] = word_agg(wt0 + k, tb[k]);
-        mine = agg_combine(mine, tw[k]);
+      for (int k = 0; k < COMPACT_WPT; k++) {
+        if (wt0 + k < c.n_words) {
+          tb[k] = word_load(c, wt0 + k);
+          tw[k] = word_agg(wt0 + k, tb[k]);
+          mine = agg_combine(mine, tw[k]);
+        }
       }
-    }
-    Agg run = warp_exclusive_scan(mine, seed);
+      Agg run = warp_exclusive_scan(mine, seed);
 #pragma unroll
-    for (int k = 0; k < COMPACT_WPT; k++) {
-      if (wt0 + k < c.n_words) {
-        emit_texts(c, wt0 + k, tb[k], run);
-        run = agg_combine(run, tw[k]);
+      for (int k = 0; k < COMPACT_WPT; k++) {
+        if (wt0 + k < c.n_words) {
+          emit_texts(c, wt0 + k, tb[k], run);
+          run = agg_combine(run, tw[k]);
+        }
       }
     }
     return;
@@ -350,11 +425,6 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
       wa[k] = word_agg(w, wb[k]);
       ta = agg_combine(ta, wa[k]);
     }
-  }
-  if (MODE == K3_REDUCE) {
-    const Agg tot = block_reduce<COMPACT_THREADS>(ta, cb.warp_agg + (size_t)blockIdx.x * (COMPACT_THREADS / 32));
-    if (threadIdx.x == 0) cb.block_agg[blockIdx.x] = tot;
-    return;
   }
   // summary of everything before this block: (groups of 1024 blocks before) + (blocks before, in the group)
   const Agg block_start = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
@@ -455,7 +525,9 @@ __global__ void compact_finalize_kernel(CompactCtx c, CompactBuffers cb, bool te
 }
 
 void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
-  compact_kernel<K3_REDUCE><<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
+  // one CTA per block of words: measured faster than a persistent grid of 8 CTAs per SM looping over the
+  // blocks (0.26 against 0.31 ms per GiB); the kernel's loop then runs once
+  compact_reduce_kernel<<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
 }
 void launch_compact_scan(const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s) {
   const uint32_t groups = (cb.n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -463,6 +535,7 @@ void launch_compact_scan(const CompactBuffers& cb, bool sentence_end_in, cudaStr
   compact_scan_top_kernel<<<1, SCAN_THREADS, 0, s>>>(cb, sentence_end_in);
 }
 void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
+  // (any grid works: the warps stride over the units; a persistent grid of 8 CTAs per SM measured the same)
   compact_kernel<K3_TEXTS><<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
 }
 int launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {

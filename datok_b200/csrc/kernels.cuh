@@ -36,6 +36,8 @@ int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start
                       cudaStream_t s, int threads);
 size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot, int threads);
 uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states, int threads);
+// measurement only: the dependent shared-memory gather chain of one byte step, nothing else (bench.py)
+int launch_gather_bound(uint32_t n_rows, uint32_t row16, uint32_t segs, int n_sms, uint32_t* sink, cudaStream_t s);
 // calibration histogram (visits per state, GPU numbering)
 void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cudaStream_t s);
 // one fix-up round over `n_list` chunks (list == nullptr: all chunks 1..n_chunks-1)

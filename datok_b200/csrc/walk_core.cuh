@@ -175,7 +175,8 @@ DATOK_HD uint32_t classify_pos(const uint8_t* in, uint32_t N, uint32_t p, const 
 
 // Machine state at the top of the reference's loop with newchar == true
 // (matrix.go:384-386), in absolute byte positions.
-struct WState {
+// (32 bytes, 16-byte aligned: one DRAM sector per chunk record, moved with two 128-bit accesses)
+struct alignas(16) WState {
   uint32_t pos;        // base + buffc
   uint32_t tstart;     // base + bufft
   uint32_t eps_pos;    // base + epsilonOffset
@@ -184,6 +185,7 @@ struct WState {
   uint16_t t;          // current state, GPU numbering
   uint16_t eps_state;  // epsilonState (0 = none)
   uint32_t flags;      // WS_* bits
+  uint32_t reserved;
 };
 constexpr uint32_t WS_PEND = 1;     // a hard-fail token ends exactly at `pos`; its END bit is still to be set
 constexpr uint32_t WS_DONE = 2;     // EOF tail finished (matrix.go:650-678)

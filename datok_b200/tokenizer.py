@@ -291,6 +291,14 @@ class MatrixTokenizer:
         L.datok_format(res._h, addr, n, flags, out, need)
         return out.raw[:need]
 
+    def gather_bound(self):
+        """byte steps per second of the bare shared-memory gather chain of the walk (measurement only)"""
+        v = C.c_double()
+        rc = _lib.lib().datok_measure_gather_bound(self._h, C.byref(v))
+        if rc:
+            _raise(rc)
+        return v.value
+
     def kernel_times(self):
         L = _lib.lib()
         names = (C.c_char_p * 16)()

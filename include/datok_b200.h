@@ -184,6 +184,11 @@ int datok_last_kernel_times(const datok_model *m, const char **names, float *ms,
 /* number of kernel launches issued by the last call */
 int datok_last_launch_count(const datok_model *m);
 
+/* Measurement only (bench.py, SURVEY.md 8d "R_gather"): byte steps per second of the bare dependent
+ * shared-memory gather chain of the walk (class byte -> row entry -> next state) in the walk's own
+ * configuration on this device: the bound of any lane-per-chunk table walk of this shape. */
+int datok_measure_gather_bound(datok_model *m, double *byte_steps_per_s);
+
 /* Page-locked host memory for inputs: host->device copies from it run at full
  * PCIe speed and asynchronously.  Any other host pointer works too, slower. */
 void *datok_host_alloc(size_t bytes);

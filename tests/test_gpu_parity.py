@@ -194,6 +194,12 @@ def test_long_document_corpus_in_windows(gpu_models, oracle_models):
         r.close()
 
 
+def test_gather_bound_measurement(gpu_models):
+    """bench.py's second bound (the bare gather chain of the walk): runs and gives a plausible rate"""
+    g = gpu_models["tokenizer_de.matok"].gather_bound()
+    assert 1e11 < g < 1e14
+
+
 def test_large_input_properties(gpu_models, oracle_models):
     """64 MiB German corpus: size-independent properties plus oracle parity on a prefix."""
     from datok_b200 import corpus
