@@ -436,7 +436,7 @@ DATOK_HD bool chunk_stitch(const DeviceModel& m, const WalkBuffers& b, uint32_t 
   if (!first_round) clear_chunk_bits(b, lo, s);
   WState Y = X;
   SpecInfo si;
-  const uint32_t err = walk_run<false, true, false>(c, Y, s, &si);
+  const uint32_t err = walk_run_inl<false, true, false>(c, Y, s, &si);
   if (err) { b.Enew[i] = Y; return false; }
   const WState A = b.exitA[i];
   // (a pending hard-fail END bit at s does not disturb the guess: it is set below)

@@ -266,9 +266,12 @@ struct SpecInfo {
 // resume_at (PROBE == false only): additionally return at the first loop top with
 // pos >= resume_at once at least one iteration has been executed -- the fast path
 // uses this to take the lane back as soon as the rare case is dealt with.
+// walk_run_inl: the body, inlined into its caller (the stitch kernel: context and state stay in registers
+// instead of a stack frame per thread); walk_run: the same, as a call (the fused walk kernel, where the
+// rare paths must stay out of the hot loop's registers).
 template <bool SPEC, bool PROBE, bool STOP_REWIND>
-DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo* spec,
-                                uint32_t resume_at = 0xFFFFFFFFu) {
+DATOK_HD uint32_t walk_run_inl(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo* spec,
+                               uint32_t resume_at = 0xFFFFFFFFu) {
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
   g_exact_calls++;
 #endif
@@ -426,6 +429,12 @@ out:
   st.pos = pos; st.tstart = tstart; st.eps_pos = eps_state ? eps_pos : 0; st.base = base; st.hw = hw;
   st.t = (uint16_t)t; st.eps_state = (uint16_t)eps_state; st.flags = flags;
   return 0;
+}
+
+template <bool SPEC, bool PROBE, bool STOP_REWIND>
+DATOK_HD_SLOW uint32_t walk_run(const WalkCtx& c, WState& st, uint32_t stop, SpecInfo* spec,
+                                uint32_t resume_at = 0xFFFFFFFFu) {
+  return walk_run_inl<SPEC, PROBE, STOP_REWIND>(c, st, stop, spec, resume_at);
 }
 
 DATOK_HD bool sync_class(const uint32_t* mask, uint32_t cl) { return (mask[cl >> 5] >> (cl & 31)) & 1u; }
