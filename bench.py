@@ -326,7 +326,7 @@ def main():
                                    "8-byte delta-coded token spans; host legs: DATOK_COMPACT8, 4 bytes per token)",
                        "bytes_per_gpu": N, "documents_per_gpu": D, "tokens_per_gpu": T, "sentences_per_gpu": S,
                        "l2": "input (>= 1 GiB) and outputs exceed the 126 MB L2; no flush needed",
-                       "chunk_bytes": int(os.environ.get("DATOK_CHUNK", "512")),
+                       "chunk_bytes": int(os.environ.get("DATOK_CHUNK", "640")),
                        "calibration": "state order specialised once on the first 8 MiB of the corpus (untimed warm-up)",
                        "timing": "CUDA events on the library's stream around the whole device path, max over ranks",
                        "ms_per_step_wall": ms_wall},
