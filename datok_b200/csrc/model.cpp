@@ -41,6 +41,13 @@ static uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16
 
 int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why) {
   // magic + 14-byte little-endian header (matrix.go:246-285)
+  if (n >= 5 && std::memcmp(d, "DATOK", 5) == 0) {
+    // LoadTokenizerFile (fomafile.go:452-484) also accepts the double-array format.  Its walk is the same loop
+    // except that an EOT does not rewind the buffer (datok.go:1019-1030); the CPU oracle has it (pinned on
+    // datok_test.go), the CUDA path does not yet.
+    why = "double-array model (DATOK): not supported yet, use the .matok model";
+    return DATOK_ERR_UNSUPPORTED_MODEL;
+  }
   if (n < 19 || std::memcmp(d, "MATOK", 5) != 0) { why = "Not a matok file"; return DATOK_ERR_FORMAT; }
   const uint8_t* h = d + 5;
   if (rd16(h) != 1) { why = "Version not compatible"; return DATOK_ERR_FORMAT; }

@@ -93,6 +93,10 @@ struct ora_model {
   int32_t *hval;
   uint32_t *array;
   size_t arraySize;
+  /* 1: MatrixTokenizer (matrix.go), 0: DaTokenizer (datok.go), converted to the same dense layout at
+   * load time.  The two transduction loops differ in one statement: the double-array one does not
+   * rewind the buffer at an EOT (datok.go:1019-1030 has no `rewindBuffer = true`, matrix.go:603 has). */
+  int eot_rewind;
 };
 
 static inline uint32_t hash_rune(int32_t r) { return (uint32_t)r * 2654435761u; }
@@ -156,6 +160,99 @@ static ora_model *parse_matrix(const uint8_t *d, size_t n) {
   if (n - p < m->arraySize * 4) { ora_free(m); return NULL; } /* :327-330 */
   m->array = (uint32_t *)malloc(m->arraySize * 4 + 4);
   for (size_t x = 0; x < m->arraySize; x++) m->array[x] = le32(d + p + x * 4); /* :332-334 */
+  m->eot_rewind = 1;
+  return m;
+}
+
+/* ParseDatok datok.go:621-729 over an in-memory image, followed by a conversion of the double array
+ * into the dense layout of the matrix (same cell meaning: target state, FIRSTBIT = non-token target).
+ * A transition of the double array (datok.go:888-902,1058-1066):
+ *     t = base(t0) + a;  valid iff t <= check(array[1]) and check(array[t]) == t0;
+ *     non-token iff check-word FIRSTBIT of array[t];  the state that follows is base(array[t]) if
+ *     array[t] is "separate" (base-word FIRSTBIT: it points to its representative), else t.
+ * States are renumbered densely in breadth-first order from state 1 (which stays 1); state identity
+ * is only observable through transitions, so the walk is the same. */
+#define DA_RESTBIT 0x3FFFFFFFu
+static ora_model *parse_datok(const uint8_t *d, size_t n) {
+  size_t p = 0;
+  if (n < 5 || memcmp(d, "DATOK", 5) != 0) return NULL; /* :651 */
+  p = 5;
+  if (n - p < 16) return NULL; /* :656-665 */
+  if (le16(d + p) != VERSION) return NULL; /* :667-672 */
+  ora_model *m = (ora_model *)calloc(1, sizeof(*m));
+  m->epsilon = le16(d + p + 2);
+  m->unknown = le16(d + p + 4);
+  m->identity = le16(d + p + 6);
+  /* final = le16(d + p + 8): not used by the transduction */
+  m->sigmaCount = le16(d + p + 10);
+  const size_t daSize = (size_t)le32(d + p + 12) / 2; /* :681 "legacy support" */
+  p += 16;
+  for (int i = 0; i < 256; i++) m->sigmaASCII[i] = m->identity; /* :686-691 */
+  uint32_t cap = 64;
+  while (cap < (uint32_t)m->sigmaCount * 4u) cap <<= 1;
+  m->hmask = cap - 1;
+  m->hkey = (int32_t *)malloc(cap * sizeof(int32_t));
+  m->hval = (int32_t *)malloc(cap * sizeof(int32_t));
+  for (uint32_t i = 0; i < cap; i++) m->hkey[i] = -1;
+  for (int x = 0; x < m->sigmaCount; x++) { /* :693-701 */
+    int w;
+    int32_t sym = ora_decode_rune(d + p, n - p, &w);
+    if (w == 0) continue;
+    p += (size_t)w;
+    if (sym != 0) {
+      if (sym < 256) m->sigmaASCII[sym] = x;
+      sigma_put(m, sym, x);
+    }
+  }
+  if (p >= n || d[p] != 'T') { ora_free(m); return NULL; } /* :703-713 */
+  p++;
+  if (n - p < daSize * 8 || daSize < 2) { ora_free(m); return NULL; } /* :722-725 */
+  const uint8_t *da = d + p; /* entry x: base = le32(da + 8x), check = le32(da + 8x + 4) */
+#define DA_BASE(x) (le32(da + 8 * (size_t)(x)))
+#define DA_CHECK(x) (le32(da + 8 * (size_t)(x) + 4))
+  const uint32_t maxIndex = DA_CHECK(1) & DA_RESTBIT; /* :891 dat.array[1].getCheck() */
+  /* breadth-first renumbering */
+  uint32_t *id = (uint32_t *)calloc(daSize, sizeof(uint32_t));
+  uint32_t *queue = (uint32_t *)malloc(daSize * sizeof(uint32_t));
+  size_t qh = 0, qt = 0;
+  id[1] = 1;
+  queue[qt++] = 1;
+  int ok = 1;
+  while (qh < qt && ok) {
+    const uint32_t t0 = queue[qh++];
+    const uint32_t b = DA_BASE(t0) & DA_RESTBIT;
+    for (int a = 1; a < m->sigmaCount; a++) {
+      const uint64_t t = (uint64_t)b + (uint64_t)a;
+      if (t > maxIndex || t >= daSize) continue;
+      if ((DA_CHECK(t) & DA_RESTBIT) != t0) continue;
+      uint32_t nx = (uint32_t)t;
+      if (DA_BASE(t) & FIRSTBIT) nx = DA_BASE(t) & DA_RESTBIT; /* representative */
+      if (nx >= daSize || nx == 0) { ok = 0; break; }
+      if (!id[nx]) { id[nx] = (uint32_t)qt + 1; queue[qt++] = nx; }
+    }
+  }
+  if (!ok) { free(id); free(queue); ora_free(m); return NULL; }
+  m->stateCount = (int)qt;
+  m->arraySize = ((size_t)m->stateCount + 1) * (size_t)m->sigmaCount;
+  m->array = (uint32_t *)calloc(m->arraySize + 1, 4);
+  const size_t S = (size_t)m->stateCount;
+  for (size_t k = 0; k < qt; k++) {
+    const uint32_t t0 = queue[k];
+    const uint32_t b = DA_BASE(t0) & DA_RESTBIT;
+    for (int a = 1; a < m->sigmaCount; a++) {
+      const uint64_t t = (uint64_t)b + (uint64_t)a;
+      if (t > maxIndex || t >= daSize) continue;
+      if ((DA_CHECK(t) & DA_RESTBIT) != t0) continue;
+      uint32_t nx = (uint32_t)t;
+      if (DA_BASE(t) & FIRSTBIT) nx = DA_BASE(t) & DA_RESTBIT;
+      m->array[(size_t)(a - 1) * S + id[t0]] = id[nx] | ((DA_CHECK(t) & FIRSTBIT) ? FIRSTBIT : 0u);
+    }
+  }
+#undef DA_BASE
+#undef DA_CHECK
+  free(id);
+  free(queue);
+  m->eot_rewind = 0;
   return m;
 }
 
@@ -179,7 +276,8 @@ ora_model *ora_load(const char *path) {
     len += (size_t)got;
   }
   gzclose(f);
-  ora_model *m = parse_matrix(buf, len);
+  /* LoadTokenizerFile fomafile.go:452-484 dispatches on the magic */
+  ora_model *m = (len >= 5 && memcmp(buf, "DATOK", 5) == 0) ? parse_datok(buf, len) : parse_matrix(buf, len);
   free(buf);
   return m;
 }
@@ -506,7 +604,7 @@ static int transduce(const ora_model *mat, const uint8_t *in, size_t n, token_wr
         }
         textEnd = 1;
         EMIT_TEXT(); /* :600 */
-        rewindBuffer = 1;
+        if (mat->eot_rewind) rewindBuffer = 1; /* matrix.go:603; absent in datok.go:1019-1030 */
       }
       if (rewindBuffer) { /* :608 */
         memmove(buffer, buffer + buffc, (size_t)(buffi - buffc) * sizeof(int32_t));

@@ -6,6 +6,12 @@
  *     matrix.go:235-337   ParseMatrix            (.matok loader)
  *     matrix.go:348-698   TransduceTokenWriter   (greedy walk, single backtrack)
  *     token_writer.go:36-175 NewTokenWriter      (flag-driven formatter)
+ * and, for the rows SURVEY.md section 8f marks "next", of the double-array path:
+ *     datok.go:621-729    ParseDatok             (.datok loader; ora_load dispatches on the magic like
+ *                                                 LoadTokenizerFile, fomafile.go:452-484, and converts
+ *                                                 the double array to the matrix's dense layout)
+ *     datok.go:781-1135   TransduceTokenWriter   (the same loop; no buffer rewind at an EOT)
+ * pinned by tests/test_oracle_golden_datok.py on datok_test.go's vectors.
  * It exists to CHECK the CUDA path.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.  Nothing under
  * datok_b200/ links, imports or executes it.

@@ -37,6 +37,9 @@ WRITER_USED = 256
 
 # models a test may reference -> shipped .matok (None = needs the foma parser, out of scope)
 FOMA_EQUIV = {"testdata/simpletok.fst": "simpletok.matok"}
+# ... and -> shipped .datok (double-array path, datok_test.go)
+FOMA_EQUIV_DA = {"testdata/simpletok.fst": "simpletok.datok"}
+OUT_DA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors_datok.json")
 
 
 class Tok:
@@ -151,8 +154,9 @@ def sig(st):
 
 
 class Extractor:
-    def __init__(self, fname):
+    def __init__(self, fname, double_array=False):
         self.fname = fname
+        self.double_array = double_array  # resolve .datok models (datok_test.go) instead of skipping them
         self.cases = []
         self.skipped = []
 
@@ -235,6 +239,10 @@ class Extractor:
                 cur = None
                 self.skipped.append(f"{self.fname}:{line} (model needs the foma parser)")
                 return
+            if data is None:
+                cur = None
+                self.skipped.append(f"{self.fname}:{line} (input is not a literal)")
+                return
             if wdirty and kind != "ttokenize":
                 raise RuntimeError(f"{self.fname}:{line}: output buffer not reset")
             cur = {"src": f"{self.fname}:{line}", "func": func, "model": model, "flags": flags,
@@ -277,8 +285,16 @@ class Extractor:
                 m = models.get(srcv)
                 models[st[0].val] = FOMA_EQUIV.get(m[1]) if isinstance(m, tuple) else None
                 continue
-            if "LoadDatokFile" in s:
-                models[st[0].val] = None
+            if "ToDoubleArray" in s and st[0].kind == "id" and st[1].val in (":=", "="):
+                m = models.get(st[2].val)
+                models[st[0].val] = FOMA_EQUIV_DA.get(m[1]) if isinstance(m, tuple) and self.double_array else None
+                continue
+            k, args = find_call(st, "LoadDatokFile")
+            if k < 0:
+                k, args = find_call(st, "LoadTokenizerFile")
+            if k >= 0 and st[0].kind == "id":
+                p = args[0].val.decode()
+                models[st[0].val] = os.path.basename(p) if (self.double_array or p.endswith(".matok")) else None
                 continue
             # w.Reset()
             if s == "w . Reset ( )":
@@ -453,6 +469,19 @@ def main():
     print(f"{len(cases)} cases, {nchecks} checks -> {OUT}")
     for s in skipped:
         print("skipped:", s)
+    # ---- the double-array path (datok.go:781-1135): datok_test.go on the shipped .datok models, plus
+    # testdata/de/{dontsplit,split}.txt, which the reference runs against tokenizer_de.datok
+    ex = Extractor("datok_test.go", double_array=True)
+    da = [c for c in ex.run() if c["checks"] and str(c.get("model", "")).endswith(".datok")]
+    for c in file_list_cases():
+        c["model"] = "tokenizer_de.datok"
+        da.append(c)
+    ncheck_da = sum(len(c["checks"]) for c in da)
+    json.dump({"reference": "KorAP/Datok 0.3.1", "generator": "tests/golden/make_golden.py",
+               "cases": da, "skipped": ex.skipped}, open(OUT_DA, "w"), indent=0, ensure_ascii=True)
+    print(f"{len(da)} double-array cases, {ncheck_da} checks -> {OUT_DA}")
+    for s in ex.skipped:
+        print("skipped (double array):", s)
 
 
 if __name__ == "__main__":

@@ -53,6 +53,8 @@ def test_loader_errors_mirror_reference(tmp_path, testdata):
     assert load_error_code(str(p)) == _lib.ERR_IO           # gzip.NewReader fails, matrix.go:222
     p = tmp_path / "magic.matok"
     p.write_bytes(gzip.compress(b"DATOK" + b"\0" * 64))
+    assert load_error_code(str(p)) == _lib.ERR_UNSUPPORTED_MODEL  # the double-array magic: refused as such
+    p.write_bytes(gzip.compress(b"MATOX" + b"\0" * 64))
     assert load_error_code(str(p)) == _lib.ERR_FORMAT       # matrix.go:258
     raw = gzip.decompress(open(os.path.join(testdata, "simpletok.matok"), "rb").read())
     p = tmp_path / "version.matok"
@@ -82,3 +84,16 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".c", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in txt and "datok_oracle" not in txt and "libdatok_emul" not in txt, f
+
+
+def test_double_array_models_are_refused_with_their_own_message(testdata):
+    """LoadTokenizerFile (fomafile.go:452-484) also takes .datok files; the CUDA path has no double-array walk
+    yet (the oracle has: tests/test_oracle_golden_datok.py) and says so instead of "not a matok file"."""
+    import ctypes as C
+    import os
+    from datok_b200 import _lib
+    L = _lib.lib()
+    err = C.c_int(0)
+    h = L.datok_load(os.path.join(testdata, "tokenizer_de.datok").encode(), 0, C.byref(err))
+    assert not h and err.value == _lib.ERR_UNSUPPORTED_MODEL
+    assert b"double-array" in L.datok_last_error()
