@@ -93,3 +93,21 @@ def test_eot_does_not_rewind_the_buffer(datok_models, oracle_models):
     assert da.text.split(b"\n")[-3].split()[0] == b"1"   # ... at 1: the EOT rune is still in the buffer
     assert [t for t in da.text.split(b"\n") if t and not t[:1].isdigit()] == \
            [t for t in ma.text.split(b"\n") if t and not t[:1].isdigit()]
+
+
+def test_fuzz_against_the_matrix_oracle(datok_models, oracle_models):
+    """differential fuzzing of the two oracles on the two encodings of the German automaton (no EOT in the
+    alphabet: an EOT inside a pending token is where the two loops legitimately part, see above)"""
+    import random
+    from test_emul_parity import _fuzz_text
+    rng = random.Random(4711)
+    da, ma = datok_models["tokenizer_de.datok"], oracle_models["tokenizer_de.matok"]
+    n = 0
+    for _ in range(400):
+        data = _fuzz_text(rng, rng.choice((7, 33, 200, 1500))).replace(b"\x04", b" ")
+        a, b = da.transduce(data, 3), ma.transduce(data, 3)
+        assert a.status == b.status, data[:60]
+        if a.status == 0:
+            assert a.text == b.text, data[:60]
+            n += 1
+    assert n > 300
