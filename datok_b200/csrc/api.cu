@@ -508,6 +508,11 @@ int do_count(datok_model* m, const WalkBuffers& b, CompactCtx& c, const CompactB
   std::memcpy(&h.err, m->h_mail + 8, sizeof h.err);
   h.invalid = m->h_mail[10];
   std::memcpy(&h.last, m->h_mail + 12, sizeof(WState));
+  if (!m->hm.eot_rewind && h.tot.n_text > 0) {
+    // a double-array model (datok.go): its walk does not rewind the buffer at an EOT, the kernels do
+    g_last_error = "double-array model (.datok): inputs with EOT bytes are not supported yet, use the .matok model";
+    return DATOK_ERR_UNSUPPORTED_MODEL;
+  }
   if (h.err != ~0ull) {  // the walk itself hit a reference panic
     const int code = (int)(h.err & 0xFF);
     g_last_error = std::string("reference would panic: ") + datok_strerror(code);

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -39,14 +40,83 @@ int32_t decode_rune(const uint8_t* p, size_t n, int* width) {
 static uint32_t rd16(const uint8_t* p) { return p[0] | (p[1] << 8); }
 static uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
+// ParseDatok (datok.go:621-729) + conversion of the double array into the matrix's cell layout, so that the
+// rest of the loader and the kernels see one kind of model.  A double-array transition (datok.go:888-902,
+// 1058-1066): u = base(t) + a is valid iff u <= check(array[1]) and check(array[u]) == t; array[u]'s check
+// word carries the non-token flag (bit 31); the state that follows is base(array[u]) if array[u] is
+// "separate" (bit 31 of its base word: it stands for a representative state), else u itself.  Reachable
+// states are numbered in breadth-first order from state 1, which stays 1.
+static int parse_datok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why) {
+  if (n < 21) { why = "Not a datok file"; return DATOK_ERR_FORMAT; }
+  const uint8_t* h = d + 5;
+  if (rd16(h) != 1) { why = "Version not compatible"; return DATOK_ERR_FORMAT; }  // datok.go:667-672
+  m.epsilon = (int)rd16(h + 2);
+  m.unknown = (int)rd16(h + 4);
+  m.identity = (int)rd16(h + 6);
+  m.sigmaCount = (int)rd16(h + 10);                 // (h + 8: the final symbol, not used by the walk)
+  const size_t da_size = (size_t)rd32(h + 12) / 2;  // datok.go:681
+  size_t p = 21;
+  for (int i = 0; i < 256; i++) m.sigmaASCII[i] = m.identity;  // datok.go:686-691
+  m.sigma.clear();
+  for (int x = 0; x < m.sigmaCount; x++) {  // datok.go:693-701
+    int w;
+    int32_t sym = decode_rune(d + p, n - p, &w);
+    if (w == 0) continue;
+    p += (size_t)w;
+    if (sym != 0) {
+      if (sym < 256) m.sigmaASCII[sym] = x;
+      m.sigma.emplace_back(sym, x);
+    }
+  }
+  if (p >= n || d[p] != 'T') { why = "Not a datok file"; return DATOK_ERR_FORMAT; }  // datok.go:703-713
+  p++;
+  if (da_size < 2 || n - p < da_size * 8) { why = "Not enough bytes read"; return DATOK_ERR_FORMAT; }  // datok.go:722-725
+  const uint8_t* da = d + p;
+  constexpr uint32_t REST = 0x3FFFFFFFu, FIRST = 0x80000000u;  // datok.go:43-45
+  auto base = [&](size_t x) { return rd32(da + 8 * x); };
+  auto check = [&](size_t x) { return rd32(da + 8 * x + 4); };
+  const uint32_t max_index = check(1) & REST;  // datok.go:891
+  // follows (t, a): 0 = no transition, else the state that follows | FIRST if the target is non-token
+  auto step = [&](uint32_t t, int a) -> uint32_t {
+    const uint64_t u = (uint64_t)(base(t) & REST) + (uint64_t)a;
+    if (u > max_index || u >= da_size || (check(u) & REST) != t) return 0;
+    uint32_t nx = (uint32_t)u;
+    if (base(u) & FIRST) nx = base(u) & REST;
+    return nx | ((check(u) & FIRST) ? FIRST : 0u);
+  };
+  std::vector<uint32_t> id(da_size, 0), order;
+  id[1] = 1;
+  order.push_back(1);
+  for (size_t k = 0; k < order.size(); k++) {
+    for (int a = 1; a < m.sigmaCount; a++) {
+      const uint32_t nx = step(order[k], a) & ~FIRST;
+      if (!nx) continue;
+      if (nx >= da_size) { why = "double array: target out of range"; return DATOK_ERR_FORMAT; }
+      if (!id[nx]) { order.push_back(nx); id[nx] = (uint32_t)order.size(); }
+    }
+  }
+  m.stateCount = (int)order.size();
+  const size_t S = order.size();
+  m.array.assign((S + 1) * (size_t)m.sigmaCount, 0);  // cell (a, t) at (a - 1) * S + t, as in a .matok image
+  for (size_t k = 0; k < S; k++)
+    for (int a = 1; a < m.sigmaCount; a++) {
+      const uint32_t e = step(order[k], a);
+      if (e) m.array[(size_t)(a - 1) * S + (k + 1)] = id[e & ~FIRST] | (e & FIRST);
+    }
+  m.eot_rewind = false;
+  return DATOK_OK;
+}
+
 int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why) {
   // magic + 14-byte little-endian header (matrix.go:246-285)
-  if (n >= 5 && std::memcmp(d, "DATOK", 5) == 0) {
-    // LoadTokenizerFile (fomafile.go:452-484) also accepts the double-array format.  Its walk is the same loop
-    // except that an EOT does not rewind the buffer (datok.go:1019-1030); the CPU oracle has it (pinned on
-    // datok_test.go), the CUDA path does not yet.
-    why = "double-array model (DATOK): not supported yet, use the .matok model";
-    return DATOK_ERR_UNSUPPORTED_MODEL;
+  if (n >= 5 && std::memcmp(d, "DATOK", 5) == 0) {  // fomafile.go:476-480
+    // The double-array path is verified against its oracle through the CPU emulation of the kernels
+    // (tests/test_emul_parity.py); its GPU parity run is still partial, so it is opt-in for now.
+    if (!std::getenv("DATOK_EXPERIMENTAL_DATOK")) {
+      why = "double-array model (DATOK): experimental, set DATOK_EXPERIMENTAL_DATOK=1 (EOT-free input only) or use the .matok model";
+      return DATOK_ERR_UNSUPPORTED_MODEL;
+    }
+    return parse_datok_image(d, n, m, why);
   }
   if (n < 19 || std::memcmp(d, "MATOK", 5) != 0) { why = "Not a matok file"; return DATOK_ERR_FORMAT; }
   const uint8_t* h = d + 5;

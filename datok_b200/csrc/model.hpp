@@ -51,6 +51,10 @@ struct HostModel {
   int32_t sigmaASCII[256];
   std::vector<std::pair<int32_t, int32_t>> sigma;  // rune -> symbol id, file order, later wins
   std::vector<uint32_t> array;
+  // false: the model came from a double-array file (.datok).  Its walk (datok.go:781-1135) is the matrix
+  // walk except that an EOT does not rewind the buffer; until the kernels have that variant, inputs that
+  // hold an EOT are refused for such a model (api.cu do_count).
+  bool eot_rewind = true;
 
   // --- GPU layout ---
   uint32_t n_classes = 0;

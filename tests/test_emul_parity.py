@@ -101,6 +101,33 @@ def test_hand_off_with_stale_bufft_at_the_chunk_end(name, oracle_models, emul_mo
             P.assert_matches_oracle(s, o, 15, f"{name} chunk={chunk} mode={mode} order={order}")
 
 
+@pytest.mark.parametrize("name", ["tokenizer_de.datok", "simpletok.datok"])
+def test_double_array_models_without_eot(name, testdata, corpus_lib, monkeypatch):
+    """.datok models (datok.go): the product's loader converts the double array to the matrix layout and the
+    kernel bodies walk it.  The double-array loop differs from the matrix loop at an EOT only (no buffer
+    rewind), so on EOT-free input the result must equal the double-array oracle's
+    (tests/test_oracle_golden_datok.py pins that oracle); inputs with an EOT are refused by the C ABI."""
+    import json
+    from oracle import pyoracle
+    monkeypatch.setenv("DATOK_EXPERIMENTAL_DATOK", "1")  # (the product's loader: opt-in for this format)
+    em = P.EmulModel(os.path.join(testdata, name))
+    om = pyoracle.OracleModel(os.path.join(testdata, name))
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_datok.json")))["cases"]
+    n = 0
+    for c in cases:
+        data = bytes.fromhex(c["input_hex"])
+        if c["model"] != name or b"\x04" in data:
+            continue
+        o = om.transduce(data, 15)
+        for chunk, mode in ((32, 0), (64, 256), (640, 886)):
+            P.assert_matches_oracle(em.transduce(data, 15, chunk, 0, mode=mode), o, 15, f"{c['src']} chunk={chunk} mode={mode}")
+        n += 1
+    assert n >= (100 if name == "tokenizer_de.datok" else 3)
+    if name == "tokenizer_de.datok":
+        a = corpus_lib.generate(4, 1 << 20, seed=5)  # the long-document corpus has no EOT
+        P.assert_matches_oracle(em.transduce(a, 15, 640, 0, mode=886), om.transduce_np(a, 15), 15, "long document")
+
+
 def _fuzz_text(rng, n):
     alphabet = [b" ", b" ", b" ", b"\n", b"\t", b".", b",", b"!", b"?", b"\x04", b"<", b">", b"\"", b"'", b"&", b";",
                 b"-", b"/", b":", b"@", b"a", b"e", b"n", b"r", b"S", b"T", b"1", b"9", "ä".encode(), "ß".encode(),

@@ -194,6 +194,43 @@ def test_long_document_corpus_in_windows(gpu_models, oracle_models):
         r.close()
 
 
+@pytest.mark.skipif(not os.environ.get("DATOK_EXPERIMENTAL_DATOK"),
+                    reason="double-array models are opt-in until this test has run green on the GPU once "
+                           "(DATOK_EXPERIMENTAL_DATOK=1 python -m pytest tests -m gpu -k double_array)")
+@pytest.mark.parametrize("name", ["tokenizer_de.datok", "simpletok.datok"])
+def test_double_array_models_without_eot(name, testdata):
+    """LoadTokenizerFile on a .datok file (fomafile.go:476-480): bit-exact against the double-array oracle on
+    EOT-free input; an input that holds an EOT is refused (the double-array loop does not rewind the buffer
+    there, datok.go:1019-1030, and the kernels have no such variant yet)"""
+    import json
+    import datok_b200 as d
+    from datok_b200 import _lib, corpus
+    from oracle import pyoracle
+    tok = d.LoadTokenizerFile(os.path.join(testdata, name))
+    assert tok is not None
+    om = pyoracle.OracleModel(os.path.join(testdata, name))
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_datok.json")))["cases"]
+    n = 0
+    for c in cases:
+        data = bytes.fromhex(c["input_hex"])
+        if c["model"] != name or b"\x04" in data:
+            continue
+        o = om.transduce(data, 15)
+        s = gpu_arrays(tok, data, 15)
+        P.assert_matches_oracle(s, o, 15, c["src"])  # (also when both say "the reference panics here")
+        if o.status == 0:
+            assert tok.format(s, data, 15) == o.text
+        n += 1
+    assert n >= (100 if name == "tokenizer_de.datok" else 3)
+    if name == "tokenizer_de.datok":
+        a = corpus.generate(corpus.GERMAN_LONGDOC, 4 << 20, seed=5)
+        P.assert_matches_oracle(gpu_arrays(tok, a, 15), om.transduce_np(a, 15), 15, "long document")
+    with pytest.raises(d.DatokError) as e:
+        tok.transduce_arrays(b"Ein Text.\x04Noch einer.", 15)
+    assert e.value.code == _lib.ERR_UNSUPPORTED_MODEL
+    tok.close()
+
+
 def test_gather_bound_measurement(gpu_models):
     """bench.py's second bound (the bare gather chain of the walk): runs and gives a plausible rate"""
     g = gpu_models["tokenizer_de.matok"].gather_bound()
