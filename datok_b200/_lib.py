@@ -55,7 +55,7 @@ class Callbacks(C.Structure):
 
 
 # every symbol include/datok_b200.h declares
-EXPORTS = ["datok_load", "datok_load_image", "datok_free", "datok_type", "datok_model_info", "datok_transduce",
+EXPORTS = ["datok_load", "datok_load_image", "datok_free", "datok_type", "datok_model_type", "datok_model_info", "datok_transduce",
            "datok_transduce_device", "datok_result_view", "datok_result_free", "datok_expand", "datok_format", "datok_replay",
            "datok_last_kernel_times", "datok_last_launch_count", "datok_measure_gather_bound", "datok_host_alloc", "datok_host_free",
            "datok_last_error", "datok_strerror"]
@@ -77,6 +77,8 @@ def lib():
     L.datok_load_image.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
     L.datok_free.argtypes = [C.c_void_p]
     L.datok_type.restype = C.c_char_p
+    L.datok_model_type.restype = C.c_char_p
+    L.datok_model_type.argtypes = [C.c_void_p]
     L.datok_model_info.restype = C.c_int
     L.datok_model_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 6
     for f in (L.datok_transduce, L.datok_transduce_device):

@@ -775,6 +775,22 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       g_last_error = std::string("reference would panic: ") + datok_strerror(code);
       return fail(code);
     }
+    if (compact8 && want_bytes && m->h_mail[10] > esc_cap) {
+      // more escape pairs than the list holds: the emit pass runs again with a list of the counted size
+      const size_t ne = m->h_mail[10];
+      if (!grow_block(m->d_out[slot][1], ne * 8, false)) { g_last_error = "cudaMalloc (escape list) failed"; return fail(DATOK_ERR_CUDA); }
+      c.esc = (uint32_t*)m->d_out[slot][1].p; c.esc_cap = (uint32_t)ne;
+      CUDA_TRYF(cudaMemsetAsync(b.counters + 3, 0, sizeof(uint32_t), s));
+      {
+        const int e = launch_compact_emit(c, cb, s);
+        if (e != 0) { g_last_error = std::string("compact_emit launch: ") + cudaGetErrorString((cudaError_t)e); return fail(DATOK_ERR_CUDA); }
+      }
+      launch_compact_finalize(c, cb, text_end_in, final_input, s);
+      m->launches += 2;
+      CUDA_TRYF(cudaEventRecord(m->ev_emit[slot], s));
+      CUDA_TRYF(cudaEventRecord(m->ev_free[islot], s));
+      CUDA_TRYF(cudaStreamSynchronize(s));
+    }
     if (compact8 && want_bytes && m->h_mail[10]) {  // rare: this piece's escape pairs (a plain, blocking copy)
       const size_t ne = m->h_mail[10], at = r->esc.size();
       r->esc.resize(at + 2 * ne);
@@ -986,6 +1002,31 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   std::memcpy(&tail.fin, m->h_mail, sizeof(StreamTotals));
   std::memcpy(&tail.err, m->h_mail + 8, sizeof tail.err);
   tail.n_esc = m->h_mail[10];
+  if (want_delta8 && tail.err == ~0ull && tail.n_esc > esc_cap) {
+    // more escape pairs than the list holds (many long tokens or gaps): the pass is repeated once with a
+    // list of the counted size -- it writes the same arrays again
+    Block big = acquire(m, (size_t)tail.n_esc * 8, false, &rc);
+    if (rc) { pt.collect(); free_result_locked(r); return rc; }
+    r->blocks.push_back(big);
+    if (!device_out) {
+      Block bigh = acquire(m, (size_t)tail.n_esc * 8, true, &rc);
+      if (rc) { pt.collect(); free_result_locked(r); return rc; }
+      r->blocks.push_back(bigh);
+      outs[7].h = bigh;
+    }
+    outs[7].d = big;
+    d_esc = big.p;
+    c.esc = (uint32_t*)d_esc; c.esc_cap = tail.n_esc;
+    CUDA_TRY(cudaMemsetAsync(b.counters + 3, 0, sizeof(uint32_t), s));
+    {
+      const int e = launch_compact_emit(c, cb, s);
+      if (e != 0) { g_last_error = std::string("compact_emit launch: ") + cudaGetErrorString((cudaError_t)e); free_result_locked(r); return DATOK_ERR_CUDA; }
+    }
+    launch_compact_finalize(c, cb, text_end_in, final_input, s);
+    m->launches += 2;
+    CUDA_TRY(cudaEventRecord(m->ev[2], s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
   pt.collect();
   if (tail.err != ~0ull) {
     const int code = (int)(tail.err & 0xFF);
@@ -1099,6 +1140,7 @@ void datok_free(datok_model* m) {
 }
 
 const char* datok_type(void) { return "MATOK"; }
+const char* datok_model_type(const datok_model* m) { return (m && !m->hm.eot_rewind) ? "DATOK" : "MATOK"; }
 
 int datok_model_info(const datok_model* m, uint32_t* state_count, uint32_t* sigma_count, uint32_t* n_classes,
                      uint32_t* epsilon, uint32_t* unknown, uint32_t* identity) {

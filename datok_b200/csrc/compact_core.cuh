@@ -312,8 +312,9 @@ DATOK_HD void emit_escape(const CompactCtx& c, uint32_t tok, uint32_t field, uin
 #else
   const uint32_t slot = (*c.esc_count)++;
 #endif
+  // beyond the capacity the pair is only counted: the host then runs the pass again with a list of that size
   if (slot < c.esc_cap) { c.esc[2 * slot] = c.base_tok + tok; c.esc[2 * slot + 1] = (field << 16) | value; }
-  else report_error(c, pos, E_COMPACT_RANGE);
+  (void)pos;
 }
 
 // FORM: 0 absolute pairs (tok_bytes / tok_pos), 1 four u16 deltas per token (tok_delta), 2 four u8 deltas

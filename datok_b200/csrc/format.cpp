@@ -21,11 +21,12 @@ struct Sink {
   uint8_t* dst;      // nullptr: only count
   size_t cap, n = 0;
   const uint8_t* src_end = nullptr;  // end of the input buffer: lets short surfaces be copied as one 16-byte block
-  inline void put(const uint8_t* p, size_t len) {
+  // in_input: p points into the input buffer (only then may the 16-byte block copy read past p + len)
+  inline void put(const uint8_t* p, size_t len, bool in_input = true) {
     if (n + len <= cap) {
       uint8_t* d = dst + n;
       if (len <= 16) {  // token surfaces are short
-        if (n + 16 <= cap && p + 16 <= src_end) std::memcpy(d, p, 16);  // fixed size: two moves; the tail is overwritten next
+        if (in_input && n + 16 <= cap && p + 16 <= src_end) std::memcpy(d, p, 16);  // fixed size: two moves; the tail is overwritten next
         else for (size_t i = 0; i < len; i++) d[i] = p[i];
       } else {
         std::memcpy(d, p, len);
@@ -66,7 +67,7 @@ void put_surface(Sink& s, const uint8_t* in, size_t lo, size_t hi, bool reencode
   while (p < hi) {
     int w;
     int32_t r = datok::decode_rune(in + p, hi - p, &w);
-    if (r == 0xFFFD && w == 1) s.put(kRep, 3); else s.put(in + p, (size_t)w);
+    if (r == 0xFFFD && w == 1) s.put(kRep, 3, false); else s.put(in + p, (size_t)w);
     p += (size_t)w;
   }
 }

@@ -185,7 +185,7 @@ class MatrixTokenizer:
 
     # -- Tokenizer interface (fomafile.go:29-33) -------------------------------
     def Type(self):
-        return _lib.lib().datok_type().decode()
+        return _lib.lib().datok_model_type(self._h).decode()
 
     def Transduce(self, r, w):
         """matrix.go:340-342"""

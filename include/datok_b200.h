@@ -131,6 +131,9 @@ void datok_free(datok_model *m);
 
 /* Tokenizer.Type() (matrix.go:102-104) -> "MATOK" */
 const char *datok_type(void);
+/* Tokenizer.Type() of a loaded model: "MATOK" (matrix.go:102-104) or, for a double-array file,
+ * "DATOK" (datok.go:252-254) -- LoadTokenizerFile dispatches on the magic (fomafile.go:476-480). */
+const char *datok_model_type(const datok_model *m);
 
 /* model introspection (reference numbering) */
 int datok_model_info(const datok_model *m, uint32_t *state_count, uint32_t *sigma_count,

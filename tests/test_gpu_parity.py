@@ -194,11 +194,8 @@ def test_long_document_corpus_in_windows(gpu_models, oracle_models):
         r.close()
 
 
-@pytest.mark.skipif(not os.environ.get("DATOK_EXPERIMENTAL_DATOK"),
-                    reason="double-array models are opt-in until this test has run green on the GPU once "
-                           "(DATOK_EXPERIMENTAL_DATOK=1 python -m pytest tests -m gpu -k double_array)")
 @pytest.mark.parametrize("name", ["tokenizer_de.datok", "simpletok.datok"])
-def test_double_array_models_without_eot(name, testdata):
+def test_double_array_models_without_eot(name, testdata, monkeypatch):
     """LoadTokenizerFile on a .datok file (fomafile.go:476-480): bit-exact against the double-array oracle on
     EOT-free input; an input that holds an EOT is refused (the double-array loop does not rewind the buffer
     there, datok.go:1019-1030, and the kernels have no such variant yet)"""
@@ -206,8 +203,9 @@ def test_double_array_models_without_eot(name, testdata):
     import datok_b200 as d
     from datok_b200 import _lib, corpus
     from oracle import pyoracle
+    monkeypatch.setenv("DATOK_EXPERIMENTAL_DATOK", "1")  # (read by the loader at every datok_load)
     tok = d.LoadTokenizerFile(os.path.join(testdata, name))
-    assert tok is not None
+    assert tok is not None and tok.Type() == "DATOK"
     om = pyoracle.OracleModel(os.path.join(testdata, name))
     cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_datok.json")))["cases"]
     n = 0
