@@ -294,7 +294,7 @@ int upload_model(datok_model* m) {
   d.table = reinterpret_cast<const uint16_t*>(m->d_tables + t2_bytes);
   d.hot16 = reinterpret_cast<const uint16_t*>(m->d_tables + t2_bytes + t1_bytes);
   d.row_shift = h.row_shift; d.start = h.start; d.n_classes = h.n_classes; d.stride2 = h.stride2;
-  d.stride16 = h.stride16; d.hot16_rows = h.hot16_rows;
+  d.stride16 = h.stride16; d.hot16_rows = h.hot16_rows; d.hot_cols = h.hot_cols;
   d.cls.ascii_cls = m->d_cls_tables;
   d.cls.latin1_cls = m->d_cls_tables + 128;
   d.cls.rune_cls = m->d_cls_tables + 256;
@@ -302,6 +302,7 @@ int upload_model(datok_model* m) {
   d.cls.n_rune = (uint32_t)nr;
   d.cls.identity_cls = h.identity_cls;
   std::memcpy(d.sync_ascii, h.sync_ascii, sizeof d.sync_ascii);
+  std::memcpy(d.sync_cls, h.sync_mask, sizeof d.sync_cls);
   m->n_hot = fused_max_hot_rows(d, m->smem_optin, (uint32_t)h.stateCount, m->fused_threads);
   if (const char* s = std::getenv("DATOK_HOT_ROWS")) {
     long v = std::atol(s);
@@ -338,18 +339,20 @@ int calibrate_locked(datok_model* m, const WalkBuffers& full) {
   b.n_chunks = sample / b.chunk + 1;
   const size_t S = (size_t)m->hm.stateCount;
   uint32_t* d_hist = nullptr;
-  CUDA_TRY(cudaMalloc(&d_hist, (S + 2) * sizeof(uint32_t)));
-  CUDA_TRY(cudaMemsetAsync(d_hist, 0, (S + 2) * sizeof(uint32_t), m->stream));
+  const size_t hist_words = S + 2 + 256;  // visits per state, then occurrences per class
+  CUDA_TRY(cudaMalloc(&d_hist, hist_words * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemsetAsync(d_hist, 0, hist_words * sizeof(uint32_t), m->stream));
   CUDA_TRY(cudaMemsetAsync(b.b_end, 0, (size_t)full.n_words * 4 * sizeof(uint32_t), m->stream));
-  launch_hist(m->dm, b, d_hist, m->stream);
-  std::vector<uint32_t> hist(S + 2);
-  CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, (S + 2) * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+  launch_hist(m->dm, b, d_hist, (uint32_t)(S + 2), m->stream);
+  std::vector<uint32_t> hist(hist_words);
+  CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, hist_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   cudaFree(d_hist);
-  std::vector<uint64_t> hist_old(S + 1, 0);
+  std::vector<uint64_t> hist_old(S + 1, 0), cls_hist(256, 0);
   for (size_t t = 1; t <= S; t++) hist_old[m->hm.old_of_new[t]] = hist[t];
+  for (size_t c = 0; c < m->hm.n_classes; c++) cls_hist[m->hm.cls_base[c]] = hist[S + 2 + c];
   std::string why;
-  int rc = build_layout(m->hm, why, hist_old.data());
+  int rc = build_layout(m->hm, why, hist_old.data(), cls_hist.data());
   if (rc) { g_last_error = why; return rc; }
   rc = upload_model(m);
   if (rc) return rc;
@@ -410,6 +413,15 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
   m->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   m->fused_threads = fused_threads_from_env();
   if (const char* s = std::getenv("DATOK_NO_CALIBRATE")) m->auto_calibrate = !(s[0] == '1');
+  if (const char* s = std::getenv("DATOK_HOT_COLS")) {  // columns of the compact rows (default: from the calibration)
+    const long v = std::atol(s);
+    if (v >= 1 && v <= 256) {
+      m->hm.force_hot_cols = (uint32_t)v;
+      std::string why;
+      const int rc2 = build_layout(m->hm, why);
+      if (rc2) { g_last_error = why; *err = rc2; datok_free(m); return nullptr; }
+    }
+  }
   int rc = upload_model(m);
   if (rc) { *err = rc; datok_free(m); return nullptr; }
   pin_table_in_l2(m);

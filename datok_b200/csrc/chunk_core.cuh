@@ -32,9 +32,10 @@ struct DeviceModel {
   const uint16_t* table;   // exact table (walk_run)
   const uint32_t* table2;  // fused table T3 (fast_run), stride2 entries per row
   const uint16_t* hot16;   // compact rows of the first hot16_rows states, stride16 entries per row
-  uint32_t row_shift, start, n_classes, stride2, stride16, hot16_rows;
+  uint32_t row_shift, start, n_classes, stride2, stride16, hot16_rows, hot_cols;
   ClsTables cls;           // pointers into device memory
   uint32_t sync_ascii[4];  // ASCII bytes the root state skips: a chunk may start right after one
+  uint32_t sync_cls[8];    // the same set as classes (HostModel.sync_mask)
 };
 
 struct WalkBuffers {
@@ -57,7 +58,7 @@ DATOK_HD WalkCtx make_walk_ctx(const DeviceModel& m, const WalkBuffers& b) {
   c.table = m.table; c.row_shift = m.row_shift; c.start = m.start;
   c.in = b.in; c.N = b.N; c.cls = m.cls;
   c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
-  c.hist = nullptr;
+  c.hist = nullptr; c.hist_cls = nullptr;
   c.final_input = b.final_input;
   return c;
 }
@@ -163,7 +164,12 @@ enum { LOOK_DEAD = 0, LOOK_EXACT = 1, LOOK_PROBE = 2 };
 #define DATOK_NEAR_BACKTRACK 8
 #endif
 constexpr uint32_t NEAR_BACKTRACK = DATOK_NEAR_BACKTRACK;  // bytes: up to this distance the exact walker re-walks
-DATOK_HD int look_ahead(const FastTables& FT, const WalkCtx& c, uint32_t t, uint32_t hi, uint32_t base, uint32_t eps_pos) {
+#if defined(DATOK_NI_LOOKAHEAD)
+DATOK_HD_SLOW
+#else
+DATOK_HD
+#endif
+int look_ahead(const FastTables& FT, const WalkCtx& c, uint32_t t, uint32_t hi, uint32_t base, uint32_t eps_pos) {
   constexpr uint32_t LOOK = 16;
   if (eps_target(FT, t) != 0) return LOOK_DEAD;
   if (hi + LOOK > c.N || hi + LOOK - base >= FAST_WINDOW_GUARD) return LOOK_EXACT;
@@ -191,6 +197,8 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   const WalkCtx c = make_walk_ctx(m, b);
   const uint32_t lo = i * b.chunk, hi = lo + b.chunk, N = b.N;
   const bool rewalk = from != nullptr;
+  FastCtx FX;
+  FX.in = b.in; FX.N = N; FX.cls = &m.cls;
 #if !defined(__CUDA_ARCH__)
   g_own_lo = lo >> 5; g_own_hi = hi >> 5;
 #endif
@@ -205,14 +213,16 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   L.first_window = (i != 0 && !rewalk);  // a guessed start: the first window's overflow check is deferred (SpecInfo)
   RawBits R;
   raw_clear(R);
-  bool started = (i == 0) || rewalk, fast = true, halted = false;
+  bool started = (i == 0) || rewalk, fast = true, halted = false, sync_carry = false;
   uint32_t sync = (i == 0) ? 0u : K_NOPOS;
   uint32_t err = 0;
   SegBits B;
   B.end = B.skip = B.sent = B.tend = 0;
   uint32_t first_seg = lo;
+  uint32_t walk_from = lo;  // first position of this walk: an epsilon point below it is not the lane's to go back to
   if (rewalk) {
     st = *from;
+    walk_from = st.pos;
     fast = false;  // the fast path takes over as soon as the state allows it (see below)
     first_seg = st.pos & ~(SEG - 1);
     if (first_seg < lo) first_seg = lo;
@@ -252,9 +262,10 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       if (seg_start - hi >= 1024u || seg_start + SEG > N || seg_start + SEG - L.base >= FAST_WINDOW_GUARD) break;
     }
     const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
-    uint32_t rs, eotm;
+    uint32_t rs, eotm, nonascii;
     bool inv = false;
-    classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, seg_cls, &rs, &eotm, &inv);
+    classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, FT.stop_cl2, seg_cls, &rs, &eotm, &inv, &nonascii);
+    const uint32_t limit = seg_end < N ? seg_end : N;
 #if defined(__CUDA_ARCH__)
     // the next segment's sector on its way while this one is walked (no registers held)
     if (seg_end < hi && seg_end + SEG <= N) asm volatile("prefetch.global.L1 [%0];" :: "l"(b.in + seg_end));
@@ -267,9 +278,17 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     B.end = B.skip = B.sent = B.tend = 0;
     if (halted) { if (!rewalk) store_seg_bits(b, w, B); continue; }
     if (!started) {
-      sync = find_sync(b.in, N, m.sync_ascii, seg_start, seg_end < hi ? seg_end : hi);
+      // (from the class buffer; a sync point at the segment's first position is found through the last byte of
+      // the segment before -- except in the chunk's first segment, where the next point does as well)
+      sync = sync_carry ? seg_start : find_sync_cls(seg_cls, nonascii, FT.sync_cls, FT.stop_cl2, seg_start, 0, 31);
+      if (sync != K_NOPOS && (sync >= hi || sync >= N)) sync = K_NOPOS;
+      {
+        const uint32_t c2 = seg_cls[31], c = c2 >> 1;
+        sync_carry = !((nonascii >> 31) & 1u) && c2 != FT.stop_cl2 && ((FT.sync_cls[c >> 5] >> (c & 31)) & 1u);
+      }
       if (sync == K_NOPOS) { store_seg_bits(b, w, B); continue; }
       started = true;
+      walk_from = sync;
       L.pos = L.tstart = L.base = L.hw_med = L.raw_from = sync;
       L.u_in = 1;
       L.t = m.start;
@@ -283,10 +302,11 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       fast = false;
     }
     bool must_walk_exact = false;  // the fast path just gave up at st.pos: the exact walker has to move first
-    const uint32_t limit = seg_end < N ? seg_end : N;
+    bool reenter = false;          // a far backtrack through the fast path: back to the segment of L.pos
+    if (fast && !in_regs) { load_seg_bits(b, w, B); in_regs = true; }  // (that segment: its words are in memory)
     for (;;) {
       if (fast) {
-        const int rc = fast_run(L, R, FT, seg_cls, seg_start, limit, eotm, B);
+        const int rc = fast_run(L, R, FT, FX, seg_cls, seg_start, limit, eotm, B);
         if (!fast_flush(L, R, B, eotm, seg_start)) {  // two SentenceEnds at one position
           if (phase == PH_PROBE) { phase = PH_GAVE_UP; break; }
           err = E_DEGENERATE;
@@ -310,6 +330,31 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
           }
           break;
         }
+#if !defined(DATOK_NO_FAST_FAR)
+        // A backtrack (matrix.go:487-497) to an epsilon point that lies before the raw range, in this or an
+        // earlier segment of the lane's own walk, while a token is pending there -- the common far backtrack
+        // (a word, then a few bytes that turn out not to belong to it, across a segment boundary): the
+        // Token boundary goes into the stored words, and the lane walks on from the point through the fast
+        // path, starting with the point's segment again (its words are in memory, like those of a re-walk's
+        // first segment).  Nothing the first pass wrote behind the point has to be taken back: the point
+        // being alive, there was no boundary and no EOT behind it, and a pending token means no skipped rune.
+        if (rc == FAST_SLOW_FAIL && L.eps_rec && ((L.eps_rec >> 16) & 3u) == 0 && !L.first_window &&
+            L.eps_p >= walk_from && L.tstart < L.eps_p && L.stale_end <= L.eps_p) {
+          const uint32_t q = L.eps_p, tgt = eps_target(FT, L.eps_rec & F3_TGT);
+          if (tgt != 0) {
+            DATOK_STAT(g_bt_far_fast);
+            if (q >= seg_start && in_regs) store_seg_bits(b, w, B);  // (the point's segment is this one)
+            set_bit(b.b_end, q);
+            if (L.hw_med < L.pos) L.hw_med = L.pos;
+            L.pos = L.tstart = L.base = L.raw_from = q;
+            L.u_in = 1;
+            L.t = tgt;
+            L.eps_rec = 0;
+            reenter = true;
+            break;
+          }
+        }
+#endif
         lane_note_first_rewind(L, B, seg_start);
         to_exact(L, B, seg_start, FT, st);              // rare case, or end of input
         fast = false;
@@ -352,6 +397,11 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       if (seg_start - st.pos > NEAR_BACKTRACK && st.pos < seg_start && can_go_fast(st)) break;
     }
     if (phase == PH_GAVE_UP) break;
+    if (reenter) {
+      seg_start = (L.pos & ~(SEG - 1)) - SEG;
+      in_regs = false;
+      continue;
+    }
     if (!fast && !halted && st.pos < seg_start && seg_start - st.pos > NEAR_BACKTRACK) {  // back to the segment of the epsilon point: its words are in memory
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
       g_nf[2]++;

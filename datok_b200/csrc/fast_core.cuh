@@ -29,9 +29,11 @@ constexpr uint32_t SEG = 32;                 // bytes per segment = bits per bit
 // fused table T3 (u32) and the compact hot rows (u16): see model.hpp
 constexpr uint32_t F3_TGT = 0x7FFFu, F3_NT = 1u << 15, F3_K1 = 1u << 16, F3_K2 = 1u << 17, F3_KANY = F3_K1 | F3_K2,
                    F3_EA = 1u << 18, F3_SLOWMARK = 1u << 31;
-constexpr uint32_t F16_TGT = 0x0FFFu, F16_NT = 1u << 12, F16_EA = 1u << 13, F16_K1 = 1u << 14, F16_K2 = 1u << 15,
-                   F16_KANY = F16_K1 | F16_K2,
+constexpr uint32_t F16_TGT = 0x07FFu, F16_NT = 1u << 11, F16_EA = 1u << 12, F16_KANY = 1u << 13, F16_K2 = 1u << 14,
                    F16_FAIL = F16_NT;  // target 0 + this flag: the full table says 0 (failure without epsilon transition)
+// number of epsilon steps <-> the two flag bits (KANY, K2) of a compact entry: 0 -> 00, 1 -> 01, 2 -> 11
+DATOK_HD uint32_t k_to_bits(uint32_t k) { return k | (k >> 1); }
+DATOK_HD uint32_t bits_to_k(uint32_t x) { return x - (x >> 1); }
 // eps_rec: [14:0] state at the loop top where the point was recorded, [17:16] epsilon steps taken
 // there before the byte was consumed, [19] valid
 constexpr uint32_t ER_VALID = 1u << 19;
@@ -43,9 +45,14 @@ struct FastTables {
   const uint32_t* t3;      // the full fused table (global memory)
   uint32_t n_hot;
   uint32_t row16;          // BYTES per compact row
+  uint32_t row16_inv;      // device only: floor(2^32 / row16) + 1 (the row of a shared-memory offset without a division)
   uint32_t stride3;        // entries per T3 row
   uint32_t hot_saddr;      // device only: shared-window address of hot16
-  const uint8_t* ascii_cls2;  // 2 * class of the ASCII bytes (shared memory in the kernel)
+  const uint8_t* ascii_cls2;  // [256]: 2 * class of the ASCII bytes, capped at stop_cl2; the other bytes map to themselves,
+                              // so that the class buffer still holds them when they are decoded (shared memory in the kernel)
+  const uint32_t* sync_cls;   // [8]: bit c set iff class c is a sync class (shared memory in the kernel)
+  uint32_t stop_cl2;       // 2 * (number of classes that have a column in the compact rows): the all-zero column.
+                           // Rarer classes are stored as this value, and so is the sentinel behind a walk range.
 };
 
 // compact entry of hot state t (< n_hot) for the doubled class cl2 = 2 * class
@@ -241,7 +248,12 @@ DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, 
 // In-place backtrack to the epsilon point recorded in the raw range of this segment
 // (matrix.go:487-497), or FAST_SLOW (nothing changed) when the exact walker has to take over.
 // Bprev: boundary words of the segment's positions before raw_from.
-DATOK_HD int fast_backtrack(FastLane& L, RawBits& R, const FastTables& T, uint32_t seg_start, uint32_t eotm,
+#if defined(DATOK_NI_BACKTRACK)
+DATOK_HD_SLOW
+#else
+DATOK_HD
+#endif
+int fast_backtrack(FastLane& L, RawBits& R, const FastTables& T, uint32_t seg_start, uint32_t eotm,
                             const SegBits& Bprev) {
   if (!L.eps_rec) { DATOK_STAT(g_bt_hard); return FAST_SLOW; }                                 // hard fail
   if (L.eps_p < L.raw_from || L.eps_p < seg_start) { DATOK_STAT(g_bt_far); return FAST_SLOW; }  // far backtrack
@@ -289,55 +301,98 @@ DATOK_HD int fast_backtrack(FastLane& L, RawBits& R, const FastTables& T, uint32
 // DOUBLED classes seg_cls[0..31] of the segment.  On FAST_SLOW nothing has been changed by the
 // failing iteration and the exact walker must take over at L.pos.
 //
-// One loop for all lanes of a warp: a lane that needs the rare path (cold state, failure) takes
-// it inside the iteration and rejoins the others at the end of the same iteration.
-// eps_rec inside the loop: [14:0] state at the loop top, [31:30] epsilon steps of that lookup
-// (the compact entry shifted up by 16); converted to the ER_* form on exit.
-DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_t* seg_cls, uint32_t seg_start,
-                      uint32_t limit, uint32_t eotm, const SegBits& Bprev) {
+// One loop for all lanes of a warp: a lane that needs the rare path (cold state, rare class, failure)
+// takes it inside the iteration and rejoins the others at the end of the same iteration (the loop's end
+// test is what makes the compiler reconverge the lanes there: with an endless loop it turns the hot path
+// into a tight loop of its own that a lane leaves at its first rare event and re-enters only when every
+// other lane has left it too -- twice the iterations per segment).
+// In the loop the latest epsilon point is (eps_bit, eps_a | eps_rec): eps_bit = the position's bit in this
+// segment (0: the point is older than the segment, L.eps_p holds it); if the lookup that recorded it went
+// through the compact rows, eps_a is the shared-memory address of that entry (state and epsilon steps are
+// recovered from it when they are needed: one select in the hot path), else eps_a is 0 and eps_rec holds
+// the ER_* record.
+struct FastCtx {  // what the rare path needs beyond the tables: the raw input, for the class of a rare rune
+  const uint8_t* in;
+  uint32_t N;
+  const ClsTables* cls;
+};
+// ER_* record of the epsilon point whose lookup was the compact entry at (row t, doubled class cl2)
+DATOK_HD uint32_t er_from_entry(const FastTables& T, uint32_t t, uint32_t cl2) {
+  const uint32_t e = h16_load(T, t, cl2);
+  return ER_VALID | t | (bits_to_k((e >> 13) & 3u) << 16);
+}
+DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCtx& X, const uint8_t* seg_cls,
+                      uint32_t seg_start, uint32_t limit, uint32_t eotm, const SegBits& Bprev) {
   if (L.pos >= limit) return FAST_OK;
   const uint32_t lim_off = limit - seg_start;
   uint32_t end_bit = lim_off < 32 ? 1u << lim_off : 0u;
 #if defined(__CUDA_ARCH__)
-  asm volatile("" : "+r"(end_bit));  // opaque: otherwise recomputed (five instructions) in every iteration of the loop below
+  asm volatile("" : "+r"(end_bit));  // opaque: otherwise recomputed in every iteration of the loop below
 #endif
   uint32_t off = L.pos - seg_start;
   uint32_t bit = 1u << off;
-  uint32_t t = L.t, eps_off = L.eps_p - seg_start;  // eps_off wraps for older points
-  uint32_t eps_rec = L.eps_rec ? ((L.eps_rec & F3_TGT) | ((L.eps_rec & F3_KANY) << 14)) : 0;
+  uint32_t t = L.t;
+  uint32_t eps_bit = (L.eps_rec && L.eps_p >= seg_start) ? 1u << (L.eps_p - seg_start) : 0u;
+  uint32_t eps_rec = L.eps_rec;  // ER_* form; only read while eps_a == 0
+  uint32_t eps_a = 0;            // device: address of the recording entry; host: 1 + (row * 65536 + doubled class)
   uint32_t c1 = R.c1, c2 = R.c2, nt = R.nt;
 #if defined(__CUDA_ARCH__)
-  uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(seg_cls);
+  const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(seg_cls);
+  uint32_t p = cls_saddr + off;   // address of the class byte of the current position
   uint32_t row16 = T.row16;
-  asm volatile("" : "+r"(cls_saddr), "+r"(row16));  // opaque, like end_bit
+  asm volatile("" : "+r"(row16));  // opaque, like end_bit
+#define DATOK_ROW_OF(addr) __umulhi((addr) - T.hot_saddr, T.row16_inv)
+#define DATOK_EPS_REC() (eps_a ? er_from_entry(T, DATOK_ROW_OF(eps_a), (eps_a - T.hot_saddr) - DATOK_ROW_OF(eps_a) * T.row16) : eps_rec)
+#else
+#define DATOK_EPS_REC() (eps_a ? er_from_entry(T, (eps_a - 1u) >> 16, (eps_a - 1u) & 0xFFFFu) : eps_rec)
 #endif
   // row of the lookup: the state's own, or the all-zero row n_hot ("see the full table") for a cold state,
   // which the loop top only sees on entry: the rare path below steps until the state is hot again
-  uint32_t tl = t < T.n_hot ? t : T.n_hot;
+  // (the hot path only carries tl: while the state is hot, t == tl; a cold state is kept in t_cold)
+  uint32_t tl = t < T.n_hot ? t : T.n_hot, t_cold = t;
   do {
     // ---- one compact-row lookup per byte ----
-    uint32_t e;
+    uint32_t e, a;
 #if defined(__CUDA_ARCH__)
     {
       uint32_t cl2;
-      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cl2) : "r"(cls_saddr + off));
-      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(T.hot_saddr + tl * row16 + cl2));
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cl2) : "r"(p));
+      a = T.hot_saddr + tl * row16 + cl2;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(a));
     }
 #else
+    a = 1u + ((tl << 16) | seg_cls[off]);
     e = h16_load(T, tl, seg_cls[off]);
 #endif
     if (DATOK_UNLIKELY((e & F16_TGT) == 0)) {
-      // ---- rare: failure (F16_FAIL), or not in the compact rows (0): cold state, target outside
-      // the hot rows, marked entry.  Steps through the full table until the state is hot again ----
+      // ---- rare: a failure (F16_FAIL), or not in the compact rows (0): cold state, rare class, target
+      // outside the hot rows, marked entry.  Steps through the full table until the state is hot again ----
+#if defined(__CUDA_ARCH__)
+      off = p - cls_saddr;
+#endif
       bool failed = e == F16_FAIL;
-      if (failed) {
+      {  // the state of this lookup, from the entry's address (tl itself is not kept across the lookup: one move less per byte)
+#if defined(__CUDA_ARCH__)
+        const uint32_t row = DATOK_ROW_OF(a);
+#else
+        const uint32_t row = (a - 1u) >> 16;
+#endif
+        t = row == T.n_hot ? t_cold : row;
+      }
+      if (failed && eps_a != 0) {
         // The common backtrack, inline: the point was recorded in this raw range by a lookup without
         // epsilon steps of its own, both states are hot, q holds no boundary or skipped rune yet and
         // nothing killed the point.  Everything else goes through fast_backtrack() below.
-        const uint32_t qo = eps_off, es = eps_rec & F3_TGT;
+        // (a recording lookup with epsilon steps of its own left a boundary at q: the `dead` test sees it)
+#if defined(__CUDA_ARCH__)
+        const uint32_t es = DATOK_ROW_OF(eps_a);
+#else
+        const uint32_t es = (eps_a - 1u) >> 16;
+#endif
+        const uint32_t qb = eps_bit;
         const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
-        if (eps_rec != 0 && (eps_rec >> 30) == 0 && qo < 32 && qo >= ro && !L.first_window && es < T.n_hot) {
-          const uint32_t qb = 1u << qo, below = qb - 1u, keep = below | qb;
+        if (qb >= (1u << ro) && !L.first_window) {
+          const uint32_t below = qb - 1u, keep = below | qb;
           const uint32_t tgt = h16_load(T, es, 2u * K_CLS_EPS);
           const uint32_t cb = R.cb;
           const uint32_t dead = ((c1 | cb) & ~keep) | (eotm & ~below & mask_below(off)) | ((c1 | c2 | cb | nt) & qb);
@@ -347,8 +402,11 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
             if (L.hw_med < pos) L.hw_med = pos;
             c1 &= below; c2 &= below; nt &= below;
             R.cb = (cb & below) | qb;
-            off = qo; bit = qb;
-            t = tl = tgt; eps_rec = 0;
+            off = ctz32(qb); bit = qb;
+            tl = tgt; eps_rec = 0; eps_a = 0; eps_bit = 0;  // (tgt is a hot state: the compact row says so)
+#if defined(__CUDA_ARCH__)
+            p = cls_saddr + off;
+#endif
             continue;
           }
         }
@@ -357,16 +415,19 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
         uint32_t e3 = 0;
         if (!failed) {
           DATOK_STAT(g_cold);
-          e3 = t3_load(T, t, (uint32_t)seg_cls[off] >> 1);
+          uint32_t cl2 = seg_cls[off];
+          if (cl2 == T.stop_cl2) cl2 = 2u * class_at(X.in, X.N, seg_start + off, *X.cls);  // a rare class: from the raw bytes
+          e3 = t3_load(T, t, cl2 >> 1);
         }
         if ((e3 & F3_TGT) == 0) {  // 0: failure without epsilon transition; marked: leave to walk_run
-          L.pos = seg_start + off; L.t = t; L.eps_p = seg_start + eps_off;
-          L.eps_rec = eps_rec ? (ER_VALID | (eps_rec & F3_TGT) | ((eps_rec >> 14) & F3_KANY)) : 0;
+          L.pos = seg_start + off; L.t = t;
+          if (eps_bit) L.eps_p = seg_start + ctz32(eps_bit);
+          L.eps_rec = DATOK_EPS_REC();
           R.c1 = c1; R.c2 = c2; R.nt = nt;
           if (e3 != 0) { DATOK_STAT(g_mark); return FAST_SLOW; }
           if (fast_backtrack(L, R, T, seg_start, eotm, Bprev) != FAST_OK) return FAST_SLOW_FAIL;
           off = L.pos - seg_start; bit = 1u << off;
-          t = L.t; eps_rec = 0;
+          t = L.t; eps_rec = 0; eps_a = 0; eps_bit = 0;
           c1 = R.c1; c2 = R.c2; nt = R.nt;
           failed = false;
         } else {
@@ -377,7 +438,7 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
           if (e3 & F3_KANY) c1 |= bit;
           if (e3 & F3_K2) c2 |= bit;
           if (e3 & F3_NT) nt |= bit;
-          if (e3 & F3_EA) { eps_off = off; eps_rec = t | ((e3 & F3_KANY) << 14); }
+          if (e3 & F3_EA) { eps_bit = bit; eps_a = 0; eps_rec = ER_VALID | t | (e3 & F3_KANY); }
           t = e3 & F3_TGT;
           off++;
           bit += bit;
@@ -385,37 +446,50 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const uint8_
         if (t < T.n_hot || bit == end_bit) break;
       }
       tl = t < T.n_hot ? t : T.n_hot;
+      t_cold = t;
+#if defined(__CUDA_ARCH__)
+      p = cls_saddr + off;
+#endif
       continue;
     }
     DATOK_STAT(g_fast);
 #if defined(DATOK_COUNT) && !defined(__CUDA_ARCH__)
-    g_hist[t]++;
+    g_hist[tl]++;
 #endif
 #if defined(__CUDA_ARCH__)
+    // (one flag per bit of the entry's high byte: the four tests become one R2P)
     asm("{\n\t.reg .pred pk, p2, pn, pe;\n\t.reg .b32 x;\n\t"
-        "and.b32 x, %5, 0xC000;\n\tsetp.ne.u32 pk, x, 0;\n\t"
-        "and.b32 x, %5, 0x8000;\n\tsetp.ne.u32 p2, x, 0;\n\t"
-        "and.b32 x, %5, 0x1000;\n\tsetp.ne.u32 pn, x, 0;\n\t"
-        "and.b32 x, %5, 0x2000;\n\tsetp.ne.u32 pe, x, 0;\n\t"
+        "and.b32 x, %5, 0x2000;\n\tsetp.ne.u32 pk, x, 0;\n\t"
+        "and.b32 x, %5, 0x4000;\n\tsetp.ne.u32 p2, x, 0;\n\t"
+        "and.b32 x, %5, 0x0800;\n\tsetp.ne.u32 pn, x, 0;\n\t"
+        "and.b32 x, %5, 0x1000;\n\tsetp.ne.u32 pe, x, 0;\n\t"
         "@pk or.b32 %0, %0, %6;\n\t"
         "@p2 or.b32 %1, %1, %6;\n\t"
         "@pn or.b32 %2, %2, %6;\n\t"
-        "@pe mov.b32 %3, %7;\n\t"
-        "@pe mad.lo.u32 %4, %5, 65536, %8;\n\t}"
-        : "+r"(c1), "+r"(c2), "+r"(nt), "+r"(eps_off), "+r"(eps_rec)
-        : "r"(e), "r"(bit), "r"(off), "r"(t));
+        "@pe mov.b32 %3, %6;\n\t"
+        "@pe mov.b32 %4, %7;\n\t}"
+        : "+r"(c1), "+r"(c2), "+r"(nt), "+r"(eps_bit), "+r"(eps_a)
+        : "r"(e), "r"(bit), "r"(a));
+    p++;
 #else
     if (e & F16_KANY) c1 |= bit;
     if (e & F16_K2) c2 |= bit;
     if (e & F16_NT) nt |= bit;
-    if (e & F16_EA) { eps_off = off; eps_rec = t | (e << 16); }
-#endif
-    t = tl = e & F16_TGT;
+    if (e & F16_EA) { eps_bit = bit; eps_a = a; }
     off++;
+#endif
+    tl = e & F16_TGT;
     bit += bit;
   } while (bit != end_bit);
-  L.pos = seg_start + off; L.t = t; L.eps_p = seg_start + eps_off;
-  L.eps_rec = eps_rec ? (ER_VALID | (eps_rec & F3_TGT) | ((eps_rec >> 14) & F3_KANY)) : 0;
+#if defined(__CUDA_ARCH__)
+  off = p - cls_saddr;
+#endif
+  t = tl == T.n_hot ? t_cold : tl;
+  L.pos = seg_start + off; L.t = t;
+  if (eps_bit) L.eps_p = seg_start + ctz32(eps_bit);
+  L.eps_rec = DATOK_EPS_REC();
+#undef DATOK_EPS_REC
+#undef DATOK_ROW_OF
   R.c1 = c1; R.c2 = c2; R.nt = nt;
   return FAST_OK;
 }
@@ -449,11 +523,14 @@ DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_sta
 
 // DOUBLED classes (2 * class: the byte offset into a compact table row) and rune starts of the
 // 32 bytes at seg_start (bytes >= N: no rune start, class unspecified).  seg_cls must be 4-byte
-// aligned.  ASCII bytes go through the LUT `ascii_cls2` (2 * class per ASCII byte) four at a
+// aligned and hold 33 bytes (the caller puts the walk's stop value behind the range).  ASCII bytes go through the LUT `ascii_cls2` (2 * class per ASCII byte) four at a
 // time; the few other bytes are decoded afterwards, one rune each.
 // *eot_word: positions holding the byte 0x04 (matrix.go:13,422).
+// Classes without a column in the compact rows are stored as stop_cl2 (the all-zero column).
+DATOK_HD uint32_t cap_cl2(uint32_t cl, uint32_t stop_cl2) { const uint32_t c2 = 2u * cl; return c2 < stop_cl2 ? c2 : stop_cl2; }
 DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start, const ClsTables& T,
-                               const uint8_t* ascii_cls2, uint8_t* seg_cls, uint32_t* rstart_word, uint32_t* eot_word, bool* any_invalid) {
+                               const uint8_t* ascii_cls2, uint32_t stop_cl2, uint8_t* seg_cls, uint32_t* rstart_word,
+                               uint32_t* eot_word, bool* any_invalid, uint32_t* nonascii_word = nullptr) {
   uint32_t words[8];
   load_segment_words(in, N, seg_start, words);
   uint32_t* out = reinterpret_cast<uint32_t*>(seg_cls);
@@ -463,8 +540,8 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
 #endif
   for (int k = 0; k < 8; k++) {
     const uint32_t v = words[k];
-    const uint32_t c0 = ascii_cls2[v & 0x7Fu], c1 = ascii_cls2[(v >> 8) & 0x7Fu];
-    const uint32_t c2 = ascii_cls2[(v >> 16) & 0x7Fu], c3 = ascii_cls2[(v >> 24) & 0x7Fu];
+    const uint32_t c0 = ascii_cls2[v & 0xFFu], c1 = ascii_cls2[(v >> 8) & 0xFFu];
+    const uint32_t c2 = ascii_cls2[(v >> 16) & 0xFFu], c3 = ascii_cls2[v >> 24];
     out[k] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);  // the LUT already holds 2 * class
     const uint32_t h = v & 0x80808080u;
     nonascii |= (((h >> 7) | (h >> 14) | (h >> 21) | (h >> 28)) & 0xFu) << (4 * k);
@@ -479,6 +556,7 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
         if (((words[k] >> (8 * j)) & 0xFFu) == 0x04u) eot |= 1u << (4 * k + j);
   }
   *eot_word = eot & valid;
+  if (nonascii_word) *nonascii_word = nonascii | ~valid;
   uint32_t rs = ~nonascii & valid;
   uint32_t m = nonascii & valid;
   while (m) {
@@ -486,12 +564,14 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
     m &= m - 1;
     const uint32_t p = seg_start + j;
     {
-      // the common case first: a well-formed two-byte rune below U+0100 (lead C2/C3: the Latin-1 letters)
-      const uint32_t b0 = in[p];
+      // the common case first: a well-formed two-byte rune below U+0100 (lead C2/C3: the Latin-1 letters).
+      // (The LUT left the bytes >= 0x80 in the class buffer as they are: no second trip to global memory.)
+      const uint32_t b0 = seg_cls[j];
       if ((b0 & 0xFEu) == 0xC2u && p + 1 < N) {
-        const uint32_t b1 = in[p + 1];
+        // (an ASCII neighbour has been replaced by its class: it is no continuation byte whatever that value looks like)
+        const uint32_t b1 = j + 1 < SEG ? (((nonascii >> (j + 1)) & 1u) ? seg_cls[j + 1] : 0u) : in[p + 1];
         if ((b1 & 0xC0u) == 0x80u) {
-          seg_cls[j] = (uint8_t)(2u * T.latin1_cls[((b0 & 1u) << 6) | (b1 & 0x3Fu)]);
+          seg_cls[j] = (uint8_t)cap_cl2(T.latin1_cls[((b0 & 1u) << 6) | (b1 & 0x3Fu)], stop_cl2);
           rs |= 1u << j;
           if (j + 1 < SEG) {
             seg_cls[j + 1] = (uint8_t)(2u * K_CLS_CONT);
@@ -503,7 +583,7 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
     }
     bool st, inv;
     const uint32_t cl = classify_pos(in, N, p, T, &st, &inv);
-    seg_cls[j] = (uint8_t)(2u * cl);
+    seg_cls[j] = (uint8_t)cap_cl2(cl, stop_cl2);
     if (st) rs |= 1u << j;
     if (inv) *any_invalid = true;
     if (st && !inv) {
@@ -517,6 +597,18 @@ DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start
     }
   }
   *rstart_word = rs;
+}
+
+// First sync point p in (seg_start + from_off, seg_start + to_off] of a classified segment: the byte before p is an
+// ASCII byte of a sync class (one the root state skips).  nonascii: the segment's bytes >= 0x80.  K_NOPOS if none.
+// (Classes without a column in the compact rows are stored as stop_cl2 and never count: a later point does as well.)
+DATOK_HD uint32_t find_sync_cls(const uint8_t* seg_cls, uint32_t nonascii, const uint32_t* sync_cls, uint32_t stop_cl2,
+                                uint32_t seg_start, uint32_t from_off, uint32_t to_off) {
+  for (uint32_t j = from_off; j < to_off; j++) {
+    const uint32_t c2 = seg_cls[j], c = c2 >> 1;
+    if (!((nonascii >> j) & 1u) && c2 != stop_cl2 && ((sync_cls[c >> 5] >> (c & 31)) & 1u)) return seg_start + j + 1;
+  }
+  return K_NOPOS;
 }
 
 // first sync point in (from, from+32] given the raw bytes: a position whose

@@ -21,6 +21,9 @@ namespace datok {
 
 constexpr int WALK_THREADS = 128;
 constexpr int LANE_CLS_STRIDE = 36;  // bytes of class scratch per lane (9 words: bank spread)
+constexpr int MAX_RUNES_SMEM = 96;   // the rune table of sigma is kept in shared memory up to this size
+constexpr int WALK_LUT_BYTES = 544 + 5 * MAX_RUNES_SMEM;  // LUTs of the walk kernel (multiple of 16)
+static_assert(WALK_LUT_BYTES % 16 == 0, "the compact rows start 16-byte aligned");
 
 // Persistent kernel, one CTA per SM.  The compact (u16) rows of the hottest states and the
 // byte->class LUTs live in shared memory; every lane owns one chunk at a time and walks it
@@ -31,28 +34,45 @@ __global__ void __launch_bounds__(THREADS, 1)
 walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n_hot) {
   extern __shared__ __align__(16) uint32_t smem[];
   if (REWALK && blockIdx.x * THREADS >= b.counters[1]) return;  // the list length is only known on the device
-  uint16_t* s_hot = reinterpret_cast<uint16_t*>(smem);
-  const uint32_t hot_entries = n_hot * m.stride16;
-  uint8_t* s_cls = reinterpret_cast<uint8_t*>(smem) + (((hot_entries + m.stride16) * 2u + 15u) & ~15u);
+  // layout: lane scratch | byte -> class LUTs | compact rows.  The first two have compile-time offsets, so a
+  // lane's scratch address is threadIdx.x * stride away from the window base wherever it is needed again.
+  uint8_t* s_cls = reinterpret_cast<uint8_t*>(smem);
   uint8_t* s_lut = s_cls + THREADS * LANE_CLS_STRIDE;
+  uint16_t* s_hot = reinterpret_cast<uint16_t*>(s_lut + WALK_LUT_BYTES);
+  const uint32_t hot_entries = n_hot * m.stride16;
   for (uint32_t k = threadIdx.x; k < hot_entries; k += THREADS) {
     uint32_t e = m.hot16[k];
     if ((e & F16_TGT) >= n_hot) e = 0;  // the target's row is not resident: that step goes through T3
     s_hot[k] = (uint16_t)e;
   }
   for (uint32_t k = threadIdx.x; k < m.stride16; k += THREADS) s_hot[hot_entries + k] = 0;  // row n_hot: "see T3"
+  // s_lut: ascii_cls[128] latin1_cls[128] | doubled, capped class per byte [256] | sync classes [32 B] |
+  // rune_key[MAX_RUNES_SMEM] u32, rune_cls[MAX_RUNES_SMEM] (the sorted non-Latin-1 runes of sigma)
+  uint32_t* s_sync = reinterpret_cast<uint32_t*>(s_lut + 512);
+  uint32_t* s_rkey = reinterpret_cast<uint32_t*>(s_lut + 544);
+  uint8_t* s_rcls = s_lut + 544 + 4 * MAX_RUNES_SMEM;
   if (threadIdx.x < 128) {
     s_lut[threadIdx.x] = m.cls.ascii_cls[threadIdx.x];
     s_lut[128 + threadIdx.x] = m.cls.latin1_cls[threadIdx.x];
-    s_lut[256 + threadIdx.x] = (uint8_t)(2u * m.cls.ascii_cls[threadIdx.x]);
+    s_lut[256 + threadIdx.x] = (uint8_t)cap_cl2(m.cls.ascii_cls[threadIdx.x], 2u * m.hot_cols);
+    s_lut[384 + threadIdx.x] = (uint8_t)(128 + threadIdx.x);
+    if (threadIdx.x < 8) s_sync[threadIdx.x] = m.sync_cls[threadIdx.x];
+    if (threadIdx.x < MAX_RUNES_SMEM && threadIdx.x < m.cls.n_rune) {
+      s_rkey[threadIdx.x] = m.cls.rune_key[threadIdx.x];
+      s_rcls[threadIdx.x] = m.cls.rune_cls[threadIdx.x];
+    }
   }
   __syncthreads();
   DeviceModel lm = m;
   lm.cls.ascii_cls = s_lut;
   lm.cls.latin1_cls = s_lut + 128;
+  if (m.cls.n_rune <= MAX_RUNES_SMEM) { lm.cls.rune_key = s_rkey; lm.cls.rune_cls = s_rcls; }
   FastTables FT;
   FT.hot16 = s_hot; FT.t3 = m.table2; FT.n_hot = n_hot; FT.row16 = m.stride16 * 2u; FT.stride3 = m.stride2;
   FT.ascii_cls2 = s_lut + 256;
+  FT.sync_cls = s_sync;
+  FT.stop_cl2 = 2u * m.hot_cols;
+  FT.row16_inv = 0xFFFFFFFFu / FT.row16 + 1u;  // (row16 is not a power of two: floor(2^32 / row16) == floor((2^32 - 1) / row16))
   {  // opaque to the compiler: otherwise the shared-window base is re-derived in every step of the hot loop
     const unsigned long long sa = __cvta_generic_to_shared(s_hot);
     asm volatile("cvt.u32.u64 %0, %1;" : "=r"(FT.hot_saddr) : "l"(sa));
@@ -78,12 +98,13 @@ int fused_threads_from_env() {
 }
 
 static size_t fused_smem_bytes_t(const DeviceModel& m, uint32_t n_hot, int threads) {
-  return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)threads * LANE_CLS_STRIDE + 384;
+  return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)threads * LANE_CLS_STRIDE + WALK_LUT_BYTES;
 }
+static_assert(LANE_CLS_STRIDE % 4 == 0, "the LUTs and the compact rows behind the lane scratch stay 4-byte aligned");
 size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot, int threads) { return fused_smem_bytes_t(m, n_hot, threads); }
 
 uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states, int threads) {
-  const size_t fixed = (size_t)threads * LANE_CLS_STRIDE + 384 + 16 + 1024 + (size_t)m.stride16 * 2;
+  const size_t fixed = (size_t)threads * LANE_CLS_STRIDE + WALK_LUT_BYTES + 16 + 1024 + (size_t)m.stride16 * 2;
   if (smem_limit <= fixed) return 1;
   size_t rows = (smem_limit - fixed) / ((size_t)m.stride16 * 2);
   if (rows > (size_t)n_states + 1) rows = (size_t)n_states + 1;
@@ -134,11 +155,12 @@ int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start
 
 // Calibration: visits per state on a sample, walked speculatively chunk by chunk
 // with the exact walker.  Wrong guesses only add noise to the ranking.
-__global__ void __launch_bounds__(WALK_THREADS) hist_kernel(DeviceModel m, WalkBuffers b, uint32_t* hist) {
+__global__ void __launch_bounds__(WALK_THREADS) hist_kernel(DeviceModel m, WalkBuffers b, uint32_t* hist, uint32_t hist_cls_offset) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b.n_chunks) return;
   WalkCtx c = make_walk_ctx(m, b);
   c.hist = hist;
+  c.hist_cls = hist + hist_cls_offset;
   const uint32_t lo = i * b.chunk, hi = lo + b.chunk;
   const uint32_t s = i == 0 ? 0u : find_sync(b.in, b.N, m.sync_ascii, lo, hi);
   if (s == K_NOPOS) return;
@@ -149,8 +171,8 @@ __global__ void __launch_bounds__(WALK_THREADS) hist_kernel(DeviceModel m, WalkB
   walk_run<true, true, false>(c, st, hi, &si);
 }
 
-void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cudaStream_t s) {
-  hist_kernel<<<(b.n_chunks + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, hist);
+void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, uint32_t hist_cls_offset, cudaStream_t s) {
+  hist_kernel<<<(b.n_chunks + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, hist, hist_cls_offset);
 }
 
 // ------------------------------------------------------------------ gather bound (measurement only)

@@ -39,7 +39,7 @@ uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_
 // measurement only: the dependent shared-memory gather chain of one byte step, nothing else (bench.py)
 int launch_gather_bound(uint32_t n_rows, uint32_t row16, uint32_t segs, int n_sms, uint32_t* sink, cudaStream_t s);
 // calibration histogram (visits per state, GPU numbering)
-void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, cudaStream_t s);
+void launch_hist(const DeviceModel& m, const WalkBuffers& b, uint32_t* hist, uint32_t hist_cls_offset, cudaStream_t s);
 // one fix-up round over `n_list` chunks (list == nullptr: all chunks 1..n_chunks-1)
 void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
 int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk_max, uint32_t n_hot, int n_sms,

@@ -171,7 +171,7 @@ int load_matok_file(const char* path, HostModel& m, std::string& why) {
   return build_layout(m, why);
 }
 
-int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
+int build_layout(HostModel& m, std::string& why, const uint64_t* hist, const uint64_t* cls_hist) {
   const int S = m.stateCount, K = m.sigmaCount, eps = m.epsilon;
   if (S < 1 || S + 1 >= 32768) { why = "state count not in 1..32766"; return DATOK_ERR_UNSUPPORTED_MODEL; }
   if (eps < 1 || eps >= K) { why = "no epsilon symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
@@ -274,13 +274,37 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
   m.n_classes = CLS_FIRST + (uint32_t)columns.size();
   if (m.n_classes > 256) { why = "more than 253 symbol classes"; return DATOK_ERR_UNSUPPORTED_MODEL; }
   m.row_shift = m.n_classes <= 128 ? 7 : 8;
-  for (int r = 0; r < 128; r++) m.ascii_cls[r] = (uint8_t)raw_ascii[r];
-  for (int r = 0; r < 128; r++) m.latin1_cls[r] = (uint8_t)raw_ascii[128 + r];
+  // class ids in order of measured frequency (the ids above are "base" ids: order of first use, the same
+  // for every layout of this model); epsilon, continuation and EOT keep their fixed ids
+  std::vector<uint32_t> perm(m.n_classes);  // base id -> class id
+  {
+    std::vector<uint32_t> by_freq;
+    for (uint32_t c = CLS_FIRST; c < m.n_classes; c++) by_freq.push_back(c);
+    if (cls_hist)
+      std::stable_sort(by_freq.begin(), by_freq.end(), [&](uint32_t x, uint32_t y) { return cls_hist[x] > cls_hist[y]; });
+    for (uint32_t c = 0; c < CLS_FIRST; c++) perm[c] = c;
+    for (size_t i = 0; i < by_freq.size(); i++) perm[by_freq[i]] = CLS_FIRST + (uint32_t)i;
+    m.cls_base.assign(m.n_classes, 0);
+    for (uint32_t c = 0; c < m.n_classes; c++) m.cls_base[perm[c]] = (uint8_t)c;
+  }
+  for (int r = 0; r < 128; r++) m.ascii_cls[r] = (uint8_t)perm[raw_ascii[r]];
+  for (int r = 0; r < 128; r++) m.latin1_cls[r] = (uint8_t)perm[raw_ascii[128 + r]];
   m.ascii_cls[4] = (uint8_t)CLS_EOT;
-  m.identity_cls = (uint8_t)ident;
+  m.identity_cls = (uint8_t)perm[ident];
   std::sort(hi.begin(), hi.end());
   m.rune_key.clear(); m.rune_cls.clear();
-  for (auto& kv : hi) { m.rune_key.push_back(kv.first); m.rune_cls.push_back((uint8_t)kv.second); }
+  for (auto& kv : hi) { m.rune_key.push_back(kv.first); m.rune_cls.push_back((uint8_t)perm[kv.second]); }
+  // columns of the compact rows: the classes that cover all but ~0.05 % of the measured bytes
+  m.hot_cols = m.n_classes;
+  if (cls_hist) {
+    uint64_t total = 0, cum = 0;
+    for (uint32_t c = 0; c < m.n_classes; c++) total += cls_hist[c];
+    cum = cls_hist[CLS_EPS] + cls_hist[CLS_CONT] + cls_hist[CLS_EOT];
+    uint32_t w = CLS_FIRST;
+    while (w < m.n_classes && (total - cum) * 2000 > total) { cum += cls_hist[m.cls_base[w]]; w++; }
+    m.hot_cols = std::max<uint32_t>(w, std::min<uint32_t>(m.n_classes, 24));
+  }
+  if (m.force_hot_cols) m.hot_cols = std::min<uint32_t>(m.n_classes, std::max<uint32_t>(m.force_hot_cols, CLS_FIRST));
 
   // --- table ---
   const size_t R = (size_t)1 << m.row_shift;
@@ -300,7 +324,7 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
     row[CLS_EPS] = conv(cell(eps, t));
     row[CLS_CONT] = (uint16_t)(m.new_of_old[t] | NT_BIT);
     row[CLS_EOT] = conv(eot_col[t]);
-    for (size_t c = 0; c < columns.size(); c++) row[CLS_FIRST + c] = conv(columns[c][t]);
+    for (size_t c = 0; c < columns.size(); c++) row[perm[CLS_FIRST + c]] = conv(columns[c][t]);
   }
   std::memset(m.sync_mask, 0, sizeof m.sync_mask);
   std::memset(m.sync_ascii, 0, sizeof m.sync_ascii);
@@ -352,18 +376,19 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist) {
     }
   }
   // --- compact rows of the hottest states ---
-  m.stride16 = ((m.n_classes + 1) / 2 | 1u) * 2;
+  // (column hot_cols and the padding behind it stay zero)
+  m.stride16 = ((m.hot_cols + 2) / 2 | 1u) * 2;
   m.hot16_rows = std::min<uint32_t>((uint32_t)S + 1, H16_MAX_ROWS);
   m.hot16.assign((size_t)m.hot16_rows * m.stride16, 0);
   for (uint32_t t = 1; t < m.hot16_rows && m.fast_ok; t++) {
     const uint32_t* row2 = &m.table2[(size_t)t * m.stride2];
     uint16_t* h = &m.hot16[(size_t)t * m.stride16];
-    for (uint32_t c = 0; c < m.n_classes; c++) {
-      const uint32_t e = row2[c], tgt = e & T3_TGT;
+    for (uint32_t c = 0; c < m.hot_cols; c++) {
+      const uint32_t e = row2[c], tgt = e & T3_TGT, k = (e >> T3_K_SHIFT) & 3u;
       if (e == 0 && c != CLS_EPS) { h[c] = (uint16_t)H16_FAIL; continue; }
       if (e == 0 || (e & T3_SLOW) || tgt >= H16_MAX_ROWS) continue;
       h[c] = (uint16_t)(tgt | ((e & T3_NTBIT) ? H16_NTBIT : 0u) | ((e & T3_EPSBIT) ? H16_EPSBIT : 0u) |
-                        (((e >> T3_K_SHIFT) & 3u) << H16_K_SHIFT));
+                        (k >= 1 ? H16_KANYBIT : 0u) | (k >= 2 ? H16_K2BIT : 0u));
     }
   }
   return DATOK_OK;

@@ -35,14 +35,20 @@ constexpr uint32_t T3_NTBIT = 1u << 15;
 constexpr uint32_t T3_K_SHIFT = 16;
 constexpr uint32_t T3_EPSBIT = 1u << 18;
 constexpr uint32_t T3_SLOW = 1u << 31;
-// compact copy of the rows of the hottest states for shared memory, entry (u16): [11:0] target
-// state, [12] non-token, [13] consuming state has an epsilon transition, [15:14] epsilon steps.
+// compact copy of the rows of the hottest states for shared memory, entry (u16): [10:0] target
+// state, [11] non-token, [12] consuming state has an epsilon transition, [13] at least one epsilon step,
+// [14] two epsilon steps -- one flag per bit of the high byte, below bit 7 of that byte: the walk moves all
+// four into predicates with one R2P instruction.
 // 0 = look the entry up in T3 (marked, or a target that is not among the hot rows); H16_FAIL = T3 holds 0.
-constexpr uint32_t H16_TGT = 0x0FFFu;
-constexpr uint32_t H16_NTBIT = 1u << 12;
-constexpr uint32_t H16_EPSBIT = 1u << 13;
-constexpr uint32_t H16_K_SHIFT = 14;
-constexpr uint32_t H16_MAX_ROWS = 4096;
+// A compact row holds the hot_cols most frequent classes only (class ids are ordered by measured
+// frequency); column hot_cols is all zero: rarer classes -- and the walk's end-of-range sentinel -- are
+// mapped there and take the path through T3.
+constexpr uint32_t H16_TGT = 0x07FFu;
+constexpr uint32_t H16_NTBIT = 1u << 11;
+constexpr uint32_t H16_EPSBIT = 1u << 12;
+constexpr uint32_t H16_KANYBIT = 1u << 13;
+constexpr uint32_t H16_K2BIT = 1u << 14;
+constexpr uint32_t H16_MAX_ROWS = 2048;
 constexpr uint32_t H16_FAIL = H16_NTBIT;  // target 0 with this flag: T3 holds 0 (failure without epsilon transition)
 
 struct HostModel {
@@ -73,8 +79,11 @@ struct HostModel {
   std::vector<uint32_t> table2;    // fused table T3, (S+1) * stride2 entries
   uint32_t stride2 = 0;            // >= n_classes
   std::vector<uint16_t> hot16;     // compact rows of states 0..hot16_rows-1, stride16 entries each
-  uint32_t stride16 = 0;           // entries per compact row; stride16 / 2 is odd (shared-memory bank spread)
+  uint32_t stride16 = 0;           // entries per compact row (> hot_cols); stride16 / 2 is odd (shared-memory bank spread)
   uint32_t hot16_rows = 0;
+  uint32_t hot_cols = 0;           // classes 0..hot_cols-1 have a column in the compact rows
+  uint32_t force_hot_cols = 0;     // != 0: that many columns whatever the histogram says (DATOK_HOT_COLS, tests)
+  std::vector<uint8_t> cls_base;   // class id -> layout-independent id (order of first use), for calibration histograms
   bool fast_ok = false;            // the fused tables are usable (else every entry is marked T3_SLOW / 0)
 };
 
@@ -83,7 +92,9 @@ int load_matok_file(const char* path, HostModel& m, std::string& why);
 int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why);
 // hist (optional): visits per reference state id (stateCount+1 entries) measured on
 // representative text; without it states are ordered breadth-first from the root.
-int build_layout(HostModel& m, std::string& why, const uint64_t* hist = nullptr);
+// cls_hist (optional): occurrences per layout-independent class id (256 entries, see cls_base): class ids
+// are then ordered by frequency and the compact rows keep the frequent ones only.
+int build_layout(HostModel& m, std::string& why, const uint64_t* hist = nullptr, const uint64_t* cls_hist = nullptr);
 
 // Go unicode/utf8.DecodeRune (what bufio.Reader.ReadRune yields, matrix.go:392)
 int32_t decode_rune(const uint8_t* p, size_t n, int* width);

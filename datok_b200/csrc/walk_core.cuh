@@ -147,8 +147,14 @@ DATOK_HD uint32_t utf8_seq(const uint8_t* in, uint32_t N, uint32_t q, uint32_t* 
 // starts are decidable from a 3-byte neighbourhood: every non-continuation byte
 // starts a rune; a continuation byte starts one (as U+FFFD) unless a well-formed
 // sequence beginning within the 3 bytes before it covers it.
-DATOK_HD uint32_t classify_pos(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables& T,
-                               bool* is_start, bool* invalid) {
+// (not inlined on the device: it is needed in several rarely taken places, and the kernel's hot code should
+// stay small enough for the instruction caches)
+#if defined(DATOK_NI_CLASSIFY)
+DATOK_HD_SLOW
+#else
+DATOK_HD
+#endif
+uint32_t classify_pos(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables& T, bool* is_start, bool* invalid) {
   uint32_t b = in[p];
   *invalid = false;
   *is_start = true;
@@ -209,15 +215,18 @@ struct WalkCtx {
   uint32_t* b_sent;
   uint32_t* b_tend;
   uint32_t* hist;         // optional: visits per state (calibration of the hot-row order)
+  uint32_t* hist_cls;     // with hist: occurrences per class (calibration of the class order)
   uint32_t final_input;   // 0: the stream continues in a later call: no end-of-input processing (matrix.go:650-695)
 };
 
-DATOK_HD uint32_t cls_at(const WalkCtx& c, uint32_t pos) {
-  const uint32_t b = c.in[pos];
-  if (b < 0x80) return c.cls.ascii_cls[b];
+// class of the byte at pos (continuation bytes of a well-formed rune: K_CLS_CONT)
+DATOK_HD uint32_t class_at(const uint8_t* in, uint32_t N, uint32_t pos, const ClsTables& T) {
+  const uint32_t b = in[pos];
+  if (b < 0x80) return T.ascii_cls[b];
   bool st, inv;
-  return classify_pos(c.in, c.N, pos, c.cls, &st, &inv);
+  return classify_pos(in, N, pos, T, &st, &inv);
 }
+DATOK_HD uint32_t cls_at(const WalkCtx& c, uint32_t pos) { return class_at(c.in, c.N, pos, c.cls); }
 
 // True iff more than 1024 runes would have been buffered: runes in [base, hw].
 // Only ever evaluated when the byte distance alone allows it, i.e. practically never.
@@ -353,8 +362,10 @@ DATOK_HD uint32_t walk_run_inl(const WalkCtx& c, WState& st, uint32_t stop, Spec
       if (c.hist) {
 #if defined(__CUDA_ARCH__)
         atomicAdd(&c.hist[t], 1u);
+        atomicAdd(&c.hist_cls[cl], 1u);
 #else
         c.hist[t]++;
+        c.hist_cls[cl]++;
 #endif
       }
       if (row[K_CLS_EPS] != 0) { eps_state = t; eps_pos = pos; }  // :442-454

@@ -40,7 +40,7 @@ struct EmulModel {
   DeviceModel dm;
 };
 
-static uint8_t g_ascii_cls2[128];
+static uint8_t g_ascii_cls2[256];
 // the kernel prologue's job: n_hot compact rows with non-resident targets zeroed
 static void make_fast_tables(const HostModel& hm, const DeviceModel& m, uint32_t n_hot, std::vector<uint16_t>& hot,
                              FastTables& FT) {
@@ -48,9 +48,9 @@ static void make_fast_tables(const HostModel& hm, const DeviceModel& m, uint32_t
   hot.assign(hm.hot16.begin(), hm.hot16.begin() + (size_t)n_hot * hm.stride16);
   for (auto& e : hot) if ((e & F16_TGT) >= n_hot) e = 0;
   hot.resize(hot.size() + hm.stride16, 0);  // the all-zero row n_hot
-  for (int i = 0; i < 128; i++) g_ascii_cls2[i] = (uint8_t)(2 * hm.ascii_cls[i]);
+  for (int i = 0; i < 128; i++) { g_ascii_cls2[i] = (uint8_t)cap_cl2(hm.ascii_cls[i], 2 * hm.hot_cols); g_ascii_cls2[128 + i] = (uint8_t)(128 + i); }
   FT.hot16 = hot.data(); FT.t3 = m.table2; FT.n_hot = n_hot; FT.row16 = hm.stride16 * 2u; FT.stride3 = m.stride2;
-  FT.hot_saddr = 0; FT.ascii_cls2 = g_ascii_cls2;
+  FT.hot_saddr = 0; FT.ascii_cls2 = g_ascii_cls2; FT.stop_cl2 = 2 * hm.hot_cols; FT.sync_cls = hm.sync_mask;
 }
 
 EmulModel* emul_load(const char* path, int* err) {
@@ -63,14 +63,38 @@ EmulModel* emul_load(const char* path, int* err) {
   m->dm.table2 = h.table2.data();
   m->dm.hot16 = h.hot16.data();
   m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.n_classes = h.n_classes; m->dm.stride2 = h.stride2;
-  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows;
+  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols;
   m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
   m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
   m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls;
   std::memcpy(m->dm.sync_ascii, h.sync_ascii, sizeof h.sync_ascii);
+  std::memcpy(m->dm.sync_cls, h.sync_mask, sizeof h.sync_mask);
   *err = 0;
   return m;
 }
+// re-lays the model out like the product's one-time calibration (api.cu calibrate_locked): class ids in
+// order of their frequency in `data`, compact rows with the frequent classes only (force_cols != 0: that many)
+int emul_calibrate(EmulModel* m, const uint8_t* data, uint32_t n, uint32_t force_cols) {
+  HostModel& h = m->hm;
+  std::vector<uint64_t> cls_hist(256, 0);
+  for (uint32_t p = 0; p < n; p++) cls_hist[h.cls_base[class_at(data, n, p, m->dm.cls)]]++;
+  h.force_hot_cols = force_cols;
+  std::string why;
+  int rc = build_layout(h, why, nullptr, n ? cls_hist.data() : nullptr);
+  if (rc) return rc;
+  m->dm.table = h.table.data();
+  m->dm.table2 = h.table2.data();
+  m->dm.hot16 = h.hot16.data();
+  m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.n_classes = h.n_classes; m->dm.stride2 = h.stride2;
+  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols;
+  m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
+  m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
+  m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls;
+  std::memcpy(m->dm.sync_ascii, h.sync_ascii, sizeof h.sync_ascii);
+  std::memcpy(m->dm.sync_cls, h.sync_mask, sizeof h.sync_mask);
+  return 0;
+}
+uint32_t emul_hot_cols(EmulModel* m) { return m->hm.hot_cols; }
 void emul_free(EmulModel* m) { delete m; }
 uint32_t emul_n_classes(EmulModel* m) { return m->hm.n_classes; }
 uint32_t emul_new_state(EmulModel* m, uint32_t old_state) { return m->hm.new_of_old[old_state]; }
@@ -117,7 +141,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
     FastTables FT;
     std::vector<uint16_t> hot;
     make_fast_tables(em->hm, m, (uint32_t)mode, hot, FT);
-    uint8_t seg_cls[32];
+    uint8_t seg_cls[36];
     for (uint32_t k = 0; k < b.n_chunks; k++)
       chunk_spec_fast(m, b, FT, order ? b.n_chunks - 1 - k : k, start_state, seg_cls);
   }

@@ -51,6 +51,10 @@ def lib():
         L.emul_transduce.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emul_result_free.argtypes = [C.POINTER(_Res)]
+        L.emul_calibrate.restype = C.c_int
+        L.emul_calibrate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.emul_hot_cols.restype = C.c_uint32
+        L.emul_hot_cols.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -71,6 +75,13 @@ class EmulModel:
         if not self._h:
             raise ValueError(f"emul: cannot load {path}: {err.value}")
         self.n_classes = lib().emul_n_classes(self._h)
+
+    def calibrate(self, data, force_cols=0):
+        """class ids by frequency in `data`, compact rows with the frequent classes only (the product's calibration)"""
+        a = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        rc = lib().emul_calibrate(self._h, a.ctypes.data if a.size else None, a.size, force_cols)
+        assert rc == 0, rc
+        return lib().emul_hot_cols(self._h)
 
     def transduce(self, data, flags, chunk=64, order=0, carry_state=0, sentence_end=0, text_end=0, mode=0):
         """mode 0: exact walker only; mode n > 0: fused fast path with n hot table rows"""

@@ -164,3 +164,26 @@ def test_carry_between_calls(oracle_models, emul_models):
     P.assert_matches_oracle(sb, ob, 15, "second shard")
     whole = om.transduce(a + b, 15)
     assert whole.text == oa.text + ob.text
+
+
+@pytest.mark.parametrize("model,kind", [("tokenizer_de.matok", 2), ("tokenizer_en.matok", 3), ("tokenizer_de.matok", 4),
+                                        ("simpletok.matok", 1)])
+def test_frequency_ordered_classes_and_narrow_rows(model, kind, testdata, oracle_models, corpus_lib):
+    """the calibrated layout: class ids ordered by frequency, compact rows holding the frequent classes only --
+    rarer classes go through the full table (fast_run's rare path), whatever the text they were measured on"""
+    em = P.EmulModel(os.path.join(testdata, model))
+    a = corpus_lib.generate(kind, 1 << 19, seed=3 + kind)
+    o = oracle_models[model].transduce_np(a, 15)
+    rng = random.Random(kind)
+    fuzz = [_fuzz_text(rng, rng.choice((33, 200, 1500, 5000))) for _ in range(60)]
+    n_cls = em.n_classes
+    for sample, force in ((a[:1 << 16], 0), (b"aaaa bbbb. ", 0), (a[:1 << 16], 5), (a[:1 << 16], 24), (b"", 0)):
+        cols = em.calibrate(sample, force)
+        assert 3 <= cols <= n_cls
+        for chunk, mode in ((640, 300), (64, 8), (256, 100000)):
+            P.assert_matches_oracle(em.transduce(a, 15, chunk, 0, mode=mode), o, 15, f"{model} cols={cols} chunk={chunk} mode={mode}")
+        for data in fuzz + ODD:
+            oo = oracle_models[model].transduce(data, 31)
+            P.assert_matches_oracle(em.transduce(data, 31, 96, 1, mode=64), oo, 31, f"{model} cols={cols} {data[:30]!r}")
+    if model == "tokenizer_de.matok" and kind == 2:
+        assert em.calibrate(a[:1 << 16], 0) < n_cls  # a German sample does not need every class in the compact rows

@@ -453,13 +453,16 @@ def test_stream_front_end(gpu_models, oracle_models):
     assert events == ref and len(events) > 1000
 
 
-@pytest.mark.parametrize("hot_rows,chunk,threads", [("8", "64", "256"), ("40", "96", "768"), ("300", "2048", "512")])
-def test_stress_configurations(hot_rows, chunk, threads, testdata, oracle_models, monkeypatch):
-    """few resident rows (most steps take the cold path through the full table), small and odd chunk sizes,
-    other CTA sizes: the rare paths of the real kernels under load"""
+@pytest.mark.parametrize("hot_rows,chunk,threads,hot_cols", [("8", "64", "256", ""), ("40", "96", "768", "12"),
+                                                             ("300", "2048", "512", ""), ("2000", "640", "1024", "30")])
+def test_stress_configurations(hot_rows, chunk, threads, hot_cols, testdata, oracle_models, monkeypatch):
+    """few resident rows (most steps take the cold path through the full table), few columns in the compact rows
+    (most classes take it), small and odd chunk sizes, other CTA sizes: the rare paths of the real kernels under load"""
     import datok_b200 as d
     from datok_b200 import corpus
     monkeypatch.setenv("DATOK_HOT_ROWS", hot_rows)
+    if hot_cols:
+        monkeypatch.setenv("DATOK_HOT_COLS", hot_cols)
     monkeypatch.setenv("DATOK_CHUNK", chunk)
     monkeypatch.setenv("DATOK_FUSED_THREADS", threads)
     rng = random.Random(int(hot_rows) * 7919 + int(chunk))
