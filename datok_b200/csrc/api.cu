@@ -301,6 +301,7 @@ int upload_model(datok_model* m) {
   d.cls.rune_key = m->d_rune_key;
   d.cls.n_rune = (uint32_t)nr;
   d.cls.identity_cls = h.identity_cls;
+  d.cls.self = nullptr;  // (set by the kernels: a copy in shared memory)
   std::memcpy(d.sync_ascii, h.sync_ascii, sizeof d.sync_ascii);
   std::memcpy(d.sync_cls, h.sync_mask, sizeof d.sync_cls);
   m->n_hot = fused_max_hot_rows(d, m->smem_optin, (uint32_t)h.stateCount, m->fused_threads);

@@ -193,12 +193,18 @@ int look_ahead(const FastTables& FT, const WalkCtx& c, uint32_t t, uint32_t hi, 
 // known state *from (its position lies in the chunk); the result goes to Enew[i] instead and the
 // rune-start words are left alone.
 DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const FastTables& FT, uint32_t i,
-                              uint32_t start_state, uint8_t* seg_cls, const WState* from = nullptr) {
+                              uint32_t start_state, uint8_t* seg_cls, const WState* from = nullptr, uint32_t stage_saddr = 0) {
   const WalkCtx c = make_walk_ctx(m, b);
   const uint32_t lo = i * b.chunk, hi = lo + b.chunk, N = b.N;
   const bool rewalk = from != nullptr;
   FastCtx FX;
   FX.in = b.in; FX.N = N; FX.cls = &m.cls;
+#if defined(DATOK_STAGE_ASYNC)
+  SegStage stage;
+  stage.slot_saddr = stage_saddr; stage.staged_for = K_NOPOS;
+#else
+  (void)stage_saddr;
+#endif
 #if !defined(__CUDA_ARCH__)
   g_own_lo = lo >> 5; g_own_hi = hi >> 5;
 #endif
@@ -264,11 +270,20 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     const uint32_t seg_end = seg_start + SEG, w = seg_start >> 5;
     uint32_t rs, eotm, nonascii;
     bool inv = false;
+#if defined(DATOK_STAGE_ASYNC)
+    classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, FT.stop_cl2, seg_cls, &rs, &eotm, &inv, &nonascii, &stage);
+#else
     classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, FT.stop_cl2, seg_cls, &rs, &eotm, &inv, &nonascii);
+#endif
     const uint32_t limit = seg_end < N ? seg_end : N;
 #if defined(__CUDA_ARCH__)
-    // the next segment's sector on its way while this one is walked (no registers held)
+    // the next segment on its way while this one is walked (no registers held): as a prefetch into L1, or
+    // (build option DATOK_STAGE_ASYNC) into the lane's staging slot through the async copy unit
+#if defined(DATOK_STAGE_ASYNC)
+    if (seg_end < hi && stage.slot_saddr) stage_segment(stage, b.in, N, seg_end);
+#else
     if (seg_end < hi && seg_end + SEG <= N) asm volatile("prefetch.global.L1 [%0];" :: "l"(b.in + seg_end));
+#endif
 #endif
     if (!rewalk && phase == PH_WALK) {
       store_word_keep(b.rstart + w, rs);
@@ -429,6 +444,9 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     in_regs = true;
   }
 
+#if defined(__CUDA_ARCH__) && defined(DATOK_STAGE_ASYNC)
+  if (stage.staged_for != K_NOPOS) asm volatile("cp.async.wait_all;" ::: "memory");  // (the slot is reused by the lane's next chunk)
+#endif
   SpecInfo si;
   si.first_hw = L.first_hw; si.had_rewind = L.first_window ? 0u : 1u;
   if (!started) st = wstate_invalid(0);
@@ -457,7 +475,7 @@ DATOK_HD void chunk_rewalk(const DeviceModel& m, const WalkBuffers& b, uint32_t 
 
 // K2c through the fast path: clears the chunk's bits from the re-walk position on, then walks.
 DATOK_HD void chunk_rewalk_fast(const DeviceModel& m, const WalkBuffers& b, const FastTables& FT, uint32_t i,
-                                uint8_t* seg_cls) {
+                                uint8_t* seg_cls, uint32_t stage_saddr = 0) {
   const uint32_t lo = i * b.chunk, hi = lo + b.chunk;
   const WState Y = b.Ytmp[i];
   const uint32_t from = (b.sync[i] == K_NOPOS) ? lo : Y.pos;
@@ -466,7 +484,7 @@ DATOK_HD void chunk_rewalk_fast(const DeviceModel& m, const WalkBuffers& b, cons
     chunk_rewalk(m, b, i);
     return;
   }
-  chunk_spec_fast(m, b, FT, i, 0, seg_cls, &Y);
+  chunk_spec_fast(m, b, FT, i, 0, seg_cls, &Y, stage_saddr);
   b.cflags[i] |= CF_OVERWRITTEN;
 }
 

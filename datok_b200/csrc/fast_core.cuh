@@ -494,9 +494,44 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
   return FAST_OK;
 }
 
-// loads the 32 raw bytes at `p` (zero padded beyond N) as 8 little-endian words
-DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_start, uint32_t* words) {
+// Asynchronous staging of a lane's next segment (device only): the 32 raw bytes go from global memory
+// into the lane's slot in shared memory through the async copy unit (cp.async, 2 x 16 bytes, no registers
+// held, L1 bypassed) while the lane walks the current segment; the next classification finds them there.
+struct SegStage {
+  uint32_t slot_saddr;   // shared-window address of the lane's 32-byte slot (0: no staging, e.g. on the host)
+  uint32_t staged_for;   // position of the segment the slot holds or is being filled with (K_NOPOS: none)
+};
+DATOK_HD void stage_segment(SegStage& S, const uint8_t* in, uint32_t N, uint32_t seg_start) {
+#if defined(__CUDA_ARCH__)
   const uint8_t* p = in + seg_start;
+  if (S.slot_saddr && seg_start + SEG <= N && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.cg.shared.global [%0 + 16], [%1 + 16], 16;"
+                 :: "r"(S.slot_saddr), "l"(p) : "memory");
+    S.staged_for = seg_start;
+  }
+#else
+  (void)S; (void)in; (void)N; (void)seg_start;
+#endif
+}
+
+// loads the 32 raw bytes at `p` (zero padded beyond N) as 8 little-endian words
+DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_start, uint32_t* words, SegStage* S = nullptr) {
+  const uint8_t* p = in + seg_start;
+#if defined(__CUDA_ARCH__)
+  if (S && S->staged_for == seg_start) {  // staged while the previous segment was walked
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(words[0]), "=r"(words[1]), "=r"(words[2]), "=r"(words[3]) : "r"(S->slot_saddr));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4 + 16];" : "=r"(words[4]), "=r"(words[5]), "=r"(words[6]), "=r"(words[7]) : "r"(S->slot_saddr));
+    S->staged_for = K_NOPOS;
+    return;
+  }
+  if (S && S->staged_for != K_NOPOS) {  // a copy for another segment is in flight (the lane went elsewhere): let it land
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    S->staged_for = K_NOPOS;
+  }
+#else
+  (void)S;
+#endif
   if (seg_start + SEG <= N && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
 #if defined(__CUDA_ARCH__)
     const uint4 a = *reinterpret_cast<const uint4*>(p);
@@ -530,9 +565,10 @@ DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_sta
 DATOK_HD uint32_t cap_cl2(uint32_t cl, uint32_t stop_cl2) { const uint32_t c2 = 2u * cl; return c2 < stop_cl2 ? c2 : stop_cl2; }
 DATOK_HD void classify_segment(const uint8_t* in, uint32_t N, uint32_t seg_start, const ClsTables& T,
                                const uint8_t* ascii_cls2, uint32_t stop_cl2, uint8_t* seg_cls, uint32_t* rstart_word,
-                               uint32_t* eot_word, bool* any_invalid, uint32_t* nonascii_word = nullptr) {
+                               uint32_t* eot_word, bool* any_invalid, uint32_t* nonascii_word = nullptr,
+                               SegStage* stage = nullptr) {
   uint32_t words[8];
-  load_segment_words(in, N, seg_start, words);
+  load_segment_words(in, N, seg_start, words, stage);
   uint32_t* out = reinterpret_cast<uint32_t*>(seg_cls);
   uint32_t nonascii = 0, eot_any = 0;
 #if defined(__CUDA_ARCH__)

@@ -21,6 +21,16 @@ namespace datok {
 
 constexpr int WALK_THREADS = 128;
 constexpr int LANE_CLS_STRIDE = 36;  // bytes of class scratch per lane (9 words: bank spread)
+// Staging slot per lane for the next segment's raw bytes (cp.async, LDGSTS): a build option, off by default.
+// Measured (profiles/r2_stage_ab.txt, 1 GiB German): walk 3.88 ms without, 4.51 ms with -- the 32 KB of slots
+// cost ~200 resident table rows and the slot bookkeeping two registers in a kernel that is at its register limit,
+// which outweighs the input latency it hides (the L1 prefetch of the next sector already hides most of it).
+#if defined(DATOK_STAGE_ASYNC)
+constexpr int LANE_STAGE_BYTES = 32;
+#else
+constexpr int LANE_STAGE_BYTES = 0;
+#endif
+constexpr int LANE_SMEM = LANE_CLS_STRIDE + LANE_STAGE_BYTES;
 constexpr int MAX_RUNES_SMEM = 96;   // the rune table of sigma is kept in shared memory up to this size
 constexpr int WALK_LUT_BYTES = 544 + 5 * MAX_RUNES_SMEM;  // LUTs of the walk kernel (multiple of 16)
 static_assert(WALK_LUT_BYTES % 16 == 0, "the compact rows start 16-byte aligned");
@@ -36,7 +46,8 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   if (REWALK && blockIdx.x * THREADS >= b.counters[1]) return;  // the list length is only known on the device
   // layout: lane scratch | byte -> class LUTs | compact rows.  The first two have compile-time offsets, so a
   // lane's scratch address is threadIdx.x * stride away from the window base wherever it is needed again.
-  uint8_t* s_cls = reinterpret_cast<uint8_t*>(smem);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(smem);           // THREADS staging slots (16-byte aligned)
+  uint8_t* s_cls = s_stage + THREADS * LANE_STAGE_BYTES;
   uint8_t* s_lut = s_cls + THREADS * LANE_CLS_STRIDE;
   uint16_t* s_hot = reinterpret_cast<uint16_t*>(s_lut + WALK_LUT_BYTES);
   const uint32_t hot_entries = n_hot * m.stride16;
@@ -67,6 +78,12 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   lm.cls.ascii_cls = s_lut;
   lm.cls.latin1_cls = s_lut + 128;
   if (m.cls.n_rune <= MAX_RUNES_SMEM) { lm.cls.rune_key = s_rkey; lm.cls.rune_cls = s_rcls; }
+  {  // the struct itself, for the out-of-line classify_pos
+    __shared__ ClsTables s_ct;
+    lm.cls.self = &s_ct;
+    if (threadIdx.x == 0) s_ct = lm.cls;
+    __syncthreads();
+  }
   FastTables FT;
   FT.hot16 = s_hot; FT.t3 = m.table2; FT.n_hot = n_hot; FT.row16 = m.stride16 * 2u; FT.stride3 = m.stride2;
   FT.ascii_cls2 = s_lut + 256;
@@ -78,13 +95,14 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
     asm volatile("cvt.u32.u64 %0, %1;" : "=r"(FT.hot_saddr) : "l"(sa));
   }
   uint8_t* my_cls = s_cls + threadIdx.x * LANE_CLS_STRIDE;
+  const uint32_t my_stage = LANE_STAGE_BYTES ? (uint32_t)__cvta_generic_to_shared(s_stage + threadIdx.x * LANE_STAGE_BYTES) : 0u;
   if (REWALK) {
     const uint32_t n = b.counters[1];
     for (uint32_t k = blockIdx.x * THREADS + threadIdx.x; k < n; k += gridDim.x * THREADS)
-      chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls);
+      chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);
   } else {
     for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * THREADS)
-      chunk_spec_fast(lm, b, FT, i, start_state, my_cls);
+      chunk_spec_fast(lm, b, FT, i, start_state, my_cls, nullptr, my_stage);
   }
 }
 
@@ -98,13 +116,13 @@ int fused_threads_from_env() {
 }
 
 static size_t fused_smem_bytes_t(const DeviceModel& m, uint32_t n_hot, int threads) {
-  return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)threads * LANE_CLS_STRIDE + WALK_LUT_BYTES;
+  return ((((size_t)n_hot + 1) * m.stride16 * 2 + 15) & ~(size_t)15) + (size_t)threads * LANE_SMEM + WALK_LUT_BYTES;
 }
 static_assert(LANE_CLS_STRIDE % 4 == 0, "the LUTs and the compact rows behind the lane scratch stay 4-byte aligned");
 size_t fused_smem_bytes(const DeviceModel& m, uint32_t n_hot, int threads) { return fused_smem_bytes_t(m, n_hot, threads); }
 
 uint32_t fused_max_hot_rows(const DeviceModel& m, size_t smem_limit, uint32_t n_states, int threads) {
-  const size_t fixed = (size_t)threads * LANE_CLS_STRIDE + WALK_LUT_BYTES + 16 + 1024 + (size_t)m.stride16 * 2;
+  const size_t fixed = (size_t)threads * LANE_SMEM + WALK_LUT_BYTES + 16 + 1024 + (size_t)m.stride16 * 2;
   if (smem_limit <= fixed) return 1;
   size_t rows = (smem_limit - fixed) / ((size_t)m.stride16 * 2);
   if (rows > (size_t)n_states + 1) rows = (size_t)n_states + 1;
@@ -156,9 +174,13 @@ int launch_walk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t start
 // Calibration: visits per state on a sample, walked speculatively chunk by chunk
 // with the exact walker.  Wrong guesses only add noise to the ranking.
 __global__ void __launch_bounds__(WALK_THREADS) hist_kernel(DeviceModel m, WalkBuffers b, uint32_t* hist, uint32_t hist_cls_offset) {
+  __shared__ ClsTables s_ct;
+  if (threadIdx.x == 0) { s_ct = m.cls; s_ct.self = &s_ct; }
+  __syncthreads();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b.n_chunks) return;
   WalkCtx c = make_walk_ctx(m, b);
+  c.cls.self = &s_ct;
   c.hist = hist;
   c.hist_cls = hist + hist_cls_offset;
   const uint32_t lo = i * b.chunk, hi = lo + b.chunk;
@@ -230,6 +252,10 @@ int launch_gather_bound(uint32_t n_rows, uint32_t row16, uint32_t segs, int n_sm
 #endif
 __global__ void __launch_bounds__(WALK_THREADS, DATOK_STITCH_MINB) stitch_kernel(DeviceModel m, WalkBuffers b, const uint32_t* list,
                                                               uint32_t n_list) {
+  __shared__ ClsTables s_ct;
+  if (threadIdx.x == 0) { s_ct = m.cls; s_ct.self = &s_ct; }
+  __syncthreads();
+  m.cls.self = &s_ct;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_list) return;
   const uint32_t i = list ? list[k] : k + 1;

@@ -107,6 +107,7 @@ struct ClsTables {
   const uint8_t* rune_cls;
   uint32_t n_rune;
   uint32_t identity_cls;      // runes not in sigma -> identity (matrix.go:430-434)
+  const ClsTables* self;      // device: a copy of this struct in shared memory, for the out-of-line classify_pos
 };
 
 DATOK_HD uint32_t class_of_rune(const ClsTables& T, uint32_t r) {
@@ -147,14 +148,32 @@ DATOK_HD uint32_t utf8_seq(const uint8_t* in, uint32_t N, uint32_t q, uint32_t* 
 // starts are decidable from a 3-byte neighbourhood: every non-continuation byte
 // starts a rune; a continuation byte starts one (as U+FFFD) unless a well-formed
 // sequence beginning within the 3 bytes before it covers it.
-// (not inlined on the device: it is needed in several rarely taken places, and the kernel's hot code should
-// stay small enough for the instruction caches)
-#if defined(DATOK_NI_CLASSIFY)
-DATOK_HD_SLOW
+DATOK_HD uint32_t classify_pos_inl(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables& T, bool* is_start, bool* invalid);
+#if defined(__CUDA_ARCH__) && defined(DATOK_OUTLINE_CLASSIFY)
+// Measured alternative (-DDATOK_OUTLINE_CLASSIFY): the body once, out of line -- it is inlined in many rarely
+// taken places (every walker instance, the look-ahead, the rare classes of the fast path: ~3700 of the walk
+// kernel's ~10000 instructions).  The kernel shrinks by a third, but the calls cost more than the instruction
+// cache gains: walk 3.67 -> 3.87 ms, stitch 0.30 -> 0.37 ms per GiB.  The tables come through a copy of the
+// struct in shared memory (T.self): a reference to a kernel-local struct would force that struct into local memory.
+// Result: class | is_start << 8 | invalid << 9.
+static __device__ __noinline__ uint32_t classify_pos_call(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables* T) {
+  bool st, inv;
+  const uint32_t cl = classify_pos_inl(in, N, p, *T, &st, &inv);
+  return cl | (st ? 256u : 0u) | (inv ? 512u : 0u);
+}
+DATOK_HD uint32_t classify_pos(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables& T, bool* is_start, bool* invalid) {
+  const uint32_t r = classify_pos_call(in, N, p, T.self);
+  *is_start = (r >> 8) & 1u;
+  *invalid = (r >> 9) & 1u;
+  return r & 0xFFu;
+}
 #else
-DATOK_HD
+DATOK_HD uint32_t classify_pos(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables& T, bool* is_start, bool* invalid) {
+  return classify_pos_inl(in, N, p, T, is_start, invalid);
+}
 #endif
-uint32_t classify_pos(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables& T, bool* is_start, bool* invalid) {
+DATOK_HD
+uint32_t classify_pos_inl(const uint8_t* in, uint32_t N, uint32_t p, const ClsTables& T, bool* is_start, bool* invalid) {
   uint32_t b = in[p];
   *invalid = false;
   *is_start = true;

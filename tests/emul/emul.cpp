@@ -66,7 +66,7 @@ EmulModel* emul_load(const char* path, int* err) {
   m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols;
   m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
   m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
-  m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls;
+  m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls; m->dm.cls.self = nullptr;
   std::memcpy(m->dm.sync_ascii, h.sync_ascii, sizeof h.sync_ascii);
   std::memcpy(m->dm.sync_cls, h.sync_mask, sizeof h.sync_mask);
   *err = 0;
@@ -89,7 +89,7 @@ int emul_calibrate(EmulModel* m, const uint8_t* data, uint32_t n, uint32_t force
   m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols;
   m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
   m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
-  m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls;
+  m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls; m->dm.cls.self = nullptr;
   std::memcpy(m->dm.sync_ascii, h.sync_ascii, sizeof h.sync_ascii);
   std::memcpy(m->dm.sync_cls, h.sync_mask, sizeof h.sync_mask);
   return 0;
