@@ -10,10 +10,10 @@ Public surface mirrors the reference's Go API for that path:
 
 plus the offset-array API (`transduce_arrays`) the C ABI is built around.
 """
-from ._lib import (COMPACT, COMPACT8, NEWLINE_AFTER_EOT, NOT_FINAL, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Carry)
+from ._lib import (COMPACT, COMPACT8, FORMAT, NEWLINE_AFTER_EOT, NOT_FINAL, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Carry)
 from .tokenizer import (DatokError, LoadMatrixFile, LoadTokenizerFile, MatrixTokenizer, NewTokenWriter,
                         ReferencePanic, Result, TokenWriter)
 
 __all__ = ["LoadTokenizerFile", "LoadMatrixFile", "MatrixTokenizer", "NewTokenWriter", "TokenWriter", "Result",
-           "TOKENS", "SENTENCES", "TOKEN_POS", "SENTENCE_POS", "NEWLINE_AFTER_EOT", "SIMPLE", "WRITER_USED", "NOT_FINAL", "COMPACT", "COMPACT8",
+           "TOKENS", "SENTENCES", "TOKEN_POS", "SENTENCE_POS", "NEWLINE_AFTER_EOT", "SIMPLE", "WRITER_USED", "NOT_FINAL", "COMPACT", "COMPACT8", "FORMAT",
            "Carry", "DatokError", "ReferencePanic"]

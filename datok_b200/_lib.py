@@ -17,6 +17,7 @@ WRITER_USED = 256
 NOT_FINAL = 512
 COMPACT = 1024
 COMPACT8 = 2048
+FORMAT = 4096
 
 OK = 0
 ERR_BUFFER_OVERFLOW, ERR_SENT_NO_TOKEN, ERR_TEXT_NO_TOKEN, ERR_TEXT_NO_SENT, ERR_DEGENERATE = 1, 2, 3, 4, 5
@@ -43,6 +44,7 @@ class View(C.Structure):
         ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float),
         ("tok_delta", C.POINTER(C.c_uint16)),
         ("tok_delta8", C.POINTER(C.c_uint8)), ("tok_esc", C.POINTER(C.c_uint32)), ("n_esc", C.c_uint64),
+        ("text", C.POINTER(C.c_uint8)), ("text_len", C.c_uint64),
     ]
 
 

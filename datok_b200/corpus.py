@@ -15,6 +15,7 @@ MODEL_FOR_KIND = {SIMPLE: "simpletok.matok", GERMAN: "tokenizer_de.matok", ENGLI
                   GERMAN_LONGDOC: "tokenizer_de.matok"}
 
 _lib = None
+_ABBR_KEEP = []
 
 
 def _load():
@@ -26,6 +27,15 @@ def _load():
         _lib = C.CDLL(path)
         _lib.datok_corpus_generate.restype = C.c_size_t
         _lib.datok_corpus_generate.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_size_t]
+        _lib.datok_corpus_set_abbreviations.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+        # abbreviations are sampled from fixture copies of the reference's lists (src/de/abbrv.txt, 5743 forms;
+        # src/en/abbrv.txt, 346): SURVEY.md 8d
+        for english, name in ((0, "de"), (1, "en")):
+            f = os.path.join(os.path.dirname(HERE), "testdata", name, "abbrv.txt")
+            if os.path.exists(f):
+                blob = open(f, "rb").read()
+                _ABBR_KEEP.append(blob)  # the library keeps the pointer
+                _lib.datok_corpus_set_abbreviations(english, blob, len(blob))
     return _lib
 
 

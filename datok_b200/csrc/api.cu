@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/datok_b200.h"
+#include "format_kernels.cuh"
 #include "kernels.cuh"
 #include "model.hpp"
 
@@ -91,7 +92,7 @@ struct datok_model {
   uint32_t* h_mail = nullptr;    // mapped pinned host memory the kernels report small results through
   uint32_t* d_mail = nullptr;    // its device address
   Block d_in[3];                 // input pieces
-  Block d_out[2][5];             // per slot: tok_bytes, tok_pos, sent_pos, sent_tok, text arrays + DocRec
+  Block d_out[2][7];             // per slot: tok_bytes, tok_pos, sent_pos, sent_tok, text arrays + DocRec, formatter scratch, text
   size_t piece_bytes = (size_t)64 << 20;  // smallest piece; also: inputs >= 2 * piece_bytes are pipelined
   bool piece_fixed = false;               // DATOK_PIECE_MB: every piece has piece_bytes (else sized per call)
   bool pipelined = true;
@@ -604,6 +605,10 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   int rc = ensure_workspace(m, carve(nullptr, (uint32_t)max_piece, m->chunk, false, b, cb));
   if (rc) return rc;
 
+  // DATOK_FORMAT: every piece is formatted on the device from its (piece-relative, absolute-form) arrays, which
+  // stay there; the texts of the pieces are copied out one after the other
+  const bool fmt = (flags & DATOK_FORMAT) != 0;
+  if (fmt) flags &= ~(uint32_t)(DATOK_COMPACT | DATOK_COMPACT8);
   // in the compact modes the token slot 0 holds the deltas (8 or 4 bytes per token); slot 1 is unused by
   // DATOK_COMPACT and holds the escape list of DATOK_COMPACT8
   const bool compact8 = (flags & DATOK_COMPACT8) != 0, compact = compact8 || (flags & DATOK_COMPACT) != 0;
@@ -652,7 +657,10 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   r->device = false;
   std::memset(&r->view, 0, sizeof r->view);
   datok_view& v = r->view;
-  Block host[8];  // tok_bytes, tok_pos, sent_pos, sent_tok, text_tok_end, text_sent_end, text_sentpos_end, text_byte_end
+  Block host[9];  // tok_bytes, tok_pos, sent_pos, sent_tok, text_tok_end, text_sent_end, text_sentpos_end, text_byte_end, text
+  uint64_t text_bytes = 0;  // DATOK_FORMAT: text written so far
+  struct PieceBase { uint64_t x0, x1, tok, sent, sentpos, byte; };
+  std::vector<PieceBase> piece_bases;  // DATOK_FORMAT: the per-text bounds come back piece-relative
   auto fail = [&](int code) {
     cudaStreamSynchronize(m->s_h2d); cudaStreamSynchronize(m->s_d2h); cudaStreamSynchronize(s);
     for (auto& hb : host) release(m, hb);
@@ -715,6 +723,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
                                 : "internal: piece does not end at a text boundary";
       return fail(DATOK_ERR_NOT_AT_BOUNDARY);
     }
+    if (fmt && h.invalid) { fail(DATOK_OK); return -2; }  // malformed UTF-8: the single-pass path formats on the host
     // ---- room for this piece's results: device slot and the host arrays ----
     const size_t nt = h.tot.n_tok, ns = (size_t)h.tot.n_sent + 1, nx = (size_t)h.tot.n_text + 1,
                  nsp = (size_t)h.tot.n_sentpos + 1;
@@ -735,12 +744,13 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
                                est(base_text, nx) * 4, est(base_text, nx) * 4, est(base_text, nx) * 4, est(base_text, nx) * 4};
       const size_t used8[8] = {base_tok * tok_rec, base_tok * 8, base_sentpos * 4, base_sent * 4, base_text * 4, base_text * 4,
                                base_text * 4, base_text * 4};
-      const bool want8[8] = {want_bytes, want_pos, want_spos, want_stok, true, true, true, true};
+      const bool want8[8] = {want_bytes && !fmt, want_pos && !fmt, want_spos && !fmt, want_stok && !fmt, true, true, true, true};
       for (int i = 0; i < 8; i++)
         if (want8[i] && !host_room(i, need8[i], used8[i])) { g_last_error = "cudaHostAlloc (results) failed"; return fail(DATOK_ERR_CUDA); }
     }
     c.base_tok = (uint32_t)base_tok; c.base_sent = (uint32_t)base_sent; c.base_sentpos = (uint32_t)base_sentpos;
     c.base_byte = (uint32_t)cut[k];
+    if (fmt) c.base_tok = c.base_sent = c.base_sentpos = c.base_byte = 0;  // (the formatter reads these arrays: piece-relative)
     c.tok_bytes = (want_bytes && !compact) ? (uint32_t*)m->d_out[slot][0].p : nullptr;
     c.tok_delta = (want_bytes && compact && !compact8) ? (uint16_t*)m->d_out[slot][0].p : nullptr;
     c.tok_delta8 = (want_bytes && compact8) ? (uint8_t*)m->d_out[slot][0].p : nullptr;
@@ -766,6 +776,16 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     pt.end();
     m->launches += 4;  // texts, emit, finalize, mailbox
     struct { StreamTotals fin; unsigned long long err; } tail;
+    FmtCtx f;
+    std::memset(&f, 0, sizeof f);
+    if (fmt) {
+      // the prefix sums of the formatter right behind the emit pass (the counts are those of the reduce pass plus
+      // the end-of-stream events, which only the last piece has: it is sized with them)
+      f.in = b.in;
+      f.tok_bytes = c.tok_bytes; f.tok_pos = c.tok_pos; f.sent_pos = c.sent_pos; f.sent_tok = c.sent_tok;
+      f.text_tok_end = c.text_tok_end; f.text_sent_end = c.text_sent_end; f.text_sentpos_end = c.text_sentpos_end;
+      f.flags = flags & 15u;
+    }
     {
       MailSrc ms;
       std::memset(&ms, 0, sizeof ms);
@@ -774,10 +794,12 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       ms.p[2] = b.counters + 3; ms.words[2] = 1; ms.off[2] = 10;
       launch_mail(ms, m->d_mail, s);
     }
-    CUDA_TRYF(cudaEventRecord(k1, s));
+    if (!fmt) CUDA_TRYF(cudaEventRecord(k1, s));
     if (trace) cudaEventRecord(tev[6 * k + 3], s);
-    CUDA_TRYF(cudaEventRecord(m->ev_emit[slot], s));
-    CUDA_TRYF(cudaEventRecord(m->ev_free[islot], s));
+    if (!fmt) {
+      CUDA_TRYF(cudaEventRecord(m->ev_emit[slot], s));
+      CUDA_TRYF(cudaEventRecord(m->ev_free[islot], s));
+    }
     CUDA_TRYF(cudaStreamSynchronize(s));
     std::memcpy(&tail.fin, m->h_mail, sizeof(StreamTotals));
     std::memcpy(&tail.err, m->h_mail + 8, sizeof tail.err);
@@ -809,8 +831,45 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
       r->esc.resize(at + 2 * ne);
       CUDA_TRYF(cudaMemcpy(r->esc.data() + at, m->d_out[slot][1].p, ne * 8, cudaMemcpyDeviceToHost));
     }
+    unsigned long long piece_text = 0;
+    if (fmt) {
+      // ---- the piece's text: prefix sums, its length, room for it, the writers ----
+      f.n_tok = tail.fin.n_tok; f.n_sent = tail.fin.n_sent; f.n_sentpos = tail.fin.n_sentpos; f.n_text = tail.fin.n_text;
+      if (!grow_block(m->d_out[slot][5], format_scratch_bytes(f.n_tok, f.n_sentpos, f.n_text), false)) {
+        g_last_error = "cudaMalloc (formatter) failed";
+        return fail(DATOK_ERR_CUDA);
+      }
+      format_carve(f, (uint8_t*)m->d_out[slot][5].p);
+      unsigned long long* d_total = reinterpret_cast<unsigned long long*>(b.counters + 4);
+      int e = launch_format_scan(f, d_total, s);
+      MailSrc ms;
+      std::memset(&ms, 0, sizeof ms);
+      ms.p[0] = reinterpret_cast<const uint32_t*>(d_total); ms.words[0] = 2; ms.off[0] = 0;
+      launch_mail(ms, m->d_mail, s);
+      m->launches += 10;
+      if (e == 0) e = (int)cudaStreamSynchronize(s);
+      if (e != 0) { g_last_error = std::string("device formatter: ") + cudaGetErrorString((cudaError_t)e); return fail(DATOK_ERR_CUDA); }
+      std::memcpy(&piece_text, m->h_mail, sizeof piece_text);
+      if (!grow_block(m->d_out[slot][6], (size_t)piece_text + 16, false)) { g_last_error = "cudaMalloc (text) failed"; return fail(DATOK_ERR_CUDA); }
+      {
+        const double done = (double)cut[k + 1], scale = last_piece ? 1.0 : 1.12 * (double)n / done;
+        const size_t need = (size_t)((double)(text_bytes + piece_text) * scale) + 4096;
+        if (!host_room(8, need, (size_t)text_bytes)) { g_last_error = "cudaHostAlloc (text) failed"; return fail(DATOK_ERR_CUDA); }
+      }
+      f.out = (uint8_t*)m->d_out[slot][6].p;
+      e = launch_format_write(f, s);
+      m->launches += 2;
+      if (e != 0) { g_last_error = std::string("device formatter: ") + cudaGetErrorString((cudaError_t)e); return fail(DATOK_ERR_CUDA); }
+      CUDA_TRYF(cudaEventRecord(k1, s));
+      CUDA_TRYF(cudaEventRecord(m->ev_emit[slot], s));
+      CUDA_TRYF(cudaEventRecord(m->ev_free[islot], s));
+      piece_bases.push_back({base_text, base_text + tail.fin.n_text, base_tok, base_sent, base_sentpos, (uint64_t)cut[k]});
+    }
     // ---- results out, behind the kernels of the following pieces ----
     CUDA_TRYF(cudaStreamWaitEvent(m->s_d2h, m->ev_emit[slot], 0));
+    if (fmt && piece_text)
+      CUDA_TRYF(cudaMemcpyAsync((uint8_t*)host[8].p + text_bytes, m->d_out[slot][6].p, (size_t)piece_text, cudaMemcpyDeviceToHost, m->s_d2h));
+    text_bytes += piece_text;
     const uint32_t* dtx = (const uint32_t*)m->d_out[slot][4].p;
     struct Cp { int hi; const void* src; size_t off, bytes; };
     const Cp cps[8] = {{0, m->d_out[slot][0].p, base_tok * tok_rec, (size_t)tail.fin.n_tok * tok_rec},
@@ -821,7 +880,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
                        {5, dtx + nx, base_text * 4, (size_t)tail.fin.n_text * 4},
                        {6, dtx + 2 * nx, base_text * 4, (size_t)tail.fin.n_text * 4},
                        {7, dtx + 3 * nx, base_text * 4, (size_t)tail.fin.n_text * 4}};
-    const bool want8[8] = {want_bytes, want_pos, want_spos, want_stok, true, true, true, true};
+    const bool want8[8] = {want_bytes && !fmt, want_pos && !fmt, want_spos && !fmt, want_stok && !fmt, true, true, true, true};
     if (trace) cudaEventRecord(tev[6 * k + 4], m->s_d2h);
     for (const Cp& cp : cps)
       if (want8[cp.hi] && cp.bytes)
@@ -863,7 +922,17 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   }
   v.n_tokens = base_tok; v.n_sentences = base_sent; v.n_texts = base_text; v.n_sent_pos = base_sentpos; v.n_runes = runes;
   v.has_invalid_utf8 = invalid;
-  v.tok_bytes = (want_bytes && !compact) ? (const uint32_t*)host[0].p : nullptr;
+  if (fmt) {
+    // the per-text bounds of a formatted result came back relative to their piece
+    uint32_t* te[4] = {(uint32_t*)host[4].p, (uint32_t*)host[5].p, (uint32_t*)host[6].p, (uint32_t*)host[7].p};
+    for (const PieceBase& pb : piece_bases)
+      for (uint64_t d = pb.x0; d < pb.x1; d++) {
+        te[0][d] += (uint32_t)pb.tok; te[1][d] += (uint32_t)pb.sent; te[2][d] += (uint32_t)pb.sentpos; te[3][d] += (uint32_t)pb.byte;
+      }
+    v.text = (const uint8_t*)host[8].p;
+    v.text_len = text_bytes;
+  }
+  v.tok_bytes = (want_bytes && !compact && !fmt) ? (const uint32_t*)host[0].p : nullptr;
   v.tok_delta = (want_bytes && compact && !compact8) ? (const uint16_t*)host[0].p : nullptr;
   v.tok_delta8 = (want_bytes && compact8) ? (const uint8_t*)host[0].p : nullptr;
   if (v.tok_delta8) {
@@ -871,9 +940,9 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     v.tok_esc = r->esc.data();
     v.n_esc = r->esc.size() / 2;
   }
-  v.tok_pos = want_pos ? (const int32_t*)host[1].p : nullptr;
-  v.sent_pos = want_spos ? (const int32_t*)host[2].p : nullptr;
-  v.sent_tok = want_stok ? (const uint32_t*)host[3].p : nullptr;
+  v.tok_pos = (want_pos && !fmt) ? (const int32_t*)host[1].p : nullptr;
+  v.sent_pos = (want_spos && !fmt) ? (const int32_t*)host[2].p : nullptr;
+  v.sent_tok = (want_stok && !fmt) ? (const uint32_t*)host[3].p : nullptr;
   v.text_tok_end = (const uint32_t*)host[4].p;
   v.text_sent_end = (const uint32_t*)host[5].p;
   v.text_sentpos_end = (const uint32_t*)host[6].p;
@@ -953,6 +1022,10 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   std::memset(&r->view, 0, sizeof r->view);
   const size_t nt = hdr.tot.n_tok, ns = (size_t)hdr.tot.n_sent + 1, nx = (size_t)hdr.tot.n_text + 1,
                np = (size_t)hdr.tot.n_sentpos + 1;
+  // DATOK_FORMAT: the device formats the text from the absolute arrays, which then stay on the device (with
+  // malformed UTF-8 in the input the host formatter does it, from the arrays: surfaces are re-encoded)
+  const bool fmt = (flags & DATOK_FORMAT) != 0, fmt_dev = fmt && !hdr.invalid;
+  if (fmt) flags &= ~(uint32_t)(DATOK_COMPACT | DATOK_COMPACT8);
   const bool compact8 = (flags & DATOK_COMPACT8) != 0, compact = compact8 || (flags & DATOK_COMPACT) != 0;
   const bool want_tok = (flags & (DATOK_TOKENS | DATOK_TOKEN_POS)) != 0;
   const bool want_delta = compact && !compact8 && want_tok, want_delta8 = compact8 && want_tok;
@@ -971,9 +1044,10 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   for (auto& o : outs) {
     if (!o.want) continue;
     o.d = acquire(m, o.bytes, false, &rc);
-    if (!device_out) o.h = acquire(m, o.bytes, true, &rc);
+    const bool to_host = !device_out && (!fmt_dev || o.dev == &d_text);  // (formatted on the device: only the per-text bounds leave it)
+    if (to_host) o.h = acquire(m, o.bytes, true, &rc);
     r->blocks.push_back(o.d);
-    if (!device_out) r->blocks.push_back(o.h);
+    if (to_host) r->blocks.push_back(o.h);
     *o.dev = o.d.p;
   }
   if (rc) { free_result_locked(r); return rc; }
@@ -1068,9 +1142,48 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
     v.carry_out.sentence_end = (lk == EV_SENT || lk == EV_TEND) ? 1u : 0u;
     v.carry_out.text_end = (tail.fin.n_text > 0 && tail.fin.tokless) ? 1u : (text_end_in ? 1u : 0u);
   }
+  // ---- the text, on the device ----
+  Block text_d, text_h;
+  unsigned long long text_len = 0;
+  if (fmt_dev) {
+    FmtCtx f;
+    std::memset(&f, 0, sizeof f);
+    f.in = b.in;
+    f.tok_bytes = c.tok_bytes; f.tok_pos = c.tok_pos; f.sent_pos = c.sent_pos; f.sent_tok = c.sent_tok;
+    f.text_tok_end = c.text_tok_end; f.text_sent_end = c.text_sent_end; f.text_sentpos_end = c.text_sentpos_end;
+    f.n_tok = tail.fin.n_tok; f.n_sent = tail.fin.n_sent; f.n_sentpos = tail.fin.n_sentpos; f.n_text = tail.fin.n_text;
+    f.flags = flags & 15u;
+    Block scratch = acquire(m, format_scratch_bytes(f.n_tok, f.n_sentpos, f.n_text), false, &rc);
+    if (rc) { free_result_locked(r); return rc; }
+    r->blocks.push_back(scratch);
+    format_carve(f, (uint8_t*)scratch.p);
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(b.counters + 4);
+    int e = launch_format_scan(f, d_total, s);
+    MailSrc ms;
+    std::memset(&ms, 0, sizeof ms);
+    ms.p[0] = reinterpret_cast<const uint32_t*>(d_total); ms.words[0] = 2; ms.off[0] = 0;
+    launch_mail(ms, m->d_mail, s);
+    m->launches += 10;
+    if (e == 0) e = (int)cudaStreamSynchronize(s);
+    if (e != 0) { g_last_error = std::string("device formatter: ") + cudaGetErrorString((cudaError_t)e); free_result_locked(r); return DATOK_ERR_CUDA; }
+    std::memcpy(&text_len, m->h_mail, sizeof text_len);
+    text_d = acquire(m, (size_t)text_len + 16, false, &rc);
+    if (!device_out) text_h = acquire(m, (size_t)text_len + 16, true, &rc);
+    if (rc) { free_result_locked(r); return rc; }
+    r->blocks.push_back(text_d);
+    if (!device_out) r->blocks.push_back(text_h);
+    f.out = (uint8_t*)text_d.p;
+    e = launch_format_write(f, s);
+    m->launches += 2;
+    if (e != 0) { g_last_error = std::string("device formatter: ") + cudaGetErrorString((cudaError_t)e); free_result_locked(r); return DATOK_ERR_CUDA; }
+    CUDA_TRY(cudaEventRecord(m->ev[2], s));
+    if (!device_out && text_len) CUDA_TRY(cudaMemcpyAsync(text_h.p, text_d.p, (size_t)text_len, cudaMemcpyDeviceToHost, s));
+    v.text = (const uint8_t*)(device_out ? text_d.p : text_h.p);
+    v.text_len = text_len;
+  }
   // ---- D2H ----
   for (auto& o : outs) {
-    if (!o.want || device_out) continue;
+    if (!o.want || device_out || !o.h.p) continue;
     size_t bytes = o.bytes;
     if (o.dev == &d_tok_bytes || o.dev == &d_tok_pos || o.dev == &d_delta) bytes = 2 * (size_t)v.n_tokens * 4;
     else if (o.dev == &d_delta8) bytes = (size_t)v.n_tokens * 4;
@@ -1082,7 +1195,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   }
   CUDA_TRY(cudaEventRecord(m->ev[3], s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  auto pick = [&](int i) -> void* { return outs[i].want ? (device_out ? outs[i].d.p : outs[i].h.p) : nullptr; };
+  auto pick = [&](int i) -> void* { return outs[i].want ? (device_out ? (fmt_dev && i != 4 ? nullptr : outs[i].d.p) : outs[i].h.p) : nullptr; };
   v.tok_bytes = (const uint32_t*)pick(0);
   v.tok_pos = (const int32_t*)pick(1);
   v.sent_pos = (const int32_t*)pick(2);
@@ -1107,6 +1220,17 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   cudaEventElapsedTime(&v.ms_h2d, m->ev[0], m->ev[1]);
   cudaEventElapsedTime(&v.ms_kernels, m->ev[1], m->ev[2]);
   cudaEventElapsedTime(&v.ms_d2h, m->ev[2], m->ev[3]);
+  if (fmt && !fmt_dev && !device_out) {
+    // malformed UTF-8: Go re-encodes those bytes (U+FFFD), surfaces are not verbatim copies -> the host formatter
+    const size_t need = datok_format(r, in, n, flags & 15u, nullptr, 0);
+    if (need == (size_t)-1) { g_last_error = "formatter: arrays missing"; free_result_locked(r); return DATOK_ERR_INVALID_ARG; }
+    Block th = acquire(m, need + 16, true, &rc);
+    if (rc) { free_result_locked(r); return rc; }
+    r->blocks.push_back(th);
+    datok_format(r, in, n, flags & 15u, (uint8_t*)th.p, need);
+    v.text = (const uint8_t*)th.p;
+    v.text_len = need;
+  }
   if (!device_out) {  // the device copies are no longer needed
     std::vector<Block> keep;
     for (auto& blk : r->blocks) { if (blk.host) keep.push_back(blk); else release(m, blk); }
@@ -1171,7 +1295,7 @@ int datok_transduce(datok_model* m, const uint8_t* in, size_t n, uint32_t flags,
                     datok_result** out) {
   if (m && out && in && n < 0xFFFFFFFFull - (1u << 20) && n >= 2 * m->piece_bytes && m->pipelined) {
     const int rc = run_pipelined(m, in, n, flags, carry_in, out);
-    if (rc != -1) return rc;  // -1: no EOT to cut at
+    if (rc != -1 && rc != -2) return rc;  // -1: no EOT to cut at; -2: DATOK_FORMAT with malformed UTF-8
   }
   return run_pipeline(m, in, false, n, flags, carry_in, false, out);
 }

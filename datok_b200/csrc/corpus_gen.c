@@ -93,6 +93,43 @@ static const char *TYPO[] = {"\xe2\x80\x9e", "\xe2\x80\x9c", "\xe2\x80\x9d", "\x
 static const char *EMOTICONS[] = {":-)", ";)", ":))", ":*(", "^___^", "T__T", "^^;", "-_-;;;", ":-*", "->", "<-"};
 static const char *TLD[] = {"de", "com", "org", "net", "info", "eu"};
 
+/* Abbreviation lists of the reference's grammar (src/de/abbrv.txt, src/en/abbrv.txt: one form per line,
+ * without the final dot), handed in by the caller from fixture copies under testdata/; without them the
+ * short built-in lists above are used.  [0] German, [1] English. */
+static const char *g_abbr_text[2];
+static size_t g_abbr_len[2];
+static uint32_t *g_abbr_off[2];
+static uint32_t g_abbr_n[2];
+#include <stdlib.h>
+void datok_corpus_set_abbreviations(int english, const char *text, size_t len) {
+  const int k = english ? 1 : 0;
+  free(g_abbr_off[k]);
+  g_abbr_off[k] = NULL; g_abbr_n[k] = 0; g_abbr_text[k] = text; g_abbr_len[k] = len;
+  if (!text || !len) return;
+  uint32_t lines = 0;
+  for (size_t i = 0; i < len; i++) lines += text[i] == '\n';
+  g_abbr_off[k] = (uint32_t *)malloc((size_t)(lines + 2) * sizeof(uint32_t));
+  size_t st = 0;
+  for (size_t i = 0; i <= len; i++) {
+    if (i == len || text[i] == '\n') {
+      /* plain forms only: no blanks (the generator puts one abbreviation into one word slot) */
+      int ok = i > st && i - st < 40;
+      for (size_t j = st; j < i && ok; j++) ok = (unsigned char)text[j] > ' ';
+      if (ok) g_abbr_off[k][g_abbr_n[k]++] = (uint32_t)st;
+      st = i + 1;
+    }
+  }
+}
+static void put_abbreviation(gen_t *g, int en) {
+  const int k = en ? 1 : 0;
+  if (g_abbr_n[k] == 0) { puts_(g, en ? PICK(g, EN_ABBR) : PICK(g, DE_ABBR)); return; }
+  const char *p = g_abbr_text[k] + g_abbr_off[k][rndn(g, g_abbr_n[k])];
+  size_t l = 0;
+  while (p + l < g_abbr_text[k] + g_abbr_len[k] && p[l] != '\n') l++;
+  put(g, p, l);
+  putc_(g, '.');
+}
+
 static void synth_word(gen_t *g, int en, int capital) {
   int syl = 1 + (int)rndn(g, 100) / 45; /* 1..3, mean ~1.8 */
   if (chance(g, 600)) syl += 2;         /* occasional compound */
@@ -154,7 +191,7 @@ static void word_slot(gen_t *g, int first) {
     puts_(g, chance(g, 5000) ? "<b>" : "\"> <i>");
     return;
   }
-  if (r < (acc += p_abbr)) { puts_(g, en ? PICK(g, EN_ABBR) : PICK(g, DE_ABBR)); return; }
+  if (r < (acc += p_abbr)) { put_abbreviation(g, en); return; }
   if (r < (acc += p_num)) { number_like(g); return; }
   if (r < (acc += p_url)) { url_like(g, en); return; }
   if (r < (acc += p_xml)) {

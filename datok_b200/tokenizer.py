@@ -13,7 +13,7 @@ import sys
 import numpy as np
 
 from . import _lib
-from ._lib import (COMPACT, COMPACT8, NEWLINE_AFTER_EOT, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Callbacks,
+from ._lib import (COMPACT, COMPACT8, FORMAT, NEWLINE_AFTER_EOT, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Callbacks,
                    Carry, EVENT_CB, TOKEN_CB)
 
 
@@ -122,6 +122,9 @@ class Result:
             self.text_sent_end = arr(v.text_sent_end, v.n_texts)
             self.text_sentpos_end = arr(v.text_sentpos_end, v.n_texts)
             self.text_byte_end = arr(v.text_byte_end, v.n_texts)
+            # DATOK_FORMAT: the TokenWriter's text, formatted on the device (a numpy view of the result's pinned memory)
+            self.text = arr(v.text, v.text_len) if v.text else None
+        self.text_len = v.text_len
 
     def expand(self):
         """datok_expand(): absolute tok_bytes / tok_pos of a DATOK_COMPACT result (host-side decode)"""
@@ -213,16 +216,13 @@ class MatrixTokenizer:
         extra = COMPACT8 | (0 if final else _lib.NOT_FINAL)  # the smallest transport form: the host decodes it anyway
         if w._stock is not None:
             st = w._stock
-            # the formatter reads the delta-coded spans directly: half the bytes over PCIe
-            flags = st["flags"] | (0 if st["init"] else WRITER_USED) | extra
+            # the stock writer's text is formatted on the device (DATOK_FORMAT) and comes back in one piece
+            flags = st["flags"] | (0 if st["init"] else WRITER_USED) | FORMAT | (0 if final else _lib.NOT_FINAL)
             res = self.transduce_arrays_raw(addr, n, flags, carry)
             try:
                 if res.n_tokens:
                     st["init"] = False
-                need = L.datok_format(res._h, addr, n, st["flags"], None, 0)
-                out = C.create_string_buffer(max(1, need))
-                L.datok_format(res._h, addr, n, st["flags"], out, need)
-                st["w"].write(out.raw[:need])
+                st["w"].write(res.text.tobytes() if res.text is not None else b"")
                 return res.carry
             finally:
                 res.close()

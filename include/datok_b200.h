@@ -44,7 +44,12 @@ enum {
   DATOK_COMPACT = 1024,
   /* Not a reference flag: like DATOK_COMPACT with one byte per value (view.tok_delta8, 4 bytes per
    * token over PCIe).  A value that does not fit is stored as 255 and listed in view.tok_esc. */
-  DATOK_COMPACT8 = 2048
+  DATOK_COMPACT8 = 2048,
+  /* Not a reference flag: the result carries the text NewTokenWriter(w, flags) writes (view.text, view.text_len),
+   * formatted on the device (token_writer.go:59-167 as parallel writes, format_core.cuh) and copied back in one
+   * piece, instead of the token / sentence arrays (NULL then; the per-text bounds are still there).  The output of
+   * Transduce / TransduceTokenWriter with a stock writer is exactly these bytes. */
+  DATOK_FORMAT = 4096
 };
 
 /* Error codes.  1..6 mirror inputs on which the Go reference panics (they are
@@ -119,6 +124,9 @@ typedef struct {
   const uint8_t *tok_delta8;
   const uint32_t *tok_esc;
   uint64_t n_esc;
+  /* DATOK_FORMAT: the formatted text (pinned host memory; a device pointer from datok_transduce_device) */
+  const uint8_t *text;
+  uint64_t text_len;
 } datok_view;
 
 /* LoadTokenizerFile (fomafile.go:452-484) for the MATOK magic / LoadMatrixFile

@@ -175,10 +175,11 @@ class OracleModel:
         finally:
             lib().ora_result_free(rp)
 
-    def transduce_np(self, arr, flags=SIMPLE):
+    def transduce_np(self, arr, flags=SIMPLE, carry_in=None):
         """same, zero-copy over a contiguous uint8 numpy array"""
         arr = np.ascontiguousarray(arr, dtype=np.uint8)
-        rp = lib().ora_transduce(self._h, arr.ctypes.data, arr.size, flags, None)
+        cin = _Carry(**carry_in) if carry_in is not None else None
+        rp = lib().ora_transduce(self._h, arr.ctypes.data, arr.size, flags, C.byref(cin) if cin else None)
         try:
             return OracleResult(rp.contents)
         finally:

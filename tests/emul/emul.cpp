@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../datok_b200/csrc/chunk_core.cuh"
+#include "../../datok_b200/csrc/format_core.cuh"
 #include "../../datok_b200/csrc/model.hpp"
 
 using namespace datok;
@@ -33,6 +34,8 @@ struct EmulResult {
   uint8_t* tok_delta8;
   uint32_t* esc;
   uint32_t n_esc;
+  uint8_t* text;        // the device formatter's bodies (format_core.cuh) over the arrays above; null with malformed UTF-8
+  uint64_t text_len;
 };
 
 struct EmulModel {
@@ -271,13 +274,48 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   const StreamTotals fin = finalize_stream(c, total, text_end_in != 0, b.final_input != 0);
   R->n_tokens = fin.n_tok; R->n_sentences = fin.n_sent; R->n_texts = fin.n_text; R->n_sent_pos = fin.n_sentpos;
   if (err_key != ~0ull) R->status = (int)(err_key & 0xFF);
+  if (R->status == 0 && !R->has_invalid) {
+    // the device formatter, item by item like its kernels (format_kernels.cu): scans, then the writers
+    FmtCtx f;
+    std::memset(&f, 0, sizeof f);
+    f.in = in; f.tok_bytes = R->tok_bytes; f.tok_pos = R->tok_pos; f.sent_pos = R->sent_pos; f.sent_tok = R->sent_tok;
+    f.text_tok_end = R->text_tok_end; f.text_sent_end = R->text_sent_end; f.text_sentpos_end = R->text_sentpos_end;
+    f.n_tok = (uint32_t)R->n_tokens; f.n_sent = (uint32_t)R->n_sentences; f.n_sentpos = (uint32_t)R->n_sent_pos;
+    f.n_text = (uint32_t)R->n_texts; f.flags = flags & 15u;
+    std::vector<uint32_t> loc[4];
+    std::vector<unsigned long long> base[4];
+    auto scan = [&](int which, uint32_t n, FmtScan& sc) {
+      loc[which].assign((size_t)n + 1, 0);
+      base[which].assign((size_t)n / FMT_TILE + 2, 0);
+      unsigned long long run = 0;
+      uint32_t in_tile = 0;
+      for (uint32_t i = 0; i <= n; i++) {
+        if ((i & (FMT_TILE - 1)) == 0) { base[which][i >> FMT_TILE_SHIFT] = run; in_tile = 0; }
+        loc[which][i] = in_tile;
+        sc.local = loc[which].data(); sc.base = base[which].data();
+        if (i < n) {
+          const uint32_t v = which == 0 ? fmt_len_tok(f, i) : which == 1 ? fmt_len_pos(f, i) : which == 2 ? fmt_len_sp(f, i) : fmt_len_text(f, i);
+          in_tile += v; run += v;
+        }
+      }
+    };
+    scan(0, f.n_tok, f.ptok); scan(1, f.n_tok, f.ppos); scan(2, f.n_sentpos, f.psp); scan(3, f.n_text, f.px);
+    R->text_len = fmt_total(f);
+    R->text = (uint8_t*)std::malloc(R->text_len + 16);
+    std::memset(R->text, 0xEE, R->text_len + 16);
+    f.out = R->text;
+    for (uint32_t k = 0; k < f.n_tok; k++) fmt_write_token(f, order ? f.n_tok - 1 - k : k);
+    for (uint32_t i = 0; i < f.n_sent; i++) fmt_write_sentence(f, i);
+    for (uint32_t i = 0; i < f.n_text; i++) fmt_write_text(f, i);
+    for (uint32_t i = 0; i < f.n_sentpos; i++) fmt_write_sentpos(f, i);
+  }
   return R;
 }
 
 void emul_result_free(EmulResult* r) {
   if (!r) return;
   std::free(r->tok_bytes); std::free(r->tok_pos); std::free(r->tok_delta); std::free(r->tok_delta8); std::free(r->esc); std::free(r->sent_pos); std::free(r->sent_tok);
-  std::free(r->text_tok_end); std::free(r->text_sent_end); std::free(r->text_sentpos_end); std::free(r->text_byte_end);
+  std::free(r->text); std::free(r->text_tok_end); std::free(r->text_sent_end); std::free(r->text_sentpos_end); std::free(r->text_byte_end);
   std::free(r);
 }
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "emul", "libdatok_emul.so")
 SRCS = [os.path.join(HERE, "emul", "emul.cpp"), os.path.join(ROOT, "datok_b200", "csrc", "model.cpp")]
 DEPS = SRCS + [os.path.join(ROOT, "datok_b200", "csrc", f) for f in
-               ("walk_core.cuh", "chunk_core.cuh", "compact_core.cuh", "fast_core.cuh", "model.hpp")]
+               ("walk_core.cuh", "chunk_core.cuh", "compact_core.cuh", "fast_core.cuh", "format_core.cuh", "model.hpp")]
 
 
 def build():
@@ -32,7 +32,8 @@ class _Res(C.Structure):
                 ("carry_state", C.c_uint32), ("has_invalid", C.c_uint32),
                 ("rounds", C.c_uint32), ("n_rewalks", C.c_uint32), ("n_stitch_mismatch", C.c_uint32),
                 ("tok_delta", C.POINTER(C.c_uint16)), ("tok_delta8", C.POINTER(C.c_uint8)),
-                ("esc", C.POINTER(C.c_uint32)), ("n_esc", C.c_uint32)]
+                ("esc", C.POINTER(C.c_uint32)), ("n_esc", C.c_uint32),
+                ("text", C.POINTER(C.c_uint8)), ("text_len", C.c_uint64)]
 
 
 _lib = None
@@ -109,6 +110,7 @@ class EmulModel:
             s.tok_delta = _arr(r.tok_delta, 4 * r.n_tokens, np.uint16)
             s.tok_delta8 = _arr(r.tok_delta8, 4 * r.n_tokens, np.uint8)
             s.tok_esc = _arr(r.esc, 2 * r.n_esc, np.uint32)
+            s.text = bytes(C.string_at(r.text, r.text_len)) if r.text else None  # the device formatter's bodies
         lib().emul_result_free(rp)
         return s
 
@@ -175,6 +177,8 @@ def assert_matches_oracle(s, o, flags, ctx=""):
             np.testing.assert_array_equal(s.text_sentpos_end, o.text_sentpos_end.astype(np.uint32),
                                           err_msg=f"{ctx}: text sent-list bounds")
     assert s.carry_state == o.carry_out["state"], f"{ctx}: carry-out state"
+    if getattr(s, "text", None) is not None and not (flags & ~31):  # the emulation runs the device formatter's bodies too
+        assert s.text == o.text, f"{ctx}: device-formatted text"
     delta = getattr(s, "tok_delta", None)
     if delta is not None and delta.size and (flags & 12):  # the emulation also fills the DATOK_COMPACT form
         tb, tp = expand_delta(delta, s.text_tok_end, s.text_byte_end)

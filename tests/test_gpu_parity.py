@@ -513,3 +513,56 @@ def test_compact8_token_deltas(model, kind, gpu_models, oracle_models, testdata,
     assert tokp.format(rp, a, 15) == o.text
     P.assert_matches_oracle(rp.expand(), o, 15, "compact8 pipelined")
     tokp.close()
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3, 4, 5, 6, 7, 8, 12, 15, 16 | 15, 16 | 12, 16 | 8, 0])
+def test_device_formatter_every_flag_combination(flags, gpu_models, oracle_models):
+    """DATOK_FORMAT: the text half of the TokenWriter on the device (format_core.cuh) == NewTokenWriter(w, flags) output;
+    malformed UTF-8 (surfaces re-encoded) takes the host formatter behind the same flag"""
+    import datok_b200 as d
+    tok = gpu_models["tokenizer_de.matok"]
+    clean = ("\nErste Zeile. Und <b>noch</b> eine!\n\x04\nZweiter Text – mit „Zitat“ usw. Ende?\x04"
+             "Dritter.\n\x04\n").encode()
+    for data in (clean, clean + b"Kaputt \xff\xc3 hier.\x04", b"abc", b"a.\x04b.\x04c", "ä ö ü ß. Noch einer".encode()):
+        o = oracle_models["tokenizer_de.matok"].transduce(data, flags)
+        try:
+            r = tok.transduce_arrays(data, flags | d.FORMAT)
+        except d.ReferencePanic as e:
+            assert e.code == P.ORACLE_TO_ERR[o.status] != 0
+            continue
+        assert o.status == 0
+        assert r.text is not None and r.text.tobytes() == o.text, (flags, data[:20])
+        assert (r.has_invalid_utf8 or r.tok_bytes.size == 0) and r.n_tokens == o.n_tokens and r.n_texts == o.n_texts
+        np.testing.assert_array_equal(r.text_byte_end, o.text_byte_end)
+        r.close()
+
+
+@pytest.mark.parametrize("kind,model", [(2, "tokenizer_de.matok"), (3, "tokenizer_en.matok"), (1, "simpletok.matok"),
+                                        (4, "tokenizer_de.matok")])
+def test_device_formatter_on_corpora(kind, model, testdata, oracle_models, monkeypatch):
+    """single pass and EOT-aligned pieces (texts of the pieces concatenated, per-text bounds rebased), a reused writer"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    a = corpus.generate(kind, 5 << 20, seed=61 + kind)
+    monkeypatch.setenv("DATOK_PIECE_MB", "1")
+    tok = d.LoadTokenizerFile(os.path.join(testdata, model))
+    for flags in (15, 31, 3, 12, 5, 2):
+        o = oracle_models[model].transduce_np(a, flags)
+        r = tok.transduce_arrays(a, flags | d.FORMAT)              # pieces (if the corpus has EOTs)
+        assert r.text.tobytes() == o.text, f"kind={kind} flags={flags}"
+        np.testing.assert_array_equal(r.text_tok_end, o.text_tok_end.astype(np.uint32))
+        np.testing.assert_array_equal(r.text_sent_end, o.text_sent_end.astype(np.uint32))
+        np.testing.assert_array_equal(r.text_byte_end, o.text_byte_end)
+        r.close()
+        half = a[:1 << 20]
+        o = oracle_models[model].transduce_np(half, flags | 256)
+        r = tok.transduce_arrays(half, flags | 256 | d.FORMAT)     # one pass, TokenWriter already used
+        assert r.text.tobytes() == o.text
+        r.close()
+    # malformed UTF-8 in a piece: the call falls back to one pass and the host formatter
+    bad = a.copy()
+    bad[3 << 20] = 0xFF
+    o = oracle_models[model].transduce_np(bad, 15)
+    r = tok.transduce_arrays(bad, 15 | d.FORMAT)
+    assert r.has_invalid_utf8 and r.text.tobytes() == o.text
+    tok.close()
