@@ -9,18 +9,20 @@ flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS.
 
 One "step" = one pass of the hot path over one corpus batch of --size bytes per GPU
 (weak scaling: every rank owns its own EOT-aligned shard, generated from its own seed).
-  value       whole-job GB/s, input resident in HBM, offset arrays left in HBM
-              (CUDA events on the library's stream, max over ranks)
-  e2e         same through datok_transduce() with HOST buffers: pinned host input ->
-              H2D -> kernels -> D2H of the offset arrays
-  roofline    (N + 8T + 8S + 8D bytes) / device time of the whole path, vs the measured
-              HBM copy peak (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU oracle port (one worker per document, all host cores) on a
-              bounded sample of the same corpus
---impl reference times that CPU path alone (the Go reference cannot be built here).
+  value           whole-job GB/s, input resident in HBM, offset arrays left in HBM, token spans delta-coded
+                  (CUDA events on the library's stream, max over ranks); value_absolute: absolute offset arrays
+  e2e             the reference-facing call with HOST buffers, like for like with the reference arm:
+                  datok_transduce(DATOK_FORMAT): pinned host input -> H2D -> kernels -> the TokenWriter's text
+                  formatted on the device -> D2H of the text
+  e2e_arrays      the same call returning the offset arrays instead (delta-coded, 4 B/token)
+  roofline        (N + 8T + 8S + 8D bytes) / device time of the whole path, vs the measured
+                  HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline    the CPU oracle port (one worker per document, all host cores) on the same corpus
+--impl reference times that CPU path alone on the same corpus (the Go reference cannot be built here).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -36,17 +38,24 @@ sys.path.insert(0, ROOT)
 FLAGS = 1 | 2 | 4 | 8  # TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS  (= `datok tokenize -p --sentence-positions`)
 MODEL = os.path.join(ROOT, "testdata", "tokenizer_de.matok")
 METRIC = "GB/s input tokenized+sentence-split (de .matok)"
+SEED = 20261018
+
+
+def workload(nbytes):
+    return (f"C2: tokenizer_de.matok, {nbytes} B synthetic German corpus per GPU, ~10 KB EOT-separated documents "
+            "(abbreviations sampled from the reference's src/de/abbrv.txt), flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS")
 
 
 def measured_traffic(n_bytes):
     """DRAM bytes (read+write) of one step from the committed ncu --set full capture of the same
-    workload (profiles/r1_traffic.json, written by scripts/ncu_traffic.py); None if absent"""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if int(t["input_bytes"]) == int(n_bytes):
-            return float(t["dram_bytes_per_step"])
-    except Exception:
-        pass
+    workload (profiles/r2_traffic.json, written by scripts/ncu_traffic.py); None if absent"""
+    for name in ("r2_traffic.json",):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if int(t["input_bytes"]) == int(n_bytes):
+                return float(t["dram_bytes_per_step"])
+        except Exception:
+            pass
     return None
 
 
@@ -77,7 +86,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
@@ -91,8 +100,9 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
 
 
-def make_corpus(nbytes, seed, pinned_alloc=None):
+def make_corpus(nbytes, seed, pinned_alloc=None, kind=None):
     from datok_b200 import corpus
+    kind = kind or corpus.GERMAN
     if pinned_alloc is not None:
         ptr = pinned_alloc(nbytes)
         if not ptr:
@@ -101,58 +111,165 @@ def make_corpus(nbytes, seed, pinned_alloc=None):
         arr = np.frombuffer(buf, dtype=np.uint8)
     else:
         arr = np.empty(nbytes, dtype=np.uint8)
-    docs = corpus.generate_blocks_into(corpus.GERMAN, seed, arr, block=64 << 20)
+    if kind == corpus.GERMAN_LONGDOC:
+        docs = corpus.generate_into(kind, seed, arr)
+    else:
+        docs = corpus.generate_blocks_into(kind, seed, arr, block=64 << 20)
     return arr, docs
 
 
-def cpu_reference_rate(arr, seconds=15.0, threads=None):
-    """the oracle port on host cores, one worker per document, on a bounded sample"""
+def cpu_reference_pass(ora, arr, threads):
+    """one pass of the oracle port over the corpus, one worker per EOT-delimited document"""
+    t0 = time.perf_counter()
+    res = ora.transduce_docs_mt(arr, FLAGS, threads)
+    return time.perf_counter() - t0, res
+
+
+def cpu_baseline(arr, seconds=12.0):
     from oracle import pyoracle
-    threads = threads or os.cpu_count() or 1
+    threads = os.cpu_count() or 1
     ora = pyoracle.OracleModel(MODEL)
-    probe = arr[: min(arr.size, 4 << 20)]
-    cut = int(np.flatnonzero(probe == 4)[-1]) + 1
-    t0 = time.perf_counter()
-    ora.transduce_docs_mt(probe[:cut], FLAGS, threads)
-    rate = cut / (time.perf_counter() - t0)
-    want = int(min(arr.size, max(cut, rate * seconds)))
-    eots = np.flatnonzero(arr[:want] == 4)
-    n = int(eots[-1]) + 1
-    passes = max(1, int(round(rate * seconds / n)))
-    t0 = time.perf_counter()
-    for _ in range(passes):
-        res = ora.transduce_docs_mt(arr[:n], FLAGS, threads)
-    dt = time.perf_counter() - t0
-    return {"value": passes * n / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-            "sample": f"{passes} pass(es) over the first {n} bytes ({res['docs']} documents) of the same corpus, "
-                      f"{dt:.1f} s, C restatement of matrix.go:348-698 + token_writer.go (Go toolchain absent)",
-            "seconds": dt, "bytes": passes * n, "tokens": res["tokens"]}
+    dt, res = cpu_reference_pass(ora, arr, threads)
+    passes, total = 1, dt
+    while total < seconds and passes < 64:
+        dt, res = cpu_reference_pass(ora, arr, threads)
+        passes += 1
+        total += dt
+    return {"value": passes * arr.size / total / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"{passes} pass(es) over the whole corpus ({arr.size} bytes, {res['docs']} documents), {total:.1f} s; "
+                      "C restatement of matrix.go:348-698 + token_writer.go writing the formatted text to memory "
+                      "(Go toolchain absent)"}
 
 
 def run_reference(args, rank, world):
+    """the reference's CPU path (oracle port) on the same corpus and flags; rank 0 only"""
     if rank != 0:
         return
-    size = min(args.size, 256 << 20)
-    arr, docs = make_corpus(size, 20261018)
-    per = []
-    base = None
+    from oracle import pyoracle
+    arr, docs = make_corpus(args.size, SEED)
+    threads = os.cpu_count() or 1
+    ora = pyoracle.OracleModel(MODEL)
+    times = []
     for i in range(args.warmup + args.steps):
-        base = cpu_reference_rate(arr, seconds=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        dt, res = cpu_reference_pass(ora, arr, threads)
         if i >= args.warmup:
-            per.append(base)
-    tot_b = sum(p["bytes"] for p in per)
-    tot_s = sum(p["seconds"] for p in per)
-    v = tot_b / tot_s / 1e9
+            times.append(dt)
+    ms = sum(times) / len(times) * 1e3
+    v = arr.size / (ms * 1e-3) / 1e9
+    sample = (f"each step one pass over the whole corpus ({arr.size} bytes, {res['docs']} documents, {res['tokens']} tokens), "
+              "one worker per document; C restatement of matrix.go:348-698 + token_writer.go writing the formatted text "
+              "to memory (Go toolchain absent)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / len(per) * 1e3,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C2: tokenizer_de.matok, synthetic German corpus, ~10 KB EOT-separated documents, "
-                                   "flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS; each step a bounded sample"},
-            "cpu_baseline": {"value": v, "unit": "GB/s", "cores": base["cores"], "kind": "port",
-                             "sample": base["sample"]},
+            "config": {"workload": workload(args.size), "bytes_per_gpu": args.size, "documents_per_gpu": docs},
+            "cpu_baseline": {"value": v, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def shard_parity(tok, d, rank, world, dist, torch, nbytes=128 << 20):
+    """ONE corpus cut into EOT-aligned shards, one per rank: every rank walks its shard from the
+    guessed carry (root state), the per-shard counts and carry-out states are all-gathered (NCCL), a shard whose
+    predecessor ended in another state is walked again from the true carry, and rank 0 compares the shards'
+    arrays -- moved to their global bases -- with its own single pass over the whole corpus.
+    One cut is seeded inside a quoted XML attribute, so that the mismatch path (matrix.go:593-605: the state
+    after an EOT is whatever the matrix says) fires whenever there is more than one rank."""
+    from datok_b200 import corpus, shard
+    a = np.empty(nbytes, dtype=np.uint8)
+    corpus.generate_blocks_into(corpus.GERMAN, SEED + 17, a, block=16 << 20)
+    if world > 1:
+        # an EOT inside a quoted attribute right behind the balanced cut position of rank 1
+        at = (nbytes // world) + 1
+        evil = b' <a href="x \x04 y">z</a> . '
+        a[at:at + len(evil)] = np.frombuffer(evil, dtype=np.uint8)
+        nxt = at + int(np.flatnonzero(a[at:at + 4096] == 4)[0])
+        assert nxt == at + evil.index(b"\x04")
+    plan = shard.plan_shards(a, world)
+    lo, hi = plan[rank]
+    last = rank == world - 1
+    seen_guess = 1 if rank else 0   # (guess: an earlier shard has produced a token)
+
+    def walk(carry_state):
+        f = FLAGS | (0 if last else d.NOT_FINAL) | (d.WRITER_USED if seen_guess else 0)
+        return tok.transduce_arrays(np.ascontiguousarray(a[lo:hi]), f, carry=d.Carry(carry_state, 1, 1, 0) if rank else None)
+
+    res = walk(1)
+    counts = [hi - lo, res.n_tokens, res.n_sentences, res.n_texts, res.n_sent_pos, res.carry_state]
+    allc, bases = shard.exchange_counts(counts)
+    rewalked = False
+    if shard.carry_mismatch(allc, rank):
+        prev = rank - 1
+        while prev > 0 and allc[prev][0] == 0:
+            prev -= 1
+        res.close()
+        res = walk(int(allc[prev][5]))
+        rewalked = True
+        counts = [hi - lo, res.n_tokens, res.n_sentences, res.n_texts, res.n_sent_pos, res.carry_state]
+        allc, bases = shard.exchange_counts(counts)
+    # digest of this shard's arrays at their global positions
+    h = hashlib.sha256()
+    for arr_, add in ((res.tok_bytes.astype(np.int64), lo), (res.tok_pos.astype(np.int64), 0), (res.sent_pos.astype(np.int64), 0),
+                      (res.sent_tok.astype(np.int64), int(bases[1])), (res.text_tok_end.astype(np.int64), int(bases[1])),
+                      (res.text_sent_end.astype(np.int64), int(bases[2])), (res.text_byte_end.astype(np.int64), lo)):
+        h.update((arr_ + add).tobytes())
+    mine = np.frombuffer(h.digest(), dtype=np.uint8).copy()
+    n_re = torch.tensor([1 if rewalked else 0], dtype=torch.int64, device="cuda")
+    dig = torch.from_numpy(mine).cuda()
+    if world > 1:
+        gathered = [torch.zeros_like(dig) for _ in range(world)]
+        dist.all_gather(gathered, dig)
+        dist.all_reduce(n_re)
+    else:
+        gathered = [dig]
+    res.close()
+    if rank != 0:
+        return None
+    whole = tok.transduce_arrays(a, FLAGS)
+    ok = True
+    T = S = X = 0
+    for r, (l, h_) in enumerate(plan):
+        c = allc[r]
+        t1, s1, x1, sp1 = T + int(c[1]), S + int(c[2]), X + int(c[3]), 0
+        hh = hashlib.sha256()
+        sp0 = int(allc[:r, 4].sum()) if r else 0
+        sp1 = sp0 + int(c[4])
+        for arr_ in (whole.tok_bytes[2 * T:2 * t1], whole.tok_pos[2 * T:2 * t1], whole.sent_pos[sp0:sp1], whole.sent_tok[S:s1],
+                     whole.text_tok_end[X:x1], whole.text_sent_end[X:x1], whole.text_byte_end[X:x1]):
+            hh.update(arr_.astype(np.int64).tobytes())
+        ok = ok and bytes(gathered[r].cpu().numpy().tobytes()) == hh.digest()
+        T, S, X = t1, s1, x1
+    ok = ok and (T, S, X) == (whole.n_tokens, whole.n_sentences, whole.n_texts)
+    whole.close()
+    return {"shard_parity": bool(ok), "shards": world, "corpus_bytes": nbytes, "shards_rewalked": int(n_re.item()),
+            "what": "one corpus, EOT-aligned shards (shard.plan_shards), per-rank datok_transduce(NOT_FINAL, guessed carry), "
+                    "NCCL all-gather of counts + carry-out, re-walk on a carry mismatch (one cut seeded inside a quoted XML "
+                    "attribute), sha256 of every shard's arrays at their global bases == rank 0's single pass"}
+
+
+def copy_ceiling(torch, arr, d2h_bytes, barrier, reps=3):
+    """what the box's copy engines allow for this step's bytes alone: H2D of the input and D2H of the result at the
+    same time, from / to pinned memory, nothing else (every rank at once: max over ranks is taken by the caller)"""
+    n = arr.size
+    src = torch.from_numpy(arr)
+    dev_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dev_out = torch.empty(max(1, d2h_bytes), dtype=torch.uint8, device="cuda")
+    back = torch.empty(max(1, d2h_bytes), dtype=torch.uint8).pin_memory()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for _ in range(reps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            dev_in.copy_(src, non_blocking=True)
+        with torch.cuda.stream(s2):
+            back.copy_(dev_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    del dev_in, dev_out, back
+    return best
 
 
 def main():
@@ -163,6 +280,7 @@ def main():
     ap.add_argument("--size", type=int, default=1 << 30, help="corpus bytes per GPU")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the C3 / C4 device legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,12 +300,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import datok_b200 as d
-    from datok_b200 import _lib
+    from datok_b200 import _lib, corpus
     tok = d.LoadTokenizerFile(MODEL, device=local)
     if tok is None:
         raise SystemExit("libdatok_b200.so could not load the model on the GPU (no fallback exists)")
     L = _lib.lib()
-    arr, docs = make_corpus(args.size, 20261018 + 1000003 * rank, pinned_alloc=L.datok_host_alloc)
+    arr, docs = make_corpus(args.size, SEED + 1000003 * rank, pinned_alloc=L.datok_host_alloc)
     N = arr.size
     d_in = torch.empty(N, dtype=torch.uint8, device="cuda")
     d_in.copy_(torch.from_numpy(arr))
@@ -199,8 +317,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident leg: delta-coded token spans, two bytes per value (the one-byte form of the
-    # host legs only pays off across PCIe) ----
+    def device_leg(ptr, n, flags, steps, warmup):
+        for _ in range(warmup):
+            tok.transduce_device(ptr, n, flags).close()
+        ms, kt, launches, counts = [], {}, 0, (0, 0, 0)
+        for _ in range(steps):
+            r = tok.transduce_device(ptr, n, flags)
+            ms.append(r.ms_kernels)
+            counts = (r.n_tokens, r.n_sentences, r.n_texts)
+            for k, v in tok.kernel_times().items():
+                kt[k] = kt.get(k, 0.0) + v
+            launches += tok.launch_count()
+            r.close()
+        return sum(ms) / len(ms), {k: round(v / steps, 4) for k, v in kt.items()}, launches, counts
+
+    # ---- device-resident legs: delta-coded token spans (two bytes per value: the one-byte form of the host legs
+    # only pays off across PCIe), then the absolute offset arrays ----
     DFLAGS = FLAGS | d.COMPACT
     for _ in range(args.warmup):
         tok.transduce_device(d_in.data_ptr(), N, DFLAGS).close()
@@ -208,24 +340,14 @@ def main():
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, ktimes, launches = [], {}, 0
-    T = S = D = 0
-    for _ in range(args.steps):
-        r = tok.transduce_device(d_in.data_ptr(), N, DFLAGS)
-        dev_ms.append(r.ms_kernels)
-        T, S, D = r.n_tokens, r.n_sentences, r.n_texts
-        for k, v in tok.kernel_times().items():
-            ktimes[k] = ktimes.get(k, 0.0) + v
-        launches += tok.launch_count()
-        r.close()
+    ms_step, kt, launches, (T, S, D) = device_leg(d_in.data_ptr(), N, DFLAGS, args.steps, 0)
     barrier()
     wall_dev = time.perf_counter() - t0
     clocks = sampler.summary()
+    stats = tok.stats()
+    ms_abs_dev, kt_abs, _, _ = device_leg(d_in.data_ptr(), N, FLAGS, max(1, min(args.steps, 3)), 1)
 
     # ---- end-to-end legs (host buffers through the C ABI) ----------------------
-    # e2e: what the Tokenizer shim calls -- DATOK_COMPACT8, 4-byte delta-coded token spans that the
-    # host formatter / replay decode while they walk the tokens anyway.  e2e_absolute: the same call
-    # returning absolute (byte, rune) offset pairs, 16 bytes per token.
     def e2e_leg(flags):
         for _ in range(min(2, args.warmup)):
             tok.transduce_arrays(arr, flags).close()
@@ -235,57 +357,58 @@ def main():
         out_bytes = 0
         for _ in range(steps):
             r = tok.transduce_arrays(arr, flags)
-            per_tok = 4 if r.tok_delta8 is not None else 8 if r.tok_delta is not None else 16
-            out_bytes = per_tok * r.n_tokens + 4 * (r.n_sent_pos + r.n_sentences + 4 * r.n_texts)
+            if flags & d.FORMAT:
+                out_bytes = int(r.text_len) + 16 * r.n_texts
+            else:
+                per_tok = 4 if r.tok_delta8 is not None else 8 if r.tok_delta is not None else 16
+                out_bytes = per_tok * r.n_tokens + 4 * (r.n_sent_pos + r.n_sentences + 4 * r.n_texts)
             r.close()
         barrier()
         return (time.perf_counter() - t0) / steps, out_bytes
 
+    wall_fmt, d2h_fmt = e2e_leg(FLAGS | d.FORMAT)        # the headline: like for like with the reference arm
+    wall_arr, d2h_arr = e2e_leg(FLAGS | d.COMPACT8)
     wall_abs, d2h_abs = e2e_leg(FLAGS)
-    wall_e2e, d2h = e2e_leg(FLAGS | d.COMPACT8)
-    h2d = N
+    t_copy = copy_ceiling(torch, arr, d2h_fmt, barrier)
 
-    # ---- the same call followed by the host half of the TokenWriter: the exact text
-    # NewTokenWriter(w, flags) writes (datok_format, all host cores) ----
-    import ctypes as C
-    import numpy as np
-    # (single-GPU runs only: the text is ~2.7x the input and every rank would hold its own copy)
-    fmt_bytes, wall_fmt = 0, float("nan")
-    if world == 1:
-        fmt_buf = np.empty(4 * N + (1 << 20), dtype=np.uint8)
+    # ---- the other corpus shapes of BASELINE.json, device-resident (rank 0 of a single-GPU run) ----
+    shapes = None
+    if world == 1 and not args.no_shapes:
+        shapes = {}
+        for name, kind, model in (("C3_english", corpus.ENGLISH, "tokenizer_en.matok"), ("C4_long_document", corpus.GERMAN_LONGDOC, "tokenizer_de.matok")):
+            t2 = d.LoadTokenizerFile(os.path.join(ROOT, "testdata", model), device=local)
+            a2, docs2 = make_corpus(N, SEED, kind=kind)
+            d2 = torch.from_numpy(a2).cuda()
+            for _ in range(2):
+                t2.transduce_device(d2.data_ptr(), N, DFLAGS).close()
+            ms2, kt2 = [], {}
+            for _ in range(3):
+                r = t2.transduce_device(d2.data_ptr(), N, DFLAGS)
+                ms2.append(r.ms_kernels)
+                kt2 = t2.kernel_times()
+                n2 = (r.n_tokens, r.n_sentences, r.n_texts)
+                r.close()
+            m2 = sum(ms2) / len(ms2)
+            shapes[name] = {"value": N / (m2 * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": m2, "model": model, "bytes": N,
+                            "documents": int(docs2), "tokens": n2[0], "sentences": n2[1], "fixup_rounds": t2.stats()["fixup_rounds"],
+                            "kernel_ms": {k: round(v, 4) for k, v in kt2.items()}}
+            t2.close()
+            del d2, a2
 
-        def fmt_once():
-            r = tok.transduce_arrays(arr, FLAGS | d.COMPACT8)
-            need = L.datok_format(r._h, arr.ctypes.data, N, FLAGS, fmt_buf.ctypes.data, fmt_buf.size)
-            r.close()
-            return int(need)
-
-        fmt_once()
-        barrier()
-        t0 = time.perf_counter()
-        fmt_steps = max(1, min(args.steps, 2))
-        for _ in range(fmt_steps):
-            fmt_bytes = fmt_once()
-        barrier()
-        wall_fmt = (time.perf_counter() - t0) / fmt_steps
-        del fmt_buf
+    # ---- one corpus sharded over the ranks: parity of the multi-GPU decomposition (outside the timed regions) ----
+    parity = shard_parity(tok, d, rank, world, dist, torch)
 
     # ---- reduce over ranks (max time; counts summed via the per-shard count exchange) -
-    ms_step = sum(dev_ms) / len(dev_ms)
-    stats = torch.tensor([ms_step, wall_dev / args.steps * 1e3, wall_e2e * 1e3, wall_abs * 1e3, wall_fmt * 1e3], dtype=torch.float64,
-                         device="cuda")
-    counts = torch.tensor([N, T, S, D], dtype=torch.int64, device="cuda")
+    st = torch.tensor([ms_step, wall_dev / args.steps * 1e3, wall_fmt * 1e3, wall_arr * 1e3, wall_abs * 1e3, ms_abs_dev, t_copy * 1e3],
+                      dtype=torch.float64, device="cuda")
+    counts = torch.tensor([N, T, S, D, d2h_fmt], dtype=torch.int64, device="cuda")
     if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        # the path's only exchange: per-shard counts -> global offset bases
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(counts) for _ in range(world)]
         dist.all_gather(gathered, counts)
-        allc = torch.stack(gathered)
-        bases = torch.cumsum(allc, 0) - allc
-        counts = allc.sum(0)
-        _ = bases
-    ms_step, ms_wall, ms_e2e, ms_abs, ms_fmt = [float(x) for x in stats.tolist()]
-    Ntot, Ttot, Stot, Dtot = [int(x) for x in counts.tolist()]
+        counts = torch.stack(gathered).sum(0)
+    ms_step, ms_wall, ms_fmt, ms_arr, ms_abs, ms_abs_dev, ms_copy = [float(x) for x in st.tolist()]
+    Ntot, Ttot, Stot, Dtot, d2h_fmt_tot = [int(x) for x in counts.tolist()]
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -294,17 +417,15 @@ def main():
         cpu = None
         if not args.no_cpu and world == 1:
             try:
-                cpu = cpu_reference_rate(arr)
-                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                cpu = cpu_baseline(arr)
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
                 cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-        kt = {k: round(v / args.steps, 4) for k, v in ktimes.items()}
         # per-kernel algorithmic traffic of one launch: bytes each kernel must move
         out_b = 8 * T + 8 * S + 16 * D  # delta-coded token spans, sentence entries, per-text bounds
         kalg = {"walk_fused": N + 5 * N // 8, "compact_reduce": 4 * N // 8, "compact_texts": 4 * N // 8,
                 "compact_emit": 5 * N // 8 + out_b}
-        kroof = {k: {"ms": kt[k], "alg_bytes": b, "gbps": b / (kt[k] * 1e-3) / 1e9,
-                     "frac": b / (kt[k] * 1e-3) / 1e9 / peak} for k, b in kalg.items() if kt.get(k)}
+        kroof = {k: {"ms": kt[k], "alg_bytes": b_, "gbps": b_ / (kt[k] * 1e-3) / 1e9,
+                     "frac": b_ / (kt[k] * 1e-3) / 1e9 / peak} for k, b_ in kalg.items() if kt.get(k)}
         dominant = max(kt, key=kt.get)
         # second bound of the walk (R_gather): the bare dependent shared-memory gather chain
         # of one byte step in the walk's own configuration, measured on this device (not part of the step)
@@ -321,13 +442,16 @@ def main():
             "metric": METRIC, "value": Ntot / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2: tokenizer_de.matok, {N} B synthetic German corpus per GPU, ~10 KB "
-                                   "EOT-separated documents, flags TOKENS|SENTENCES|TOKEN_POS|SENTENCE_POS (device leg: DATOK_COMPACT, "
-                                   "8-byte delta-coded token spans; host legs: DATOK_COMPACT8, 4 bytes per token)",
+            "value_absolute": {"value": Ntot / (ms_abs_dev * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_abs_dev,
+                               "what": "the same device-resident leg leaving absolute (byte, rune) offset pairs in HBM "
+                                       "(16 B/token) instead of delta-coded spans (8 B/token)", "kernel_ms": kt_abs},
+            "config": {"workload": workload(N),
                        "bytes_per_gpu": N, "documents_per_gpu": D, "tokens_per_gpu": T, "sentences_per_gpu": S,
+                       "device_leg": "DATOK_COMPACT: 8-byte delta-coded token spans (value); absolute arrays: value_absolute",
                        "l2": "input (>= 1 GiB) and outputs exceed the 126 MB L2; no flush needed",
-                       "chunk_bytes": int(os.environ.get("DATOK_CHUNK", "640")),
-                       "calibration": "state order specialised once on the first 8 MiB of the corpus (untimed warm-up)",
+                       "chunk_bytes": stats["chunk_bytes"], "fixup_rounds": stats["fixup_rounds"],
+                       "resident_table_rows": stats["hot_rows"], "resident_class_columns": stats["hot_cols"],
+                       "calibration": "state and class order specialised once on the first 8 MiB of the corpus (untimed warm-up)",
                        "timing": "CUDA events on the library's stream around the whole device path, max over ranks",
                        "ms_per_step_wall": ms_wall},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -337,17 +461,24 @@ def main():
                                    "per-kernel rooflines in kernels",
                          "dominant_kernel": dominant, "kernel_ms": kt, "kernels": kroof, "gather": gather},
             "cpu_baseline": cpu,
-            "e2e": {"value": Ntot / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                    "path": "datok_transduce(DATOK_COMPACT8): pinned host input, EOT-aligned pieces, H2D | kernels | D2H "
-                            "overlapped; token spans delta-coded (4 B/token), decoded by the host formatter"},
-            "e2e_absolute": {"value": Ntot / (ms_abs * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": Ntot / (ms_fmt * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N,
+                    "d2h_bytes_per_step": d2h_fmt_tot // world, "ms_per_step": ms_fmt,
+                    "path": "datok_transduce(DATOK_FORMAT): pinned host input, EOT-aligned pieces, H2D | kernels + device "
+                            "formatter | D2H overlapped; the result is the text NewTokenWriter(w, TOKENS|SENTENCES|TOKEN_POS|"
+                            "SENTENCE_POS) writes -- what the reference arm produces",
+                    "copy_ceiling": {"value": Ntot / (ms_copy * 1e-3) / 1e9, "unit": "GB/s of input", "ms": ms_copy,
+                                     "frac": ms_copy / ms_fmt,
+                                     "what": "the same bytes (H2D input, D2H text) through the copy engines alone, all ranks at "
+                                             "once, max over ranks: the end-to-end bound of this box"}},
+            "e2e_arrays": {"value": Ntot / (ms_arr * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N,
+                           "d2h_bytes_per_step": d2h_arr, "ms_per_step": ms_arr,
+                           "path": "datok_transduce(DATOK_COMPACT8): offset arrays instead of text, token spans delta-coded (4 B/token)"},
+            "e2e_absolute": {"value": Ntot / (ms_abs * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N,
                              "d2h_bytes_per_step": d2h_abs, "ms_per_step": ms_abs,
-                             "path": "same call without DATOK_COMPACT8: absolute (byte, rune) offset pairs, 16 B/token"},
-            "e2e_formatted": None if world > 1 else {"value": Ntot / (ms_fmt * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_fmt,
-                              "text_bytes_per_step": fmt_bytes, "host_threads": os.cpu_count(),
-                              "path": "datok_transduce(DATOK_COMPACT8) + datok_format(): the text NewTokenWriter(w, TOKENS|SENTENCES|"
-                                      "TOKEN_POS|SENTENCE_POS) writes, formatted on the host cores"},
+                             "path": "the same call returning absolute (byte, rune) offset pairs, 16 B/token"},
+            "other_shapes": shapes,
+            "shard_parity": parity["shard_parity"] if parity else None,
+            "sharding": parity,
             "gpu_launches": launches,
             "clocks": clocks,
         }

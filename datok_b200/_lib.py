@@ -59,7 +59,7 @@ class Callbacks(C.Structure):
 # every symbol include/datok_b200.h declares
 EXPORTS = ["datok_load", "datok_load_image", "datok_free", "datok_type", "datok_model_type", "datok_model_info", "datok_transduce",
            "datok_transduce_device", "datok_result_view", "datok_result_free", "datok_expand", "datok_format", "datok_replay",
-           "datok_last_kernel_times", "datok_last_launch_count", "datok_measure_gather_bound", "datok_host_alloc", "datok_host_free",
+           "datok_last_kernel_times", "datok_last_launch_count", "datok_last_stats", "datok_measure_gather_bound", "datok_host_alloc", "datok_host_free",
            "datok_last_error", "datok_strerror"]
 
 _lib = None
@@ -99,6 +99,8 @@ def lib():
     L.datok_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.datok_last_launch_count.restype = C.c_int
     L.datok_last_launch_count.argtypes = [C.c_void_p]
+    L.datok_last_stats.restype = C.c_int
+    L.datok_last_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
     L.datok_measure_gather_bound.restype = C.c_int
     L.datok_measure_gather_bound.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.datok_host_alloc.restype = C.c_void_p

@@ -1331,6 +1331,15 @@ int datok_last_kernel_times(const datok_model* m, const char** names, float* ms,
 
 int datok_last_launch_count(const datok_model* m) { return m ? m->launches : 0; }
 
+int datok_last_stats(const datok_model* m, uint32_t* fixup_rounds, uint32_t* hot_rows, uint32_t* hot_cols, uint32_t* chunk_bytes) {
+  if (!m) return DATOK_ERR_INVALID_ARG;
+  if (fixup_rounds) *fixup_rounds = m->last_rounds;
+  if (hot_rows) *hot_rows = m->n_hot;
+  if (hot_cols) *hot_cols = m->hm.hot_cols;
+  if (chunk_bytes) *chunk_bytes = m->chunk;
+  return DATOK_OK;
+}
+
 int datok_measure_gather_bound(datok_model* m, double* byte_steps_per_s) {
   if (!m || !byte_steps_per_s) return DATOK_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(m->mu);

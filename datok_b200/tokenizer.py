@@ -309,6 +309,12 @@ class MatrixTokenizer:
     def launch_count(self):
         return _lib.lib().datok_last_launch_count(self._h)
 
+    def stats(self):
+        """fix-up rounds of the last call; resident table rows / class columns and chunk size of the current layout"""
+        v = [C.c_uint32() for _ in range(4)]
+        _lib.lib().datok_last_stats(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("fixup_rounds", "hot_rows", "hot_cols", "chunk_bytes"), (x.value for x in v)))
+
 
 def LoadTokenizerFile(file, device=0):
     """fomafile.go:452-484 for the MATOK magic.  Returns None on any error, like the

@@ -194,6 +194,10 @@ int datok_replay(const datok_result *r, const uint8_t *in, size_t n, const datok
 int datok_last_kernel_times(const datok_model *m, const char **names, float *ms, int cap);
 /* number of kernel launches issued by the last call */
 int datok_last_launch_count(const datok_model *m);
+/* of the last call: fix-up rounds of the speculative walk; of the model's current layout: table rows and class
+ * columns resident in shared memory, bytes per speculative chunk (any pointer may be NULL) */
+int datok_last_stats(const datok_model *m, uint32_t *fixup_rounds, uint32_t *hot_rows, uint32_t *hot_cols,
+                     uint32_t *chunk_bytes);
 
 /* Measurement only (bench.py, SURVEY.md 8d "R_gather"): byte steps per second of the bare dependent
  * shared-memory gather chain of the walk (class byte -> row entry -> next state) in the walk's own

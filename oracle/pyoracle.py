@@ -109,7 +109,9 @@ class OracleResult:
 
     def __init__(self, r):
         self.status = r.status
-        self.text = bytes(C.string_at(r.text, r.text_len)) if r.text_len else b""
+        # (a numpy copy: ctypes.string_at takes a C int length, and the text of a full-size corpus exceeds 2 GiB)
+        self.text_np = np.ctypeslib.as_array(r.text, shape=(r.text_len,)).copy() if r.text_len else np.zeros(0, np.uint8)
+        self._text = None
         nt = r.n_tokens
         self.n_tokens = nt
         self.tok_byte_start = _arr(r.tok_byte_start, nt, np.uint32)
@@ -131,6 +133,13 @@ class OracleResult:
         self.stats = dict(runes=r.n_runes, iterations=r.n_iterations, backtracks=r.n_backtracks,
                           backtrack_runes=r.n_backtrack_runes, hardfail=r.n_hardfail,
                           max_window=r.max_window)
+
+
+    @property
+    def text(self):
+        if self._text is None:
+            self._text = self.text_np.tobytes()
+        return self._text
 
 
 class OracleModel:

@@ -76,7 +76,7 @@ def _compare_stream(r, text, slabs):
         np.testing.assert_array_equal(r.text_sent_end[X:x1].astype(np.int64) - S, o.text_sent_end.astype(np.int64), err_msg=ctx + ": text sentence bounds")
         np.testing.assert_array_equal(r.text_sentpos_end[X:x1].astype(np.int64) - SP, o.text_sentpos_end.astype(np.int64), err_msg=ctx + ": text sent-list bounds")
         np.testing.assert_array_equal(r.text_byte_end[X:x1].astype(np.int64) - lo, o.text_byte_end, err_msg=ctx + ": text byte ends")
-        ot = np.frombuffer(o.text, dtype=np.uint8)
+        ot = o.text_np
         assert np.array_equal(text[B:B + ot.size], ot), ctx + ": formatted text"
         T, S, SP, X, B = t1, s1, sp1, x1, B + ot.size
     assert (T, S, SP, X) == (r.n_tokens, r.n_sentences, r.n_sent_pos, r.n_texts) and B == text.size
