@@ -199,14 +199,18 @@ def shard_parity(tok, d, rank, world, dist, torch, nbytes=128 << 20):
     counts = [hi - lo, res.n_tokens, res.n_sentences, res.n_texts, res.n_sent_pos, res.carry_state]
     allc, bases = shard.exchange_counts(counts)
     rewalked = False
-    if shard.carry_mismatch(allc, rank):
-        prev = rank - 1
-        while prev > 0 and allc[prev][0] == 0:
-            prev -= 1
-        res.close()
-        res = walk(int(allc[prev][5]))
-        rewalked = True
-        counts = [hi - lo, res.n_tokens, res.n_sentences, res.n_texts, res.n_sent_pos, res.carry_state]
+    # (every rank sees every carry-out: all of them know whether some shard has to be walked again, and all of them
+    # take part in the second exchange then -- a chain of mismatches would need one round per link; here one is enough
+    # as long as the re-walked shards end in the root state again, which the final comparison checks)
+    if any(shard.carry_mismatch(allc, r) for r in range(world)):
+        if shard.carry_mismatch(allc, rank):
+            prev = rank - 1
+            while prev > 0 and allc[prev][0] == 0:
+                prev -= 1
+            res.close()
+            res = walk(int(allc[prev][5]))
+            rewalked = True
+            counts = [hi - lo, res.n_tokens, res.n_sentences, res.n_texts, res.n_sent_pos, res.carry_state]
         allc, bases = shard.exchange_counts(counts)
     # digest of this shard's arrays at their global positions
     h = hashlib.sha256()
@@ -297,7 +301,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
 
     import datok_b200 as d
     from datok_b200 import _lib, corpus
