@@ -245,8 +245,30 @@ def shard_parity(tok, d, rank, world, dist, torch, nbytes=128 << 20):
         ok = ok and bytes(gathered[r].cpu().numpy().tobytes()) == hh.digest()
         T, S, X = t1, s1, x1
     ok = ok and (T, S, X) == (whole.n_tokens, whole.n_sentences, whole.n_texts)
+    # the same decomposition behind the boundary: ONE process, datok_transduce_sharded over all GPUs of the box
+    # (a thread per device, ncclCommInitAll + ncclAllGather of the counts inside the library)
+    c_abi = None
+    if world > 1:
+        try:
+            toks = [tok] + [d.LoadTokenizerFile(MODEL, device=i) for i in range(1, world)]
+            rs, bases2, bounds2, info = d.transduce_sharded(toks, a, FLAGS)
+            tb = np.concatenate([r.tok_bytes.astype(np.int64) + bounds2[i] for i, r in enumerate(rs)])
+            same = (np.array_equal(tb, whole.tok_bytes.astype(np.int64)) and
+                    np.array_equal(np.concatenate([r.tok_pos for r in rs]), whole.tok_pos) and
+                    np.array_equal(np.concatenate([r.sent_pos for r in rs]), whole.sent_pos) and
+                    np.array_equal(np.concatenate([r.sent_tok.astype(np.int64) + bases2[i][1] for i, r in enumerate(rs)]), whole.sent_tok.astype(np.int64)) and
+                    np.array_equal(np.concatenate([r.text_byte_end.astype(np.int64) + bounds2[i] for i, r in enumerate(rs)]), whole.text_byte_end.astype(np.int64)))
+            c_abi = {"parity": bool(same), "devices": world, **info}
+            for r in rs:
+                r.close()
+            for t in toks[1:]:
+                t.close()
+        except Exception as e:  # reported, never hidden
+            c_abi = {"parity": False, "error": str(e)}
+        ok = ok and bool(c_abi.get("parity"))
     whole.close()
     return {"shard_parity": bool(ok), "shards": world, "corpus_bytes": nbytes, "shards_rewalked": int(n_re.item()),
+            "c_abi_sharded": c_abi,
             "what": "one corpus, EOT-aligned shards (shard.plan_shards), per-rank datok_transduce(NOT_FINAL, guessed carry), "
                     "NCCL all-gather of counts + carry-out, re-walk on a carry mismatch (one cut seeded inside a quoted XML "
                     "attribute), sha256 of every shard's arrays at their global bases == rank 0's single pass"}

@@ -12,8 +12,8 @@ plus the offset-array API (`transduce_arrays`) the C ABI is built around.
 """
 from ._lib import (COMPACT, COMPACT8, FORMAT, NEWLINE_AFTER_EOT, NOT_FINAL, SENTENCE_POS, SENTENCES, SIMPLE, TOKEN_POS, TOKENS, WRITER_USED, Carry)
 from .tokenizer import (DatokError, LoadMatrixFile, LoadTokenizerFile, MatrixTokenizer, NewTokenWriter,
-                        ReferencePanic, Result, TokenWriter)
+                        ReferencePanic, Result, TokenWriter, transduce_sharded)
 
 __all__ = ["LoadTokenizerFile", "LoadMatrixFile", "MatrixTokenizer", "NewTokenWriter", "TokenWriter", "Result",
            "TOKENS", "SENTENCES", "TOKEN_POS", "SENTENCE_POS", "NEWLINE_AFTER_EOT", "SIMPLE", "WRITER_USED", "NOT_FINAL", "COMPACT", "COMPACT8", "FORMAT",
-           "Carry", "DatokError", "ReferencePanic"]
+           "Carry", "DatokError", "ReferencePanic", "transduce_sharded"]

@@ -60,7 +60,9 @@ class Callbacks(C.Structure):
 EXPORTS = ["datok_load", "datok_load_image", "datok_free", "datok_type", "datok_model_type", "datok_model_info", "datok_transduce",
            "datok_transduce_device", "datok_result_view", "datok_result_free", "datok_expand", "datok_format", "datok_replay",
            "datok_last_kernel_times", "datok_last_launch_count", "datok_last_stats", "datok_measure_gather_bound", "datok_host_alloc", "datok_host_free",
-           "datok_last_error", "datok_strerror"]
+           "datok_last_error", "datok_strerror", "datok_stream_open", "datok_stream_push", "datok_stream_finish",
+           "datok_stream_bytes_done", "datok_stream_close", "datok_plan_shards", "datok_transduce_sharded", "datok_sharded_last_error",
+           "datok_sharded_last_info"]
 
 _lib = None
 
@@ -106,6 +108,24 @@ def lib():
     L.datok_host_alloc.restype = C.c_void_p
     L.datok_host_alloc.argtypes = [C.c_size_t]
     L.datok_host_free.argtypes = [C.c_void_p]
+    L.datok_stream_open.restype = C.c_void_p
+    L.datok_stream_open.argtypes = [C.c_void_p, C.c_uint32]
+    for f in (L.datok_stream_push,):
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.datok_stream_finish.restype = C.c_int
+    L.datok_stream_finish.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.datok_stream_bytes_done.restype = C.c_uint64
+    L.datok_stream_bytes_done.argtypes = [C.c_void_p]
+    L.datok_stream_close.argtypes = [C.c_void_p]
+    L.datok_plan_shards.restype = C.c_int
+    L.datok_plan_shards.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint64)]
+    L.datok_transduce_sharded.restype = C.c_int
+    L.datok_transduce_sharded.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_size_t, C.c_uint32,
+                                          C.POINTER(Carry), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.datok_sharded_last_error.restype = C.c_char_p
+    L.datok_sharded_last_info.restype = C.c_int
+    L.datok_sharded_last_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.datok_last_error.restype = C.c_char_p
     L.datok_strerror.restype = C.c_char_p
     L.datok_strerror.argtypes = [C.c_int]

@@ -42,6 +42,13 @@ static thread_local std::string g_last_error;
 
 namespace {
 
+// every entry point that selects the model's device leaves the caller's current device as it was
+struct DeviceGuard {
+  int dev = -1;
+  DeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+  ~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 struct Block {
   void* p = nullptr;
   size_t bytes = 0;
@@ -152,6 +159,7 @@ void free_result_locked(datok_result* r) {
 }
 
 void destroy_model(datok_model* m) {
+  DeviceGuard guard;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   for (auto& b : m->cache) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
@@ -364,6 +372,7 @@ int calibrate_locked(datok_model* m, const WalkBuffers& full) {
 }
 
 datok_model* finish_load(datok_model* m, int device, int* err) {
+  DeviceGuard guard;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
     g_last_error = "no usable CUDA device (this library has no CPU path)";
@@ -587,6 +596,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
   if (np < 2) return -1;
 
   std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(m->device));
   cudaStream_t s = m->stream;
   std::memset(m->t_ms, 0, sizeof m->t_ms);
@@ -964,6 +974,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   if (!m || !out || (!in && n)) { g_last_error = "invalid argument"; return DATOK_ERR_INVALID_ARG; }
   if (n >= 0xFFFFFFFFull - (1u << 20)) { g_last_error = "input too large for one call"; return DATOK_ERR_TOO_LARGE; }
   std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(m->device));
   const uint32_t N = (uint32_t)n;
   cudaStream_t s = m->stream;
@@ -1343,6 +1354,7 @@ int datok_last_stats(const datok_model* m, uint32_t* fixup_rounds, uint32_t* hot
 int datok_measure_gather_bound(datok_model* m, double* byte_steps_per_s) {
   if (!m || !byte_steps_per_s) return DATOK_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(m->mu);
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(m->device));
   const uint32_t row16 = m->dm.stride16 * 2u, segs = 256;
   int rc = ensure_workspace(m, 4096);

@@ -241,19 +241,58 @@ class MatrixTokenizer:
             res.close()
 
     def _transduce_stream(self, r, w, batch_bytes):
-        pending = b""
-        carry = None
-        while True:
-            block = r.read(batch_bytes)
-            if not block:
-                break
-            pending += block
-            cut = pending.rfind(b"\x04") + 1  # batches end right after an EOT: a text boundary (matrix.go:593-605)
-            if cut == 0:
-                continue                        # no text ends in here yet: keep reading
-            carry = self._transduce_batch(pending[:cut], w, carry, False)
-            pending = pending[cut:]
-        self._transduce_batch(pending, w, carry, True)
+        """the io.Reader front-end through the C ABI's datok_stream_* (what the Go shim calls): blocks are pushed as
+        they are read, the library cuts them after EOT bytes and carries the state from batch to batch"""
+        L = _lib.lib()
+        stock = w._stock
+        flags = (stock["flags"] | FORMAT | (0 if stock["init"] else WRITER_USED)) if stock is not None else (TOKENS | SENTENCES | COMPACT8)
+        st = L.datok_stream_open(self._h, flags)
+        if not st:
+            raise DatokError(_lib.ERR_INVALID_ARG, "datok_stream_open failed")
+        keep = []  # custom writers: the replay needs the batch's input bytes
+
+        def deliver(handle, data):
+            res = Result(handle)
+            try:
+                if stock is not None:
+                    if res.n_tokens:
+                        stock["init"] = False
+                    stock["w"].write(res.text.tobytes() if res.text is not None else b"")
+                else:
+                    def on_token(_u, buf, buf_bytes, _off_bytes, off_runes):
+                        w.Token(off_runes, list(_go_runes(C.string_at(buf, buf_bytes))))
+                    cb = Callbacks(None, TOKEN_CB(on_token), EVENT_CB(lambda _u: w.SentenceEnd(0)), EVENT_CB(lambda _u: w.TextEnd(0)))
+                    buf = C.create_string_buffer(data, len(data)) if data else None
+                    rc = L.datok_replay(res._h, buf, len(data), C.byref(cb))
+                    if rc:
+                        _raise(rc)
+            finally:
+                res.close()
+
+        try:
+            pending = b""
+            while True:
+                block = r.read(batch_bytes)
+                if not block:
+                    break
+                out = C.c_void_p()
+                done0 = L.datok_stream_bytes_done(st)
+                rc = L.datok_stream_push(st, block, len(block), C.byref(out))
+                if rc:
+                    _raise(rc)
+                pending += block
+                if out.value:
+                    n = L.datok_stream_bytes_done(st) - done0
+                    deliver(out.value, pending[:n])
+                    pending = pending[n:]
+            out = C.c_void_p()
+            rc = L.datok_stream_finish(st, C.byref(out))
+            if rc:
+                _raise(rc)
+            if out.value:
+                deliver(out.value, pending)
+        finally:
+            L.datok_stream_close(st)
         w.Flush()  # matrix.go:374 defer w.Flush()
         return True
 
@@ -341,3 +380,27 @@ def load_error_code(file, device=0):
         L.datok_free(h)
         return 0
     return err.value
+
+
+def transduce_sharded(toks, data, flags=TOKENS | SENTENCES | TOKEN_POS | SENTENCE_POS, carry=None):
+    """datok_transduce_sharded: one corpus over the GPUs the tokenizers `toks` live on (one model instance per device).
+    Returns (results per shard, bases [n_shards x 5: bytes, tokens, sentences, texts, sent entries], bounds, info)."""
+    L = _lib.lib()
+    addr, n, keep = _as_buffer(data)
+    nd = len(toks)
+    models = (C.c_void_p * nd)(*[t._h for t in toks])
+    devices = (C.c_int * nd)(*[t.device for t in toks])
+    outs = (C.c_void_p * nd)()
+    bases = (C.c_uint64 * (5 * nd))()
+    bounds = (C.c_uint64 * (nd + 1))()
+    cin = C.byref(carry) if carry is not None else None
+    rc = L.datok_transduce_sharded(models, devices, nd, addr, n, flags, cin, outs, bases, bounds)
+    if rc:
+        msg = (L.datok_sharded_last_error() or b"").decode("utf-8", "replace")
+        if 1 <= rc <= 5:
+            raise ReferencePanic(rc, msg)
+        raise DatokError(rc, msg)
+    used, rew = C.c_int(), C.c_int()
+    L.datok_sharded_last_info(C.byref(used), C.byref(rew))
+    return ([Result(outs[i]) for i in range(nd)], np.array(list(bases), dtype=np.int64).reshape(nd, 5),
+            [int(x) for x in bounds], {"used_nccl": bool(used.value), "shards_rewalked": rew.value})

@@ -168,6 +168,35 @@ int datok_transduce_device(datok_model *m, const uint8_t *d_in, size_t n, uint32
 const datok_view *datok_result_view(const datok_result *r);
 void datok_result_free(datok_result *r);
 
+/* ---- streaming front-end: the reference reads any io.Reader (matrix.go:373,388-408; cmd/datok.go:108-132 incl.
+ * STDIN).  The caller pushes blocks as they arrive; a push transduces everything up to the last EOT seen so far (a
+ * text boundary, matrix.go:593-605) and hands back that batch's result (*out is NULL while no text has ended yet);
+ * finish() transduces the rest with the end-of-input processing (matrix.go:650-695).  The walk state, sentenceEnd /
+ * textEnd and the writer's `init` flag travel from batch to batch inside the stream; `flags` are those of
+ * datok_transduce (DATOK_FORMAT: every result carries its part of the TokenWriter's text, to be written in order). */
+typedef struct datok_stream datok_stream;
+datok_stream *datok_stream_open(datok_model *m, uint32_t flags);
+int datok_stream_push(datok_stream *s, const uint8_t *data, size_t n, datok_result **out);
+int datok_stream_finish(datok_stream *s, datok_result **out);
+uint64_t datok_stream_bytes_done(const datok_stream *s);
+void datok_stream_close(datok_stream *s);
+
+/* ---- one corpus over the GPUs of a box.  models[i] is the same model file loaded on devices[i].
+ * The input is cut into ndev byte-balanced shards that end right after an EOT (datok_plan_shards; bounds has
+ * n_shards + 1 entries), shard i is transduced on device i -- all concurrently, each from the guess "root state,
+ * behind a finished text, a token has been seen" --, the per-shard counts {bytes, tokens, sentences, texts, sent
+ * entries} and carry-out states are all-gathered over NCCL (NVLink / NVSwitch; bound at run time), and a shard whose
+ * guess turns out wrong (matrix.go:593-605: the state behind an EOT is whatever the matrix says) is transduced again
+ * from the true carry.  outs[i] is shard i's result with shard-relative indices and byte offsets; bases (5 per
+ * shard, may be NULL) holds what to add: {bytes, tokens, sentences, texts, sent entries} before the shard. */
+int datok_plan_shards(const uint8_t *in, size_t n, int n_shards, uint64_t *bounds);
+int datok_transduce_sharded(datok_model *const *models, const int *devices, int ndev, const uint8_t *in, size_t n,
+                            uint32_t flags, const datok_carry *carry_in, datok_result **outs, uint64_t *bases,
+                            uint64_t *bounds_out);
+const char *datok_sharded_last_error(void);
+/* of the last sharded call on this thread: whether the exchange went through NCCL, how many shards were redone */
+int datok_sharded_last_info(int *used_nccl, int *shards_rewalked);
+
 /* Rebuilds the absolute token arrays of a DATOK_COMPACT / DATOK_COMPACT8 result on the host: tok_bytes (2 per token)
  * and / or tok_pos (2 per token); either may be NULL. */
 int datok_expand(const datok_result *r, uint32_t *tok_bytes, int32_t *tok_pos);

@@ -566,3 +566,63 @@ def test_device_formatter_on_corpora(kind, model, testdata, oracle_models, monke
     r = tok.transduce_arrays(bad, 15 | d.FORMAT)
     assert r.has_invalid_utf8 and r.text.tobytes() == o.text
     tok.close()
+
+
+def test_stream_through_the_c_abi(gpu_models, oracle_models):
+    """datok_stream_open / push / finish: arbitrary block sizes (blocks without any EOT, blocks ending inside a token),
+    the carry inside the stream, DATOK_FORMAT text per batch == the reference's single stream"""
+    import ctypes as C
+    import datok_b200 as d
+    from datok_b200 import _lib, corpus
+    from datok_b200.tokenizer import Result
+    L = _lib.lib()
+    tok = gpu_models["tokenizer_de.matok"]
+    a = corpus.generate(2, 3 << 20, seed=5).tobytes() + "Kein EOT am Ende. Letzter Satz".encode()
+    for flags in (15, 31, 3):
+        o = oracle_models["tokenizer_de.matok"].transduce(a, flags)
+        for block in (1000, 70_000, 1 << 20, 8 << 20):
+            st = L.datok_stream_open(tok._h, flags | d.FORMAT)
+            text, n_tok, results = [], 0, 0
+            for lo in range(0, len(a), block):
+                out = C.c_void_p()
+                assert L.datok_stream_push(st, a[lo:lo + block], len(a[lo:lo + block]), C.byref(out)) == 0
+                if out.value:
+                    r = Result(out.value); text.append(r.text.tobytes()); n_tok += r.n_tokens; results += 1; r.close()
+            out = C.c_void_p()
+            assert L.datok_stream_finish(st, C.byref(out)) == 0
+            r = Result(out.value); text.append(r.text.tobytes()); n_tok += r.n_tokens; r.close()
+            assert L.datok_stream_bytes_done(st) == len(a)
+            L.datok_stream_close(st)
+            assert b"".join(text) == o.text and n_tok == o.n_tokens, (flags, block)
+            assert results >= (1 if block >= (1 << 20) else 10)
+
+
+def test_sharded_call_on_one_device(testdata, oracle_models):
+    """datok_transduce_sharded with several model instances on one GPU (the exchange then stays on the host): shards +
+    bases == the single stream, including a cut inside a quoted XML attribute whose shard has to be walked again"""
+    import datok_b200 as d
+    from datok_b200 import corpus
+    path = os.path.join(testdata, "tokenizer_de.matok")
+    toks = [d.LoadTokenizerFile(path) for _ in range(3)]
+    a = corpus.generate(2, 3 << 20, seed=12)
+    at = a.size // 3 + 1
+    evil = b' <a href="x \x04 y">z</a> . '
+    a[at:at + len(evil)] = np.frombuffer(evil, dtype=np.uint8)
+    o = oracle_models["tokenizer_de.matok"].transduce_np(a, 15)
+    res, bases, bounds, info = d.transduce_sharded(toks, a, 15)
+    assert info["shards_rewalked"] >= 1 and bounds[0] == 0 and bounds[-1] == a.size
+    tb = np.concatenate([r.tok_bytes.astype(np.int64) + bounds[i] for i, r in enumerate(res)])
+    np.testing.assert_array_equal(tb[0::2], o.tok_byte_start)
+    np.testing.assert_array_equal(tb[1::2], o.tok_byte_end)
+    np.testing.assert_array_equal(np.concatenate([r.tok_pos for r in res]), o.tok_pos)
+    np.testing.assert_array_equal(np.concatenate([r.sent_pos for r in res]), o.sent_pos)
+    np.testing.assert_array_equal(np.concatenate([r.sent_tok.astype(np.int64) + bases[i][1] for i, r in enumerate(res)]), o.sent_tok_idx.astype(np.int64))
+    np.testing.assert_array_equal(np.concatenate([r.text_tok_end.astype(np.int64) + bases[i][1] for i, r in enumerate(res)]), o.text_tok_end.astype(np.int64))
+    assert [int(b[0]) for b in bases] == bounds[:-1] and int(bases[2][1]) == res[0].n_tokens + res[1].n_tokens
+    # the formatted text of the shards, in order, is the stream's text
+    res2, _, _, _ = d.transduce_sharded(toks, a, 15 | d.FORMAT)
+    assert b"".join(r.text.tobytes() for r in res2) == o.text
+    for r in res + res2:
+        r.close()
+    for t in toks:
+        t.close()
