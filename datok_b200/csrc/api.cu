@@ -304,6 +304,7 @@ int upload_model(datok_model* m) {
   d.hot16 = reinterpret_cast<const uint16_t*>(m->d_tables + t2_bytes + t1_bytes);
   d.row_shift = h.row_shift; d.start = h.start; d.n_classes = h.n_classes; d.stride2 = h.stride2;
   d.stride16 = h.stride16; d.hot16_rows = h.hot16_rows; d.hot_cols = h.hot_cols;
+  d.eot_rewind = h.eot_rewind ? 1u : 0u;
   d.cls.ascii_cls = m->d_cls_tables;
   d.cls.latin1_cls = m->d_cls_tables + 128;
   d.cls.rune_cls = m->d_cls_tables + 256;
@@ -510,6 +511,7 @@ int do_count(datok_model* m, const WalkBuffers& b, CompactCtx& c, const CompactB
   c.in = b.in; c.N = b.N; c.n_words = b.n_words;
   c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
   c.flags = flags; c.err_key = b.err_key;
+  c.eot_rewind = m->hm.eot_rewind ? 1u : 0u;
   pt.begin(T_REDUCE);
   launch_compact_reduce(c, cb, s);
   pt.end();
@@ -531,11 +533,6 @@ int do_count(datok_model* m, const WalkBuffers& b, CompactCtx& c, const CompactB
   std::memcpy(&h.err, m->h_mail + 8, sizeof h.err);
   h.invalid = m->h_mail[10];
   std::memcpy(&h.last, m->h_mail + 12, sizeof(WState));
-  if (!m->hm.eot_rewind && h.tot.n_text > 0) {
-    // a double-array model (datok.go): its walk does not rewind the buffer at an EOT, the kernels do
-    g_last_error = "double-array model (.datok): inputs with EOT bytes are not supported yet, use the .matok model";
-    return DATOK_ERR_UNSUPPORTED_MODEL;
-  }
   if (h.err != ~0ull) {  // the walk itself hit a reference panic
     const int code = (int)(h.err & 0xFF);
     g_last_error = std::string("reference would panic: ") + datok_strerror(code);
@@ -1302,9 +1299,23 @@ int datok_model_info(const datok_model* m, uint32_t* state_count, uint32_t* sigm
   return DATOK_OK;
 }
 
+// A double-array model (datok.go) does not rewind its buffer at an EOT (datok.go:1019-1030): a text's first Token call
+// reaches back into the text before, so a stream of such a model cannot be cut at an EOT (no DATOK_NOT_FINAL, no
+// pieces), and the delta-coded transport forms, whose cursors restart at every text, do not apply: absolute arrays.
+static int check_norewind(const datok_model* m, uint32_t& flags) {
+  if (!m || m->hm.eot_rewind) return DATOK_OK;
+  if (flags & DATOK_NOT_FINAL) {
+    g_last_error = "double-array model (.datok): its stream cannot be continued behind an EOT (DATOK_NOT_FINAL)";
+    return DATOK_ERR_UNSUPPORTED_MODEL;
+  }
+  flags &= ~(uint32_t)(DATOK_COMPACT | DATOK_COMPACT8);
+  return DATOK_OK;
+}
+
 int datok_transduce(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, const datok_carry* carry_in,
                     datok_result** out) {
-  if (m && out && in && n < 0xFFFFFFFFull - (1u << 20) && n >= 2 * m->piece_bytes && m->pipelined) {
+  if (const int rc = check_norewind(m, flags)) return rc;
+  if (m && m->hm.eot_rewind && out && in && n < 0xFFFFFFFFull - (1u << 20) && n >= 2 * m->piece_bytes && m->pipelined) {
     const int rc = run_pipelined(m, in, n, flags, carry_in, out);
     if (rc != -1 && rc != -2) return rc;  // -1: no EOT to cut at; -2: DATOK_FORMAT with malformed UTF-8
   }
@@ -1313,6 +1324,7 @@ int datok_transduce(datok_model* m, const uint8_t* in, size_t n, uint32_t flags,
 
 int datok_transduce_device(datok_model* m, const uint8_t* d_in, size_t n, uint32_t flags,
                            const datok_carry* carry_in, datok_result** out) {
+  if (const int rc = check_norewind(m, flags)) return rc;
   return run_pipeline(m, d_in, true, n, flags, carry_in, true, out);
 }
 

@@ -33,6 +33,7 @@ struct DeviceModel {
   const uint32_t* table2;  // fused table T3 (fast_run), stride2 entries per row
   const uint16_t* hot16;   // compact rows of the first hot16_rows states, stride16 entries per row
   uint32_t row_shift, start, n_classes, stride2, stride16, hot16_rows, hot_cols;
+  uint32_t eot_rewind;     // 0: a double-array model (datok.go): an EOT does not rewind the buffer
   ClsTables cls;           // pointers into device memory
   uint32_t sync_ascii[4];  // ASCII bytes the root state skips: a chunk may start right after one
   uint32_t sync_cls[8];    // the same set as classes (HostModel.sync_mask)
@@ -59,6 +60,7 @@ DATOK_HD WalkCtx make_walk_ctx(const DeviceModel& m, const WalkBuffers& b) {
   c.in = b.in; c.N = b.N; c.cls = m.cls;
   c.b_end = b.b_end; c.b_skip = b.b_skip; c.b_sent = b.b_sent; c.b_tend = b.b_tend;
   c.hist = nullptr; c.hist_cls = nullptr;
+  c.eot_rewind = m.eot_rewind;
   c.final_input = b.final_input;
   return c;
 }
@@ -178,7 +180,7 @@ int look_ahead(const FastTables& FT, const WalkCtx& c, uint32_t t, uint32_t hi, 
     const uint32_t e3 = t3_load(FT, t, cl);
     if (e3 & F3_SLOWMARK) return LOOK_EXACT;
     if ((e3 & F3_TGT) == 0) return hi + k - eps_pos <= NEAR_BACKTRACK ? LOOK_EXACT : LOOK_PROBE;
-    if ((e3 & (F3_KANY | F3_EA)) || cl == K_CLS_EOT) return LOOK_DEAD;
+    if ((e3 & (F3_KANY | F3_EA)) || (cl == K_CLS_EOT && FT.eot_rewind)) return LOOK_DEAD;
     t = e3 & F3_TGT;
   }
   return LOOK_PROBE;
@@ -276,6 +278,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     classify_segment(b.in, N, seg_start, m.cls, FT.ascii_cls2, FT.stop_cl2, seg_cls, &rs, &eotm, &inv, &nonascii);
 #endif
     const uint32_t limit = seg_end < N ? seg_end : N;
+    const uint32_t eotk = FT.eot_rewind ? eotm : 0u;  // the EOTs that rewind the buffer (none in the double-array walk)
 #if defined(__CUDA_ARCH__)
     // the next segment on its way while this one is walked (no registers held): as a prefetch into L1, or
     // (build option DATOK_STAGE_ASYNC) into the lane's staging slot through the async copy unit
@@ -321,8 +324,8 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
     if (fast && !in_regs) { load_seg_bits(b, w, B); in_regs = true; }  // (that segment: its words are in memory)
     for (;;) {
       if (fast) {
-        const int rc = fast_run(L, R, FT, FX, seg_cls, seg_start, limit, eotm, B);
-        if (!fast_flush(L, R, B, eotm, seg_start)) {  // two SentenceEnds at one position
+        const int rc = fast_run(L, R, FT, FX, seg_cls, seg_start, limit, eotk, B);
+        if (!fast_flush(L, R, B, eotk, eotm, seg_start)) {  // two SentenceEnds at one position
           if (phase == PH_PROBE) { phase = PH_GAVE_UP; break; }
           err = E_DEGENERATE;
           st = wstate_invalid(E_DEGENERATE);
@@ -370,7 +373,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
           }
         }
 #endif
-        lane_note_first_rewind(L, B, seg_start);
+        lane_note_first_rewind(L, B, seg_start, FT.eot_rewind);
         to_exact(L, B, seg_start, FT, st);              // rare case, or end of input
         fast = false;
         must_walk_exact = true;
@@ -433,12 +436,12 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
       g_probe[1]++;
 #endif
       if (!L.eps_rec || L.eps_p >= hi) { phase = PH_HANDED_OFF; break; }
-      L.base = lane_base(L, B, seg_start);
+      L.base = lane_base(L, B, seg_start, FT.eot_rewind);
       continue;
     }
     if (fast && !halted) {
-      lane_note_first_rewind(L, B, seg_start);
-      L.base = lane_base(L, B, seg_start);
+      lane_note_first_rewind(L, B, seg_start, FT.eot_rewind);
+      L.base = lane_base(L, B, seg_start, FT.eot_rewind);
     }
     if (in_regs) store_seg_bits(b, w, B);
     in_regs = true;

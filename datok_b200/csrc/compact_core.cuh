@@ -100,6 +100,8 @@ struct CompactCtx {
   const uint32_t* b_sent;
   const uint32_t* b_tend;
   uint32_t flags;          // TokenWriter Bits (+ F_WRITER_USED)
+  uint32_t eot_rewind;     // 0: double-array walk -- the buffer is not rewound at an EOT (datok.go:1019-1030): the first
+                           // Token call of a text carries the runes since the last token of the text before
   // this input is a piece of a longer stream: what the pieces before it produced (added to every
   // index / byte offset written to the outputs; DocRec and Agg stay piece-relative)
   uint32_t base_tok, base_sent, base_sentpos, base_byte;
@@ -148,6 +150,16 @@ DATOK_HD uint32_t next_clear(const uint32_t* w, uint32_t n_words, uint32_t p) {
 // (token_writer.go:66-68): posC-- whenever a Token call arrives with posC == 0 and
 // buf[0] == '\n'.  posC is 0 at the first Token of a text, and again after a
 // chunk that was exactly "\n".  (The `init` exemption is applied by the caller.)
+// double-array walk: the text's first buffer starts at D, the end of the last token before the EOT at p (0: none
+// yet); buf[0] is that rune.  One Token call at posC == 0 at most: its buffer spans the EOT, it is longer than "\n".
+DATOK_HD uint32_t newline_adjust_norewind(const CompactCtx& c, uint32_t D, uint32_t p) {
+  if (!(c.flags & F_NL_AFTER_EOT)) return 0;
+  if (D >= c.N || c.in[D] != '\n') return 0;
+  const uint32_t e = next_set(c.b_end, c.n_words, p + 1);   // the first token of the text behind the EOT ...
+  if (e == K_NOPOS) return 0;
+  const uint32_t q = next_set(c.b_tend, c.n_words, p + 1);  // ... if the text has one
+  return (q != K_NOPOS && q < e) ? 0u : 1u;
+}
 DATOK_HD uint32_t newline_adjust(const CompactCtx& c, uint32_t D) {
   if (!(c.flags & F_NL_AFTER_EOT)) return 0;
   uint32_t adj = 0, b = D;
@@ -257,7 +269,9 @@ DATOK_HD void emit_texts(const CompactCtx& c, uint32_t w, const WordBits& b, con
     // token-less text (token_writer.go:135,145): no END since the text started
     uint32_t last_end = A.last_end_pos;
     if (b.e & le) last_end = (w << 5) + 31u - clz32(b.e & le);
-    if (last_end == K_NOPOS || last_end <= doc_start) {
+    // (a token that ends exactly at doc_start holds the EOT before it: possible in a double-array walk only, where the
+    // EOT can stay in the buffer -- it was handed out after that TextEnd and belongs to this text)
+    if (last_end == K_NOPOS || last_end < doc_start || (last_end == doc_start && (c.eot_rewind || doc_start == 0))) {
       if (c.flags & F_TOKEN_POS) report_error(c, p, E_TEXT_NO_TOKEN);
       else if (c.flags & F_SENTENCE_POS) report_error(c, p, E_TEXT_NO_SENT);
     }
@@ -266,9 +280,21 @@ DATOK_HD void emit_texts(const CompactCtx& c, uint32_t w, const WordBits& b, con
     c.text_sentpos_end[text] = c.base_sentpos + sentpos;
     c.text_byte_end[text] = c.base_byte + p + 1;
     DocRec d;
-    d.start = p + 1;
-    d.rank = A.n_rune + popc32(b.rs & le);
-    d.adj = newline_adjust(c, p + 1);
+    if (c.eot_rewind) {
+      d.start = p + 1;
+      d.rank = A.n_rune + popc32(b.rs & le);
+      d.adj = newline_adjust(c, p + 1);
+    } else {
+      // no rewind at the EOT: the next text's first buffer starts where the last token ended (stream start: 0)
+      const uint32_t any_end = (b.e & le) ? (w << 5) + 31u - clz32(b.e & le) : A.last_end_pos;
+      if (any_end == K_NOPOS) { d.start = 0; d.rank = 0; }
+      else {
+        d.start = any_end;
+        d.rank = (b.e & le) ? A.n_rune + popc32(b.rs & mask_below(31u - clz32(b.e & le)))
+                            : A.n_rune - count_range(c.rstart, any_end, w << 5);
+      }
+      d.adj = newline_adjust_norewind(c, d.start, p);
+    }
     d.tok = tok;
     c.docs[text + 1] = d;
     doc_start = p + 1;
@@ -438,7 +464,8 @@ DATOK_HD StreamTotals finalize_stream(const CompactCtx& c, const Agg& tot, bool 
   r.last_kind = agg_last(tot);
   r.reserved = 0;
   const uint32_t doc_start = tot.doc_start == K_NOPOS ? 0u : tot.doc_start;
-  const bool have_tok = tot.last_end_pos != K_NOPOS && tot.last_end_pos > doc_start;
+  const bool have_tok = tot.last_end_pos != K_NOPOS &&
+                        (tot.last_end_pos > doc_start || (tot.last_end_pos == doc_start && !c.eot_rewind && doc_start != 0));
   r.tokless = have_tok ? 0u : 1u;
   if (!final_input) return r;
   const DocRec d = c.docs[tot.n_text];

@@ -51,6 +51,7 @@ struct FastTables {
   const uint8_t* ascii_cls2;  // [256]: 2 * class of the ASCII bytes, capped at stop_cl2; the other bytes map to themselves,
                               // so that the class buffer still holds them when they are decoded (shared memory in the kernel)
   const uint32_t* sync_cls;   // [8]: bit c set iff class c is a sync class (shared memory in the kernel)
+  uint32_t eot_rewind;     // 1: an EOT rewinds the buffer (matrix walk); 0: it does not (double-array walk, datok.go:1019-1030)
   uint32_t stop_cl2;       // 2 * (number of classes that have a column in the compact rows): the all-zero column.
                            // Rarer classes are stored as this value, and so is the sentinel behind a walk range.
 };
@@ -132,7 +133,9 @@ struct Derived {
   uint32_t end, sent, skip, tend, deg;
   uint32_t u_at_pos;       // u at position po
 };
-DATOK_HD Derived derive_bits(const RawBits& R, uint32_t eotm, uint32_t ro, uint32_t po, uint32_t u_in) {
+// eotm: the EOTs that rewind the buffer (all of them in the matrix walk, none in the double-array walk, where an
+// EOT is an ordinary skipped rune); tendm: all EOTs -- every consumed one fires TextEnd.
+DATOK_HD Derived derive_bits(const RawBits& R, uint32_t eotm, uint32_t ro, uint32_t po, uint32_t u_in, uint32_t tendm) {
   Derived D;
   const uint32_t lim = mask_below(po) & mask_from(ro);
   const uint32_t eot = eotm & lim;
@@ -146,7 +149,7 @@ DATOK_HD Derived derive_bits(const RawBits& R, uint32_t eotm, uint32_t ro, uint3
   D.end = n1 & ~D.u;
   D.sent = (n1 & D.u) | n2;
   D.skip = (D.u | n1) & R.nt;
-  D.tend = eot;
+  D.tend = tendm & lim;
   D.deg = (n2 & D.u) | (R.c2 & R.cb);
   return D;
 }
@@ -179,15 +182,15 @@ DATOK_HD bool eps_alive(const FastLane& L, const RawBits& R, uint32_t eotm, uint
 }
 
 // last rewind point, taking the boundary bits of the current segment into account
-DATOK_HD uint32_t lane_base(const FastLane& L, const SegBits& B, uint32_t seg_start) {
+DATOK_HD uint32_t lane_base(const FastLane& L, const SegBits& B, uint32_t seg_start, uint32_t eot_rewind) {
   uint32_t base = L.base;
   if (B.end) { const uint32_t p = seg_start + 31u - clz32(B.end); if (p > base) base = p; }
-  if (B.tend) { const uint32_t p = seg_start + 32u - clz32(B.tend); if (p > base) base = p; }
+  if (eot_rewind && B.tend) { const uint32_t p = seg_start + 32u - clz32(B.tend); if (p > base) base = p; }
   return base;
 }
 // a guessed start's first window closes with the first END/TEND bit of the lane
-DATOK_HD void lane_note_first_rewind(FastLane& L, const SegBits& B, uint32_t seg_start) {
-  const uint32_t m = B.end | B.tend;
+DATOK_HD void lane_note_first_rewind(FastLane& L, const SegBits& B, uint32_t seg_start, uint32_t eot_rewind) {
+  const uint32_t m = B.end | (eot_rewind ? B.tend : 0u);
   if (L.first_window && m) { L.first_hw = seg_start + ctz32(m); L.first_window = 0; }
 }
 
@@ -210,10 +213,10 @@ DATOK_HD void to_fast(const WState& st, FastLane& L, RawBits& R) {
 // Closes the raw range [raw_from, pos) of the segment: merges its boundary words into B and
 // moves the lane's token start / unstarted flag to pos.  Returns false on a degenerate event
 // sequence.  Afterwards the raw masks are empty and raw_from == pos.
-DATOK_HD bool fast_flush(FastLane& L, RawBits& R, SegBits& B, uint32_t eotm, uint32_t seg_start) {
+DATOK_HD bool fast_flush(FastLane& L, RawBits& R, SegBits& B, uint32_t eotm, uint32_t tendm, uint32_t seg_start) {
   const uint32_t po = L.pos - seg_start;
   const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
-  const Derived D = derive_bits(R, eotm, ro, po, L.u_in);
+  const Derived D = derive_bits(R, eotm, ro, po, L.u_in, tendm);
   const bool alive = eps_alive(L, R, eotm, seg_start, po);
   B.end |= D.end; B.sent |= D.sent; B.skip |= D.skip; B.tend |= D.tend;
   L.tstart = derived_tstart(L, R, D, seg_start, po);
@@ -226,7 +229,7 @@ DATOK_HD bool fast_flush(FastLane& L, RawBits& R, SegBits& B, uint32_t eotm, uin
 
 // fast lane (flushed: raw range empty) -> exact state
 DATOK_HD void to_exact(const FastLane& L, const SegBits& B, uint32_t seg_start, const FastTables& T, WState& st) {
-  const uint32_t base = lane_base(L, B, seg_start);
+  const uint32_t base = lane_base(L, B, seg_start, T.eot_rewind);
   st.pos = L.pos; st.tstart = L.tstart; st.base = base; st.t = (uint16_t)L.t;
   st.flags = 0;
   uint32_t es = 0;
@@ -268,7 +271,7 @@ int fast_backtrack(FastLane& L, RawBits& R, const FastTables& T, uint32_t seg_st
   uint32_t zone = 0;
   if (DATOK_UNLIKELY(L.first_window || (R.nt & qb))) {
     const uint32_t ro = L.raw_from > seg_start ? L.raw_from - seg_start : 0;
-    const Derived D = derive_bits(R, eotm, ro, po, L.u_in);
+    const Derived D = derive_bits(R, eotm, ro, po, L.u_in, eotm);
     if (!((D.u | D.n1) & qb) && L.first_window) {  // Token + rewind (:565-572): closes a guessed start's first window
       const uint32_t m = ((D.end | D.tend) & (qb - 1u)) | Bprev.end | Bprev.tend;
       L.first_hw = m ? seg_start + ctz32(m) : L.hw_med;

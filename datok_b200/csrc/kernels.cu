@@ -89,6 +89,7 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   FT.ascii_cls2 = s_lut + 256;
   FT.sync_cls = s_sync;
   FT.stop_cl2 = 2u * m.hot_cols;
+  FT.eot_rewind = m.eot_rewind;
   FT.row16_inv = 0xFFFFFFFFu / FT.row16 + 1u;  // (row16 is not a power of two: floor(2^32 / row16) == floor((2^32 - 1) / row16))
   {  // opaque to the compiler: otherwise the shared-window base is re-derived in every step of the hot loop
     const unsigned long long sa = __cvta_generic_to_shared(s_hot);

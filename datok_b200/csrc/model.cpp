@@ -97,6 +97,7 @@ static int parse_datok_image(const uint8_t* d, size_t n, HostModel& m, std::stri
   }
   m.stateCount = (int)order.size();
   const size_t S = order.size();
+  if (S + 1 >= 32768) { why = "state count not in 1..32766"; return DATOK_ERR_UNSUPPORTED_MODEL; }  // (before the matrix is allocated)
   m.array.assign((S + 1) * (size_t)m.sigmaCount, 0);  // cell (a, t) at (a - 1) * S + t, as in a .matok image
   for (size_t k = 0; k < S; k++)
     for (int a = 1; a < m.sigmaCount; a++) {
@@ -110,12 +111,6 @@ static int parse_datok_image(const uint8_t* d, size_t n, HostModel& m, std::stri
 int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why) {
   // magic + 14-byte little-endian header (matrix.go:246-285)
   if (n >= 5 && std::memcmp(d, "DATOK", 5) == 0) {  // fomafile.go:476-480
-    // The double-array path is verified against its oracle through the CPU emulation of the kernels
-    // (tests/test_emul_parity.py); its GPU parity run is still partial, so it is opt-in for now.
-    if (!std::getenv("DATOK_EXPERIMENTAL_DATOK")) {
-      why = "double-array model (DATOK): experimental, set DATOK_EXPERIMENTAL_DATOK=1 (EOT-free input only) or use the .matok model";
-      return DATOK_ERR_UNSUPPORTED_MODEL;
-    }
     return parse_datok_image(d, n, m, why);
   }
   if (n < 19 || std::memcmp(d, "MATOK", 5) != 0) { why = "Not a matok file"; return DATOK_ERR_FORMAT; }
@@ -372,6 +367,9 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist, const uin
         cur = r[CLS_EPS] & 0x7FFFu;
         k++;
       }
+      // double-array walk: an EOT does not rewind the buffer (datok.go:1019-1030).  Its steps are left to the exact
+      // walker, which knows that rule; the fast path then never sees a consumed EOT of such a model.
+      if (c == CLS_EOT && !m.eot_rewind) e = T3_SLOW;
       row2[c] = m.fast_ok ? e : T3_SLOW;
     }
   }

@@ -215,6 +215,8 @@ struct alignas(16) WState {
 constexpr uint32_t WS_PEND = 1;     // a hard-fail token ends exactly at `pos`; its END bit is still to be set
 constexpr uint32_t WS_DONE = 2;     // EOF tail finished (matrix.go:650-678)
 constexpr uint32_t WS_INVALID = 4;  // no usable state (void chunk not yet walked, or walker stopped on error)
+constexpr uint32_t WS_EPS_OVER_EOT = 8;  // double-array walk only: an EOT was consumed behind the pending epsilon point
+                                         // (a backtrack to it would read the EOT, and fire TextEnd, a second time)
 constexpr uint32_t WS_ERR_SHIFT = 8;  // error code that stopped the walker
 
 DATOK_HD bool wstate_equal(const WState& a, const WState& b) {
@@ -236,6 +238,8 @@ struct WalkCtx {
   uint32_t* hist;         // optional: visits per state (calibration of the hot-row order)
   uint32_t* hist_cls;     // with hist: occurrences per class (calibration of the class order)
   uint32_t final_input;   // 0: the stream continues in a later call: no end-of-input processing (matrix.go:650-695)
+  uint32_t eot_rewind;    // 1: matrix walk -- an EOT rewinds the buffer (matrix.go:601-603); 0: double-array walk -- it
+                          // does not (datok.go:1019-1030): window, token start and epsilon point live on across the EOT
 };
 
 // class of the byte at pos (continuation bytes of a well-formed rune: K_CLS_CONT)
@@ -387,7 +391,7 @@ DATOK_HD uint32_t walk_run_inl(const WalkCtx& c, WState& st, uint32_t stop, Spec
         c.hist_cls[cl]++;
 #endif
       }
-      if (row[K_CLS_EPS] != 0) { eps_state = t; eps_pos = pos; }  // :442-454
+      if (row[K_CLS_EPS] != 0) { eps_state = t; eps_pos = pos; flags &= ~WS_EPS_OVER_EOT; }  // :442-454
       const uint32_t nt = row[cl];                                // :463
       if (nt != 0) {
         // ---- transition consumes the byte (matrix.go:579-605) ----
@@ -398,14 +402,22 @@ DATOK_HD uint32_t walk_run_inl(const WalkCtx& c, WState& st, uint32_t stop, Spec
           tstart = pos;
         }
         if (cl == K_CLS_EOT) {  // :593-605
-          if (probing) { eps_state = 0; continue; }  // the rewind kills the pending epsilon point
-          set_bit(c.b_tend, before);
-          if (hw < before) hw = before;
-          if (tstart > pos) {  // stale bufft is reset by the rewind (:622)
-            clear_range(c.b_skip, pos, tstart < stop ? tstart : stop);
+          if (c.eot_rewind) {
+            if (probing) { eps_state = 0; continue; }  // the rewind kills the pending epsilon point
+            set_bit(c.b_tend, before);
+            if (hw < before) hw = before;
+            if (tstart > pos) {  // stale bufft is reset by the rewind (:622)
+              clear_range(c.b_skip, pos, tstart < stop ? tstart : stop);
+            }
+            DATOK_REWIND(pos);
+            tstart = pos;
+          } else {  // datok.go:1019-1030: SentenceEnd / TextEnd, the buffer stays as it is
+            if (!probing) {
+              set_bit(c.b_tend, before);
+              if (hw < before) hw = before;
+            }
+            if (eps_state != 0 && eps_pos <= before) flags |= WS_EPS_OVER_EOT;
           }
-          DATOK_REWIND(pos);
-          tstart = pos;
         }
         t = nt & 0x7FFFu;
         continue;
@@ -415,6 +427,7 @@ DATOK_HD uint32_t walk_run_inl(const WalkCtx& c, WState& st, uint32_t stop, Spec
     if (hw < pos) hw = pos;
     if (eps_state != 0) {
       // backtrack to the last state that had an epsilon transition (:487-497)
+      if (flags & WS_EPS_OVER_EOT) { err = E_DEGENERATE; goto out; }  // (the reference would fire the TextEnd twice: not representable)
       const uint32_t t0 = eps_state;
       eps_state = 0;
       pos = eps_pos;
@@ -456,6 +469,7 @@ out:
     eps_state = 0;
   }
   if (SPEC) { if (first_window) { spec->first_hw = hw; spec->had_rewind = 0; } }
+  if (!eps_state) flags &= ~WS_EPS_OVER_EOT;
   st.pos = pos; st.tstart = tstart; st.eps_pos = eps_state ? eps_pos : 0; st.base = base; st.hw = hw;
   st.t = (uint16_t)t; st.eps_state = (uint16_t)eps_state; st.flags = flags;
   return 0;

@@ -14,14 +14,19 @@ package datokb200
 #include <stdlib.h>
 #include "datok_b200.h"
 
-// cgo cannot call Go closures from C directly; the replay goes through these
-// exported trampolines (see //export below).
-extern void goDatokToken(void *user, const uint8_t *buf, size_t bufBytes, size_t offBytes, int32_t offRunes);
+// cgo cannot call Go closures from C directly; the replay goes through exported trampolines (//export
+// below).  cgo declares exported functions without `const` in _cgo_export.h, so the prototypes here
+// match that and the pointers are cast where the callback table is filled.
+extern void goDatokToken(void *user, uint8_t *buf, size_t bufBytes, size_t offBytes, int32_t offRunes);
 extern void goDatokSentenceEnd(void *user);
 extern void goDatokTextEnd(void *user);
 
 static int datok_replay_go(const datok_result *r, const uint8_t *in, size_t n, void *user) {
-  datok_callbacks cb = { user, goDatokToken, goDatokSentenceEnd, goDatokTextEnd };
+  datok_callbacks cb;
+  cb.user = user;
+  cb.token = (void (*)(void *, const uint8_t *, size_t, size_t, int32_t))goDatokToken;
+  cb.sentence_end = goDatokSentenceEnd;
+  cb.text_end = goDatokTextEnd;
   return datok_replay(r, in, n, &cb);
 }
 */
@@ -37,7 +42,7 @@ import (
 	datok "github.com/KorAP/datok"
 )
 
-// Tokenizer implements datok.Tokenizer for .matok models on one B200.
+// Tokenizer implements datok.Tokenizer for .matok (and .datok) models on one B200.
 type Tokenizer struct {
 	model *C.datok_model
 }
@@ -45,8 +50,13 @@ type Tokenizer struct {
 // compile-time check: same interface as the reference (fomafile.go:29-33)
 var _ datok.Tokenizer = (*Tokenizer)(nil)
 
-// LoadTokenizerFile mirrors datok.LoadTokenizerFile (fomafile.go:452-484) for the
-// MATOK magic: nil on any error, the reason is logged.
+// BlockBytes is how much of the reader one push hands to the GPU.  The reference keeps a window of
+// at most 1024 runes (matrix.go:365); here memory is bounded by one block plus the text that is still
+// open at its end.
+var BlockBytes = 64 << 20
+
+// LoadTokenizerFile mirrors datok.LoadTokenizerFile (fomafile.go:452-484): nil on any error, the
+// reason is logged.
 func LoadTokenizerFile(file string, device int) *Tokenizer {
 	cs := C.CString(file)
 	defer C.free(unsafe.Pointer(cs))
@@ -62,12 +72,86 @@ func LoadTokenizerFile(file string, device int) *Tokenizer {
 // Close releases the GPU resident model.
 func (t *Tokenizer) Close() { C.datok_free(t.model); t.model = nil }
 
-// Type is "MATOK" (matrix.go:102-104).
-func (t *Tokenizer) Type() string { return C.GoString(C.datok_type()) }
+// Type is "MATOK" (matrix.go:102-104) or "DATOK" (datok.go:252-254), by the file's magic.
+func (t *Tokenizer) Type() string { return C.GoString(C.datok_model_type(t.model)) }
 
-// Transduce mirrors matrix.go:340-342.
+func check(rc C.int) bool {
+	if rc == C.DATOK_OK {
+		return true
+	}
+	if rc <= C.DATOK_ERR_DEGENERATE {
+		panic(errors.New(C.GoString(C.datok_strerror(rc)))) // the reference panics here too
+	}
+	log.Println(C.GoString(C.datok_last_error()))
+	return false
+}
+
+// stream pushes the reader through datok_stream_* block by block (cmd/datok.go:108-132: any io.Reader,
+// STDIN included) and hands every batch result, with the input bytes it covers, to deliver.
+func (t *Tokenizer) stream(r io.Reader, flags C.uint32_t, deliver func(res *C.datok_result, in []byte)) bool {
+	st := C.datok_stream_open(t.model, flags)
+	if st == nil {
+		return false
+	}
+	defer C.datok_stream_close(st)
+	block := make([]byte, BlockBytes)
+	var pending []byte // bytes pushed but not covered by a result yet (only kept for the replay)
+	for {
+		n, err := io.ReadFull(r, block)
+		if n > 0 {
+			var res *C.datok_result
+			done0 := uint64(C.datok_stream_bytes_done(st))
+			if !check(C.datok_stream_push(st, (*C.uint8_t)(unsafe.Pointer(&block[0])), C.size_t(n), &res)) {
+				return false
+			}
+			pending = append(pending, block[:n]...)
+			if res != nil {
+				k := uint64(C.datok_stream_bytes_done(st)) - done0
+				deliver(res, pending[:k])
+				C.datok_result_free(res)
+				pending = append(pending[:0], pending[k:]...)
+			}
+		}
+		if err == io.EOF || err == io.ErrUnexpectedEOF {
+			break
+		}
+		if err != nil {
+			log.Fatalln(err) // matrix.go:401
+			return false
+		}
+	}
+	var res *C.datok_result
+	if !check(C.datok_stream_finish(st, &res)) {
+		return false
+	}
+	if res != nil {
+		deliver(res, pending)
+		C.datok_result_free(res)
+	}
+	return true
+}
+
+// Transduce mirrors matrix.go:340-342.  The stock SIMPLE writer's text is formatted on the device
+// (DATOK_FORMAT) and written as it comes back.
 func (t *Tokenizer) Transduce(r io.Reader, w io.Writer) bool {
-	return t.TransduceTokenWriter(r, datok.NewTokenWriter(w, datok.SIMPLE))
+	ok := t.stream(r, C.uint32_t(C.DATOK_TOKENS|C.DATOK_SENTENCES|C.DATOK_FORMAT), func(res *C.datok_result, _ []byte) {
+		v := C.datok_result_view(res)
+		if v.text_len > 0 {
+			w.Write(unsafe.Slice((*byte)(unsafe.Pointer(v.text)), int(v.text_len)))
+		}
+	})
+	return ok
+}
+
+// TransduceFlags is Transduce for any flag set of NewTokenWriter (token_writer.go:17-25): the text the
+// stock writer would produce, formatted on the device.
+func (t *Tokenizer) TransduceFlags(r io.Reader, w io.Writer, flags datok.Bits) bool {
+	return t.stream(r, C.uint32_t(flags)|C.uint32_t(C.DATOK_FORMAT), func(res *C.datok_result, _ []byte) {
+		v := C.datok_result_view(res)
+		if v.text_len > 0 {
+			w.Write(unsafe.Slice((*byte)(unsafe.Pointer(v.text)), int(v.text_len)))
+		}
+	})
 }
 
 // TransduceTokenWriter mirrors matrix.go:348-698: the input is transduced on the GPU
@@ -77,30 +161,16 @@ func (t *Tokenizer) Transduce(r io.Reader, w io.Writer) bool {
 // make this function panic with the same cause.
 func (t *Tokenizer) TransduceTokenWriter(r io.Reader, w *datok.TokenWriter) bool {
 	defer w.Flush() // matrix.go:374
-	in, err := io.ReadAll(r)
-	if err != nil {
-		log.Fatalln(err) // matrix.go:401
-		return false
-	}
-	var p *C.uint8_t
-	if len(in) > 0 {
-		p = (*C.uint8_t)(unsafe.Pointer(&in[0]))
-	}
-	var res *C.datok_result
-	// DATOK_COMPACT8: the replay only needs the delta-coded spans (4 bytes per token over PCIe)
-	rc := C.datok_transduce(t.model, p, C.size_t(len(in)), C.uint32_t(C.DATOK_TOKENS|C.DATOK_SENTENCES|C.DATOK_COMPACT8), nil, &res)
-	if rc != C.DATOK_OK {
-		if rc <= C.DATOK_ERR_DEGENERATE {
-			panic(errors.New(C.GoString(C.datok_strerror(rc)))) // the reference panics here too
-		}
-		log.Println(C.GoString(C.datok_last_error()))
-		return false
-	}
-	defer C.datok_result_free(res)
 	h := cgo.NewHandle(w)
 	defer h.Delete()
-	C.datok_replay_go(res, p, C.size_t(len(in)), unsafe.Pointer(&h))
-	return true
+	// DATOK_COMPACT8: the replay only needs the delta-coded spans (4 bytes per token over PCIe)
+	return t.stream(r, C.uint32_t(C.DATOK_TOKENS|C.DATOK_SENTENCES|C.DATOK_COMPACT8), func(res *C.datok_result, in []byte) {
+		var p *C.uint8_t
+		if len(in) > 0 {
+			p = (*C.uint8_t)(unsafe.Pointer(&in[0]))
+		}
+		C.datok_replay_go(res, p, C.size_t(len(in)), unsafe.Pointer(&h))
+	})
 }
 
 //export goDatokToken

@@ -34,7 +34,7 @@ int run(int argc, char** argv, HostModel& hm, bool report) {
   uint32_t chunk = argc > 3 ? atoi(argv[3]) : 256, hot_rows = argc > 4 ? atoi(argv[4]) : 440;
   DeviceModel m; memset(&m, 0, sizeof m);
   m.table = hm.table.data(); m.table2 = hm.table2.data(); m.row_shift = hm.row_shift; m.start = hm.start;
-  m.n_classes = hm.n_classes; m.stride2 = hm.stride2; m.hot16 = hm.hot16.data(); m.stride16 = hm.stride16; m.hot16_rows = hm.hot16_rows; m.hot_cols = hm.hot_cols;
+  m.n_classes = hm.n_classes; m.stride2 = hm.stride2; m.hot16 = hm.hot16.data(); m.stride16 = hm.stride16; m.hot16_rows = hm.hot16_rows; m.hot_cols = hm.hot_cols; m.eot_rewind = hm.eot_rewind ? 1u : 0u;
   m.cls.ascii_cls = hm.ascii_cls; m.cls.latin1_cls = hm.latin1_cls; m.cls.rune_key = hm.rune_key.data();
   m.cls.rune_cls = hm.rune_cls.data(); m.cls.n_rune = hm.rune_key.size(); m.cls.identity_cls = hm.identity_cls;
   memcpy(m.sync_ascii, hm.sync_ascii, sizeof hm.sync_ascii); memcpy(m.sync_cls, hm.sync_mask, sizeof hm.sync_mask);
@@ -53,7 +53,7 @@ int run(int argc, char** argv, HostModel& hm, bool report) {
   hot.resize(hot.size() + hm.stride16, 0);
   uint8_t lut2[256]; for (int i = 0; i < 128; i++) { lut2[i] = cap_cl2(hm.ascii_cls[i], 2 * hm.hot_cols); lut2[128 + i] = 128 + i; }
   FastTables FT; FT.hot16 = hot.data(); FT.t3 = m.table2; FT.n_hot = hot_rows; FT.row16 = hm.stride16 * 2; FT.stride3 = m.stride2;
-  FT.hot_saddr = 0; FT.ascii_cls2 = lut2; FT.stop_cl2 = 2 * hm.hot_cols; FT.sync_cls = hm.sync_mask;
+  FT.hot_saddr = 0; FT.ascii_cls2 = lut2; FT.stop_cl2 = 2 * hm.hot_cols; FT.sync_cls = hm.sync_mask; FT.eot_rewind = hm.eot_rewind ? 1u : 0u;
   uint8_t cls[36];
   for (uint32_t i = 0; i < b.n_chunks; i++) chunk_spec_fast(m, b, FT, i, m.start, cls);
   if (report) printf("bytes %zu chunks %u\nfast steps %llu (cold %llu = %.3f%%)\nbacktracks in place %llu (%.3f%% of steps), stale zones %llu, inline %llu\n"

@@ -34,6 +34,7 @@ struct EmulResult {
   uint8_t* tok_delta8;
   uint32_t* esc;
   uint32_t n_esc;
+  uint32_t eot_rewind;  // 0: a double-array model -- the delta-coded forms (cursors restart at every text) do not apply
   uint8_t* text;        // the device formatter's bodies (format_core.cuh) over the arrays above; null with malformed UTF-8
   uint64_t text_len;
 };
@@ -53,7 +54,7 @@ static void make_fast_tables(const HostModel& hm, const DeviceModel& m, uint32_t
   hot.resize(hot.size() + hm.stride16, 0);  // the all-zero row n_hot
   for (int i = 0; i < 128; i++) { g_ascii_cls2[i] = (uint8_t)cap_cl2(hm.ascii_cls[i], 2 * hm.hot_cols); g_ascii_cls2[128 + i] = (uint8_t)(128 + i); }
   FT.hot16 = hot.data(); FT.t3 = m.table2; FT.n_hot = n_hot; FT.row16 = hm.stride16 * 2u; FT.stride3 = m.stride2;
-  FT.hot_saddr = 0; FT.ascii_cls2 = g_ascii_cls2; FT.stop_cl2 = 2 * hm.hot_cols; FT.sync_cls = hm.sync_mask;
+  FT.hot_saddr = 0; FT.ascii_cls2 = g_ascii_cls2; FT.stop_cl2 = 2 * hm.hot_cols; FT.sync_cls = hm.sync_mask; FT.eot_rewind = hm.eot_rewind ? 1u : 0u;
 }
 
 EmulModel* emul_load(const char* path, int* err) {
@@ -66,7 +67,7 @@ EmulModel* emul_load(const char* path, int* err) {
   m->dm.table2 = h.table2.data();
   m->dm.hot16 = h.hot16.data();
   m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.n_classes = h.n_classes; m->dm.stride2 = h.stride2;
-  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols;
+  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols; m->dm.eot_rewind = h.eot_rewind ? 1u : 0u;
   m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
   m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
   m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls; m->dm.cls.self = nullptr;
@@ -89,7 +90,7 @@ int emul_calibrate(EmulModel* m, const uint8_t* data, uint32_t n, uint32_t force
   m->dm.table2 = h.table2.data();
   m->dm.hot16 = h.hot16.data();
   m->dm.row_shift = h.row_shift; m->dm.start = h.start; m->dm.n_classes = h.n_classes; m->dm.stride2 = h.stride2;
-  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols;
+  m->dm.stride16 = h.stride16; m->dm.hot16_rows = h.hot16_rows; m->dm.hot_cols = h.hot_cols; m->dm.eot_rewind = h.eot_rewind ? 1u : 0u;
   m->dm.cls.ascii_cls = h.ascii_cls; m->dm.cls.latin1_cls = h.latin1_cls;
   m->dm.cls.rune_key = h.rune_key.data(); m->dm.cls.rune_cls = h.rune_cls.data();
   m->dm.cls.n_rune = (uint32_t)h.rune_key.size(); m->dm.cls.identity_cls = h.identity_cls; m->dm.cls.self = nullptr;
@@ -149,6 +150,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       chunk_spec_fast(m, b, FT, order ? b.n_chunks - 1 - k : k, start_state, seg_cls);
   }
   R->has_invalid = counters[2];
+  R->eot_rewind = m.eot_rewind;
 
   FastTables FTr;
   std::vector<uint16_t> hot_r;
@@ -193,7 +195,7 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   CompactCtx c;
   std::memset(&c, 0, sizeof c);
   c.in = in; c.N = N; c.n_words = b.n_words; c.rstart = b.rstart; c.b_end = b.b_end; c.b_skip = b.b_skip;
-  c.b_sent = b.b_sent; c.b_tend = b.b_tend; c.flags = flags; c.err_key = &err_key;
+  c.b_sent = b.b_sent; c.b_tend = b.b_tend; c.flags = flags; c.err_key = &err_key; c.eot_rewind = m.eot_rewind;
   const uint32_t TPB = 256, WPT = 2, WPB = TPB * WPT;
   const uint32_t nblk = (b.n_words + WPB - 1) / WPB;
   std::vector<Agg> block_agg(nblk), block_carry(nblk);

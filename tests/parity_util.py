@@ -33,7 +33,7 @@ class _Res(C.Structure):
                 ("rounds", C.c_uint32), ("n_rewalks", C.c_uint32), ("n_stitch_mismatch", C.c_uint32),
                 ("tok_delta", C.POINTER(C.c_uint16)), ("tok_delta8", C.POINTER(C.c_uint8)),
                 ("esc", C.POINTER(C.c_uint32)), ("n_esc", C.c_uint32),
-                ("text", C.POINTER(C.c_uint8)), ("text_len", C.c_uint64)]
+                ("eot_rewind", C.c_uint32), ("text", C.POINTER(C.c_uint8)), ("text_len", C.c_uint64)]
 
 
 _lib = None
@@ -107,8 +107,9 @@ class EmulModel:
             s.text_byte_end = _arr(r.text_byte_end, r.n_texts, np.uint32)
             s.carry_state = r.carry_state
             s.has_invalid = r.has_invalid
-            s.tok_delta = _arr(r.tok_delta, 4 * r.n_tokens, np.uint16)
-            s.tok_delta8 = _arr(r.tok_delta8, 4 * r.n_tokens, np.uint8)
+            # (a double-array model has no delta-coded forms: its cursors do not restart at a text)
+            s.tok_delta = _arr(r.tok_delta, 4 * r.n_tokens, np.uint16) if r.eot_rewind else None
+            s.tok_delta8 = _arr(r.tok_delta8, 4 * r.n_tokens, np.uint8) if r.eot_rewind else None
             s.tok_esc = _arr(r.esc, 2 * r.n_esc, np.uint32)
             s.text = bytes(C.string_at(r.text, r.text_len)) if r.text else None  # the device formatter's bodies
         lib().emul_result_free(rp)

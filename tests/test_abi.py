@@ -53,7 +53,7 @@ def test_loader_errors_mirror_reference(tmp_path, testdata):
     assert load_error_code(str(p)) == _lib.ERR_IO           # gzip.NewReader fails, matrix.go:222
     p = tmp_path / "magic.matok"
     p.write_bytes(gzip.compress(b"DATOK" + b"\0" * 64))
-    assert load_error_code(str(p)) == _lib.ERR_UNSUPPORTED_MODEL  # the double-array magic: opt-in (below)
+    assert load_error_code(str(p)) == _lib.ERR_FORMAT       # the double-array magic with an empty array (datok.go:667-725)
     p.write_bytes(gzip.compress(b"MATOX" + b"\0" * 64))
     assert load_error_code(str(p)) == _lib.ERR_FORMAT       # matrix.go:258
     raw = gzip.decompress(open(os.path.join(testdata, "simpletok.matok"), "rb").read())
@@ -86,22 +86,13 @@ def test_product_does_not_touch_the_oracle():
                 assert "pyoracle" not in txt and "datok_oracle" not in txt and "libdatok_emul" not in txt, f
 
 
-def test_double_array_models_are_opt_in(testdata, monkeypatch, tmp_path):
-    """LoadTokenizerFile (fomafile.go:452-484) also takes .datok files.  The loader converts the double array
-    (datok.go:621-729) to the matrix layout, but only with DATOK_EXPERIMENTAL_DATOK=1: the path is verified
-    through the CPU emulation (tests/test_emul_parity.py), its GPU parity run is still partial.  Without the
-    variable the format is refused with a message of its own."""
-    import ctypes as C
+def test_double_array_models_load_by_magic(testdata, monkeypatch, tmp_path):
+    """LoadTokenizerFile (fomafile.go:452-484) dispatches on the magic: .datok files load like .matok files (the loader
+    converts the double array, datok.go:621-729, to the matrix layout; the kernels know that its walk does not rewind
+    the buffer at an EOT)."""
     import torch
     from datok_b200 import _lib
     from datok_b200.tokenizer import load_error_code
-    L = _lib.lib()
-    monkeypatch.delenv("DATOK_EXPERIMENTAL_DATOK", raising=False)
-    err = C.c_int(0)
-    h = L.datok_load(os.path.join(testdata, "tokenizer_de.datok").encode(), 0, C.byref(err))
-    assert not h and err.value == _lib.ERR_UNSUPPORTED_MODEL
-    assert b"double-array" in L.datok_last_error()
-    monkeypatch.setenv("DATOK_EXPERIMENTAL_DATOK", "1")
     p = tmp_path / "empty.datok"
     p.write_bytes(gzip.compress(b"DATOK" + b"\0" * 64))
     assert load_error_code(str(p)) == _lib.ERR_FORMAT       # an empty double array (datok.go:703-725)

@@ -195,36 +195,51 @@ def test_long_document_corpus_in_windows(gpu_models, oracle_models):
 
 
 @pytest.mark.parametrize("name", ["tokenizer_de.datok", "simpletok.datok"])
-def test_double_array_models_without_eot(name, testdata, monkeypatch):
-    """LoadTokenizerFile on a .datok file (fomafile.go:476-480): bit-exact against the double-array oracle on
-    EOT-free input; an input that holds an EOT is refused (the double-array loop does not rewind the buffer
-    there, datok.go:1019-1030, and the kernels have no such variant yet)"""
+def test_double_array_models(name, testdata):
+    """LoadTokenizerFile on a .datok file (fomafile.go:476-480): bit-exact against the double-array oracle, with and
+    without EOT bytes -- the double-array loop does not rewind the buffer at an EOT (datok.go:1019-1030), so a text's
+    first Token call reaches back to the last token of the text before (tests/test_emul_parity.py has the details)"""
     import json
     import datok_b200 as d
     from datok_b200 import _lib, corpus
     from oracle import pyoracle
-    monkeypatch.setenv("DATOK_EXPERIMENTAL_DATOK", "1")  # (read by the loader at every datok_load)
+    from test_emul_parity import ODD
     tok = d.LoadTokenizerFile(os.path.join(testdata, name))
     assert tok is not None and tok.Type() == "DATOK"
     om = pyoracle.OracleModel(os.path.join(testdata, name))
     cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_datok.json")))["cases"]
     n = 0
-    for c in cases:
-        data = bytes.fromhex(c["input_hex"])
-        if c["model"] != name or b"\x04" in data:
-            continue
-        o = om.transduce(data, 15)
-        s = gpu_arrays(tok, data, 15)
-        P.assert_matches_oracle(s, o, 15, c["src"])  # (also when both say "the reference panics here")
-        if o.status == 0:
-            assert tok.format(s, data, 15) == o.text
+    eot_inputs = ["Erste.\n\n\n\n\x04\nNächst.\x04".encode(), b"\nThis.\n\x04\nAnd.\n\x04\n", b"This.\n\x04And.\n\x04\n", b"Tree\n\x04\n",
+                  b"Ein Text. \x04 \n Noch einer, mit Rand . \x04\x04 Ende", b"<a href=\"x \x04 y\">z</a> . \x04"]
+    for data in [bytes.fromhex(c["input_hex"]) for c in cases if c["model"] == name] + ODD + eot_inputs:
+        for flags in (15, 31, 3):
+            o = om.transduce(data, flags)
+            s = gpu_arrays(tok, data, flags)
+            P.assert_matches_oracle(s, o, flags, f"{name} {data[:30]!r} flags={flags}")  # (also when both say "the reference panics here")
+            if o.status == 0:
+                assert tok.format(s, data, flags) == o.text
+                rf = tok.transduce_arrays(data, flags | d.FORMAT)
+                assert rf.text.tobytes() == o.text
+                # the delta-coded forms do not apply (their cursors restart at a text): absolute arrays come back
+                rc = tok.transduce_arrays(data, flags | d.COMPACT8)
+                assert rc.tok_delta8 is None and rc.n_tokens == o.n_tokens
         n += 1
     assert n >= (100 if name == "tokenizer_de.datok" else 3)
     if name == "tokenizer_de.datok":
         a = corpus.generate(corpus.GERMAN_LONGDOC, 4 << 20, seed=5)
         P.assert_matches_oracle(gpu_arrays(tok, a, 15), om.transduce_np(a, 15), 15, "long document")
+        a = corpus.generate(corpus.GERMAN, 4 << 20, seed=6)   # ~10 KB documents, each ended by an EOT
+        for flags in (15, 31):
+            o = om.transduce_np(a, flags)
+            P.assert_matches_oracle(gpu_arrays(tok, a, flags), o, flags, f"documents flags={flags}")
+            rf = tok.transduce_arrays(a, flags | d.FORMAT)
+            assert rf.text.tobytes() == o.text
+        w = io.BytesIO()
+        assert tok.TransduceTokenWriter(io.BytesIO(a.tobytes()), d.NewTokenWriter(w, 15))
+        assert w.getvalue() == om.transduce_np(a, 15).text
+    # its stream cannot be cut behind an EOT
     with pytest.raises(d.DatokError) as e:
-        tok.transduce_arrays(b"Ein Text.\x04Noch einer.", 15)
+        tok.transduce_arrays(b"Ein Text.\x04", 15 | d.NOT_FINAL)
     assert e.value.code == _lib.ERR_UNSUPPORTED_MODEL
     tok.close()
 
