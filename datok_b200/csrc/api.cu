@@ -463,9 +463,32 @@ int do_walk(datok_model* m, WalkBuffers& b, uint32_t start_state, PhaseTimer& pt
   const uint32_t* list = nullptr;  // round 1: every chunk but the first
   uint32_t* cur = b.list_cur;
   uint32_t* nxt = b.list_next;
+  uint32_t single_rounds = 0;  // consecutive rounds whose list held one chunk: a chain of dependent chunks
   while (n_list) {
     m->last_rounds++;
     b.list_next = nxt;
+    single_rounds = (n_list == 1 && list) ? single_rounds + 1 : 0;
+    if (single_rounds > 3) {
+      // text without sync points (no whitespace the root state skips: minified markup, CSV ...): every chunk waits
+      // for its predecessor's exit state.  The chain is followed on the device, thousands of chunks per launch,
+      // instead of one host-synchronised round per chunk.
+      pt.begin(T_STITCH);
+      launch_chain(m->dm, b, list, 4096, s);
+      pt.end();
+      m->launches += 2;
+      {
+        MailSrc ms;
+        std::memset(&ms, 0, sizeof ms);
+        ms.p[0] = b.counters; ms.words[0] = 2; ms.off[0] = 0;
+        launch_mail(ms, m->d_mail, s);
+      }
+      CUDA_TRY(cudaMemsetAsync(b.counters, 0, 2 * sizeof(uint32_t), s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      n_list = m->h_mail[0];
+      std::swap(cur, nxt);
+      list = cur;
+      continue;
+    }
     pt.begin(T_STITCH);
     launch_stitch(m->dm, b, list, n_list, s);
     pt.end();

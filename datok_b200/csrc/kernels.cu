@@ -288,6 +288,28 @@ __global__ void __launch_bounds__(256) collect_errors_kernel(WalkBuffers b) {
     atomicMin(b.err_key, ((unsigned long long)(i * b.chunk) << 8) | 0xFEu);
 }
 
+// A single chain of dependent chunks (text without sync points: every chunk can only be walked once its
+// predecessor's exit state is known) followed on the device: stitch, re-walk, commit, next chunk -- up to
+// max_steps chunks per launch instead of one host-synchronised round per chunk.
+__global__ void chain_kernel(DeviceModel m, WalkBuffers b, const uint32_t* list, uint32_t max_steps) {
+  __shared__ ClsTables s_ct;
+  s_ct = m.cls; s_ct.self = &s_ct;
+  m.cls.self = &s_ct;
+  uint32_t i = list[0], n_next = 0;
+  for (uint32_t steps = 0;; steps++) {
+    if (chunk_stitch(m, b, i, false)) chunk_rewalk(m, b, i);
+    const bool changed = chunk_commit(b, i);
+    if (!changed || i + 1 >= b.n_chunks) break;
+    i++;
+    if (steps + 1 == max_steps) { b.list_next[0] = i; n_next = 1; break; }
+  }
+  b.counters[0] = n_next;
+  b.counters[1] = 0;
+}
+void launch_chain(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t max_steps, cudaStream_t s) {
+  chain_kernel<<<1, 1, 0, s>>>(m, b, list, max_steps);
+}
+
 void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s) {
   if (!n_list) return;
   stitch_kernel<<<(n_list + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, s>>>(m, b, list, n_list);

@@ -45,6 +45,9 @@ void launch_stitch(const DeviceModel& m, const WalkBuffers& b, const uint32_t* l
 int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk_max, uint32_t n_hot, int n_sms,
                         cudaStream_t s);
 void launch_commit(const WalkBuffers& b, const uint32_t* list, uint32_t n_list, cudaStream_t s);
+// one chain of dependent chunks, starting at list[0], followed on the device for up to max_steps chunks; leaves the
+// next round's list (0 or 1 entries) in b.list_next / b.counters[0]
+void launch_chain(const DeviceModel& m, const WalkBuffers& b, const uint32_t* list, uint32_t max_steps, cudaStream_t s);
 void launch_collect_errors(const WalkBuffers& b, cudaStream_t s);
 
 // up to four small device regions (32-bit words) -> mapped host memory at word offsets off[k]

@@ -641,3 +641,21 @@ def test_sharded_call_on_one_device(testdata, oracle_models):
         r.close()
     for t in toks:
         t.close()
+
+
+def test_text_without_sync_points(gpu_models, oracle_models):
+    """no whitespace the root state skips (minified markup, CSV, URL lists): every chunk depends on its predecessor's
+    exit state; the chain is followed on the device (chain_kernel) instead of one host round per chunk"""
+    import time
+    tok, om = gpu_models["tokenizer_de.matok"], oracle_models["tokenizer_de.matok"]
+    data = (b"http://example.com/a/b/c?d=e&f=g," * 60000)[: 2 << 20]
+    o = om.transduce(data, 15)
+    t0 = time.perf_counter()
+    r = tok.transduce_arrays(data, 15)
+    dt = time.perf_counter() - t0
+    P.assert_matches_oracle(r, o, 15, "no sync points")
+    rounds = tok.stats()["fixup_rounds"]
+    assert rounds < 64, rounds          # (one host round per chunk would be ~3300)
+    assert dt < 5.0, dt
+    data = (b'{"k":[1,2,3],"s":"x"},' * 40000)[: 1 << 20]
+    P.assert_matches_oracle(gpu_arrays(tok, data, 3), om.transduce(data, 3), 3, "minified json")
