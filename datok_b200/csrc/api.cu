@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -75,7 +76,7 @@ struct datok_model {
   size_t smem_optin = 0;
   uint32_t n_hot = 1;
   int fused_threads = 1024;
-  bool calibrated = false;
+  std::atomic<bool> calibrated{false};
   bool auto_calibrate = true;
   // workspace (grow only)
   uint8_t* ws = nullptr;
@@ -104,9 +105,19 @@ struct datok_model {
   bool piece_fixed = false;               // DATOK_PIECE_MB: every piece has piece_bytes (else sized per call)
   bool pipelined = true;
   // results hold pooled buffers of their model: the model outlives them
-  int live_results = 0;
-  bool freed_by_user = false;
+  std::atomic<int> live_results{0};   // (counted on the primary for all of its execution contexts)
+  std::atomic<bool> freed_by_user{false};
+  // Concurrent calls on one model (the reference's model is immutable and shareable, matrix.go:16-26): a call runs on
+  // an execution context -- stream, workspace, staging buffers, mailbox -- of its own.  The model handed to the caller
+  // is the primary context; further ones are clones that share its device-resident tables and are created when a call
+  // finds every context busy (DATOK_MAX_CONCURRENCY, default 4, bounds them).
+  datok_model* primary = nullptr;     // clones: the model they belong to
+  std::vector<datok_model*> clones;   // primary: its clones (guarded by ctx_mu)
+  std::mutex ctx_mu;
+  bool busy = false;                  // guarded by the primary's ctx_mu
+  int max_ctx = 4;
 };
+static datok_model* root_of(datok_model* m) { return m->primary ? m->primary : m; }
 
 struct datok_result {
   datok_model* model = nullptr;
@@ -154,19 +165,23 @@ void release(datok_model* m, const Block& b) {
 void free_result_locked(datok_result* r) {
   datok_model* m = r->model;
   for (auto& b : r->blocks) release(m, b);
-  m->live_results--;
+  root_of(m)->live_results--;
   delete r;
 }
 
 void destroy_model(datok_model* m) {
   DeviceGuard guard;
+  for (datok_model* c : m->clones) destroy_model(c);
+  m->clones.clear();
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   for (auto& b : m->cache) { if (b.host) cudaFreeHost(b.p); else cudaFree(b.p); }
   if (m->ws) cudaFree(m->ws);
-  if (m->d_tables) cudaFree(m->d_tables);
-  if (m->d_cls_tables) cudaFree(m->d_cls_tables);
-  if (m->d_rune_key) cudaFree(m->d_rune_key);
+  if (!m->primary) {  // (a clone shares the tables of its primary)
+    if (m->d_tables) cudaFree(m->d_tables);
+    if (m->d_cls_tables) cudaFree(m->d_cls_tables);
+    if (m->d_rune_key) cudaFree(m->d_rune_key);
+  }
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 3; i++) {
     for (cudaEvent_t e : {m->ev_in[i], m->ev_free[i]}) if (e) cudaEventDestroy(e);
@@ -372,6 +387,7 @@ int calibrate_locked(datok_model* m, const WalkBuffers& full) {
   return DATOK_OK;
 }
 
+static bool init_context(datok_model* m);
 datok_model* finish_load(datok_model* m, int device, int* err) {
   DeviceGuard guard;
   int ndev = 0;
@@ -392,29 +408,16 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
     return nullptr;
   }
   m->device = device;
-  if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    g_last_error = "cudaStreamCreate failed";
-    *err = DATOK_ERR_CUDA;
-    delete m;
-    return nullptr;
-  }
-  for (auto& e : m->ev) cudaEventCreate(&e);
-  if (cudaHostAlloc((void**)&m->h_mail, 4096, cudaHostAllocMapped) != cudaSuccess ||
-      cudaHostGetDevicePointer((void**)&m->d_mail, m->h_mail, 0) != cudaSuccess) {
-    g_last_error = "cudaHostAlloc (mailbox) failed";
+  if (!init_context(m)) {
+    g_last_error = "creating the model's streams / mailbox failed";
+    cudaGetLastError();
     *err = DATOK_ERR_CUDA;
     datok_free(m);
     return nullptr;
   }
-  cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking);
-  for (int i = 0; i < 3; i++) {
-    cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming);
-  }
-  for (int i = 0; i < 2; i++) {
-    cudaEventCreateWithFlags(&m->ev_emit[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming);
+  if (const char* s = std::getenv("DATOK_MAX_CONCURRENCY")) {
+    const long v = std::atol(s);
+    if (v >= 1 && v <= 64) m->max_ctx = (int)v;
   }
   if (const char* s = std::getenv("DATOK_NO_PIPELINE")) m->pipelined = !(s[0] == '1');
   if (const char* s = std::getenv("DATOK_PIECE_MB")) {
@@ -443,6 +446,45 @@ datok_model* finish_load(datok_model* m, int device, int* err) {
   }
   *err = DATOK_OK;
   return m;
+}
+
+// the per-context resources of finish_load (stream, events, mailbox, copy streams)
+static bool init_context(datok_model* m) {
+  if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+  for (auto& e : m->ev) cudaEventCreate(&e);
+  if (cudaHostAlloc((void**)&m->h_mail, 4096, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&m->d_mail, m->h_mail, 0) != cudaSuccess)
+    return false;
+  cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking);
+  for (int i = 0; i < 3; i++) {
+    cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming);
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&m->ev_emit[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming);
+  }
+  return true;
+}
+
+// another execution context of P: its own stream, workspace and buffers, P's device-resident tables
+static datok_model* clone_context(datok_model* P) {
+  DeviceGuard guard;
+  if (cudaSetDevice(P->device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  datok_model* c = new datok_model();
+  c->primary = P;
+  c->hm = P->hm;  // (host-side numbering tables; the device tables are shared)
+  c->device = P->device;
+  c->d_tables = P->d_tables; c->d_tables_bytes = P->d_tables_bytes;
+  c->d_cls_tables = P->d_cls_tables; c->d_rune_key = P->d_rune_key;
+  c->dm = P->dm;
+  c->n_sms = P->n_sms; c->smem_optin = P->smem_optin; c->n_hot = P->n_hot; c->fused_threads = P->fused_threads;
+  c->calibrated = true; c->auto_calibrate = false;
+  c->chunk = P->chunk; c->piece_bytes = P->piece_bytes; c->piece_fixed = P->piece_fixed; c->pipelined = P->pipelined;
+  if (!init_context(c)) { cudaGetLastError(); destroy_model(c); return nullptr; }
+  pin_table_in_l2(c);
+  return c;
 }
 
 // K1+K2: clear, fused walk, fix-up rounds (host-synchronised on the round counters), error collection
@@ -683,7 +725,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
 
   datok_result* r = new datok_result();
   r->model = m;
-  m->live_results++;
+  root_of(m)->live_results++;
   r->device = false;
   std::memset(&r->view, 0, sizeof r->view);
   datok_view& v = r->view;
@@ -1048,7 +1090,7 @@ int run_pipeline(datok_model* m, const uint8_t* in, bool in_is_device, size_t n,
   // output arrays: sized from the scan totals (+1 for the end-of-stream events)
   datok_result* r = new datok_result();
   r->model = m;
-  m->live_results++;
+  root_of(m)->live_results++;
   r->device = device_out;
   std::memset(&r->view, 0, sizeof r->view);
   const size_t nt = hdr.tot.n_tok, ns = (size_t)hdr.tot.n_sent + 1, nx = (size_t)hdr.tot.n_text + 1,
@@ -1298,13 +1340,8 @@ datok_model* datok_load_image(const uint8_t* image, size_t n, int device, int* e
 
 void datok_free(datok_model* m) {
   if (!m) return;
-  bool destroy;
-  {
-    std::lock_guard<std::mutex> lock(m->mu);
-    m->freed_by_user = true;
-    destroy = m->live_results == 0;
-  }
-  if (destroy) destroy_model(m);  // otherwise the last datok_result_free() does it
+  m->freed_by_user = true;
+  if (m->live_results == 0) destroy_model(m);  // otherwise the last datok_result_free() does it
 }
 
 const char* datok_type(void) { return "MATOK"; }
@@ -1320,6 +1357,23 @@ int datok_model_info(const datok_model* m, uint32_t* state_count, uint32_t* sigm
   if (unknown) *unknown = (uint32_t)m->hm.unknown;
   if (identity) *identity = (uint32_t)m->hm.identity;
   return DATOK_OK;
+}
+
+// An idle execution context of the model for one call (released by ctx_release).
+static datok_model* ctx_acquire(datok_model* P) {
+  std::lock_guard<std::mutex> lock(P->ctx_mu);
+  if (!P->busy) { P->busy = true; return P; }
+  for (datok_model* c : P->clones)
+    if (!c->busy) { c->busy = true; return c; }
+  // a new context only once the table layout is final (the one-time calibration re-uploads the tables)
+  if ((P->calibrated || !P->auto_calibrate) && (int)P->clones.size() + 1 < P->max_ctx) {
+    if (datok_model* c = clone_context(P)) { c->busy = true; P->clones.push_back(c); return c; }
+  }
+  return nullptr;  // every context is busy: the call queues on the primary
+}
+static void ctx_release(datok_model* P, datok_model* c) {
+  std::lock_guard<std::mutex> lock(P->ctx_mu);
+  c->busy = false;
 }
 
 // A double-array model (datok.go) does not rewind its buffer at an EOT (datok.go:1019-1030): a text's first Token call
@@ -1338,17 +1392,25 @@ static int check_norewind(const datok_model* m, uint32_t& flags) {
 int datok_transduce(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, const datok_carry* carry_in,
                     datok_result** out) {
   if (const int rc = check_norewind(m, flags)) return rc;
-  if (m && m->hm.eot_rewind && out && in && n < 0xFFFFFFFFull - (1u << 20) && n >= 2 * m->piece_bytes && m->pipelined) {
-    const int rc = run_pipelined(m, in, n, flags, carry_in, out);
-    if (rc != -1 && rc != -2) return rc;  // -1: no EOT to cut at; -2: DATOK_FORMAT with malformed UTF-8
-  }
-  return run_pipeline(m, in, false, n, flags, carry_in, false, out);
+  if (!m) { g_last_error = "invalid argument"; return DATOK_ERR_INVALID_ARG; }
+  datok_model* x = ctx_acquire(m);   // (nullptr: all busy -- queue on the primary's mutex)
+  datok_model* c = x ? x : m;
+  int rc = -1;
+  if (c->hm.eot_rewind && out && in && n < 0xFFFFFFFFull - (1u << 20) && n >= 2 * c->piece_bytes && c->pipelined)
+    rc = run_pipelined(c, in, n, flags, carry_in, out);  // -1: no EOT to cut at; -2: DATOK_FORMAT with malformed UTF-8
+  if (rc == -1 || rc == -2) rc = run_pipeline(c, in, false, n, flags, carry_in, false, out);
+  if (x) ctx_release(m, x);
+  return rc;
 }
 
 int datok_transduce_device(datok_model* m, const uint8_t* d_in, size_t n, uint32_t flags,
                            const datok_carry* carry_in, datok_result** out) {
   if (const int rc = check_norewind(m, flags)) return rc;
-  return run_pipeline(m, d_in, true, n, flags, carry_in, true, out);
+  if (!m) { g_last_error = "invalid argument"; return DATOK_ERR_INVALID_ARG; }
+  datok_model* x = ctx_acquire(m);
+  const int rc = run_pipeline(x ? x : m, d_in, true, n, flags, carry_in, true, out);
+  if (x) ctx_release(m, x);
+  return rc;
 }
 
 const datok_view* datok_result_view(const datok_result* r) { return r ? &r->view : nullptr; }
@@ -1356,13 +1418,12 @@ const datok_view* datok_result_view(const datok_result* r) { return r ? &r->view
 void datok_result_free(datok_result* r) {
   if (!r) return;
   datok_model* m = r->model;
-  bool destroy;
+  datok_model* root = root_of(m);
   {
     std::lock_guard<std::mutex> lock(m->mu);
     free_result_locked(r);
-    destroy = m->freed_by_user && m->live_results == 0;
   }
-  if (destroy) destroy_model(m);
+  if (root->freed_by_user && root->live_results == 0) destroy_model(root);
 }
 
 int datok_last_kernel_times(const datok_model* m, const char** names, float* ms, int cap) {

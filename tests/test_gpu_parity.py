@@ -659,3 +659,35 @@ def test_text_without_sync_points(gpu_models, oracle_models):
     assert dt < 5.0, dt
     data = (b'{"k":[1,2,3],"s":"x"},' * 40000)[: 1 << 20]
     P.assert_matches_oracle(gpu_arrays(tok, data, 3), om.transduce(data, 3), 3, "minified json")
+
+
+def test_concurrent_calls_on_one_model(gpu_models, oracle_models):
+    """the reference's model is immutable and shareable across goroutines (matrix.go:16-26): calls from several threads
+    on one model run side by side, each on an execution context of its own, and give the single-call results"""
+    import threading
+    import datok_b200 as d
+    from datok_b200 import corpus
+    tok, om = gpu_models["tokenizer_de.matok"], oracle_models["tokenizer_de.matok"]
+    big = corpus.generate(2, 8 << 20, seed=91)
+    tok.transduce_arrays(big, 15).close()      # (the one-time calibration happens here)
+    inputs = [corpus.generate(2, (1 << 20) + 4096 * i, seed=100 + i) for i in range(6)]
+    want = [om.transduce_np(a, 15) for a in inputs]
+    errors = []
+
+    def work(i):
+        try:
+            for rep in range(4):
+                r = tok.transduce_arrays(inputs[i], 15)
+                P.assert_matches_oracle(r, want[i], 15, f"thread {i} rep {rep}")
+                rf = tok.transduce_arrays(inputs[i], 15 | d.FORMAT)
+                assert rf.text.tobytes() == want[i].text
+                r.close(); rf.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)[:300]))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
