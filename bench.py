@@ -307,6 +307,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-shapes", action="store_true", help="skip the C3 / C4 device legs")
+    ap.add_argument("--c5-slices", type=int, default=0,
+                    help="BASELINE.json's C5 (64 GB over 8 GPUs = 8 GB per GPU): additionally run this many further corpus "
+                         "slices of --size bytes per GPU, each from its own seed (the host never holds more than one)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -422,6 +425,33 @@ def main():
             t2.close()
             del d2, a2
 
+    # ---- C5: many slices per GPU, each generated from its own seed into the same pinned buffer ----
+    c5 = None
+    if args.c5_slices > 0:
+        dev_ms, e2e_s, toks = 0.0, 0.0, 0
+        for k in range(args.c5_slices):
+            corpus.generate_blocks_into(corpus.GERMAN, SEED + 1000003 * rank + 7001 * (k + 1), arr, block=64 << 20)
+            d_in.copy_(torch.from_numpy(arr))
+            torch.cuda.synchronize()
+            r = tok.transduce_device(d_in.data_ptr(), N, DFLAGS)
+            dev_ms += r.ms_kernels
+            toks += r.n_tokens
+            r.close()
+            barrier()
+            t0 = time.perf_counter()
+            r = tok.transduce_arrays(arr, FLAGS | d.FORMAT)
+            r.close()
+            barrier()
+            e2e_s += time.perf_counter() - t0
+        c5v = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(c5v, op=dist.ReduceOp.MAX)
+        c5 = {"slices_per_gpu": args.c5_slices, "bytes_per_gpu": args.c5_slices * N, "bytes_total": args.c5_slices * N * world,
+              "value": args.c5_slices * N * world / (float(c5v[0]) * 1e-3) / 1e9, "e2e": args.c5_slices * N * world / (float(c5v[1]) * 1e-3) / 1e9,
+              "unit": "GB/s", "tokens_rank0": toks,
+              "what": "every slice a fresh corpus (own seed) of --size bytes; device time summed over the slices (max over ranks), "
+                      "e2e = datok_transduce(DATOK_FORMAT) wall time summed over the slices"}
+
     # ---- one corpus sharded over the ranks: parity of the multi-GPU decomposition (outside the timed regions) ----
     parity = shard_parity(tok, d, rank, world, dist, torch)
 
@@ -504,6 +534,7 @@ def main():
                              "d2h_bytes_per_step": d2h_abs, "ms_per_step": ms_abs,
                              "path": "the same call returning absolute (byte, rune) offset pairs, 16 B/token"},
             "other_shapes": shapes,
+            "c5": c5,
             "shard_parity": parity["shard_parity"] if parity else None,
             "sharding": parity,
             "gpu_launches": launches,
