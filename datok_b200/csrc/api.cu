@@ -157,7 +157,7 @@ void release(datok_model* m, const Block& b) {
   if (!b.p) return;
   size_t cached = 0;
   for (auto& c : m->cache) cached += c.bytes;
-  if (m->cache.size() < 64 && cached < ((size_t)8 << 30)) { m->cache.push_back(b); return; }
+  if (m->cache.size() < 64 && cached < ((size_t)16 << 30)) { m->cache.push_back(b); return; }
   if (b.host) cudaFreeHost(b.p); else cudaFree(b.p);
 }
 
@@ -378,6 +378,12 @@ int calibrate_locked(datok_model* m, const WalkBuffers& full) {
   for (size_t t = 1; t <= S; t++) hist_old[m->hm.old_of_new[t]] = hist[t];
   for (size_t c = 0; c < m->hm.n_classes; c++) cls_hist[m->hm.cls_base[c]] = hist[S + 2 + c];
   std::string why;
+  {  // what the walk kernel can spend on compact rows (kernels.cu fused_max_hot_rows)
+    DeviceModel probe = m->dm;
+    probe.stride16 = 2;  // (4-byte rows: the row count then is the byte budget / 4)
+    probe.hot16_rows = 0x7FFFFFFF;
+    m->hm.row_budget_bytes = 4u * fused_max_hot_rows(probe, m->smem_optin, 0x7FFFFFF0u, m->fused_threads);
+  }
   int rc = build_layout(m->hm, why, hist_old.data(), cls_hist.data());
   if (rc) { g_last_error = why; return rc; }
   rc = upload_model(m);

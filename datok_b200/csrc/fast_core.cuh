@@ -342,6 +342,16 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
 #if defined(__CUDA_ARCH__)
   const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(seg_cls);
   uint32_t p = cls_saddr + off;   // address of the class byte of the current position
+  // hc: shared-window address of the row's column for the byte at p, i.e. T.hot_saddr + its doubled class.  The class
+  // byte of the NEXT position is fetched while the current lookup is in flight (it does not depend on the state), so
+  // the per-byte dependency chain is one multiply-add, the row lookup and one AND -- not two loads back to back.
+  uint32_t hc;
+#if defined(DATOK_NO_CLASS_PREFETCH)
+#define DATOK_LOAD_HC() ((void)0)
+#else
+#define DATOK_LOAD_HC() do { uint32_t c_; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c_) : "r"(p)); hc = T.hot_saddr + c_; } while (0)
+#endif
+  DATOK_LOAD_HC();
   uint32_t row16 = T.row16;
   asm volatile("" : "+r"(row16));  // opaque, like end_bit
 #define DATOK_ROW_OF(addr) __umulhi((addr) - T.hot_saddr, T.row16_inv)
@@ -357,12 +367,21 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
     // ---- one compact-row lookup per byte ----
     uint32_t e, a;
 #if defined(__CUDA_ARCH__)
+#if defined(DATOK_NO_CLASS_PREFETCH)
     {
       uint32_t cl2;
       asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cl2) : "r"(p));
       a = T.hot_saddr + tl * row16 + cl2;
       asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(a));
     }
+#else
+    uint32_t cl2n;
+    {
+      a = tl * row16 + hc;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(a));
+      asm volatile("ld.shared.u8 %0, [%1 + 1];" : "=r"(cl2n) : "r"(p));  // (behind the range: a scratch byte, never used)
+    }
+#endif
 #else
     a = 1u + ((tl << 16) | seg_cls[off]);
     e = h16_load(T, tl, seg_cls[off]);
@@ -409,6 +428,7 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
             tl = tgt; eps_rec = 0; eps_a = 0; eps_bit = 0;  // (tgt is a hot state: the compact row says so)
 #if defined(__CUDA_ARCH__)
             p = cls_saddr + off;
+            DATOK_LOAD_HC();
 #endif
             continue;
           }
@@ -452,6 +472,7 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
       t_cold = t;
 #if defined(__CUDA_ARCH__)
       p = cls_saddr + off;
+      DATOK_LOAD_HC();
 #endif
       continue;
     }
@@ -474,6 +495,9 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
         : "+r"(c1), "+r"(c2), "+r"(nt), "+r"(eps_bit), "+r"(eps_a)
         : "r"(e), "r"(bit), "r"(a));
     p++;
+#if !defined(DATOK_NO_CLASS_PREFETCH)
+    hc = T.hot_saddr + cl2n;
+#endif
 #else
     if (e & F16_KANY) c1 |= bit;
     if (e & F16_K2) c2 |= bit;
@@ -493,6 +517,7 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
   L.eps_rec = DATOK_EPS_REC();
 #undef DATOK_EPS_REC
 #undef DATOK_ROW_OF
+#undef DATOK_LOAD_HC
   R.c1 = c1; R.c2 = c2; R.nt = nt;
   return FAST_OK;
 }

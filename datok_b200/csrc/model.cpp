@@ -4,6 +4,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -289,9 +290,35 @@ int build_layout(HostModel& m, std::string& why, const uint64_t* hist, const uin
   std::sort(hi.begin(), hi.end());
   m.rune_key.clear(); m.rune_cls.clear();
   for (auto& kv : hi) { m.rune_key.push_back(kv.first); m.rune_cls.push_back((uint8_t)perm[kv.second]); }
-  // columns of the compact rows: the classes that cover all but ~0.05 % of the measured bytes
+  // Columns of the compact rows.  Fewer columns mean more resident rows (fewer steps in a state without a row)
+  // but more bytes of a class without a column; both kinds of step go through the full table.  With both
+  // histograms and the kernel's shared-memory budget the count that minimises their sum is taken (a rare class
+  // costs about twice a cold state: its class has to be decoded from the raw bytes again); with the class
+  // histogram alone, the classes that cover all but ~0.05 % of the measured bytes.
   m.hot_cols = m.n_classes;
-  if (cls_hist) {
+  if (cls_hist && hist && m.row_budget_bytes) {
+    std::vector<uint64_t> visits;  // visits per state, hottest first
+    uint64_t vis_total = 0;
+    for (int t = 1; t <= S; t++) { visits.push_back(hist[t]); vis_total += hist[t]; }
+    std::sort(visits.begin(), visits.end(), std::greater<uint64_t>());
+    std::vector<uint64_t> vis_prefix(visits.size() + 1, 0);
+    for (size_t i = 0; i < visits.size(); i++) vis_prefix[i + 1] = vis_prefix[i] + visits[i];
+    uint64_t cls_total = 0;
+    for (uint32_t c = 0; c < m.n_classes; c++) cls_total += cls_hist[c];
+    std::vector<uint64_t> cls_prefix(m.n_classes + 1, 0);  // by class id (frequency order behind the three fixed ones)
+    for (uint32_t c = 0; c < m.n_classes; c++) cls_prefix[c + 1] = cls_prefix[c] + cls_hist[m.cls_base[c]];
+    double best = 1e300;
+    for (uint32_t w = m.n_classes; w >= std::min<uint32_t>(m.n_classes, 24); w--) {
+      const uint32_t stride = ((w + 2) / 2 | 1u) * 2;
+      size_t rows = m.row_budget_bytes / ((size_t)stride * 2);
+      if (rows > visits.size()) rows = visits.size();
+      if (rows > H16_MAX_ROWS - 1) rows = H16_MAX_ROWS - 1;
+      const double cold = vis_total ? (double)(vis_total - vis_prefix[rows]) / (double)vis_total : 0.0;
+      const double rare = cls_total ? (double)(cls_total - cls_prefix[w]) / (double)cls_total : 0.0;
+      const double cost = cold + 2.0 * rare;
+      if (cost < best - 1e-12) { best = cost; m.hot_cols = w; }
+    }
+  } else if (cls_hist) {
     uint64_t total = 0, cum = 0;
     for (uint32_t c = 0; c < m.n_classes; c++) total += cls_hist[c];
     cum = cls_hist[CLS_EPS] + cls_hist[CLS_CONT] + cls_hist[CLS_EOT];

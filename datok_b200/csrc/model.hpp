@@ -83,6 +83,8 @@ struct HostModel {
   uint32_t hot16_rows = 0;
   uint32_t hot_cols = 0;           // classes 0..hot_cols-1 have a column in the compact rows
   uint32_t force_hot_cols = 0;     // != 0: that many columns whatever the histogram says (DATOK_HOT_COLS, tests)
+  uint32_t row_budget_bytes = 0;   // shared memory the kernel has for compact rows (0: unknown): with both histograms the
+                                   // column count is the one that leaves the fewest steps to the full table
   std::vector<uint8_t> cls_base;   // class id -> layout-independent id (order of first use), for calibration histograms
   bool fast_ok = false;            // the fused tables are usable (else every entry is marked T3_SLOW / 0)
 };

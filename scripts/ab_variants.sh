@@ -4,5 +4,5 @@
 size=$1; kind=$2; shift; shift
 for lib in "$@"; do
   echo "== $lib $kind $size"
-  DATOK_B200_LIB=$PWD/$lib python scripts/profile_one.py $size $kind 2>&1 | tail -1
+  DATOK_B200_LIB=$PWD/$lib python scripts/profile_one.py $size $kind 2>&1 | tail -2 | head -1
 done

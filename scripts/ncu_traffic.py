@@ -1,9 +1,9 @@
 """sums dram__bytes_read/write over the kernels of ONE step (from the last walk_fused launch to the end)
-of an `ncu --set full` raw CSV (ncu -i X.ncu-rep --page raw --csv) and writes profiles/r1_traffic.json
+of an `ncu --set full` raw CSV (ncu -i X.ncu-rep --page raw --csv) and writes profiles/r2_traffic.json
 plus a per-kernel table.  usage: ncu_traffic.py raw.csv input_bytes [out.json]"""
 import csv, json, sys
 raw, n_bytes = sys.argv[1], int(sys.argv[2])
-out = sys.argv[3] if len(sys.argv) > 3 else "profiles/r1_traffic.json"
+out = sys.argv[3] if len(sys.argv) > 3 else "profiles/r2_traffic.json"
 rows = list(csv.reader(open(raw)))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}

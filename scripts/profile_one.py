@@ -18,3 +18,4 @@ for i in range(2):
     r = tok.transduce_device(d_in.data_ptr(), size, 15 | d.COMPACT)
     print(i, r.n_tokens, r.ms_kernels, {k: round(v, 3) for k, v in tok.kernel_times().items()}, flush=True)
     r.close()
+print("layout", tok.stats())
