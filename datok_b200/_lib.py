@@ -57,7 +57,7 @@ class Callbacks(C.Structure):
 
 
 # every symbol include/datok_b200.h declares
-EXPORTS = ["datok_load", "datok_load_image", "datok_free", "datok_type", "datok_model_type", "datok_model_info", "datok_transduce",
+EXPORTS = ["datok_load", "datok_load_image", "datok_load_foma", "datok_compile_foma", "datok_save", "datok_write_image", "datok_free", "datok_type", "datok_model_type", "datok_model_info", "datok_transduce",
            "datok_transduce_device", "datok_result_view", "datok_result_free", "datok_expand", "datok_format", "datok_replay",
            "datok_last_kernel_times", "datok_last_launch_count", "datok_last_stats", "datok_measure_gather_bound", "datok_host_alloc", "datok_host_free",
            "datok_last_error", "datok_strerror", "datok_stream_open", "datok_stream_push", "datok_stream_finish",
@@ -80,6 +80,14 @@ def lib():
     L.datok_load_image.restype = C.c_void_p
     L.datok_load_image.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
     L.datok_free.argtypes = [C.c_void_p]
+    L.datok_load_foma.restype = C.c_void_p
+    L.datok_load_foma.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+    L.datok_compile_foma.restype = C.c_int
+    L.datok_compile_foma.argtypes = [C.c_char_p, C.c_char_p]
+    L.datok_save.restype = C.c_int
+    L.datok_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.datok_write_image.restype = C.c_size_t
+    L.datok_write_image.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.datok_type.restype = C.c_char_p
     L.datok_model_type.restype = C.c_char_p
     L.datok_model_type.argtypes = [C.c_void_p]

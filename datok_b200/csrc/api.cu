@@ -1344,6 +1344,42 @@ datok_model* datok_load_image(const uint8_t* image, size_t n, int device, int* e
   return finish_load(m, device, err);
 }
 
+datok_model* datok_load_foma(const char* path, int device, int* err) {
+  int dummy;
+  if (!err) err = &dummy;
+  datok_model* m = new datok_model();
+  std::string why;
+  int rc = load_foma_file(path, m->hm, why);
+  if (rc) { g_last_error = why; *err = rc; delete m; return nullptr; }
+  return finish_load(m, device, err);
+}
+
+int datok_compile_foma(const char* foma_path, const char* matok_path) {
+  HostModel hm;
+  std::string why;
+  int rc = load_foma_file(foma_path, hm, why);  // (with the layout build: a model the kernels cannot run is reported here)
+  if (!rc) rc = save_matok_file(hm, matok_path, why);
+  if (rc) g_last_error = why;
+  return rc;
+}
+
+int datok_save(const datok_model* m, const char* path) {
+  if (!m || !path) return DATOK_ERR_INVALID_ARG;
+  std::string why;
+  int rc = save_matok_file(m->hm, path, why);
+  if (rc) g_last_error = why;
+  return rc;
+}
+
+size_t datok_write_image(const datok_model* m, uint8_t* dst, size_t cap) {
+  if (!m) return 0;
+  std::vector<uint8_t> img;
+  std::string why;
+  if (write_matok_image(m->hm, img, why)) { g_last_error = why; return 0; }
+  if (dst && cap >= img.size()) std::memcpy(dst, img.data(), img.size());
+  return img.size();
+}
+
 void datok_free(datok_model* m) {
   if (!m) return;
   m->freed_by_user = true;

@@ -126,7 +126,7 @@ DATOK_HD void note_invalid_utf8(const WalkBuffers& b) {
 // A lane fills a 32-byte sector of each bitmap with 8 word stores spread over 8 segments; the partly
 // written sectors are asked to stay in L2 until then (evict_last) instead of going to DRAM piecemeal.
 DATOK_HD void store_word_keep(uint32_t* p, uint32_t v) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(DATOK_BITS_PLAIN_STORE)
   asm volatile(
       "{\n\t.reg .b64 pol;\n\t"
       "createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"

@@ -144,16 +144,15 @@ int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why
   return DATOK_OK;
 }
 
-int load_matok_file(const char* path, HostModel& m, std::string& why) {
+static int gunzip_file(const char* path, std::vector<uint8_t>& img, std::string& why) {
   FILE* f = std::fopen(path, "rb");
   if (!f) { why = std::string("cannot open ") + path; return DATOK_ERR_IO; }
   unsigned char mg[2] = {0, 0};
   size_t got = std::fread(mg, 1, 2, f);
   std::fclose(f);
-  if (got != 2 || mg[0] != 0x1f || mg[1] != 0x8b) { why = "gzip: invalid header"; return DATOK_ERR_IO; }  // matrix.go:222-226
+  if (got != 2 || mg[0] != 0x1f || mg[1] != 0x8b) { why = "gzip: invalid header"; return DATOK_ERR_IO; }  // fomafile.go:64-68
   gzFile gz = gzopen(path, "rb");
   if (!gz) { why = "gzopen failed"; return DATOK_ERR_IO; }
-  std::vector<uint8_t> img;
   std::vector<uint8_t> chunk(1 << 20);
   for (;;) {
     int r = gzread(gz, chunk.data(), (unsigned)chunk.size());
@@ -162,16 +161,256 @@ int load_matok_file(const char* path, HostModel& m, std::string& why) {
     img.insert(img.end(), chunk.begin(), chunk.begin() + r);
   }
   gzclose(gz);
-  int rc = parse_matok_image(img.data(), img.size(), m, why);
+  return DATOK_OK;
+}
+
+int load_matok_file(const char* path, HostModel& m, std::string& why) {
+  std::vector<uint8_t> img;
+  int rc = gunzip_file(path, img, why);
+  if (rc) return rc;
+  rc = parse_matok_image(img.data(), img.size(), m, why);
   if (rc) return rc;
   return build_layout(m, why);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The compile path: LoadFomaFile (fomafile.go:56-72) + ParseFoma (fomafile.go:77-450) + ToMatrix
+// (matrix.go:30-99), i.e. what `datok convert` runs before Save (cmd/datok.go:63).  The foma text format:
+//   ##props##   one line; field 6 "is_deterministic" and field 9 "is_epsilon_free" have to be 1, field 2 is the
+//               state count
+//   ##sigma##   "<number> <symbol>" per line; the symbol is one rune, one of the @_..._@ specials, or a
+//               multi-character symbol (not supported by the tokenizer: arcs on it are dropped)
+//   ##states##  arcs, 5 / 4 / 3 / 2 numbers per line (state in out target final | state in target final |
+//               in out target | in target); "-1 ..." ends the list
+// Symbol numbers and states are shifted by one (0 = "no symbol" / failure state).  Only three kinds of arc are
+// accepted: x:x, x:epsilon (a non-token arc, FIRSTBIT) and epsilon:@_TOKEN_BOUND_@ (stored in the epsilon row).
+namespace {
+struct Arc { int sym; int target; bool nontoken; };
+
+bool atoi_go(const std::string& s, int& out) {  // strconv.Atoi
+  size_t i = (s.size() && (s[0] == '-' || s[0] == '+')) ? 1 : 0;
+  if (i == s.size()) return false;
+  long long v = 0;
+  for (; i < s.size(); i++) {
+    if (s[i] < '0' || s[i] > '9') return false;
+    v = v * 10 + (s[i] - '0');
+    if (v > 0x7fffffffLL) return false;
+  }
+  out = (int)(s[0] == '-' ? -v : v);
+  return true;
+}
+std::vector<std::string> split_blank(const std::string& s) {  // strings.Split(s, " ")
+  std::vector<std::string> out(1);
+  for (char c : s) { if (c == ' ') out.emplace_back(); else out.back().push_back(c); }
+  return out;
+}
+}  // namespace
+
+int compile_foma_image(const uint8_t* d, size_t n, HostModel& m, std::string& why) {
+  int epsilon = -1, unknown = -1, identity = -1, final_sym = -1, tokenend = -1;
+  int sigma_count = 0, state_count = -1;
+  std::map<int, int32_t> rune_of_sym;      // Automaton.sigmaRev
+  std::map<int, bool> multi_char;          // Automaton.sigmaMCS
+  std::vector<std::vector<Arc>> arcs;      // Automaton.transitions (a later arc of the same symbol replaces the earlier)
+  enum Mode { START, PROPS, SIGMA, STATES, DONE } mode = START;
+  int cur_state = 0, in_sym = 0, out_sym = 0, target = 0, is_final = 0;  // the parser keeps these across lines
+  auto add_arc = [&](int state, int sym, int tgt, bool nt) -> bool {
+    if (state < 0 || state > state_count) return false;  // transitions[state+1]: index out of range in the reference
+    for (Arc& a : arcs[(size_t)state])
+      if (a.sym == sym) { a.target = tgt; a.nontoken = nt; return true; }
+    arcs[(size_t)state].push_back({sym, tgt, nt});
+    return true;
+  };
+  size_t pos = 0;
+  auto next_line = [&](std::string& line) -> bool {  // bufio ReadString('\n'); an unterminated last line is dropped
+    const void* q = pos < n ? std::memchr(d + pos, '\n', n - pos) : nullptr;
+    if (!q) return false;
+    const size_t e = (size_t)((const uint8_t*)q - d);
+    line.assign((const char*)d + pos, e - pos);
+    pos = e + 1;
+    return true;
+  };
+  std::string line;
+  while (next_line(line)) {
+    if (line.compare(0, 2, "##") == 0) {
+      if (line.compare(0, 9, "##props##") == 0) mode = PROPS;
+      else if (line.compare(0, 10, "##states##") == 0) { mode = STATES; final_sym = ++sigma_count; }  // fomafile.go:118-123
+      else if (line.compare(0, 9, "##sigma##") == 0) mode = SIGMA;
+      else if (line.compare(0, 7, "##end##") == 0) mode = DONE;
+      else if (line.compare(0, 10, "##foma-net") != 0) break;  // "Unknown input line" ends the parse
+      continue;
+    }
+    if (mode == PROPS) {
+      const auto f = split_blank(line);
+      if (f.size() < 13) { why = "foma: short ##props## line"; return DATOK_ERR_FORMAT; }
+      if (f[6] != "1") { why = "The FST needs to be deterministic"; return DATOK_ERR_FORMAT; }       // fomafile.go:159
+      if (f[9] != "1") { why = "The FST needs to be epsilon free"; return DATOK_ERR_FORMAT; }        // fomafile.go:164
+      int v;
+      if (!atoi_go(f[1], v)) { why = "Can't read arccount"; return DATOK_ERR_FORMAT; }
+      if (!atoi_go(f[2], v) || v < 0) { why = "Can't read statecount"; return DATOK_ERR_FORMAT; }
+      state_count = v;
+      arcs.assign((size_t)v + 1, {});
+    } else if (mode == SIGMA) {
+      const size_t sp = line.find(' ');
+      if (sp == std::string::npos) { why = "foma: sigma line without a symbol"; return DATOK_ERR_FORMAT; }
+      int number;
+      if (!atoi_go(line.substr(0, sp), number) || number < -1) { why = "foma: bad symbol number"; return DATOK_ERR_FORMAT; }
+      number++;  // fomafile.go:382
+      sigma_count = number;
+      const std::string sym = line.substr(sp + 1);
+      size_t n_runes = 0;
+      int32_t first_rune = 0;
+      for (size_t q = 0; q < sym.size();) {
+        int w;
+        const int32_t r = decode_rune((const uint8_t*)sym.data() + q, sym.size() - q, &w);
+        if (n_runes++ == 0) first_rune = r;
+        q += (size_t)w;
+      }
+      if (n_runes == 1) {
+        rune_of_sym[number] = first_rune;
+      } else if (n_runes > 1) {
+        if (sym == "@_EPSILON_SYMBOL_@") epsilon = number;
+        else if (sym == "@_UNKNOWN_SYMBOL_@") unknown = number;
+        else if (sym == "@_IDENTITY_SYMBOL_@") identity = number;
+        else if (sym == "@_TOKEN_SYMBOL_@" || sym == "@_TOKEN_BOUND_@") tokenend = number;
+        else multi_char[number] = true;
+      } else {  // "<number> " followed by an empty line: the symbol is '\n' (fomafile.go:425-439)
+        std::string rest;
+        if (!next_line(rest)) { why = "foma: unexpected end in ##sigma##"; return DATOK_ERR_FORMAT; }
+        if (!rest.empty()) multi_char[number] = true; else rune_of_sym[number] = '\n';
+      }
+    } else if (mode == STATES) {
+      const auto f = split_blank(line);
+      if (f[0] == "-1") continue;
+      int e[5] = {0, 0, 0, 0, 0};
+      bool numeric = true;
+      for (size_t k = 0; k < f.size() && k < 5; k++) numeric = numeric && atoi_go(f[k], e[k]);
+      if (!numeric) continue;  // "Unable to translate": the line is skipped
+      if (state_count < 0) { why = "foma: ##states## before ##props##"; return DATOK_ERR_FORMAT; }
+      if (f.size() == 5) { cur_state = e[0]; in_sym = e[1]; out_sym = e[2]; target = e[3]; is_final = e[4]; }
+      else if (f.size() == 4 && e[1] == -1) {  // a state without outgoing arcs
+        cur_state = e[0]; is_final = e[3];
+        if (is_final == 1 && !add_arc(cur_state + 1, final_sym, 0, false)) { why = "foma: state out of range"; return DATOK_ERR_FORMAT; }
+        continue;
+      }
+      else if (f.size() == 4) { cur_state = e[0]; in_sym = out_sym = e[1]; target = e[2]; is_final = e[3]; }
+      else if (f.size() == 3) { in_sym = e[0]; out_sym = e[1]; target = e[2]; }
+      else if (f.size() == 2) { in_sym = out_sym = e[0]; target = e[1]; }
+      in_sym++; out_sym++;  // fomafile.go:287-288
+      bool nontoken = false;
+      if (in_sym != out_sym) {
+        if (out_sym == tokenend && in_sym == epsilon) { /* token boundary: lives in the epsilon row */ }
+        else if (out_sym == epsilon) nontoken = true;
+        else { why = "Unsupported transition: " + std::to_string(cur_state) + " -> " + std::to_string(target); return DATOK_ERR_FORMAT; }
+      } else if (in_sym == tokenend) {
+        continue;  // tokenend accepting arcs are ignored
+      } else if (in_sym == epsilon) {
+        why = "General epsilon transitions are not supported"; return DATOK_ERR_FORMAT;
+      } else if (multi_char.count(in_sym)) {
+        continue;  // arcs on multi-character symbols are ignored
+      }
+      if (cur_state + 1 < 0 || cur_state + 1 > state_count) { why = "foma: state out of range"; return DATOK_ERR_FORMAT; }
+      if (in_sym >= 0) add_arc(cur_state + 1, in_sym, target + 1, nontoken);
+      if (is_final == 1) add_arc(cur_state + 1, final_sym, 0, false);  // the '#' arc of Mizobuchi et al.: target 0
+    }
+  }
+  if (state_count < 0) { why = "foma: no ##props## section"; return DATOK_ERR_FORMAT; }
+
+  // ToMatrix (matrix.go:30-99)
+  m = HostModel();
+  m.epsilon = epsilon; m.unknown = unknown; m.identity = identity; m.stateCount = state_count;
+  int max_sym = 0;
+  for (int i = 0; i < 256; i++) m.sigmaASCII[i] = identity != -1 ? identity : 0;
+  if (identity != -1) max_sym = identity;
+  for (auto& kv : rune_of_sym) {
+    if (kv.second < 256) m.sigmaASCII[kv.second] = kv.first;
+    m.sigma.emplace_back(kv.second, kv.first);
+    max_sym = std::max(max_sym, kv.first);
+  }
+  m.sigmaCount = max_sym + 1;
+  const size_t S = (size_t)state_count;
+  m.array.assign((S + 1) * (size_t)(max_sym + 1), 0);
+  std::vector<char> seen(S + 2, 0);
+  std::vector<int> todo;
+  if (S >= 1) { todo.push_back(1); seen[1] = 1; }
+  while (!todo.empty()) {  // only what is reachable from state 1 is stored (matrix.go:76-96)
+    const int t = todo.back();
+    todo.pop_back();
+    for (const Arc& a : arcs[(size_t)t]) {
+      const long long cell = ((long long)a.sym - 1) * (long long)S + t;
+      if (cell < 0 || (size_t)cell >= m.array.size()) { why = "foma: symbol outside the matrix"; return DATOK_ERR_FORMAT; }
+      m.array[(size_t)cell] = (uint32_t)a.target | (a.nontoken ? 0x80000000u : 0u);
+      if (a.target > state_count) { why = "stateCount is smaller"; return DATOK_ERR_FORMAT; }  // matrix.go:78
+      if (a.target >= 1 && !seen[(size_t)a.target]) { seen[(size_t)a.target] = 1; todo.push_back(a.target); }
+    }
+  }
+  m.eot_rewind = true;
+  return DATOK_OK;
+}
+
+int load_foma_file(const char* path, HostModel& m, std::string& why) {
+  std::vector<uint8_t> img;
+  int rc = gunzip_file(path, img, why);
+  if (rc) return rc;
+  rc = compile_foma_image(img.data(), img.size(), m, why);
+  if (rc) return rc;
+  return build_layout(m, why);
+}
+
+// WriteTo (matrix.go:126-210): magic, 14-byte header, the runes of sigma by symbol number (0 where a number
+// has no rune), 'M', the cells
+static void put_rune(std::vector<uint8_t>& o, int32_t r) {  // bufio.Writer.WriteRune
+  if (r < 0 || r > 0x10FFFF || (r >= 0xD800 && r <= 0xDFFF)) r = 0xFFFD;
+  if (r < 0x80) o.push_back((uint8_t)r);
+  else if (r < 0x800) { o.push_back((uint8_t)(0xC0 | (r >> 6))); o.push_back((uint8_t)(0x80 | (r & 0x3F))); }
+  else if (r < 0x10000) { o.push_back((uint8_t)(0xE0 | (r >> 12))); o.push_back((uint8_t)(0x80 | ((r >> 6) & 0x3F))); o.push_back((uint8_t)(0x80 | (r & 0x3F))); }
+  else { o.push_back((uint8_t)(0xF0 | (r >> 18))); o.push_back((uint8_t)(0x80 | ((r >> 12) & 0x3F))); o.push_back((uint8_t)(0x80 | ((r >> 6) & 0x3F))); o.push_back((uint8_t)(0x80 | (r & 0x3F))); }
+}
+int write_matok_image(const HostModel& m, std::vector<uint8_t>& out, std::string& why) {
+  if (!m.eot_rewind) { why = "not a matrix model"; return DATOK_ERR_INVALID_ARG; }
+  std::map<int32_t, int32_t> sym_of_rune;
+  for (auto& kv : m.sigma) sym_of_rune[kv.first] = kv.second;
+  int top = 0;
+  for (auto& kv : sym_of_rune) top = std::max(top, kv.second);
+  std::vector<int32_t> runes((size_t)top + 1, 0);
+  for (auto& kv : sym_of_rune) runes[(size_t)kv.second] = kv.first;
+  out.clear();
+  out.insert(out.end(), {'M', 'A', 'T', 'O', 'K'});
+  auto put16 = [&](uint32_t v) { out.push_back((uint8_t)v); out.push_back((uint8_t)(v >> 8)); };
+  put16(1); put16((uint32_t)m.epsilon); put16((uint32_t)m.unknown); put16((uint32_t)m.identity);
+  put16((uint32_t)m.stateCount); put16((uint32_t)m.stateCount >> 16);
+  put16((uint32_t)runes.size());
+  for (int32_t r : runes) put_rune(out, r);
+  out.push_back('M');
+  out.reserve(out.size() + 4 * m.array.size());
+  for (uint32_t v : m.array) { put16(v); put16(v >> 16); }
+  return DATOK_OK;
+}
+// Save (matrix.go:107-123)
+int save_matok_file(const HostModel& m, const char* path, std::string& why) {
+  std::vector<uint8_t> img;
+  int rc = write_matok_image(m, img, why);
+  if (rc) return rc;
+  gzFile gz = gzopen(path, "wb");
+  if (!gz) { why = std::string("cannot create ") + path; return DATOK_ERR_IO; }
+  size_t off = 0;
+  while (off < img.size()) {
+    const unsigned step = (unsigned)std::min<size_t>(img.size() - off, 1u << 30);
+    if (gzwrite(gz, img.data() + off, step) != (int)step) { gzclose(gz); why = "gzip: write error"; return DATOK_ERR_IO; }
+    off += step;
+  }
+  if (gzclose(gz) != Z_OK) { why = "gzip: close error"; return DATOK_ERR_IO; }
+  return DATOK_OK;
 }
 
 int build_layout(HostModel& m, std::string& why, const uint64_t* hist, const uint64_t* cls_hist) {
   const int S = m.stateCount, K = m.sigmaCount, eps = m.epsilon;
   if (S < 1 || S + 1 >= 32768) { why = "state count not in 1..32766"; return DATOK_ERR_UNSUPPORTED_MODEL; }
   if (eps < 1 || eps >= K) { why = "no epsilon symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
-  if (m.identity < 1 || m.identity >= K) { why = "no identity symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
+  // identity == -1: a model compiled in memory from a foma file without @_IDENTITY_SYMBOL_@ (matrix.go:43,430,459):
+  // runes outside sigma have no symbol and every lookup on them fails.  (A *loaded* file never has -1: the u16
+  // header field reads back as 65535, for which the reference indexes out of range.)
+  if (m.identity != -1 && (m.identity < 1 || m.identity >= K)) { why = "no identity symbol"; return DATOK_ERR_UNSUPPORTED_MODEL; }
   auto cell = [&](int a, int t) -> uint32_t {  // matrix.go:463; a==0 never matches (matrix.go:459)
     if (a < 1 || a >= K) return 0;
     return m.array[(size_t)(a - 1) * S + t];

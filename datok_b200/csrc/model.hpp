@@ -92,6 +92,12 @@ struct HostModel {
 // error codes are the DATOK_ERR_* values of include/datok_b200.h
 int load_matok_file(const char* path, HostModel& m, std::string& why);
 int parse_matok_image(const uint8_t* d, size_t n, HostModel& m, std::string& why);
+// the compile path: LoadFomaFile + ParseFoma (fomafile.go:56-450) + ToMatrix (matrix.go:30-99) over a gzipped
+// foma file / its gunzipped text; WriteTo / Save (matrix.go:107-210) of a matrix model
+int load_foma_file(const char* path, HostModel& m, std::string& why);
+int compile_foma_image(const uint8_t* d, size_t n, HostModel& m, std::string& why);
+int write_matok_image(const HostModel& m, std::vector<uint8_t>& out, std::string& why);
+int save_matok_file(const HostModel& m, const char* path, std::string& why);
 // hist (optional): visits per reference state id (stateCount+1 entries) measured on
 // representative text; without it states are ordered breadth-first from the root.
 // cls_hist (optional): occurrences per layout-independent class id (256 entries, see cls_base): class ids

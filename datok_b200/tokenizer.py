@@ -190,6 +190,25 @@ class MatrixTokenizer:
     def Type(self):
         return _lib.lib().datok_model_type(self._h).decode()
 
+    def Save(self, file):
+        """matrix.go:107-123: gzip(WriteTo).  Returns (bytes of the image, None) or (0, DatokError)."""
+        L = _lib.lib()
+        rc = L.datok_save(self._h, str(file).encode())
+        if rc:
+            return 0, DatokError(rc, (L.datok_last_error() or b"").decode("utf-8", "replace"))
+        return L.datok_write_image(self._h, None, 0), None
+
+    def WriteTo(self, w):
+        """matrix.go:126-210: the uncompressed image into a binary writer; returns the byte count"""
+        L = _lib.lib()
+        n = L.datok_write_image(self._h, None, 0)
+        if not n:
+            raise DatokError(_lib.ERR_INVALID_ARG, (L.datok_last_error() or b"").decode("utf-8", "replace"))
+        buf = C.create_string_buffer(n)
+        L.datok_write_image(self._h, buf, n)
+        w.write(buf.raw)
+        return n
+
     def Transduce(self, r, w):
         """matrix.go:340-342"""
         return self.TransduceTokenWriter(r, NewTokenWriter(w, SIMPLE))
@@ -369,6 +388,47 @@ def LoadTokenizerFile(file, device=0):
 
 
 LoadMatrixFile = LoadTokenizerFile  # matrix.go:214
+
+
+class Automaton:
+    """What LoadFomaFile returns (fomafile.go:36-52): the parsed foma file, waiting for ToMatrix().  The
+    intermediate representation lives inside the library; this object only remembers the file."""
+
+    def __init__(self, file):
+        self.file = str(file)
+
+    def ToMatrix(self, device=0):
+        """matrix.go:30-99 -- the matrix model, in memory and resident on `device`.  None on error."""
+        L = _lib.lib()
+        err = C.c_int()
+        h = L.datok_load_foma(self.file.encode(), device, C.byref(err))
+        if not h:
+            msg = (L.datok_last_error() or b"").decode("utf-8", "replace")
+            print(f"datok: {msg or L.datok_strerror(err.value).decode()}", file=sys.stderr)
+            return None
+        return MatrixTokenizer(h, device)
+
+
+def LoadFomaFile(file):
+    """fomafile.go:56-72.  None (like the reference's nil) when the file cannot be read as gzip."""
+    try:
+        with open(file, "rb") as f:
+            if f.read(2) != b"\x1f\x8b":
+                print("datok: gzip: invalid header", file=sys.stderr)
+                return None
+    except OSError as e:
+        print(f"datok: {e}", file=sys.stderr)
+        return None
+    return Automaton(file)
+
+
+def convert(foma_file, matok_file):
+    """`datok convert -i foma_file -o matok_file` (cmd/datok.go:63): compile without touching a device.
+    Raises DatokError with the reference's message."""
+    L = _lib.lib()
+    rc = L.datok_compile_foma(str(foma_file).encode(), str(matok_file).encode())
+    if rc:
+        raise DatokError(rc, (L.datok_last_error() or b"").decode("utf-8", "replace"))
 
 
 def load_error_code(file, device=0):

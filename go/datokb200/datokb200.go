@@ -36,6 +36,7 @@ import (
 	"errors"
 	"io"
 	"log"
+	"os"
 	"runtime/cgo"
 	"unsafe"
 
@@ -67,6 +68,71 @@ func LoadTokenizerFile(file string, device int) *Tokenizer {
 		return nil
 	}
 	return &Tokenizer{model: m}
+}
+
+// Automaton stands for what datok.LoadFomaFile returns (fomafile.go:36-52): a foma file waiting for
+// ToMatrix.  The parsed intermediate representation lives inside the library.
+type Automaton struct {
+	file   string
+	device int
+}
+
+// LoadFomaFile mirrors datok.LoadFomaFile (fomafile.go:56-72).
+func LoadFomaFile(file string, device int) *Automaton {
+	f, err := os.Open(file)
+	if err != nil {
+		log.Print(err)
+		return nil
+	}
+	f.Close()
+	return &Automaton{file: file, device: device}
+}
+
+// ToMatrix mirrors Automaton.ToMatrix (matrix.go:30-99): ParseFoma and the matrix build run in the
+// library (datok_load_foma), the model is resident on the device when this returns.
+func (a *Automaton) ToMatrix() *Tokenizer {
+	cs := C.CString(a.file)
+	defer C.free(unsafe.Pointer(cs))
+	var rc C.int
+	m := C.datok_load_foma(cs, C.int(a.device), &rc)
+	if m == nil {
+		log.Println(C.GoString(C.datok_last_error()))
+		return nil
+	}
+	return &Tokenizer{model: m}
+}
+
+// Save mirrors MatrixTokenizer.Save (matrix.go:107-123): the gzipped WriteTo image.
+func (t *Tokenizer) Save(file string) (n int64, err error) {
+	cs := C.CString(file)
+	defer C.free(unsafe.Pointer(cs))
+	if rc := C.datok_save(t.model, cs); rc != C.DATOK_OK {
+		return 0, errors.New(C.GoString(C.datok_last_error()))
+	}
+	return int64(C.datok_write_image(t.model, nil, 0)), nil
+}
+
+// WriteTo mirrors MatrixTokenizer.WriteTo (matrix.go:126-210).
+func (t *Tokenizer) WriteTo(w io.Writer) (n int64, err error) {
+	size := C.datok_write_image(t.model, nil, 0)
+	if size == 0 {
+		return 0, errors.New(C.GoString(C.datok_last_error()))
+	}
+	buf := make([]byte, int(size))
+	C.datok_write_image(t.model, (*C.uint8_t)(unsafe.Pointer(&buf[0])), size)
+	k, err := w.Write(buf)
+	return int64(k), err
+}
+
+// Convert is `datok convert -i fomaFile -o matokFile` (cmd/datok.go:63) without touching a device.
+func Convert(fomaFile, matokFile string) error {
+	a, b := C.CString(fomaFile), C.CString(matokFile)
+	defer C.free(unsafe.Pointer(a))
+	defer C.free(unsafe.Pointer(b))
+	if rc := C.datok_compile_foma(a, b); rc != C.DATOK_OK {
+		return errors.New(C.GoString(C.datok_last_error()))
+	}
+	return nil
 }
 
 // Close releases the GPU resident model.

@@ -135,6 +135,18 @@ typedef struct {
 datok_model *datok_load(const char *path, int device, int *err);
 /* same, from an in-memory gunzipped MATOK image (ParseMatrix, matrix.go:235) */
 datok_model *datok_load_image(const uint8_t *image, size_t n, int device, int *err);
+/* The compile path.  LoadFomaFile(path).ToMatrix() (fomafile.go:56-450, matrix.go:30-99): parses a gzipped foma
+ * file that follows the tokenizer's conventions and builds the matrix model in memory, ready on `device`.
+ * (A model without @_IDENTITY_SYMBOL_@ only exists in this in-memory form, as in the reference.) */
+datok_model *datok_load_foma(const char *path, int device, int *err);
+/* `datok convert -i foma_path -o matok_path` (cmd/datok.go:63: LoadFomaFile, ToMatrix, Save).  Host only: no
+ * device is touched.  0 or a DATOK_ERR_* code (datok_last_error() has the reference's message). */
+int datok_compile_foma(const char *foma_path, const char *matok_path);
+/* MatrixTokenizer.Save (matrix.go:107-123): gzip(WriteTo).  DATOK_ERR_INVALID_ARG for a double-array model. */
+int datok_save(const datok_model *m, const char *path);
+/* MatrixTokenizer.WriteTo (matrix.go:126-210): the uncompressed image.  Returns its size; written to dst when
+ * cap is large enough.  0 on error. */
+size_t datok_write_image(const datok_model *m, uint8_t *dst, size_t cap);
 void datok_free(datok_model *m);
 
 /* Tokenizer.Type() (matrix.go:102-104) -> "MATOK" */

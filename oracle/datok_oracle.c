@@ -82,6 +82,12 @@ static int encode_rune(int32_t r, uint8_t *out) {
   return 4;
 }
 
+/* -------------------------------------------------------- growable arrays */
+
+#define VEC(T) struct { T *p; size_t n, cap; }
+#define VPUSH(v, x) do { if ((v).n == (v).cap) { (v).cap = (v).cap ? (v).cap * 2 : 1024; \
+      (v).p = realloc((v).p, (v).cap * sizeof(*(v).p)); } (v).p[(v).n++] = (x); } while (0)
+
 /* ----------------------------------------------------------------- model */
 
 struct ora_model {
@@ -256,8 +262,8 @@ static ora_model *parse_datok(const uint8_t *d, size_t n) {
   return m;
 }
 
-/* LoadMatrixFile matrix.go:214-231 (gzip -> ParseMatrix) */
-ora_model *ora_load(const char *path) {
+/* gzip.NewReader + read to the end (matrix.go:214-231, fomafile.go:56-72) */
+static uint8_t *read_gz(const char *path, size_t *len_out) {
   gzFile f = gzopen(path, "rb");
   if (!f) return NULL;
   /* gzopen transparently reads non-gzip files; the reference's gzip.NewReader
@@ -276,10 +282,270 @@ ora_model *ora_load(const char *path) {
     len += (size_t)got;
   }
   gzclose(f);
+  *len_out = len;
+  return buf;
+}
+
+/* LoadMatrixFile matrix.go:214-231 (gzip -> ParseMatrix) */
+ora_model *ora_load(const char *path) {
+  size_t len = 0;
+  uint8_t *buf = read_gz(path, &len);
+  if (!buf) return NULL;
   /* LoadTokenizerFile fomafile.go:452-484 dispatches on the magic */
   ora_model *m = (len >= 5 && memcmp(buf, "DATOK", 5) == 0) ? parse_datok(buf, len) : parse_matrix(buf, len);
   free(buf);
   return m;
+}
+
+/* ------------------------------------------------- foma -> matrix (compile path)
+ * LoadFomaFile fomafile.go:56-72, ParseFoma fomafile.go:77-450, ToMatrix matrix.go:30-99.
+ * The Automaton's transitions ([]map[int]*edge) are kept as one flat list of edges; a later edge of the
+ * same (state, symbol) replaces the earlier one like the map assignment does. */
+typedef struct { int state, alpha, end; uint8_t nontoken; } foma_edge;
+
+static int split_fields(char *line, char **f, int maxf) { /* strings.Split(line, " ") */
+  int n = 0;
+  f[n++] = line;
+  for (char *c = line; *c; c++)
+    if (*c == ' ') { *c = 0; if (n < maxf) f[n++] = c + 1; else return maxf + 1; }
+  return n;
+}
+static int go_atoi(const char *s, int *out) { /* strconv.Atoi: optional sign, digits only */
+  const char *c = s;
+  if (*c == '+' || *c == '-') c++;
+  if (!*c) return 0;
+  long long v = 0;
+  for (; *c; c++) { if (*c < '0' || *c > '9') return 0; v = v * 10 + (*c - '0'); if (v > 0x7fffffffLL) return 0; }
+  *out = (int)(s[0] == '-' ? -v : v);
+  return 1;
+}
+
+static ora_model *parse_foma(uint8_t *d, size_t n) {
+  enum { M_NONE0 = 0, M_PROPS = 1, M_SIGMA = 2, M_STATES = 3, M_NONE = 4 }; /* fomafile.go:14-19 */
+  int epsilon = -1, unknown = -1, identity = -1, final_sym = -1, tokenend = -1; /* :83-88 */
+  int sigmaCount = 0, stateCount = -1;
+  int state = 0, inSym = 0, outSym = 0, end = 0, final = 0; /* :91, live across lines */
+  int mode = M_NONE0;
+  /* sigmaRev / sigmaMCS, indexed by symbol number */
+  size_t symcap = 1024;
+  int32_t *sigmaRev = (int32_t *)malloc(symcap * sizeof(int32_t)); /* -1: no entry */
+  uint8_t *isMCS = (uint8_t *)calloc(symcap, 1);
+  for (size_t i = 0; i < symcap; i++) sigmaRev[i] = -1;
+  VEC(foma_edge) edges = {0};
+  ora_model *m = NULL;
+  size_t p = 0;
+  while (p < n) {
+    uint8_t *nl = (uint8_t *)memchr(d + p, '\n', n - p);
+    if (!nl) break; /* ReadString hits io.EOF: the partial last line is dropped (:101-107) */
+    char *line = (char *)(d + p);
+    size_t len = (size_t)(nl - (d + p)); /* without the '\n' */
+    p += len + 1;
+    *nl = 0;
+    if (len >= 2 && line[0] == '#' && line[1] == '#') { /* :111-136 */
+      if (!strncmp(line, "##props##", 9)) mode = M_PROPS;
+      else if (!strncmp(line, "##states##", 10)) { mode = M_STATES; sigmaCount++; final_sym = sigmaCount; }
+      else if (!strncmp(line, "##sigma##", 9)) mode = M_SIGMA;
+      else if (!strncmp(line, "##end##", 7)) mode = M_NONE;
+      else if (strncmp(line, "##foma-net", 10) != 0) break; /* "Unknown input line": leaves the loop */
+      continue;
+    }
+    if (mode == M_PROPS) { /* :141-186 */
+      char *f[16];
+      int nf = split_fields(line, f, 16);
+      if (nf < 13) goto fail; /* elem[12] would panic */
+      if (strcmp(f[6], "1") != 0) goto fail; /* deterministic */
+      if (strcmp(f[9], "1") != 0) goto fail; /* epsilon free */
+      int v;
+      if (!go_atoi(f[1], &v)) goto fail; /* arccount */
+      if (!go_atoi(f[2], &v)) goto fail;
+      stateCount = v;
+      continue;
+    }
+    if (mode == M_STATES) { /* :187-372 */
+      char *f[8];
+      int nf = split_fields(line, f, 6);
+      int e[5] = {0, 0, 0, 0, 0};
+      if (!strcmp(f[0], "-1")) continue; /* :190 */
+      int bad = 0;
+      for (int k = 0; k < nf && k < 5; k++)
+        if (!go_atoi(f[k], &e[k])) { bad = 1; break; }
+      if (bad) continue; /* `break` leaves the switch: the line is skipped */
+      switch (nf) { /* :232-279 */
+        case 5: state = e[0]; inSym = e[1]; outSym = e[2]; end = e[3]; final = e[4]; break;
+        case 4:
+          if (e[1] == -1) {
+            state = e[0]; final = e[3];
+            if (stateCount < 0 || state + 1 < 0 || state + 1 > stateCount) goto fail;
+            /* final state without outgoing edges: transitions[state+1][final] = &edge{} -- an edge to
+             * state 0, which ToMatrix stores as 0: kept only for its index check */
+            if (final == 1) { foma_edge fe = {state + 1, final_sym, 0, 0}; VPUSH(edges, fe); }
+            continue;
+          }
+          state = e[0]; inSym = e[1]; end = e[2]; final = e[3]; outSym = inSym;
+          break;
+        case 3: inSym = e[0]; outSym = e[1]; end = e[2]; break;
+        case 2: inSym = e[0]; end = e[1]; outSym = inSym; break;
+        default: break; /* no case: the values of the previous line stand */
+      }
+      int nontoken = 0, tok_end = 0;
+      inSym++; outSym++; /* :287-288 */
+      if (inSym != outSym) { /* :291-313 */
+        if (outSym == tokenend && inSym == epsilon) tok_end = 1;
+        else if (outSym == epsilon) nontoken = 1;
+        else goto fail; /* "Unsupported transition" */
+      } else if (inSym == tokenend) {
+        continue; /* :314-316 */
+      } else if (inSym == epsilon) {
+        goto fail; /* :317-319 */
+      } else if (inSym >= 0 && (size_t)inSym < symcap && isMCS[inSym]) {
+        continue; /* :320-324 */
+      }
+      (void)tok_end;
+      if (stateCount < 0 || state + 1 < 0 || state + 1 > stateCount) goto fail; /* transitions[state+1]: index out of range */
+      if (inSym >= 0) { foma_edge fe = {state + 1, inSym, end + 1, (uint8_t)nontoken}; VPUSH(edges, fe); } /* :336-344 */
+      if (final == 1) { foma_edge fe = {state + 1, final_sym, 0, 0}; VPUSH(edges, fe); } /* :347-351 */
+      continue;
+    }
+    if (mode == M_SIGMA) { /* :374-443 */
+      char *sp = strchr(line, ' '); /* strings.SplitN(line, " ", 2) */
+      if (!sp) goto fail; /* elem[1] would panic */
+      *sp = 0;
+      const char *sym = sp + 1;
+      size_t symlen = len - (size_t)(sym - line);
+      int number;
+      if (!go_atoi(line, &number)) goto fail;
+      number++;
+      if (number < 0) goto fail;
+      sigmaCount = number;
+      if ((size_t)number >= symcap) {
+        size_t nc = symcap;
+        while ((size_t)number >= nc) nc *= 2;
+        sigmaRev = (int32_t *)realloc(sigmaRev, nc * sizeof(int32_t));
+        isMCS = (uint8_t *)realloc(isMCS, nc);
+        for (size_t i = symcap; i < nc; i++) { sigmaRev[i] = -1; isMCS[i] = 0; }
+        symcap = nc;
+      }
+      /* utf8.RuneCountInString */
+      size_t nr = 0, q = 0;
+      int32_t first = 0;
+      while (q < symlen) {
+        int w;
+        int32_t r = ora_decode_rune((const uint8_t *)sym + q, symlen - q, &w);
+        if (nr == 0) first = r;
+        nr++; q += (size_t)w;
+      }
+      int32_t symbol;
+      if (nr == 1) symbol = first;
+      else if (nr > 1) {
+        if (!strcmp(sym, "@_EPSILON_SYMBOL_@")) epsilon = number;
+        else if (!strcmp(sym, "@_UNKNOWN_SYMBOL_@")) unknown = number;
+        else if (!strcmp(sym, "@_IDENTITY_SYMBOL_@")) identity = number;
+        else if (!strcmp(sym, "@_TOKEN_SYMBOL_@") || !strcmp(sym, "@_TOKEN_BOUND_@")) tokenend = number;
+        else isMCS[number] = 1;
+        continue;
+      } else { /* the symbol is the line feed: its line ends right after the blank (:425-439) */
+        if (p >= n) goto fail;
+        uint8_t *nl2 = (uint8_t *)memchr(d + p, '\n', n - p);
+        if (!nl2) goto fail;
+        size_t l2 = (size_t)(nl2 - (d + p)) + 1;
+        p += l2;
+        if (l2 != 1) { isMCS[number] = 1; continue; }
+        symbol = '\n';
+      }
+      sigmaRev[number] = symbol;
+      continue;
+    }
+  }
+  if (stateCount < 0) goto fail; /* (no ##props##: ToMatrix would run on an automaton without states) */
+  {
+    /* ToMatrix matrix.go:30-99 */
+    m = (ora_model *)calloc(1, sizeof(*m));
+    m->epsilon = epsilon; m->unknown = unknown; m->identity = identity; m->stateCount = stateCount;
+    m->eot_rewind = 1;
+    int max = 0;
+    if (identity != -1) { for (int i = 0; i < 256; i++) m->sigmaASCII[i] = identity; max = identity; } /* :43-48 */
+    uint32_t cap = 64;
+    while (cap < (uint32_t)(sigmaCount + 2) * 4u) cap <<= 1;
+    m->hmask = cap - 1;
+    m->hkey = (int32_t *)malloc(cap * sizeof(int32_t));
+    m->hval = (int32_t *)malloc(cap * sizeof(int32_t));
+    for (uint32_t i = 0; i < cap; i++) m->hkey[i] = -1;
+    for (int num = 0; num <= sigmaCount && (size_t)num < symcap; num++) { /* :50-65 */
+      if (sigmaRev[num] < 0) continue;
+      if (sigmaRev[num] < 256) m->sigmaASCII[sigmaRev[num]] = num;
+      sigma_put(m, sigmaRev[num], num);
+      if (num > max) max = num;
+    }
+    m->sigmaCount = max + 1;
+    m->arraySize = ((size_t)stateCount + 1) * (size_t)(max + 1); /* :71 */
+    m->array = (uint32_t *)calloc(m->arraySize + 1, 4);
+    /* edges of a state, in file order; only the states reachable from state 1 are stored (:76-96) */
+    const size_t S = (size_t)stateCount;
+    size_t *first = (size_t *)calloc(S + 2, sizeof(size_t));
+    for (size_t k = 0; k < edges.n; k++) first[edges.p[k].state + 1]++;
+    for (size_t t = 1; t <= S + 1; t++) first[t] += first[t - 1];
+    size_t *fill = (size_t *)malloc((S + 2) * sizeof(size_t));
+    memcpy(fill, first, (S + 2) * sizeof(size_t));
+    foma_edge *by_state = (foma_edge *)malloc((edges.n + 1) * sizeof(foma_edge));
+    for (size_t k = 0; k < edges.n; k++) by_state[fill[edges.p[k].state]++] = edges.p[k];
+    uint8_t *remember = (uint8_t *)calloc(S + 2, 1);
+    int *stack = (int *)malloc((S + 2) * sizeof(int));
+    size_t sp = 0;
+    int okm = 1;
+    if (S >= 1) { stack[sp++] = 1; remember[1] = 1; }
+    while (sp && okm) {
+      const int t = stack[--sp];
+      for (size_t k = first[t]; k < first[t + 1]; k++) {
+        const foma_edge *fe = &by_state[k];
+        const long long idx = ((long long)fe->alpha - 1) * (long long)S + t;
+        if (idx < 0 || (size_t)idx >= m->arraySize) { okm = 0; break; } /* Go: index out of range */
+        m->array[idx] = (uint32_t)fe->end | (fe->nontoken ? FIRSTBIT : 0u); /* later edges replace earlier ones */
+        if (fe->end > stateCount) { okm = 0; break; } /* :78 panic("stateCount is smaller") */
+        if (fe->end >= 1 && !remember[fe->end]) { remember[fe->end] = 1; stack[sp++] = fe->end; }
+      }
+    }
+    free(first); free(fill); free(by_state); free(remember); free(stack);
+    if (!okm) { ora_free(m); m = NULL; }
+  }
+fail:
+  free(sigmaRev); free(isMCS); free(edges.p);
+  return m;
+}
+
+ora_model *ora_load_foma(const char *path) {
+  size_t len = 0;
+  uint8_t *buf = read_gz(path, &len);
+  if (!buf) return NULL;
+  ora_model *m = parse_foma(buf, len);
+  free(buf);
+  return m;
+}
+
+/* WriteTo matrix.go:126-210: the uncompressed image Save() gzips.  malloc'd, ora_free_bytes. */
+uint8_t *ora_write_matrix(const ora_model *m, size_t *out_len) {
+  int max = 0;
+  for (uint32_t i = 0; i <= m->hmask; i++)
+    if (m->hkey[i] != -1 && m->hval[i] > max) max = m->hval[i];
+  int32_t *sigmalist = (int32_t *)calloc((size_t)max + 1, sizeof(int32_t));
+  for (uint32_t i = 0; i <= m->hmask; i++)
+    if (m->hkey[i] != -1) sigmalist[m->hval[i]] = m->hkey[i];
+  uint8_t *out = (uint8_t *)malloc(5 + 14 + 4 * ((size_t)max + 1) + 1 + 4 * m->arraySize);
+  size_t p = 0;
+  memcpy(out, "MATOK", 5); p = 5;
+#define PUT16(v) do { out[p++] = (uint8_t)((v) & 0xFF); out[p++] = (uint8_t)(((v) >> 8) & 0xFF); } while (0)
+  PUT16(VERSION); PUT16((uint32_t)m->epsilon); PUT16((uint32_t)m->unknown); PUT16((uint32_t)m->identity);
+  { uint32_t sc = (uint32_t)m->stateCount; PUT16(sc); PUT16(sc >> 16); }
+  PUT16((uint32_t)(max + 1));
+#undef PUT16
+  for (int k = 0; k <= max; k++) p += (size_t)encode_rune(sigmalist[k], out + p);
+  out[p++] = 'M';
+  for (size_t x = 0; x < m->arraySize; x++) {
+    const uint32_t v = m->array[x];
+    out[p++] = (uint8_t)v; out[p++] = (uint8_t)(v >> 8); out[p++] = (uint8_t)(v >> 16); out[p++] = (uint8_t)(v >> 24);
+  }
+  free(sigmalist);
+  *out_len = p;
+  return out;
 }
 
 void ora_free(ora_model *m) {
@@ -298,15 +564,10 @@ const int32_t *ora_sigma_ascii(const ora_model *m) { return m->sigmaASCII; }
 int ora_sigma_lookup(const ora_model *m, int32_t r, int *ok) {
   if (r < 256) return m->sigmaASCII[r];       /* matrix.go:421-425 */
   int a = sigma_get(m, r, ok);                /* :427 */
-  if (!*ok) a = m->identity;                  /* :430-434 */
+  if (!*ok && m->identity != -1) a = m->identity; /* :430-434 */
   return a;
 }
 
-/* -------------------------------------------------------- growable arrays */
-
-#define VEC(T) struct { T *p; size_t n, cap; }
-#define VPUSH(v, x) do { if ((v).n == (v).cap) { (v).cap = (v).cap ? (v).cap * 2 : 1024; \
-      (v).p = realloc((v).p, (v).cap * sizeof(*(v).p)); } (v).p[(v).n++] = (x); } while (0)
 
 typedef VEC(uint8_t) vec_u8;
 typedef VEC(int32_t) vec_i32;
@@ -532,7 +793,7 @@ static int transduce(const ora_model *mat, const uint8_t *in, size_t n, token_wr
           a = mat->sigmaASCII[chr];
         } else {
           a = sigma_get(mat, chr, &ok); /* :427 */
-          if (!ok) a = identity;        /* :430-434 */
+          if (!ok && identity != -1) a = identity; /* :430-434 */
         }
         t0 = t; /* :437 */
         if (array[(size_t)(epsilon - 1) * S + t0] != 0) { /* :442 */
@@ -543,7 +804,11 @@ static int transduce(const ora_model *mat, const uint8_t *in, size_t n, token_wr
       if (a == 0) { /* :459 */
         t = 0;
       } else {
-        t = array[(size_t)(a - 1) * S + t0]; /* :463 */
+        /* Go checks the index: a model with an identity but without an unknown symbol (unknown == -1 in memory,
+         * 65535 once saved and loaded) panics here on the retry of :478-485 */
+        const long long ix = ((long long)a - 1) * (long long)S + (long long)t0;
+        if (ix < 0 || (size_t)ix >= mat->arraySize) return ORA_PANIC_INDEX;
+        t = array[(size_t)ix]; /* :463 */
       }
       st->n_iter++;
       if (st->hist) st->hist[t0]++;

@@ -6,6 +6,9 @@
  *     matrix.go:235-337   ParseMatrix            (.matok loader)
  *     matrix.go:348-698   TransduceTokenWriter   (greedy walk, single backtrack)
  *     token_writer.go:36-175 NewTokenWriter      (flag-driven formatter)
+ *     fomafile.go:56-450  LoadFomaFile/ParseFoma, matrix.go:30-99 ToMatrix, matrix.go:126-210 WriteTo
+ *                         (the compile path foma -> .matok; pinned by tests/test_foma_compile.py on the
+ *                         reference's own compiled artefacts and matrix_test.go's vectors)
  * and, for the rows SURVEY.md section 8f marks "next", of the double-array path:
  *     datok.go:621-729    ParseDatok             (.datok loader; ora_load dispatches on the magic like
  *                                                 LoadTokenizerFile, fomafile.go:452-484, and converts
@@ -55,7 +58,8 @@ enum {
   ORA_PANIC_TEXT_NO_SENT = 4,    /* token_writer.go:145 sent[0] */
   ORA_PANIC_TOKEN_SLICE = 5,     /* token_writer.go:85 buf[offset:], offset>len */
   ORA_PANIC_EMPTY_BUF = 6,       /* token_writer.go:66 buf[0] on empty buf */
-  ORA_ERR_LOOP = 7               /* endless epsilon loop (matrix.go:633 TODO) */
+  ORA_ERR_LOOP = 7,              /* endless epsilon loop (matrix.go:633 TODO) */
+  ORA_PANIC_INDEX = 8            /* matrix.go:463 array index out of range (symbol outside the matrix) */
 };
 
 typedef struct ora_model ora_model;
@@ -63,6 +67,11 @@ typedef struct ora_model ora_model;
 /* LoadMatrixFile matrix.go:214-231.  NULL on any error (reference: nil). */
 ora_model *ora_load(const char *path);
 void ora_free(ora_model *m);
+/* LoadFomaFile(path).ToMatrix()  (fomafile.go:56-450, matrix.go:30-99): the compile path.  NULL where the
+ * reference returns nil or panics. */
+ora_model *ora_load_foma(const char *path);
+/* WriteTo (matrix.go:126-210): the uncompressed MATOK image; malloc'd, release with ora_free_bytes */
+uint8_t *ora_write_matrix(const ora_model *m, size_t *out_len);
 
 /* model introspection (for tests and for checking the GPU re-layout) */
 int ora_epsilon(const ora_model *m);

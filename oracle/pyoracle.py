@@ -70,6 +70,10 @@ def lib():
         L.ora_load.restype = C.c_void_p
         L.ora_load.argtypes = [C.c_char_p]
         L.ora_free.argtypes = [C.c_void_p]
+        L.ora_load_foma.restype = C.c_void_p
+        L.ora_load_foma.argtypes = [C.c_char_p]
+        L.ora_write_matrix.restype = C.c_void_p
+        L.ora_write_matrix.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         for f in ("ora_epsilon", "ora_unknown", "ora_identity", "ora_state_count", "ora_sigma_count"):
             getattr(L, f).restype = C.c_int
             getattr(L, f).argtypes = [C.c_void_p]
@@ -143,8 +147,12 @@ class OracleResult:
 
 
 class OracleModel:
-    def __init__(self, path):
-        self._h = lib().ora_load(os.fsencode(path))
+    def __init__(self, path, foma=None):
+        """foma=True: `path` is a foma file, compiled in memory like LoadFomaFile(path).ToMatrix();
+        default: by extension (.fst)"""
+        if foma is None:
+            foma = str(path).endswith(".fst")
+        self._h = (lib().ora_load_foma if foma else lib().ora_load)(os.fsencode(path))
         if not self._h:
             raise ValueError(f"oracle: cannot load {path}")
         L = lib()
@@ -158,6 +166,15 @@ class OracleModel:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.ora_free(self._h)
             self._h = None
+
+    def write_matrix(self):
+        """WriteTo (matrix.go:126-210): the uncompressed MATOK image"""
+        n = C.c_size_t()
+        p = lib().ora_write_matrix(self._h, C.byref(n))
+        try:
+            return C.string_at(p, n.value)
+        finally:
+            lib().ora_free_bytes(C.cast(p, C.POINTER(C.c_uint8)))
 
     def array(self):
         n = C.c_size_t()

@@ -37,6 +37,7 @@ struct EmulResult {
   uint32_t eot_rewind;  // 0: a double-array model -- the delta-coded forms (cursors restart at every text) do not apply
   uint8_t* text;        // the device formatter's bodies (format_core.cuh) over the arrays above; null with malformed UTF-8
   uint64_t text_len;
+  uint32_t delta_range;  // 1: a delta of the compact forms does not fit (DATOK_ERR_COMPACT_RANGE): the absolute arrays stand alone
 };
 
 struct EmulModel {
@@ -60,7 +61,9 @@ static void make_fast_tables(const HostModel& hm, const DeviceModel& m, uint32_t
 EmulModel* emul_load(const char* path, int* err) {
   EmulModel* m = new EmulModel();
   std::string why;
-  int rc = load_matok_file(path, m->hm, why);
+  const size_t pl = std::strlen(path);
+  const bool foma = pl > 4 && !std::strcmp(path + pl - 4, ".fst");  // the compile path: LoadFomaFile(path).ToMatrix()
+  int rc = foma ? load_foma_file(path, m->hm, why) : load_matok_file(path, m->hm, why);
   if (rc) { *err = rc; delete m; return nullptr; }
   HostModel& h = m->hm;
   m->dm.table = h.table.data();
@@ -235,6 +238,11 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   c.text_sentpos_end = R->text_sentpos_end; c.text_byte_end = R->text_byte_end;
   c.docs = docs.data();
   docs[0] = doc_stream_start(c);
+  // the delta-coded forms report into a key of their own: a range error there (DATOK_ERR_COMPACT_RANGE, only raised by
+  // a call that asks for DATOK_COMPACT) leaves the absolute form intact
+  unsigned long long err_key_delta = ~0ull;
+  CompactCtx cd = c;
+  cd.err_key = &err_key_delta;
   for (int pass = 0; pass < 2; pass++) {  // 0: texts, 1: tokens + sentences
     for (uint32_t kb = 0; kb < nblk; kb++) {
       uint32_t blk = order ? nblk - 1 - kb : kb;
@@ -255,9 +263,9 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
             const WordMasks wm = word_masks(wb, agg_last(carry));
             emit_tokens<0>(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
                            nullptr, staged ? blk_tok0 : 0u);
-            emit_tokens<1>(c, w, wb, wm, carry, nullptr, nullptr, staged ? s_td.data() : c.tok_delta,
+            emit_tokens<1>(cd, w, wb, wm, carry, nullptr, nullptr, staged ? s_td.data() : c.tok_delta,
                            staged ? blk_tok0 : 0u);
-            emit_tokens<2>(c, w, wb, wm, carry, nullptr, nullptr,
+            emit_tokens<2>(cd, w, wb, wm, carry, nullptr, nullptr,
                            staged ? s_t8.data() : reinterpret_cast<uint16_t*>(c.tok_delta8), staged ? blk_tok0 : 0u);
             emit_sentences(c, w, wb, wm, carry);
           }
@@ -276,6 +284,10 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   const StreamTotals fin = finalize_stream(c, total, text_end_in != 0, b.final_input != 0);
   R->n_tokens = fin.n_tok; R->n_sentences = fin.n_sent; R->n_texts = fin.n_text; R->n_sent_pos = fin.n_sentpos;
   if (err_key != ~0ull) R->status = (int)(err_key & 0xFF);
+  if (err_key_delta != ~0ull) {
+    if ((err_key_delta & 0xFF) == E_COMPACT_RANGE) R->delta_range = 1;
+    else if (R->status == 0) R->status = (int)(err_key_delta & 0xFF);
+  }
   if (R->status == 0 && !R->has_invalid) {
     // the device formatter, item by item like its kernels (format_kernels.cu): scans, then the writers
     FmtCtx f;

@@ -40,6 +40,11 @@ FOMA_EQUIV = {"testdata/simpletok.fst": "simpletok.matok"}
 # ... and -> shipped .datok (double-array path, datok_test.go)
 FOMA_EQUIV_DA = {"testdata/simpletok.fst": "simpletok.datok"}
 OUT_DA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors_datok.json")
+OUT_FOMA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors_foma.json")
+# foma files small enough to commit next to the shipped models (testdata/); the others (abbr_bench, simple_bench)
+# are only used by benchmarks
+FOMA_FIXTURES = {"simpletok.fst", "bauamt.fst", "wahlamt.fst", "ignorable_mcs.fst", "clitic_test.fst",
+                 "tokenizer_de.fst", "tokenizer_en.fst"}
 
 
 class Tok:
@@ -154,9 +159,12 @@ def sig(st):
 
 
 class Extractor:
-    def __init__(self, fname, double_array=False):
+    def __init__(self, fname, double_array=False, foma=False):
         self.fname = fname
         self.double_array = double_array  # resolve .datok models (datok_test.go) instead of skipping them
+        # foma: a model built by LoadFomaFile(x).ToMatrix() / .ToDoubleArray() resolves to the foma file itself
+        # (the compile path: the harness compiles testdata/<x>.fst instead of loading a shipped model)
+        self.foma = foma
         self.cases = []
         self.skipped = []
 
@@ -283,10 +291,16 @@ class Extractor:
             if "ToMatrix" in s and st[0].kind == "id" and st[1].val in (":=", "="):
                 srcv = st[2].val
                 m = models.get(srcv)
+                if self.foma and isinstance(m, tuple):
+                    models[st[0].val] = os.path.basename(m[1])
+                    continue
                 models[st[0].val] = FOMA_EQUIV.get(m[1]) if isinstance(m, tuple) else None
                 continue
             if "ToDoubleArray" in s and st[0].kind == "id" and st[1].val in (":=", "="):
                 m = models.get(st[2].val)
+                if self.foma and isinstance(m, tuple):
+                    models[st[0].val] = os.path.basename(m[1])
+                    continue
                 models[st[0].val] = FOMA_EQUIV_DA.get(m[1]) if isinstance(m, tuple) and self.double_array else None
                 continue
             k, args = find_call(st, "LoadDatokFile")
@@ -482,6 +496,25 @@ def main():
     print(f"{len(da)} double-array cases, {ncheck_da} checks -> {OUT_DA}")
     for s in ex.skipped:
         print("skipped (double array):", s)
+    # ---- the compile path (fomafile.go:56-450 + matrix.go:30-99): the cases of matrix_test.go that build their
+    # model with LoadFomaFile(x).ToMatrix(), and those of datok_test.go that build it with .ToDoubleArray() from
+    # the same kind of file and hold no EOT (the two walks only differ at an EOT, datok.go:1019-1030): both pin
+    # ParseFoma, the first also ToMatrix.
+    fo = []
+    fskip = []
+    for f, da in (("matrix_test.go", False), ("datok_test.go", True)):
+        ex = Extractor(f, double_array=da, foma=True)
+        for c in ex.run():
+            if not c["checks"] or not str(c.get("model", "")).endswith(".fst") or c["model"] not in FOMA_FIXTURES:
+                continue
+            if da and b"\x04" in bytes.fromhex(c["input_hex"]):
+                fskip.append(c["src"] + " (double-array case with an EOT)")
+                continue
+            c["via"] = "ToDoubleArray" if da else "ToMatrix"
+            fo.append(c)
+    json.dump({"reference": "KorAP/Datok 0.3.1", "generator": "tests/golden/make_golden.py",
+               "cases": fo, "skipped": fskip}, open(OUT_FOMA, "w"), indent=0, ensure_ascii=True)
+    print(f"{len(fo)} compile-path cases, {sum(len(c['checks']) for c in fo)} checks -> {OUT_FOMA}")
 
 
 if __name__ == "__main__":

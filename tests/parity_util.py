@@ -33,7 +33,8 @@ class _Res(C.Structure):
                 ("rounds", C.c_uint32), ("n_rewalks", C.c_uint32), ("n_stitch_mismatch", C.c_uint32),
                 ("tok_delta", C.POINTER(C.c_uint16)), ("tok_delta8", C.POINTER(C.c_uint8)),
                 ("esc", C.POINTER(C.c_uint32)), ("n_esc", C.c_uint32),
-                ("eot_rewind", C.c_uint32), ("text", C.POINTER(C.c_uint8)), ("text_len", C.c_uint64)]
+                ("eot_rewind", C.c_uint32), ("text", C.POINTER(C.c_uint8)), ("text_len", C.c_uint64),
+                ("delta_range", C.c_uint32)]
 
 
 _lib = None
@@ -108,8 +109,11 @@ class EmulModel:
             s.carry_state = r.carry_state
             s.has_invalid = r.has_invalid
             # (a double-array model has no delta-coded forms: its cursors do not restart at a text)
-            s.tok_delta = _arr(r.tok_delta, 4 * r.n_tokens, np.uint16) if r.eot_rewind else None
-            s.tok_delta8 = _arr(r.tok_delta8, 4 * r.n_tokens, np.uint8) if r.eot_rewind else None
+            # (... and a delta that does not fit 16 bits -- DATOK_ERR_COMPACT_RANGE for a DATOK_COMPACT call -- leaves none)
+            have_delta = r.eot_rewind and not r.delta_range
+            s.delta_range = bool(r.delta_range)
+            s.tok_delta = _arr(r.tok_delta, 4 * r.n_tokens, np.uint16) if have_delta else None
+            s.tok_delta8 = _arr(r.tok_delta8, 4 * r.n_tokens, np.uint8) if have_delta else None
             s.tok_esc = _arr(r.esc, 2 * r.n_esc, np.uint32)
             s.text = bytes(C.string_at(r.text, r.text_len)) if r.text else None  # the device formatter's bodies
         lib().emul_result_free(rp)

@@ -691,3 +691,70 @@ def test_concurrent_calls_on_one_model(gpu_models, oracle_models):
     for t in th:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("name", ["simpletok.fst", "bauamt.fst", "wahlamt.fst", "ignorable_mcs.fst", "clitic_test.fst",
+                                  "tokenizer_de.fst"])
+def test_foma_compiled_models(name, testdata, tmp_path):
+    """The compile path on the device: LoadFomaFile(x).ToMatrix() (fomafile.go:56-450, matrix.go:30-99) gives a model
+    that transduces bit-exactly like the oracle's compile of the same file -- the cases matrix_test.go / datok_test.go
+    run on foma-built models (bauamt / wahlamt have no identity symbol: every rune outside sigma is a hard failure),
+    the odd inputs, random strings -- and Save / WriteTo (matrix.go:107-210) reproduce the shipped .matok files."""
+    import gzip
+    import json
+    import datok_b200 as d
+    from datok_b200 import corpus
+    from oracle import pyoracle
+    path = os.path.join(testdata, name)
+    auto = d.LoadFomaFile(path)
+    assert auto is not None
+    tok = auto.ToMatrix()
+    assert tok is not None and tok.Type() == "MATOK"
+    om = pyoracle.OracleModel(path)
+    assert (tok.state_count, tok.sigma_count, tok.epsilon) == (om.state_count, om.sigma_count, om.epsilon)
+    # WriteTo == the oracle's image; for the models the reference ships, == the shipped file
+    w = io.BytesIO()
+    n = tok.WriteTo(w)
+    assert n == len(w.getvalue()) and w.getvalue() == om.write_matrix()
+    shipped = os.path.join(testdata, name[:-4] + ".matok")
+    if os.path.exists(shipped):
+        saved = tmp_path / "saved.matok"
+        nbytes, err = tok.Save(saved)
+        assert err is None and nbytes == n
+        assert gzip.open(saved).read() == gzip.open(shipped).read()
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_foma.json")))["cases"]
+    for c in cases:
+        if c["model"] != name:
+            continue
+        data = bytes.fromhex(c["input_hex"])
+        out = io.BytesIO()
+        assert tok.TransduceTokenWriter(io.BytesIO(data), d.NewTokenWriter(out, c["flags"] & 0xFF))
+        check_output(c, out.getvalue())
+        assert out.getvalue() == om.transduce(data, c["flags"]).text
+    rng = random.Random(len(name))
+    alphabet = ["a", "b", "m", "t", "u", "i", "d", "w", "h", "l", " ", "\n", "\t", ".", "!", "?", "<", ">", "'", "ä", "中",
+                "bau", "bauamt", "wahl", "wahlamt", "<ab>", "\x04", "He's", "don't "]
+    inputs = list(ODD) + ["".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 4000))).encode() for _ in range(40)]
+    if name == "tokenizer_de.fst":
+        inputs = inputs[:60] + [corpus.generate(corpus.GERMAN, 2 << 20, seed=11).tobytes()]
+    for data in inputs:
+        for flags in (15, 31, 3):
+            o = om.transduce(data, flags)
+            if o.status == 8:   # the reference indexes outside its matrix (identity without unknown symbol): no parity domain
+                continue
+            s = gpu_arrays(tok, data, flags)
+            P.assert_matches_oracle(s, o, flags, f"{name} {data[:30]!r} flags={flags}")
+            if o.status == 0 and not getattr(s, "has_invalid_utf8", 0):
+                rf = tok.transduce_arrays(data, flags | d.FORMAT)
+                assert rf.text.tobytes() == o.text
+    tok.close()
+    # `datok convert`: host only, the file it writes loads like any shipped model
+    if os.path.exists(shipped):
+        conv = tmp_path / "conv.matok"
+        d.convert(path, conv)
+        t2 = d.LoadTokenizerFile(conv)
+        assert t2 is not None
+        for data in (b"bau", b"wald gehen", "Der alte Mann. Er geht.".encode()):
+            o = om.transduce(data, 15)
+            P.assert_matches_oracle(gpu_arrays(t2, data, 15), o, 15, f"{name} converted")
+        t2.close()
