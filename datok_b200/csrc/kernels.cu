@@ -102,8 +102,15 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
     for (uint32_t k = blockIdx.x * THREADS + threadIdx.x; k < n; k += gridDim.x * THREADS)
       chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);
   } else {
-    for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < b.n_chunks; i += gridDim.x * THREADS)
-      chunk_spec_fast(lm, b, FT, i, start_state, my_cls, nullptr, my_stage);
+    for (;;) {
+      uint32_t base = 0;
+      if ((threadIdx.x & 31u) == 0) base = atomicAdd(&b.counters[6], 32u);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (base >= b.n_chunks) break;
+      const uint32_t i = base + (threadIdx.x & 31u);
+      if (i < b.n_chunks) chunk_spec_fast(lm, b, FT, i, start_state, my_cls, nullptr, my_stage);
+      __syncwarp();
+    }
   }
 }
 
