@@ -203,7 +203,7 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   FX.in = b.in; FX.N = N; FX.cls = &m.cls;
 #if defined(DATOK_STAGE_ASYNC)
   SegStage stage;
-  stage.slot_saddr = stage_saddr; stage.staged_for = K_NOPOS;
+  stage_init(stage, stage_saddr);
 #else
   (void)stage_saddr;
 #endif
@@ -448,7 +448,10 @@ DATOK_HD void chunk_spec_fast(const DeviceModel& m, const WalkBuffers& b, const 
   }
 
 #if defined(__CUDA_ARCH__) && defined(DATOK_STAGE_ASYNC)
-  if (stage.staged_for != K_NOPOS) asm volatile("cp.async.wait_all;" ::: "memory");  // (the slot is reused by the lane's next chunk)
+  if (stage.staged_for != K_NOPOS) stage_wait(stage);  // (the slot is reused by the lane's next chunk)
+#if defined(DATOK_STAGE_TMA)
+  if (stage.slot_saddr) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(stage.slot_saddr + 32u) : "memory");
+#endif
 #endif
   SpecInfo si;
   si.first_hw = L.first_hw; si.had_rewind = L.first_window ? 0u : 1u;

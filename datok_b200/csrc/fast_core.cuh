@@ -324,6 +324,8 @@ DATOK_HD uint32_t er_from_entry(const FastTables& T, uint32_t t, uint32_t cl2) {
   const uint32_t e = h16_load(T, t, cl2);
   return ER_VALID | t | (bits_to_k((e >> 13) & 3u) << 16);
 }
+// offset of the position whose bit is `bit` (0: the bit has been shifted out behind position 31)
+DATOK_HD uint32_t off_of_bit(uint32_t bit) { return bit ? 31u - clz32(bit) : 32u; }
 DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCtx& X, const uint8_t* seg_cls,
                       uint32_t seg_start, uint32_t limit, uint32_t eotm, const SegBits& Bprev) {
   if (L.pos >= limit) return FAST_OK;
@@ -340,8 +342,16 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
   uint32_t eps_a = 0;            // device: address of the recording entry; host: 1 + (row * 65536 + doubled class)
   uint32_t c1 = R.c1, c2 = R.c2, nt = R.nt;
 #if defined(__CUDA_ARCH__)
-  const uint32_t cls_saddr = (uint32_t)__cvta_generic_to_shared(seg_cls);
-  uint32_t p = cls_saddr + off;   // address of the class byte of the current position
+  // On the device the position is carried as (p, bit) only: p = shared-window address of the position's class byte.
+  // The offset is recovered from `bit` where the rare paths need it -- the address of the lane's class buffer would
+  // have to be re-derived from the thread index each time (the hot loop leaves no register for it).
+  uint32_t p = (uint32_t)__cvta_generic_to_shared(seg_cls) + off;
+#define DATOK_CUR_OFF() (31u - clz32(bit))  /* inside the loop the bit is never shifted out */
+#define DATOK_END_OFF() off_of_bit(bit)
+#define DATOK_CUR_CLS(dst) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(dst) : "r"(p))
+#define DATOK_MOVE_TO(new_off) do { const uint32_t no_ = (new_off); p += no_ - DATOK_CUR_OFF(); bit = 1u << no_; } while (0)
+#define DATOK_MOVE_TO_BIT(nb) do { const uint32_t nb_ = (nb); p += (31u - clz32(nb_)) - DATOK_CUR_OFF(); bit = nb_; } while (0)
+#define DATOK_STEP() do { p++; bit += bit; } while (0)
   // hc: shared-window address of the row's column for the byte at p, i.e. T.hot_saddr + its doubled class.  The class
   // byte of the NEXT position is fetched while the current lookup is in flight (it does not depend on the state), so
   // the per-byte dependency chain is one multiply-add, the row lookup and one AND -- not two loads back to back.
@@ -358,6 +368,12 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
 #define DATOK_EPS_REC() (eps_a ? er_from_entry(T, DATOK_ROW_OF(eps_a), (eps_a - T.hot_saddr) - DATOK_ROW_OF(eps_a) * T.row16) : eps_rec)
 #else
 #define DATOK_EPS_REC() (eps_a ? er_from_entry(T, (eps_a - 1u) >> 16, (eps_a - 1u) & 0xFFFFu) : eps_rec)
+#define DATOK_CUR_OFF() off
+#define DATOK_END_OFF() off
+#define DATOK_CUR_CLS(dst) ((dst) = seg_cls[off])
+#define DATOK_MOVE_TO(new_off) do { off = (new_off); bit = 1u << off; } while (0)
+#define DATOK_MOVE_TO_BIT(nb) do { bit = (nb); off = ctz32(bit); } while (0)
+#define DATOK_STEP() do { off++; bit += bit; } while (0)
 #endif
   // row of the lookup: the state's own, or the all-zero row n_hot ("see the full table") for a cold state,
   // which the loop top only sees on entry: the rare path below steps until the state is hot again
@@ -389,9 +405,6 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
     if (DATOK_UNLIKELY((e & F16_TGT) == 0)) {
       // ---- rare: a failure (F16_FAIL), or not in the compact rows (0): cold state, rare class, target
       // outside the hot rows, marked entry.  Steps through the full table until the state is hot again ----
-#if defined(__CUDA_ARCH__)
-      off = p - cls_saddr;
-#endif
       bool failed = e == F16_FAIL;
       {  // the state of this lookup, from the entry's address (tl itself is not kept across the lookup: one move less per byte)
 #if defined(__CUDA_ARCH__)
@@ -417,17 +430,16 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
           const uint32_t below = qb - 1u, keep = below | qb;
           const uint32_t tgt = h16_load(T, es, 2u * K_CLS_EPS);
           const uint32_t cb = R.cb;
-          const uint32_t dead = ((c1 | cb) & ~keep) | (eotm & ~below & mask_below(off)) | ((c1 | c2 | cb | nt) & qb);
+          const uint32_t dead = ((c1 | cb) & ~keep) | (eotm & ~below & (bit - 1u)) | ((c1 | c2 | cb | nt) & qb);
           if (tgt != 0 && dead == 0) {
             DATOK_STAT(g_bt_ok); DATOK_STAT(g_bt_inline);
-            const uint32_t pos = seg_start + off;
+            const uint32_t pos = seg_start + DATOK_CUR_OFF();
             if (L.hw_med < pos) L.hw_med = pos;
             c1 &= below; c2 &= below; nt &= below;
             R.cb = (cb & below) | qb;
-            off = ctz32(qb); bit = qb;
+            DATOK_MOVE_TO_BIT(qb);
             tl = tgt; eps_rec = 0; eps_a = 0; eps_bit = 0;  // (tgt is a hot state: the compact row says so)
 #if defined(__CUDA_ARCH__)
-            p = cls_saddr + off;
             DATOK_LOAD_HC();
 #endif
             continue;
@@ -438,18 +450,19 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
         uint32_t e3 = 0;
         if (!failed) {
           DATOK_STAT(g_cold);
-          uint32_t cl2 = seg_cls[off];
-          if (cl2 == T.stop_cl2) cl2 = 2u * class_at(X.in, X.N, seg_start + off, *X.cls);  // a rare class: from the raw bytes
+          uint32_t cl2;
+          DATOK_CUR_CLS(cl2);
+          if (cl2 == T.stop_cl2) cl2 = 2u * class_at(X.in, X.N, seg_start + DATOK_CUR_OFF(), *X.cls);  // a rare class: from the raw bytes
           e3 = t3_load(T, t, cl2 >> 1);
         }
         if ((e3 & F3_TGT) == 0) {  // 0: failure without epsilon transition; marked: leave to walk_run
-          L.pos = seg_start + off; L.t = t;
+          L.pos = seg_start + DATOK_CUR_OFF(); L.t = t;
           if (eps_bit) L.eps_p = seg_start + ctz32(eps_bit);
           L.eps_rec = DATOK_EPS_REC();
           R.c1 = c1; R.c2 = c2; R.nt = nt;
           if (e3 != 0) { DATOK_STAT(g_mark); return FAST_SLOW; }
           if (fast_backtrack(L, R, T, seg_start, eotm, Bprev) != FAST_OK) return FAST_SLOW_FAIL;
-          off = L.pos - seg_start; bit = 1u << off;
+          DATOK_MOVE_TO(L.pos - seg_start);
           t = L.t; eps_rec = 0; eps_a = 0; eps_bit = 0;
           c1 = R.c1; c2 = R.c2; nt = R.nt;
           failed = false;
@@ -463,15 +476,13 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
           if (e3 & F3_NT) nt |= bit;
           if (e3 & F3_EA) { eps_bit = bit; eps_a = 0; eps_rec = ER_VALID | t | (e3 & F3_KANY); }
           t = e3 & F3_TGT;
-          off++;
-          bit += bit;
+          DATOK_STEP();
         }
         if (t < T.n_hot || bit == end_bit) break;
       }
       tl = t < T.n_hot ? t : T.n_hot;
       t_cold = t;
 #if defined(__CUDA_ARCH__)
-      p = cls_saddr + off;
       DATOK_LOAD_HC();
 #endif
       continue;
@@ -508,33 +519,77 @@ DATOK_HD int fast_run(FastLane& L, RawBits& R, const FastTables& T, const FastCt
     tl = e & F16_TGT;
     bit += bit;
   } while (bit != end_bit);
-#if defined(__CUDA_ARCH__)
-  off = p - cls_saddr;
-#endif
   t = tl == T.n_hot ? t_cold : tl;
-  L.pos = seg_start + off; L.t = t;
+  L.pos = seg_start + DATOK_END_OFF(); L.t = t;
   if (eps_bit) L.eps_p = seg_start + ctz32(eps_bit);
   L.eps_rec = DATOK_EPS_REC();
 #undef DATOK_EPS_REC
 #undef DATOK_ROW_OF
 #undef DATOK_LOAD_HC
+#undef DATOK_CUR_OFF
+#undef DATOK_END_OFF
+#undef DATOK_CUR_CLS
+#undef DATOK_MOVE_TO
+#undef DATOK_MOVE_TO_BIT
+#undef DATOK_STEP
   R.c1 = c1; R.c2 = c2; R.nt = nt;
   return FAST_OK;
 }
 
-// Asynchronous staging of a lane's next segment (device only): the 32 raw bytes go from global memory
-// into the lane's slot in shared memory through the async copy unit (cp.async, 2 x 16 bytes, no registers
-// held, L1 bypassed) while the lane walks the current segment; the next classification finds them there.
+// Asynchronous staging of a lane's next segment (device only, build options): the 32 raw bytes go from global
+// memory into the lane's slot in shared memory while the lane walks the current segment; the next classification
+// finds them there.
+//   DATOK_STAGE_ASYNC  through the async copy unit: cp.async (LDGSTS), 2 x 16 bytes, L1 bypassed
+//   DATOK_STAGE_TMA    through the TMA engine: one cp.async.bulk (UBLKCP) of 32 bytes per lane and segment, completion
+//                      on the lane's own mbarrier (transaction bytes), waited for with try_wait.parity
+// Both are measured slower than plain loads + an L1 prefetch (profiles/r2_stage_ab.txt): the slots displace resident
+// table rows, and the latency they hide is already hidden by the 32 warps of the CTA.
 struct SegStage {
-  uint32_t slot_saddr;   // shared-window address of the lane's 32-byte slot (0: no staging, e.g. on the host)
+  uint32_t slot_saddr;   // shared-window address of the lane's 32-byte slot (0: no staging, e.g. on the host);
+                         // DATOK_STAGE_TMA: the lane's mbarrier sits 32 bytes behind it
   uint32_t staged_for;   // position of the segment the slot holds or is being filled with (K_NOPOS: none)
+  uint32_t parity;       // DATOK_STAGE_TMA: phase of the mbarrier that the next wait completes
 };
+DATOK_HD void stage_init(SegStage& S, uint32_t slot_saddr) {
+  S.slot_saddr = slot_saddr; S.staged_for = K_NOPOS; S.parity = 0;
+#if defined(__CUDA_ARCH__) && defined(DATOK_STAGE_TMA)
+  if (slot_saddr) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(slot_saddr + 32u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
+}
+DATOK_HD void stage_wait(SegStage& S) {  // the copy in flight (if any) has landed
+#if defined(__CUDA_ARCH__)
+#if defined(DATOK_STAGE_TMA)
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(S.slot_saddr + 32u), "r"(S.parity) : "memory");
+  }
+  S.parity ^= 1u;
+#else
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+#endif
+  S.staged_for = K_NOPOS;
+}
 DATOK_HD void stage_segment(SegStage& S, const uint8_t* in, uint32_t N, uint32_t seg_start) {
 #if defined(__CUDA_ARCH__)
   const uint8_t* p = in + seg_start;
   if (S.slot_saddr && seg_start + SEG <= N && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+#if defined(DATOK_STAGE_TMA)
+    // (the slot was last read with ordinary loads: order them before the async-proxy write)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 32;" :: "r"(S.slot_saddr + 32u) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 32, [%2];"
+                 :: "r"(S.slot_saddr), "l"(p), "r"(S.slot_saddr + 32u) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.cg.shared.global [%0 + 16], [%1 + 16], 16;"
                  :: "r"(S.slot_saddr), "l"(p) : "memory");
+#endif
     S.staged_for = seg_start;
   }
 #else
@@ -547,16 +602,12 @@ DATOK_HD void load_segment_words(const uint8_t* in, uint32_t N, uint32_t seg_sta
   const uint8_t* p = in + seg_start;
 #if defined(__CUDA_ARCH__)
   if (S && S->staged_for == seg_start) {  // staged while the previous segment was walked
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(words[0]), "=r"(words[1]), "=r"(words[2]), "=r"(words[3]) : "r"(S->slot_saddr));
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4 + 16];" : "=r"(words[4]), "=r"(words[5]), "=r"(words[6]), "=r"(words[7]) : "r"(S->slot_saddr));
-    S->staged_for = K_NOPOS;
+    stage_wait(*S);
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(words[0]), "=r"(words[1]), "=r"(words[2]), "=r"(words[3]) : "r"(S->slot_saddr) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4 + 16];" : "=r"(words[4]), "=r"(words[5]), "=r"(words[6]), "=r"(words[7]) : "r"(S->slot_saddr) : "memory");
     return;
   }
-  if (S && S->staged_for != K_NOPOS) {  // a copy for another segment is in flight (the lane went elsewhere): let it land
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    S->staged_for = K_NOPOS;
-  }
+  if (S && S->staged_for != K_NOPOS) stage_wait(*S);  // a copy for another segment is in flight (the lane went elsewhere): let it land
 #else
   (void)S;
 #endif

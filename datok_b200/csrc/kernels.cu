@@ -25,7 +25,12 @@ constexpr int LANE_CLS_STRIDE = 36;  // bytes of class scratch per lane (9 words
 // Measured (profiles/r2_stage_ab.txt, 1 GiB German): walk 3.88 ms without, 4.51 ms with -- the 32 KB of slots
 // cost ~200 resident table rows and the slot bookkeeping two registers in a kernel that is at its register limit,
 // which outweighs the input latency it hides (the L1 prefetch of the next sector already hides most of it).
-#if defined(DATOK_STAGE_ASYNC)
+#if defined(DATOK_STAGE_TMA)
+#if !defined(DATOK_STAGE_ASYNC)
+#error "DATOK_STAGE_TMA is a flavour of DATOK_STAGE_ASYNC: define both"
+#endif
+constexpr int LANE_STAGE_BYTES = 48;  // slot + the lane's mbarrier (16-byte aligned slots)
+#elif defined(DATOK_STAGE_ASYNC)
 constexpr int LANE_STAGE_BYTES = 32;
 #else
 constexpr int LANE_STAGE_BYTES = 0;
