@@ -392,8 +392,11 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& 
   return prefix;
 }
 
-// Ordered block reduction; the result is valid in thread 0.  warp_out (optional): the block's
-// THREADS / 32 warp totals.
+// Ordered block reduction; the result is valid in thread THREADS / 32 - 1.  warp_out (optional): for each of the block's
+// THREADS / 32 warps the summary of the warps BEFORE it in the block (what the texts and emit passes seed their
+// warp scans with: one combine instead of a loop over the warps before), with WAGG_HAS_TEXT set in `kinds` when
+// the warp's own words hold a TextEnd (the texts pass only visits those).
+constexpr uint32_t WAGG_HAS_TEXT = 1u << 31;
 template <int THREADS>
 __device__ __forceinline__ Agg block_reduce(const Agg& mine, Agg* warp_out) {
   __shared__ Agg s_warp[THREADS / 32];
@@ -404,15 +407,33 @@ __device__ __forceinline__ Agg block_reduce(const Agg& mine, Agg* warp_out) {
     Agg o = agg_shfl_down(v, d);
     if ((lane & (2 * d - 1)) == 0) v = agg_combine(v, o);  // lanes lane..lane+2d-1, in order
   }
-  if (lane == 0) {
-    s_warp[warp] = v;
-    if (warp_out) warp_out[warp] = v;
-  }
+  if (lane == 0) s_warp[warp] = v;
   __syncthreads();
-  Agg tot = s_warp[0];
-  if (threadIdx.x == 0)
-    for (int wi = 1; wi < THREADS / 32; wi++) tot = agg_combine(tot, s_warp[wi]);
+  Agg tot = agg_zero();
+  if (warp == 0) {  // ordered scan of the warp totals by the first warp: lane j ends up with the warps before warp j
+    constexpr int WARPS = THREADS / 32;
+    const Agg own = lane < WARPS ? s_warp[lane] : agg_zero();
+    Agg incl = own;
+#pragma unroll
+    for (int d = 1; d < WARPS; d <<= 1) {
+      Agg o = agg_shfl_up(incl, d);
+      if (lane >= d) incl = agg_combine(o, incl);
+    }
+    Agg ex = agg_shfl_up(incl, 1);
+    if (lane == 0) ex = agg_zero();
+    tot = incl;  // (lane WARPS - 1: the block)
+    if (warp_out && lane < WARPS) {
+      if (own.n_text) ex.kinds |= WAGG_HAS_TEXT;
+      warp_out[lane] = ex;
+    }
+  }
   return tot;
+}
+// the summary of the warps before warp `unit % WARPS` in its block, as left by the reduce pass
+__device__ __forceinline__ Agg load_warp_prefix(const Agg* warp_agg, size_t unit) {
+  Agg a = warp_agg[unit];
+  a.kinds &= ~WAGG_HAS_TEXT;
+  return a;
 }
 
 // Ordered exclusive scan within one warp, combined after `seed`.
@@ -431,7 +452,7 @@ __device__ __forceinline__ Agg warp_exclusive_scan(const Agg& mine, const Agg& s
 enum { K3_REDUCE = 0, K3_TEXTS = 1, K3_EMIT = 2 };
 
 // K3a: a CTA takes one block of THREADS * WPT words after the other (grid-stride) and leaves its summary in
-// block_agg[block] (and the warp totals in warp_agg) -- the same units the texts and emit passes use.
+// block_agg[block] (and the warp prefixes in warp_agg) -- the same units the texts and emit passes use.
 __global__ void __launch_bounds__(COMPACT_THREADS) compact_reduce_kernel(CompactCtx c, CompactBuffers cb) {
   for (uint32_t vb = blockIdx.x; vb < cb.n_blocks; vb += gridDim.x) {
     const uint32_t w0 = (vb * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
@@ -442,7 +463,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_reduce_kernel(Compact
       if (w < c.n_words) ta = agg_combine(ta, word_agg(w, word_load(c, w)));
     }
     const Agg tot = block_reduce<COMPACT_THREADS>(ta, cb.warp_agg + (size_t)vb * (COMPACT_THREADS / 32));
-    if (threadIdx.x == 0) cb.block_agg[vb] = tot;
+    if (threadIdx.x == COMPACT_THREADS / 32 - 1) cb.block_agg[vb] = tot;
     __syncthreads();  // block_reduce's shared slots are reused by the next block
   }
 }
@@ -457,40 +478,42 @@ template <int MODE>
 __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, CompactBuffers cb) {
   extern __shared__ __align__(16) uint32_t s_stage[];
   if (MODE == K3_TEXTS) {
-    // TextEnds are rare (one per text).  A warp takes one warp unit of the reduce pass after
-    // the other (32 * COMPACT_WPT words, whose prefix that pass left behind) and moves on at once when
-    // the unit's TEND words hold none -- the pass is one read of that bitmap.
+    // TextEnds are rare (one per text).  The reduce pass has marked the warp units (32 * COMPACT_WPT words) that
+    // hold one: a warp reads 32 marks at a time and visits the marked units only, each with the whole warp.
     if (blockIdx.x == 0 && threadIdx.x == 0) c.docs[0] = doc_stream_start(c);
     constexpr uint32_t UNIT = 32 * COMPACT_WPT, WARPS = COMPACT_THREADS / 32;
-    const uint32_t n_units = (c.n_words + UNIT - 1) / UNIT, lane = threadIdx.x & 31;
-    for (uint32_t u = blockIdx.x * WARPS + (threadIdx.x >> 5); u < n_units; u += gridDim.x * WARPS) {
-      const uint32_t wt0 = u * UNIT + lane * COMPACT_WPT;
-      uint32_t anyt = 0;
+    const uint32_t n_units = cb.n_blocks * WARPS, lane = threadIdx.x & 31;
+    const uint32_t n_groups = (n_units + 31) / 32;
+    for (uint32_t g = blockIdx.x * WARPS + (threadIdx.x >> 5); g < n_groups; g += gridDim.x * WARPS) {
+      const uint32_t mu = g * 32 + lane;
+      uint32_t marks = __ballot_sync(0xFFFFFFFFu, mu < n_units && (cb.warp_agg[mu].kinds & WAGG_HAS_TEXT) != 0);
+      while (marks) {
+        const uint32_t u = g * 32 + (uint32_t)__ffs((int)marks) - 1u;
+        marks &= marks - 1;
+        const uint32_t wt0 = u * UNIT + lane * COMPACT_WPT;
+        WordBits tb[COMPACT_WPT];
 #pragma unroll
-      for (int k = 0; k < COMPACT_WPT; k++)
-        if (wt0 + k < c.n_words) anyt |= c.b_tend[wt0 + k];
-      if (!__any_sync(0xFFFFFFFFu, anyt != 0)) continue;
-      const uint32_t blk = u / WARPS, warp = u % WARPS;  // the reduce pass's block and warp of this unit
-      Agg seed = agg_combine(cb.super_carry[blk / SCAN_THREADS], cb.block_carry[blk]);
-      const Agg* wagg = cb.warp_agg + (size_t)blk * WARPS;
-      for (uint32_t wi = 0; wi < warp; wi++) seed = agg_combine(seed, wagg[wi]);
-      WordBits tb[COMPACT_WPT];
-      Agg tw[COMPACT_WPT];
-      Agg mine = agg_zero();
+        for (int k = 0; k < COMPACT_WPT; k++)
+          if (wt0 + k < c.n_words) tb[k] = word_load(c, wt0 + k);
+        const uint32_t blk = u / WARPS;  // the reduce pass's block of this unit
+        const Agg seed = agg_combine(agg_combine(cb.super_carry[blk / SCAN_THREADS], cb.block_carry[blk]),
+                                     load_warp_prefix(cb.warp_agg, u));
+        Agg tw[COMPACT_WPT];
+        Agg mine = agg_zero();
 #pragma unroll
-      for (int k = 0; k < COMPACT_WPT; k++) {
-        if (wt0 + k < c.n_words) {
-          tb[k] = word_load(c, wt0 + k);
-          tw[k] = word_agg(wt0 + k, tb[k]);
-          mine = agg_combine(mine, tw[k]);
+        for (int k = 0; k < COMPACT_WPT; k++) {
+          if (wt0 + k < c.n_words) {
+            tw[k] = word_agg(wt0 + k, tb[k]);
+            mine = agg_combine(mine, tw[k]);
+          }
         }
-      }
-      Agg run = warp_exclusive_scan(mine, seed);
+        Agg run = warp_exclusive_scan(mine, seed);
 #pragma unroll
-      for (int k = 0; k < COMPACT_WPT; k++) {
-        if (wt0 + k < c.n_words) {
-          emit_texts(c, wt0 + k, tb[k], run);
-          run = agg_combine(run, tw[k]);
+        for (int k = 0; k < COMPACT_WPT; k++) {
+          if (wt0 + k < c.n_words) {
+            emit_texts(c, wt0 + k, tb[k], run);
+            run = agg_combine(run, tw[k]);
+          }
         }
       }
     }
@@ -512,12 +535,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   // summary of everything before this block: (groups of 1024 blocks before) + (blocks before, in the group)
   const Agg block_start = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
   // prefix of this thread: warps before it in the block (totals left by the reduce pass), lanes before it
-  Agg seed = block_start;
-  {
-    const Agg* wagg = cb.warp_agg + (size_t)blockIdx.x * (COMPACT_THREADS / 32);
-    const int warp = threadIdx.x >> 5;
-    for (int wi = 0; wi < warp; wi++) seed = agg_combine(seed, wagg[wi]);
-  }
+  const Agg seed = agg_combine(block_start, load_warp_prefix(cb.warp_agg, (size_t)blockIdx.x * (COMPACT_THREADS / 32) + (threadIdx.x >> 5)));
   Agg carry = warp_exclusive_scan(ta, seed);
   // K3_EMIT
   const uint32_t blk_tok0 = block_start.n_tok, blk_ntok = cb.block_agg[blockIdx.x].n_tok;
@@ -618,8 +636,13 @@ void launch_compact_scan(const CompactBuffers& cb, bool sentence_end_in, cudaStr
   compact_scan_top_kernel<<<1, SCAN_THREADS, 0, s>>>(cb, sentence_end_in);
 }
 void launch_compact_texts(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
-  // (any grid works: the warps stride over the units; a persistent grid of 8 CTAs per SM measured the same)
-  compact_kernel<K3_TEXTS><<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
+  // (any grid works: the warps stride over groups of 32 warp units)
+  constexpr uint32_t WARPS = COMPACT_THREADS / 32;
+  const uint32_t n_groups = (cb.n_blocks * WARPS + 31) / 32;
+  uint32_t blocks = (n_groups + WARPS - 1) / WARPS;
+  if (blocks > 148u * 8u) blocks = 148u * 8u;
+  if (blocks == 0) blocks = 1;  // (docs[0] is written by block 0)
+  compact_kernel<K3_TEXTS><<<blocks, COMPACT_THREADS, 0, s>>>(c, cb);
 }
 int launch_compact_emit(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
   const int smem_max = 4 * STAGE_TOKENS * (int)sizeof(uint32_t);

@@ -11,7 +11,7 @@ namespace datok {
 struct CompactBuffers {
   Agg* block_agg;
   Agg* block_carry;
-  Agg* warp_agg;           // COMPACT_THREADS / 32 warp totals per block (for the texts pass)
+  Agg* warp_agg;           // per block and warp: summary of the warps before it in the block (+ WAGG_HAS_TEXT mark)
   Agg* super_agg;          // one per group of SCAN_THREADS blocks
   Agg* super_carry;
   Agg* total;              // [0] stream summary after the scan, [1] StreamTotals after finalize
