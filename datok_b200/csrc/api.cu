@@ -945,6 +945,7 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
     }
     // ---- results out, behind the kernels of the following pieces ----
     CUDA_TRYF(cudaStreamWaitEvent(m->s_d2h, m->ev_emit[slot], 0));
+    if (trace) cudaEventRecord(tev[6 * k + 4], m->s_d2h);
     if (fmt && piece_text)
       CUDA_TRYF(cudaMemcpyAsync((uint8_t*)host[8].p + text_bytes, m->d_out[slot][6].p, (size_t)piece_text, cudaMemcpyDeviceToHost, m->s_d2h));
     text_bytes += piece_text;
@@ -959,7 +960,6 @@ int run_pipelined(datok_model* m, const uint8_t* in, size_t n, uint32_t flags, c
                        {6, dtx + 2 * nx, base_text * 4, (size_t)tail.fin.n_text * 4},
                        {7, dtx + 3 * nx, base_text * 4, (size_t)tail.fin.n_text * 4}};
     const bool want8[8] = {want_bytes && !fmt, want_pos && !fmt, want_spos && !fmt, want_stok && !fmt, true, true, true, true};
-    if (trace) cudaEventRecord(tev[6 * k + 4], m->s_d2h);
     for (const Cp& cp : cps)
       if (want8[cp.hi] && cp.bytes)
         CUDA_TRYF(cudaMemcpyAsync((uint8_t*)host[cp.hi].p + cp.off, cp.src, cp.bytes, cudaMemcpyDeviceToHost, m->s_d2h));

@@ -48,7 +48,12 @@ template <int THREADS, bool REWALK>
 __global__ void __launch_bounds__(THREADS, 1)
 walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n_hot) {
   extern __shared__ __align__(16) uint32_t smem[];
-  if (REWALK && blockIdx.x * THREADS >= b.counters[1]) return;  // the list length is only known on the device
+  // (the list length is only known on the device.  A short list -- the usual case: a fraction of a percent of the
+  // chunks -- is walked one chunk per WARP, lane 0 only: the kernel's time then is the latency of one chunk's walk,
+  // and a lane that walks alone neither waits for the slowest lane of its warp at every segment nor sits through
+  // the other lanes' rare paths.  A long list is walked one chunk per lane like the first walk.)
+  const bool sparse = REWALK && b.counters[1] <= gridDim.x * (THREADS / 32);
+  if (REWALK && blockIdx.x * (sparse ? THREADS / 32 : THREADS) >= b.counters[1]) return;
   // layout: lane scratch | byte -> class LUTs | compact rows.  The first two have compile-time offsets, so a
   // lane's scratch address is threadIdx.x * stride away from the window base wherever it is needed again.
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(smem);           // THREADS staging slots (16-byte aligned)
@@ -104,8 +109,13 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   const uint32_t my_stage = LANE_STAGE_BYTES ? (uint32_t)__cvta_generic_to_shared(s_stage + threadIdx.x * LANE_STAGE_BYTES) : 0u;
   if (REWALK) {
     const uint32_t n = b.counters[1];
-    for (uint32_t k = blockIdx.x * THREADS + threadIdx.x; k < n; k += gridDim.x * THREADS)
-      chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);
+    if (sparse) {
+      const uint32_t k = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+      if (k < n && (threadIdx.x & 31u) == 0) chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);
+    } else {
+      for (uint32_t k = blockIdx.x * THREADS + threadIdx.x; k < n; k += gridDim.x * THREADS)
+        chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);
+    }
   } else {
     for (;;) {
       uint32_t base = 0;
@@ -158,7 +168,7 @@ static int launch_walk_fused_t(const DeviceModel& m, const WalkBuffers& b, uint3
 }
 
 // K2c: the mismatched chunks, with the hot rows in shared memory like the first walk
-constexpr int REWALK_THREADS = 256;
+constexpr int REWALK_THREADS = 512;
 int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_rewalk_max, uint32_t n_hot, int n_sms,
                         cudaStream_t s) {
   if (!n_rewalk_max) return 0;
@@ -168,7 +178,8 @@ int launch_rewalk_fused(const DeviceModel& m, const WalkBuffers& b, uint32_t n_r
                                          (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  uint32_t blocks = (n_rewalk_max + REWALK_THREADS - 1) / REWALK_THREADS;
+  // (one CTA per SM whenever the list could need them: the device picks one chunk per warp if the list is short)
+  uint32_t blocks = (n_rewalk_max + REWALK_THREADS / 32 - 1) / (REWALK_THREADS / 32);
   if (blocks > (uint32_t)n_sms) blocks = (uint32_t)n_sms;
   walk_fused_kernel<REWALK_THREADS, true><<<blocks, REWALK_THREADS, smem, s>>>(m, b, 0, n_hot);
   return (int)cudaGetLastError();
