@@ -48,12 +48,18 @@ template <int THREADS, bool REWALK>
 __global__ void __launch_bounds__(THREADS, 1)
 walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n_hot) {
   extern __shared__ __align__(16) uint32_t smem[];
-  // (the list length is only known on the device.  A short list -- the usual case: a fraction of a percent of the
-  // chunks -- is walked one chunk per WARP, lane 0 only: the kernel's time then is the latency of one chunk's walk,
-  // and a lane that walks alone neither waits for the slowest lane of its warp at every segment nor sits through
-  // the other lanes' rare paths.  A long list is walked one chunk per lane like the first walk.)
-  const bool sparse = REWALK && b.counters[1] <= gridDim.x * (THREADS / 32);
-  if (REWALK && blockIdx.x * (sparse ? THREADS / 32 : THREADS) >= b.counters[1]) return;
+  // (the list length is only known on the device.  The list is spread over all warps of the grid, `per` chunks to
+  // a warp (lanes 0..per-1).  The usual list -- a fraction of a percent of the chunks -- gives one chunk per warp:
+  // the kernel's time then is the latency of one chunk's walk, and a lane that walks alone neither waits for the
+  // slowest lane of its warp at every segment nor sits through the other lanes' rare paths.  Lists too long for
+  // that are walked one chunk per lane like the first walk.)
+  uint32_t per = 0;
+  if (REWALK) {
+    const uint32_t n = b.counters[1], W = gridDim.x * (THREADS / 32);
+    per = (n + W - 1) / W;
+    if (per > 32) per = 0;  // dense
+    if (blockIdx.x * (per ? per * (THREADS / 32) : THREADS) >= n) return;
+  }
   // layout: lane scratch | byte -> class LUTs | compact rows.  The first two have compile-time offsets, so a
   // lane's scratch address is threadIdx.x * stride away from the window base wherever it is needed again.
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(smem);           // THREADS staging slots (16-byte aligned)
@@ -109,9 +115,9 @@ walk_fused_kernel(DeviceModel m, WalkBuffers b, uint32_t start_state, uint32_t n
   const uint32_t my_stage = LANE_STAGE_BYTES ? (uint32_t)__cvta_generic_to_shared(s_stage + threadIdx.x * LANE_STAGE_BYTES) : 0u;
   if (REWALK) {
     const uint32_t n = b.counters[1];
-    if (sparse) {
-      const uint32_t k = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-      if (k < n && (threadIdx.x & 31u) == 0) chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);
+    if (per) {
+      const uint32_t lane = threadIdx.x & 31u, k = (blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * per + lane;
+      if (lane < per && k < n) chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);
     } else {
       for (uint32_t k = blockIdx.x * THREADS + threadIdx.x; k < n; k += gridDim.x * THREADS)
         chunk_rewalk_fast(lm, b, FT, b.list_rewalk[k], my_cls, my_stage);

@@ -661,6 +661,34 @@ def test_text_without_sync_points(gpu_models, oracle_models):
     P.assert_matches_oracle(gpu_arrays(tok, data, 3), om.transduce(data, 3), 3, "minified json")
 
 
+def _markup_text(nbytes, seed):
+    """text whose whitespace mostly sits inside quoted attributes: the guess at a chunk's sync point (root state, nothing
+    pending) is wrong for most chunks, so the re-walk list is long"""
+    rnd = random.Random(seed)
+    words = "ein langer Titel mit vielen Worten hier und dort aber nicht immer so wie gedacht".split()
+    out, n = [], 0
+    while n < nbytes:
+        s = '<a href="x y" title="%s">%s</a> %s. ' % (" ".join(rnd.choice(words) for _ in range(rnd.randint(3, 14))),
+                                                     rnd.choice(words).capitalize(),
+                                                     " ".join(rnd.choice(words) for _ in range(rnd.randint(0, 6))))
+        out.append(s)
+        n += len(s)
+    return "".join(out)[:nbytes].encode()
+
+
+@pytest.mark.parametrize("nbytes,chunk", [(3000, "64"), (96 << 10, "64"), (2 << 20, "64"), (12 << 20, "64"), (2 << 20, "640")])
+def test_rewalk_list_shapes(nbytes, chunk, testdata, oracle_models, monkeypatch):
+    """the re-walk kernel spreads its list over the warps of the grid (one chunk per warp for a short list, k lanes per
+    warp for a longer one, one chunk per lane beyond that): lists of a few, thousands and >100 000 wrong guesses"""
+    import datok_b200 as d
+    data = _markup_text(nbytes, 11)
+    o = oracle_models["tokenizer_de.matok"].transduce(data, 15)
+    monkeypatch.setenv("DATOK_CHUNK", chunk)
+    tok = d.LoadTokenizerFile(os.path.join(testdata, "tokenizer_de.matok"))
+    P.assert_matches_oracle(tok.transduce_arrays(data, 15), o, 15, f"markup {nbytes} B, chunk {chunk}")
+    tok.close()
+
+
 def test_concurrent_calls_on_one_model(gpu_models, oracle_models):
     """the reference's model is immutable and shareable across goroutines (matrix.go:16-26): calls from several threads
     on one model run side by side, each on an execution context of its own, and give the single-call results"""
