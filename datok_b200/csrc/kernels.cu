@@ -409,39 +409,42 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& 
   return prefix;
 }
 
-// Ordered block reduction; the result is valid in thread THREADS / 32 - 1.  warp_out (optional): for each of the block's
-// THREADS / 32 warps the summary of the warps BEFORE it in the block (what the texts and emit passes seed their
-// warp scans with: one combine instead of a loop over the warps before), with WAGG_HAS_TEXT set in `kinds` when
-// the warp's own words hold a TextEnd (the texts pass only visits those).
+// Ordered block reduction of the reduce pass.  The texts and emit passes work in UNITS of 32 * COMPACT_WPT words (one
+// warp of theirs); the reduce pass may give a thread more words (REDUCE_WPT, a multiple of COMPACT_WPT: fewer, longer
+// threads measured faster for this pass), a unit then is LANES = 32 * COMPACT_WPT / REDUCE_WPT of its lanes.
+// unit_out: for each of the block's units the summary of the units BEFORE it in the block (what the other passes seed
+// their warp scans with: one combine instead of a loop), with WAGG_HAS_TEXT set in `kinds` when the unit's own words
+// hold a TextEnd (the texts pass only visits those).  Returns the block's summary, valid in thread UNITS - 1.
 constexpr uint32_t WAGG_HAS_TEXT = 1u << 31;
-template <int THREADS>
-__device__ __forceinline__ Agg block_reduce(const Agg& mine, Agg* warp_out) {
-  __shared__ Agg s_warp[THREADS / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <int THREADS, int LANES>
+__device__ __forceinline__ Agg block_reduce_units(const Agg& mine, Agg* unit_out) {
+  constexpr int UNITS = THREADS / LANES;
+  static_assert(LANES <= 32 && (LANES & (LANES - 1)) == 0 && UNITS <= 32, "unit shape");
+  __shared__ Agg s_unit[UNITS];
+  const int lane = threadIdx.x & 31;
   Agg v = mine;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
+  for (int d = 1; d < LANES; d <<= 1) {
     Agg o = agg_shfl_down(v, d);
     if ((lane & (2 * d - 1)) == 0) v = agg_combine(v, o);  // lanes lane..lane+2d-1, in order
   }
-  if (lane == 0) s_warp[warp] = v;
+  if ((lane & (LANES - 1)) == 0) s_unit[threadIdx.x / LANES] = v;
   __syncthreads();
   Agg tot = agg_zero();
-  if (warp == 0) {  // ordered scan of the warp totals by the first warp: lane j ends up with the warps before warp j
-    constexpr int WARPS = THREADS / 32;
-    const Agg own = lane < WARPS ? s_warp[lane] : agg_zero();
+  if (threadIdx.x < 32) {  // ordered scan of the unit totals by the first warp: lane j ends up with the units before unit j
+    const Agg own = lane < UNITS ? s_unit[lane] : agg_zero();
     Agg incl = own;
 #pragma unroll
-    for (int d = 1; d < WARPS; d <<= 1) {
+    for (int d = 1; d < UNITS; d <<= 1) {
       Agg o = agg_shfl_up(incl, d);
       if (lane >= d) incl = agg_combine(o, incl);
     }
     Agg ex = agg_shfl_up(incl, 1);
     if (lane == 0) ex = agg_zero();
-    tot = incl;  // (lane WARPS - 1: the block)
-    if (warp_out && lane < WARPS) {
+    tot = incl;  // (lane UNITS - 1: the block)
+    if (lane < UNITS) {
       if (own.n_text) ex.kinds |= WAGG_HAS_TEXT;
-      warp_out[lane] = ex;
+      unit_out[lane] = ex;
     }
   }
   return tot;
@@ -470,18 +473,23 @@ enum { K3_REDUCE = 0, K3_TEXTS = 1, K3_EMIT = 2 };
 
 // K3a: a CTA takes one block of THREADS * WPT words after the other (grid-stride) and leaves its summary in
 // block_agg[block] (and the warp prefixes in warp_agg) -- the same units the texts and emit passes use.
-__global__ void __launch_bounds__(COMPACT_THREADS) compact_reduce_kernel(CompactCtx c, CompactBuffers cb) {
+constexpr int REDUCE_WPT = DATOK_REDUCE_WPT;
+constexpr int REDUCE_THREADS = COMPACT_THREADS * COMPACT_WPT / REDUCE_WPT;  // the same block of words as the other passes
+static_assert(REDUCE_WPT % COMPACT_WPT == 0 && REDUCE_THREADS % 32 == 0 && REDUCE_THREADS * REDUCE_WPT == COMPACT_THREADS * COMPACT_WPT,
+              "the reduce pass covers the blocks of the texts / emit passes");
+__global__ void __launch_bounds__(REDUCE_THREADS) compact_reduce_kernel(CompactCtx c, CompactBuffers cb) {
+  constexpr int UNITS = COMPACT_THREADS / 32;
   for (uint32_t vb = blockIdx.x; vb < cb.n_blocks; vb += gridDim.x) {
-    const uint32_t w0 = (vb * COMPACT_THREADS + threadIdx.x) * COMPACT_WPT;
+    const uint32_t w0 = (vb * REDUCE_THREADS + threadIdx.x) * REDUCE_WPT;
     Agg ta = agg_zero();
 #pragma unroll
-    for (int k = 0; k < COMPACT_WPT; k++) {
+    for (int k = 0; k < REDUCE_WPT; k++) {
       const uint32_t w = w0 + k;
       if (w < c.n_words) ta = agg_combine(ta, word_agg(w, word_load(c, w)));
     }
-    const Agg tot = block_reduce<COMPACT_THREADS>(ta, cb.warp_agg + (size_t)vb * (COMPACT_THREADS / 32));
-    if (threadIdx.x == COMPACT_THREADS / 32 - 1) cb.block_agg[vb] = tot;
-    __syncthreads();  // block_reduce's shared slots are reused by the next block
+    const Agg tot = block_reduce_units<REDUCE_THREADS, 32 * COMPACT_WPT / REDUCE_WPT>(ta, cb.warp_agg + (size_t)vb * UNITS);
+    if (threadIdx.x == UNITS - 1) cb.block_agg[vb] = tot;
+    __syncthreads();  // the shared slots are reused by the next block
   }
 }
 
@@ -645,7 +653,7 @@ __global__ void compact_finalize_kernel(CompactCtx c, CompactBuffers cb, bool te
 void launch_compact_reduce(const CompactCtx& c, const CompactBuffers& cb, cudaStream_t s) {
   // one CTA per block of words: measured faster than a persistent grid of 8 CTAs per SM looping over the
   // blocks (0.26 against 0.31 ms per GiB); the kernel's loop then runs once
-  compact_reduce_kernel<<<cb.n_blocks, COMPACT_THREADS, 0, s>>>(c, cb);
+  compact_reduce_kernel<<<cb.n_blocks, REDUCE_THREADS, 0, s>>>(c, cb);
 }
 void launch_compact_scan(const CompactBuffers& cb, bool sentence_end_in, cudaStream_t s) {
   const uint32_t groups = (cb.n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
