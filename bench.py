@@ -59,6 +59,15 @@ def measured_traffic(n_bytes):
     return None
 
 
+def profiled_counters():
+    """counters of the two dominant kernels from the committed ncu source-level captures of the same code and
+    corpus (profiles/r2_kernel_counters.json): context for the roofline figure, not measured in this run"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_counters.json")))
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -516,7 +525,8 @@ def main():
                          "algorithmic_bytes": alg_bytes, "formula": "N + 8*tokens + 8*sentences + 8*documents",
                          "kernel": "whole device path (all kernels of one step); per-kernel ms in kernel_ms, "
                                    "per-kernel rooflines in kernels",
-                         "dominant_kernel": dominant, "kernel_ms": kt, "kernels": kroof, "gather": gather},
+                         "dominant_kernel": dominant, "kernel_ms": kt, "kernels": kroof, "gather": gather,
+                         "profiled_counters": profiled_counters()},
             "cpu_baseline": cpu,
             "e2e": {"value": Ntot / (ms_fmt * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N,
                     "d2h_bytes_per_step": d2h_fmt_tot // world, "ms_per_step": ms_fmt,
