@@ -60,7 +60,7 @@ def measured_traffic(n_bytes):
 
 
 def profiled_counters():
-    """counters of the two dominant kernels from the committed ncu source-level captures of the same code and
+    """counters of the walk, emit and stitch kernels from the committed ncu source-level captures of the same code and
     corpus (profiles/r2_kernel_counters.json): context for the roofline figure, not measured in this run"""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_counters.json")))

@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactCtx c, 
   }
   // summary of everything before this block: (groups of 1024 blocks before) + (blocks before, in the group)
   const Agg block_start = agg_combine(cb.super_carry[blockIdx.x / SCAN_THREADS], cb.block_carry[blockIdx.x]);
-  // prefix of this thread: warps before it in the block (totals left by the reduce pass), lanes before it
+  // prefix of this thread: warps before it in the block (their summary, left by the reduce pass), lanes before it
   const Agg seed = agg_combine(block_start, load_warp_prefix(cb.warp_agg, (size_t)blockIdx.x * (COMPACT_THREADS / 32) + (threadIdx.x >> 5)));
   Agg carry = warp_exclusive_scan(ta, seed);
   // K3_EMIT
