@@ -90,6 +90,16 @@ DATOK_HD Agg agg_combine(const Agg& A, const Agg& B) {
   return R;
 }
 
+// What the reduce pass leaves per warp unit (32 * COMPACT_WPT words) for the texts and emit passes: the summary of the
+// units BEFORE it in its block, with WAGG_HAS_TEXT set in `kinds` (whose kinds use 16 bits) when the unit's own words
+// hold a TextEnd.
+constexpr uint32_t WAGG_HAS_TEXT = 1u << 31;
+DATOK_HD Agg load_warp_prefix(const Agg* warp_agg, size_t unit) {
+  Agg a = warp_agg[unit];
+  a.kinds &= ~WAGG_HAS_TEXT;
+  return a;
+}
+
 struct CompactCtx {
   const uint8_t* in;       // input bytes (for the NEWLINE_AFTER_EOT test, token_writer.go:66)
   uint32_t N;

@@ -415,7 +415,6 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& mine, const Agg& 
 // unit_out: for each of the block's units the summary of the units BEFORE it in the block (what the other passes seed
 // their warp scans with: one combine instead of a loop), with WAGG_HAS_TEXT set in `kinds` when the unit's own words
 // hold a TextEnd (the texts pass only visits those).  Returns the block's summary, valid in thread UNITS - 1.
-constexpr uint32_t WAGG_HAS_TEXT = 1u << 31;
 template <int THREADS, int LANES>
 __device__ __forceinline__ Agg block_reduce_units(const Agg& mine, Agg* unit_out) {
   constexpr int UNITS = THREADS / LANES;
@@ -448,12 +447,6 @@ __device__ __forceinline__ Agg block_reduce_units(const Agg& mine, Agg* unit_out
     }
   }
   return tot;
-}
-// the summary of the warps before warp `unit % WARPS` in its block, as left by the reduce pass
-__device__ __forceinline__ Agg load_warp_prefix(const Agg* warp_agg, size_t unit) {
-  Agg a = warp_agg[unit];
-  a.kinds &= ~WAGG_HAS_TEXT;
-  return a;
 }
 
 // Ordered exclusive scan within one warp, combined after `seed`.

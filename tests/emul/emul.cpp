@@ -201,16 +201,22 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   c.b_sent = b.b_sent; c.b_tend = b.b_tend; c.flags = flags; c.err_key = &err_key; c.eot_rewind = m.eot_rewind;
   const uint32_t TPB = 256, WPT = 2, WPB = TPB * WPT;
   const uint32_t nblk = (b.n_words + WPB - 1) / WPB;
-  std::vector<Agg> block_agg(nblk), block_carry(nblk);
+  // like the reduce kernel: per block its summary, per warp unit (32 threads * WPT words) the summary of the units
+  // before it in the block, marked when the unit itself holds a TextEnd
+  const uint32_t UPB = TPB / 32, UW = 32 * WPT;  // units per block, words per unit
+  std::vector<Agg> block_agg(nblk), block_carry(nblk), unit_prefix((size_t)nblk * UPB);
   for (uint32_t blk = 0; blk < nblk; blk++) {
     Agg acc = agg_zero();
-    for (uint32_t t = 0; t < TPB; t++) {
-      Agg ta = agg_zero();
-      for (uint32_t k = 0; k < WPT; k++) {
-        uint32_t w = blk * WPB + t * WPT + k;
-        if (w < b.n_words) ta = agg_combine(ta, word_agg(w, word_load(c, w)));
+    for (uint32_t u = 0; u < UPB; u++) {
+      Agg ua = agg_zero();
+      for (uint32_t k = 0; k < UW; k++) {
+        uint32_t w = blk * WPB + u * UW + k;
+        if (w < b.n_words) ua = agg_combine(ua, word_agg(w, word_load(c, w)));
       }
-      acc = agg_combine(acc, ta);
+      Agg ex = acc;
+      if (ua.n_text) ex.kinds |= WAGG_HAS_TEXT;
+      unit_prefix[(size_t)blk * UPB + u] = ex;
+      acc = agg_combine(acc, ua);
     }
     block_agg[blk] = acc;
   }
@@ -243,7 +249,22 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
   unsigned long long err_key_delta = ~0ull;
   CompactCtx cd = c;
   cd.err_key = &err_key_delta;
-  for (int pass = 0; pass < 2; pass++) {  // 0: texts, 1: tokens + sentences
+  {  // texts pass: the marked units only, in any order, each seeded with block carry + unit prefix (like the kernel)
+    const uint32_t n_units = nblk * UPB;
+    for (uint32_t ku = 0; ku < n_units; ku++) {
+      const uint32_t u = order ? n_units - 1 - ku : ku;
+      if (!(unit_prefix[u].kinds & WAGG_HAS_TEXT)) continue;
+      Agg carry = agg_combine(block_carry[u / UPB], load_warp_prefix(unit_prefix.data(), u));
+      for (uint32_t k = 0; k < UW; k++) {
+        const uint32_t w = u * UW + k;
+        if (w >= b.n_words) continue;
+        const WordBits wb = word_load(c, w);
+        emit_texts(c, w, wb, carry);
+        carry = agg_combine(carry, word_agg(w, wb));
+      }
+    }
+  }
+  for (int pass = 1; pass < 2; pass++) {  // tokens + sentences
     for (uint32_t kb = 0; kb < nblk; kb++) {
       uint32_t blk = order ? nblk - 1 - kb : kb;
       Agg carry = block_carry[blk];
@@ -254,12 +275,13 @@ EmulResult* emul_transduce(EmulModel* em, const uint8_t* in, uint32_t N, uint32_
       std::vector<int32_t> s_tp(2 * 64 + 2);
       std::vector<uint16_t> s_td(4 * 64 + 4), s_t8(2 * 64 + 4);
       for (uint32_t t = 0; t < TPB; t++) {
+        // (a warp of the emit kernel seeds its scan with the block's carry and its unit's prefix)
+        if (t % 32 == 0) carry = agg_combine(block_carry[blk], load_warp_prefix(unit_prefix.data(), (size_t)blk * UPB + t / 32));
         for (uint32_t k = 0; k < WPT; k++) {
           uint32_t w = blk * WPB + t * WPT + k;
           if (w >= b.n_words) continue;
           const WordBits wb = word_load(c, w);
-          if (pass == 0) emit_texts(c, w, wb, carry);
-          else if (wb.e | wb.s | wb.t) {
+          if (wb.e | wb.s | wb.t) {
             const WordMasks wm = word_masks(wb, agg_last(carry));
             emit_tokens<0>(c, w, wb, wm, carry, staged ? s_tb.data() : c.tok_bytes, staged ? s_tp.data() : c.tok_pos,
                            nullptr, staged ? blk_tok0 : 0u);
